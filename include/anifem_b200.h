@@ -1,0 +1,138 @@
+/* anifem_b200.h -- C ABI of the B200-native element-matrix + global-assembly path.
+ *
+ * This is the drop-in boundary: plain C, pointers + sizes, no C++/torch
+ * types.  Every entry point names the reference interface it replaces (paths relative to the
+ * AniFem++ tree, INMOST-DEV/INMOST-FEM).  The C++ mirror of the reference API that sits on top
+ * of this file (Ani::fem3Dtet<...>, Ani::Assembler) lives in inmost-fem_b200/include/anifem_b200/.
+ *
+ * Conventions
+ *   - FP64 values, column-major dense matrices, exactly as the reference (fem/fem_memory.h:55-64).
+ *   - `mem_space` says where the caller's buffers live: AFB_HOST (copied through the context's
+ *     stream) or AFB_DEVICE (used in place / copied device-to-device).  The context owns device
+ *     copies of mesh, dof tables, pattern and plan; callers own everything they pass in.
+ *   - One context per GPU, single owner, all work on the context's CUDA stream.
+ *   - Return codes: 0 ok; -1 a local matrix/rhs value is not finite (assembler.inl:419-424,
+ *     475-479); -2 bad mesh element (assembler.inl:309-312); <= -3 usage errors (the reference
+ *     throws std::runtime_error there): -3 unsupported operator/space, -4 CUDA/runtime failure,
+ *     -5 identity/scalar tensor with incompatible operator dimensions (diff_tensor.h:315-317),
+ *     -6 call order / missing state (assembler.inl:195-196,316-317), -7 bad argument.
+ *   - There is NO CPU fallback: without a CUDA device every compute entry point fails with -4.
+ */
+#ifndef ANIFEM_B200_H
+#define ANIFEM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct afb_ctx afb_ctx;
+
+enum { AFB_HOST = 0, AFB_DEVICE = 1 };
+
+/* values = Ani::OperatorType (fem/operators.h:36-44) */
+enum { AFB_IDEN = 1, AFB_GRAD = 2, AFB_DIV = 3 };
+/* values = Ani::FiniteElement (fem/operators.h:24-34) */
+enum { AFB_FEM_P0 = 1, AFB_FEM_P1 = 2, AFB_FEM_P2 = 3, AFB_FEM_P3 = 4 };
+/* values = Ani::TensorType (fem/diff_tensor.h:17-22) */
+enum { AFB_TENSOR_NULL = 1, AFB_TENSOR_SCALAR = 2, AFB_TENSOR_SYMMETRIC = 3, AFB_TENSOR_GENERAL = 4 };
+/* where the coefficient varies: replaces DfuncTraits<..., isConstant> + the per-point callback
+ * (fem/diff_tensor.h:36-53): CONST = one tensor, PER_TET = one per tetrahedron (callback ignoring x),
+ * PER_POINT = one per quadrature point, the FusiveTensor layout D[len*(n + q*r)] (diff_tensor.h:112-124) */
+enum { AFB_COEF_CONST = 0, AFB_COEF_PER_TET = 1, AFB_COEF_PER_POINT = 2 };
+
+/* One volume form  int_T (D OpA(u)) . OpB(v) dx  = one fem3Dtet<OpA,OpB,Traits> call
+ * (fem/operations/int_tet.h:17-29).  Operator<op, FemFix<fem>> when vec == 1,
+ * Operator<op, FemVec<3,fem>> when vec == 3 (fem/operators.h:50-67,127-155,320-353).
+ * D is in the layout a reference user callback writes: a col-major (jdim x idim) matrix
+ * K(k,j) at D[k + jdim*j], jdim = Dim(OpB), idim = Dim(OpA) (fem/operations/core.h:27-40);
+ * 1 value for TENSOR_SCALAR, unused for TENSOR_NULL. */
+typedef struct afb_form {
+    int opA, femA, vecA;   /* trial side: columns of the element matrix */
+    int opB, femB, vecB;   /* test side: rows of the element matrix */
+    int quad_order;        /* 0..20, tetrahedron_quadrature_formulas(order) (fem/quadrature_formulas.h:214) */
+    int tensor_type;       /* AFB_TENSOR_* */
+    int coef_layout;       /* AFB_COEF_* */
+    int coef_space;        /* AFB_HOST / AFB_DEVICE: where D lives */
+    const double* D;
+    double alpha;          /* the block is scaled by alpha before it is added */
+    int row_off, col_off;  /* offset of the block inside the (nrow_loc x ncol_loc) element matrix */
+} afb_form;
+
+/* ---- context --------------------------------------------------------------------------------- */
+/* cuda_stream: a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or NULL for a private one. */
+int afb_ctx_create(int device, void* cuda_stream, afb_ctx** out);
+void afb_ctx_destroy(afb_ctx* ctx);
+const char* afb_last_error(const afb_ctx* ctx); /* ctx may be NULL: last error of the calling thread */
+int afb_sync(afb_ctx* ctx);
+/* number of kernels this library launched on the context since the last reset (bench evidence) */
+int64_t afb_launch_count(afb_ctx* ctx, int reset);
+
+/* ---- element level: replaces Ani::fem3Dtet (fem/operations/int_tet.inl:3-57) ------------------ */
+/* Batched element matrices: XYk are 3 x f col-major (fem/geometry.h:108-122), A is nfB x (nfA*f)
+ * col-major, block r at column offset nfA*r (core.h:41).  The tets need not be oriented. */
+int afb_fem3dtet_batched(afb_ctx* ctx, const afb_form* form, int64_t f,
+                         const double* XY0, const double* XY1, const double* XY2, const double* XY3,
+                         double* A, int mem_space);
+/* Nfa / Dim of an operator (Operator<>::Nfa, ::Dim) */
+int afb_op_dims(int op, int fem, int vec, int* nfa, int* dim);
+/* quadrature rule (fem/quadrature_formulas.cpp:526,1493-1502): returns q, fills p[4q], w[q] if non-NULL */
+int afb_tet_quadrature(int order, double* p, double* w, int capacity);
+/* physical quadrature points XYG[3*(n + q*r)] (core.inl:249-269), for building PER_POINT coefficients */
+int afb_quad_points(afb_ctx* ctx, int order, int64_t f, const double* XY0, const double* XY1,
+                    const double* XY2, const double* XY3, double* XYG, int mem_space);
+
+/* ---- mesh: the per-cell inputs of AssemblerT::Assemble (assembler.inl:353-364) ---------------- */
+/* SoA coordinates + connectivity.  Copies into the context. */
+int afb_mesh_set(afb_ctx* ctx, int64_t nnode, const double* x, const double* y, const double* z,
+                 int64_t ntet, const int32_t* v0, const int32_t* v1, const int32_t* v2, const int32_t* v3,
+                 int mem_space);
+/* GenerateParallelepiped on [0,size]^3 (utils/mesh_utils.cpp:20-48,110-145): the (bx,by,bz)+(lx,ly,lz)
+ * block of hexes of an nx*ny*nz cube, 6 tets per hex, nodes in (i,j,k) order; built on the device. */
+int afb_mesh_cube(afb_ctx* ctx, int nx, int ny, int nz, double size,
+                  int bx, int by, int bz, int lx, int ly, int lz);
+/* reorderNodesOnTetrahedron (inmost_interface/ordering.inl:8-26): swap nodes 2,3 where det < 0 */
+int afb_mesh_orient(afb_ctx* ctx);
+int afb_mesh_get(afb_ctx* ctx, int64_t* nnode, int64_t* ntet, double* xyz_soa /*3*nnode*/, int32_t* v_soa /*4*ntet*/, int mem_space);
+
+/* ---- dof map: m_indexesR / m_indexesC of fill_assemble_templates (assembler.inl:139-184) ------ */
+/* Explicit tables: elem2row[i + nrow_loc*e], elem2col[j + ncol_loc*e] hold assemble_index_encode
+ * codes sign*(id+1), 0 = row skipped (ghost) (assembler.inl:49-55).  Rows live in
+ * [row_begin,row_end) = [getBegInd(),getEndInd()), columns in [0,ncols_global). */
+int afb_dofmap_set(afb_ctx* ctx, int nrow_loc, int ncol_loc, const int64_t* elem2row, const int64_t* elem2col,
+                   int64_t row_begin, int64_t row_end, int64_t ncols_global, int mem_space);
+/* GlobEnumeration NATURAL on one rank (global_enumerator.cpp:562-605,702-777): variables
+ * (fem[v], vec[v]) numbered (VAR, DIM, ELEM_TYPE, ELEM_ID, DOF_ID); edges/faces get ids in
+ * lexicographic order of their sorted node pairs/triples (our stand-in for INMOST GlobalIDs).
+ * Same trial and test space. Builds the tables on the device. */
+int afb_dofmap_natural(afb_ctx* ctx, int nvars, const int* fem, const int* vec);
+int afb_dofmap_get(afb_ctx* ctx, int* nrow_loc, int* ncol_loc, int64_t* row_begin, int64_t* row_end,
+                   int64_t* ncols_global, int64_t* elem2row, int64_t* elem2col, int mem_space);
+
+/* ---- pattern: AssembleTemplate (assembler.inl:589-695) + forced diagonal (:114-136) ----------- */
+/* Structural CSR over the owned rows, columns ascending, built on the device from the dof map;
+ * also builds the gather plan (row -> contributing element rows, slot table) used by afb_assemble. */
+int afb_pattern_build(afb_ctx* ctx, int64_t* nnz);
+int afb_pattern_get(afb_ctx* ctx, int64_t* rowptr /*nrows+1*/, int32_t* colind /*nnz*/, int mem_space);
+
+/* ---- assembly: AssemblerT::Assemble / AssembleMatrix / AssembleRHS (assembler.inl:313-488,
+ * 497-580, 704-865) with is_mtx_include_template = use_ordered_insert = true ------------------ */
+/* csr_val[nnz] and rhs[nrows] (either may be NULL).  accumulate != 0 adds to the existing contents
+ * like the reference (assembler.inl:305-306), otherwise they are overwritten.  Entries with
+ * |A_e(i,j)| <= drop_val are not added (assembler.h:212, assembler.inl:416).  rhs forms use the
+ * reference's RHS trick OpA = IDEN(P0) (tests/fem/operations/int_tet_test.cpp:448-501): opA/femA/vecA
+ * of an rhs form must be (AFB_IDEN, AFB_FEM_P0, 1).  Deterministic: fixed summation order
+ * (ascending element index per row), no atomics. */
+int afb_assemble(afb_ctx* ctx, int nforms, const afb_form* forms, int nrhs_forms, const afb_form* rhs_forms,
+                 double* csr_val, double* rhs, int accumulate, double drop_val, int mem_space);
+
+/* phase times of the last afb_assemble in ms (CUDA events on the context stream):
+ * [0] element kernels, [1] gather/scatter, [2] copies; mirrors GetTimeEvalLocFunc / GetTimeFillMapTemplate
+ * style getters (assembler.inl:949-964) */
+int afb_last_times(afb_ctx* ctx, double* ms3);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ANIFEM_B200_H */

@@ -1,0 +1,278 @@
+"""inmost-fem_b200: B200-native element-matrix + global-assembly path behind the AniFem++ API.
+
+This Python module is plumbing only: a ctypes binding of the C ABI in include/anifem_b200.h
+(libanifem_b200.so, hand-written CUDA for sm_100a) used by tests/ and bench.py.  The product is
+the shared library; the C++ mirror of the reference API lives in include/anifem_b200/*.hpp.
+There is no CPU fallback: if the library is missing or no GPU is present, calls fail loudly.
+
+Load it with `__graft_entry__.load_package()` (the directory name is not a Python identifier).
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libanifem_b200.so")
+
+HOST, DEVICE = 0, 1
+IDEN, GRAD, DIV = 1, 2, 3
+P0, P1, P2, P3 = 1, 2, 3, 4
+TENSOR_NULL, TENSOR_SCALAR, TENSOR_SYMMETRIC, TENSOR_GENERAL = 1, 2, 3, 4
+COEF_CONST, COEF_PER_TET, COEF_PER_POINT = 0, 1, 2
+
+_dp = ctypes.POINTER(ctypes.c_double)
+_i32p = ctypes.POINTER(ctypes.c_int32)
+_i64p = ctypes.POINTER(ctypes.c_int64)
+
+
+class AfbForm(ctypes.Structure):
+    """struct afb_form of include/anifem_b200.h"""
+    _fields_ = [("opA", ctypes.c_int), ("femA", ctypes.c_int), ("vecA", ctypes.c_int),
+                ("opB", ctypes.c_int), ("femB", ctypes.c_int), ("vecB", ctypes.c_int),
+                ("quad_order", ctypes.c_int), ("tensor_type", ctypes.c_int), ("coef_layout", ctypes.c_int),
+                ("coef_space", ctypes.c_int), ("D", ctypes.c_void_p), ("alpha", ctypes.c_double),
+                ("row_off", ctypes.c_int), ("col_off", ctypes.c_int)]
+
+
+EXPORTS = ["afb_ctx_create", "afb_ctx_destroy", "afb_last_error", "afb_sync", "afb_launch_count",
+           "afb_fem3dtet_batched", "afb_op_dims", "afb_tet_quadrature", "afb_quad_points",
+           "afb_mesh_set", "afb_mesh_cube", "afb_mesh_orient", "afb_mesh_get",
+           "afb_dofmap_set", "afb_dofmap_natural", "afb_dofmap_get",
+           "afb_pattern_build", "afb_pattern_get", "afb_assemble", "afb_last_times"]
+
+
+def build(verbose=False):
+    """compile libanifem_b200.so for sm_100a in-tree (nvcc cross-compiles without a GPU)"""
+    out = subprocess.run(["make", "-C", HERE, "-j8"], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("building libanifem_b200.so failed:\n" + out.stdout + out.stderr)
+    if verbose:
+        print(out.stdout)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libanifem_b200.so is not built (run __graft_entry__.build()); there is no CPU fallback")
+        L = ctypes.CDLL(LIB_PATH)
+        vp, ci, c64, cd = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double
+        L.afb_ctx_create.argtypes = [ci, vp, ctypes.POINTER(vp)]
+        L.afb_ctx_destroy.argtypes = [vp]
+        L.afb_ctx_destroy.restype = None
+        L.afb_last_error.argtypes = [vp]
+        L.afb_last_error.restype = ctypes.c_char_p
+        L.afb_sync.argtypes = [vp]
+        L.afb_launch_count.argtypes = [vp, ci]
+        L.afb_launch_count.restype = c64
+        L.afb_fem3dtet_batched.argtypes = [vp, ctypes.POINTER(AfbForm), c64, vp, vp, vp, vp, vp, ci]
+        L.afb_op_dims.argtypes = [ci, ci, ci, ctypes.POINTER(ci), ctypes.POINTER(ci)]
+        L.afb_tet_quadrature.argtypes = [ci, vp, vp, ci]
+        L.afb_quad_points.argtypes = [vp, ci, c64, vp, vp, vp, vp, vp, ci]
+        L.afb_mesh_set.argtypes = [vp, c64, vp, vp, vp, c64, vp, vp, vp, vp, ci]
+        L.afb_mesh_cube.argtypes = [vp, ci, ci, ci, cd, ci, ci, ci, ci, ci, ci]
+        L.afb_mesh_orient.argtypes = [vp]
+        L.afb_mesh_get.argtypes = [vp, _i64p, _i64p, vp, vp, ci]
+        L.afb_dofmap_set.argtypes = [vp, ci, ci, vp, vp, c64, c64, c64, ci]
+        L.afb_dofmap_natural.argtypes = [vp, ci, ctypes.POINTER(ci), ctypes.POINTER(ci)]
+        L.afb_dofmap_get.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(ci), _i64p, _i64p, _i64p, vp, vp, ci]
+        L.afb_pattern_build.argtypes = [vp, _i64p]
+        L.afb_pattern_get.argtypes = [vp, vp, vp, ci]
+        L.afb_assemble.argtypes = [vp, ci, ctypes.POINTER(AfbForm), ci, ctypes.POINTER(AfbForm), vp, vp, ci, cd, ci]
+        L.afb_last_times.argtypes = [vp, _dp]
+        _lib = L
+    return _lib
+
+
+class AfbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("anifem_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def _ptr(a):
+    """(address, mem_space) of a numpy array (host) or a torch tensor (host or cuda)"""
+    if a is None:
+        return None, HOST
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data, HOST
+    # torch tensor
+    assert a.is_contiguous()
+    return a.data_ptr(), (DEVICE if a.is_cuda else HOST)
+
+
+def op_dims(op, fem, vec):
+    nfa, dim = ctypes.c_int(), ctypes.c_int()
+    rc = lib().afb_op_dims(op, fem, vec, ctypes.byref(nfa), ctypes.byref(dim))
+    if rc:
+        raise AfbError(rc, "unsupported operator/space")
+    return nfa.value, dim.value
+
+
+def tet_quadrature(order):
+    q = lib().afb_tet_quadrature(order, None, None, 0)
+    if q < 0:
+        raise AfbError(q, "quadrature order must be in 0..20")
+    p, w = np.zeros(4 * q), np.zeros(q)
+    lib().afb_tet_quadrature(order, p.ctypes.data, w.ctypes.data, q)
+    return p.reshape(q, 4), w
+
+
+def make_form(opA, femA, vecA, opB, femB, vecB, order, ttype, layout, D=None, alpha=1.0, row_off=0, col_off=0):
+    """afb_form + a reference to D so that it outlives the call (the reference takes the tensor
+    functor by const-ref with the same lifetime rule, fem/diff_tensor.h:67-70)"""
+    addr, space = _ptr(D)
+    f = AfbForm(opA, femA, vecA, opB, femB, vecB, order, ttype, layout, space, addr, alpha, row_off, col_off)
+    f._keep = D
+    return f
+
+
+class Context:
+    """One assembly context = one GPU + one stream (afb_ctx)."""
+
+    def __init__(self, device=0, stream=None):
+        self._h = ctypes.c_void_p()
+        rc = lib().afb_ctx_create(device, stream, ctypes.byref(self._h))
+        if rc:
+            raise AfbError(rc, lib().afb_last_error(None).decode())
+
+    def close(self):
+        if self._h:
+            lib().afb_ctx_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, allow=()):
+        if rc < 0 and rc not in allow:
+            raise AfbError(rc, lib().afb_last_error(self._h).decode())
+        return rc
+
+    def sync(self):
+        self._ck(lib().afb_sync(self._h))
+
+    def launch_count(self, reset=False):
+        return int(lib().afb_launch_count(self._h, 1 if reset else 0))
+
+    # ---- element level -------------------------------------------------------------------------
+    def fem3dtet(self, form, XY, out=None):
+        """Batched Ani::fem3Dtet: XY (4, f, 3) numpy -> A (f, nfA, nfB) numpy with
+        A[r, ia, ib] = reference A.data[ib + nfB*(ia + nfA*r)]"""
+        XY = np.ascontiguousarray(XY, dtype=np.float64)
+        f = XY.shape[1]
+        nfa, _ = op_dims(form.opA, form.femA, form.vecA)
+        nfb, _ = op_dims(form.opB, form.femB, form.vecB)
+        A = np.zeros((f, nfa, nfb)) if out is None else out
+        xs = [np.ascontiguousarray(XY[k]) for k in range(4)]
+        self._ck(lib().afb_fem3dtet_batched(self._h, ctypes.byref(form), f, xs[0].ctypes.data, xs[1].ctypes.data,
+                                            xs[2].ctypes.data, xs[3].ctypes.data, A.ctypes.data, HOST))
+        return A
+
+    def quad_points(self, order, XY):
+        XY = np.ascontiguousarray(XY, dtype=np.float64)
+        f = XY.shape[1]
+        q = tet_quadrature(order)[1].size
+        out = np.zeros((f, q, 3))
+        xs = [np.ascontiguousarray(XY[k]) for k in range(4)]
+        self._ck(lib().afb_quad_points(self._h, order, f, xs[0].ctypes.data, xs[1].ctypes.data, xs[2].ctypes.data,
+                                       xs[3].ctypes.data, out.ctypes.data, HOST))
+        return out
+
+    # ---- mesh ----------------------------------------------------------------------------------
+    def mesh_set(self, coords, tets):
+        """coords (nnode,3) float64, tets (ntet,4) integer (numpy, host)"""
+        coords = np.asarray(coords, dtype=np.float64)
+        xs = [np.ascontiguousarray(coords[:, k]) for k in range(3)]
+        vs = [np.ascontiguousarray(np.asarray(tets)[:, k], dtype=np.int32) for k in range(4)]
+        self._ck(lib().afb_mesh_set(self._h, coords.shape[0], xs[0].ctypes.data, xs[1].ctypes.data, xs[2].ctypes.data,
+                                    len(vs[0]), vs[0].ctypes.data, vs[1].ctypes.data, vs[2].ctypes.data, vs[3].ctypes.data, HOST))
+
+    def mesh_cube(self, nx, ny, nz, size=1.0, block=None):
+        bx, by, bz, lx, ly, lz = (0, 0, 0, nx, ny, nz) if block is None else block
+        self._ck(lib().afb_mesh_cube(self._h, nx, ny, nz, size, bx, by, bz, lx, ly, lz))
+
+    def mesh_orient(self):
+        self._ck(lib().afb_mesh_orient(self._h))
+
+    def mesh_sizes(self):
+        nn, nt = ctypes.c_int64(), ctypes.c_int64()
+        self._ck(lib().afb_mesh_get(self._h, ctypes.byref(nn), ctypes.byref(nt), None, None, HOST))
+        return nn.value, nt.value
+
+    def mesh_get(self):
+        nn, nt = self.mesh_sizes()
+        xyz = np.zeros((3, nn))
+        v = np.zeros((4, nt), dtype=np.int32)
+        self._ck(lib().afb_mesh_get(self._h, None, None, xyz.ctypes.data, v.ctypes.data, HOST))
+        return np.ascontiguousarray(xyz.T), np.ascontiguousarray(v.T)
+
+    # ---- dof map -------------------------------------------------------------------------------
+    def dofmap_set(self, rowcode, colcode, row_begin, row_end, ncols_global):
+        rowcode = np.ascontiguousarray(rowcode, dtype=np.int64)
+        colcode = np.ascontiguousarray(colcode, dtype=np.int64)
+        self._ck(lib().afb_dofmap_set(self._h, rowcode.shape[1], colcode.shape[1], rowcode.ctypes.data, colcode.ctypes.data,
+                                      row_begin, row_end, ncols_global, HOST))
+
+    def dofmap_natural(self, variables):
+        n = len(variables)
+        fem = (ctypes.c_int * n)(*[v[0] for v in variables])
+        vec = (ctypes.c_int * n)(*[v[1] for v in variables])
+        self._ck(lib().afb_dofmap_natural(self._h, n, fem, vec))
+
+    def dofmap_info(self):
+        nr, nc = ctypes.c_int(), ctypes.c_int()
+        rb, re, ng = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        self._ck(lib().afb_dofmap_get(self._h, ctypes.byref(nr), ctypes.byref(nc), ctypes.byref(rb), ctypes.byref(re),
+                                      ctypes.byref(ng), None, None, HOST))
+        return nr.value, nc.value, rb.value, re.value, ng.value
+
+    def dofmap_get(self):
+        nr, nc, rb, re, ng = self.dofmap_info()
+        _, nt = self.mesh_sizes()
+        row = np.zeros((nt, nr), dtype=np.int64)
+        col = np.zeros((nt, nc), dtype=np.int64)
+        self._ck(lib().afb_dofmap_get(self._h, None, None, None, None, None, row.ctypes.data, col.ctypes.data, HOST))
+        return row, col
+
+    # ---- pattern -------------------------------------------------------------------------------
+    def pattern_build(self):
+        nnz = ctypes.c_int64()
+        self._ck(lib().afb_pattern_build(self._h, ctypes.byref(nnz)))
+        self.nnz = nnz.value
+        return nnz.value
+
+    def pattern_get(self):
+        _, _, rb, re, _ = self.dofmap_info()
+        rowptr = np.zeros(re - rb + 1, dtype=np.int64)
+        colind = np.zeros(max(self.nnz, 1), dtype=np.int32)
+        self._ck(lib().afb_pattern_get(self._h, rowptr.ctypes.data, colind.ctypes.data, HOST))
+        return rowptr, colind[:self.nnz]
+
+    # ---- assembly ------------------------------------------------------------------------------
+    def assemble(self, forms, rhs_forms, val=None, rhs=None, accumulate=False, drop_val=1e-100):
+        """val / rhs: numpy arrays (host) or torch cuda tensors (device), both in the same space.
+        Returns the reference's status code (0 ok, -1 non-finite local value)."""
+        fa = (AfbForm * max(1, len(forms)))(*forms)
+        fr = (AfbForm * max(1, len(rhs_forms)))(*rhs_forms)
+        pv, sv = _ptr(val)
+        pr, sr = _ptr(rhs)
+        space = sv if val is not None else sr
+        if val is not None and rhs is not None:
+            assert sv == sr
+        return self._ck(lib().afb_assemble(self._h, len(forms), fa, len(rhs_forms), fr, pv, pr, 1 if accumulate else 0,
+                                           drop_val, space), allow=(-1,))
+
+    def last_times(self):
+        t = (ctypes.c_double * 3)()
+        lib().afb_last_times(self._h, t)
+        return {"element_ms": t[0], "gather_ms": t[1], "copy_ms": t[2]}

@@ -1,0 +1,279 @@
+// Element-matrix kernels (K1): batched replacement of Ani::fem3Dtet / internalFem3Dtet
+// (reference: fem/operations/int_tet.inl:30-57, core.inl:217-367; tensor application
+// fem/diff_tensor.h:276-994; contraction core.inl:28-60; band structure of vector spaces
+// fem/operators.h:127-155, DIV :320-353).
+//
+// k_element_generic: one warp per tetrahedron, any operator/space/tensor combination.
+//   geometry   -> every lane redundantly: edge vectors, PSI = inverse Jacobian, |T| (registers)
+//   tables     -> physical base gradients Ub[d][n][a] = sum_j PSI[j + 3d] * G^[n][a][j]   (shared)
+//   DU         -> DU[k][n][ia] = w_n |T| sum_j K(k,j) U[j,n,ia], band of ia only           (shared)
+//   A(ib,ia)   -> sum_n sum_d Vb[d][n][b] * DU[band(ib)+d][n][ia], entries strided over lanes,
+//                 accumulators in registers, quadrature points processed in shared-memory chunks
+// The reference tables phi / G^ are element independent and come from afb_tables.cpp.
+#include <cstdio>
+
+#include "afb_internal.h"
+
+namespace {
+
+struct GeomSrc {
+    const double *x, *y, *z;
+    const int32_t *v0, *v1, *v2, *v3;
+    const double* XY[4];  // 3 x f col-major each, used when x == nullptr
+};
+
+__device__ __forceinline__ void load_tet(const GeomSrc& g, long long e, double P[4][3]) {
+    if (g.x) {
+        const int n0 = __ldg(g.v0 + e), n1 = __ldg(g.v1 + e), n2 = __ldg(g.v2 + e), n3 = __ldg(g.v3 + e);
+        const int nn[4] = {n0, n1, n2, n3};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            P[k][0] = __ldg(g.x + nn[k]);
+            P[k][1] = __ldg(g.y + nn[k]);
+            P[k][2] = __ldg(g.z + nn[k]);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            P[k][0] = __ldg(g.XY[k] + 3 * e + 0);
+            P[k][1] = __ldg(g.XY[k] + 3 * e + 1);
+            P[k][2] = __ldg(g.XY[k] + 3 * e + 2);
+        }
+    }
+}
+
+// PSI[j + 3k] = (M^-1)(j,k), M columns = P1-P0, P2-P0, P3-P0; returns det  (cofactor inverse)
+__device__ __forceinline__ double jacobian_inverse(const double P[4][3], double PSI[9]) {
+    double m[9];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) m[i + 3 * c] = P[c + 1][i] - P[0][i];
+    const double c00 = m[4] * m[8] - m[7] * m[5];
+    const double c01 = m[7] * m[2] - m[1] * m[8];
+    const double c02 = m[1] * m[5] - m[4] * m[2];
+    const double det = m[0] * c00 + m[3] * c01 + m[6] * c02;
+    const double id = 1.0 / det;
+    // inv(j,k) = cof(k,j)/det ; stored at PSI[j + 3k]
+    PSI[0] = c00 * id;                           // inv(0,0)
+    PSI[3] = c01 * id;                           // inv(0,1)
+    PSI[6] = c02 * id;                           // inv(0,2)
+    PSI[1] = (m[6] * m[5] - m[3] * m[8]) * id;   // inv(1,0)
+    PSI[4] = (m[0] * m[8] - m[6] * m[2]) * id;   // inv(1,1)
+    PSI[7] = (m[3] * m[2] - m[0] * m[5]) * id;   // inv(1,2)
+    PSI[2] = (m[3] * m[7] - m[6] * m[4]) * id;   // inv(2,0)
+    PSI[5] = (m[6] * m[1] - m[0] * m[7]) * id;   // inv(2,1)
+    PSI[8] = (m[0] * m[4] - m[3] * m[1]) * id;   // inv(2,2)
+    return det;
+}
+
+template <int ACC>
+__global__ void __launch_bounds__(128) k_element_generic(FormDev F, long long f, GeomSrc g, double* __restrict__ out,
+                                                         int ia0, int nia, int words_per_warp) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const long long e = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
+    if (e >= f) return;
+    double* sm = smem + (size_t)wib * words_per_warp;
+    const bool gradA = F.opA != AFB_IDEN, gradB = F.opB != AFB_IDEN;
+    double* UbA = sm;                                            // [dbA][qc][nfbA] if gradA
+    double* UbB = UbA + (gradA ? 3 * F.qc * F.nfbA : 0);         // [dbB][qc][nfbB] if gradB && !same
+    double* DU = UbB + ((gradB && !F.same) ? 3 * F.qc * F.nfbB : 0);  // [jdim][qc][nia]
+    if (F.same) UbB = UbA;
+
+    double P[4][3], PSI[9];
+    load_tet(g, e, P);
+    const double det = jacobian_inverse(P, PSI);
+    const double vol = fabs(det) * (1.0 / 6.0);
+
+    double acc[ACC];
+#pragma unroll
+    for (int t = 0; t < ACC; ++t) acc[t] = 0.0;
+    const int nent = F.nfb * nia;
+
+    for (int n0 = 0; n0 < F.q; n0 += F.qc) {
+        const int qn = min(F.qc, F.q - n0);
+        // ---- physical base gradients
+        if (gradA) {
+            for (int it = lane; it < qn * F.nfbA; it += 32) {
+                const int nl = it / F.nfbA, a = it - nl * F.nfbA;
+                const double* G = F.grdA + ((size_t)(n0 + nl) * F.nfbA + a) * 3;
+                const double g0 = __ldg(G), g1 = __ldg(G + 1), g2 = __ldg(G + 2);
+#pragma unroll
+                for (int d = 0; d < 3; ++d)
+                    UbA[(d * F.qc + nl) * F.nfbA + a] = PSI[0 + 3 * d] * g0 + PSI[1 + 3 * d] * g1 + PSI[2 + 3 * d] * g2;
+            }
+        }
+        if (gradB && !F.same) {
+            for (int it = lane; it < qn * F.nfbB; it += 32) {
+                const int nl = it / F.nfbB, b = it - nl * F.nfbB;
+                const double* G = F.grdB + ((size_t)(n0 + nl) * F.nfbB + b) * 3;
+                const double g0 = __ldg(G), g1 = __ldg(G + 1), g2 = __ldg(G + 2);
+#pragma unroll
+                for (int d = 0; d < 3; ++d)
+                    UbB[(d * F.qc + nl) * F.nfbB + b] = PSI[0 + 3 * d] * g0 + PSI[1 + 3 * d] * g1 + PSI[2 + 3 * d] * g2;
+            }
+        }
+        __syncwarp();
+        // ---- DU[k][nl][ial] = w vol sum_j K(k,j) U[j]
+        for (int it = lane; it < F.jdim * qn * nia; it += 32) {
+            const int ial = it % nia;
+            const int r2 = it / nia;
+            const int nl = r2 % qn, k = r2 / qn;
+            const int ia = ia0 + ial;
+            const int c = ia / F.nfbA, a = ia - c * F.nfbA;
+            const int n = n0 + nl;
+            const double wv = __ldg(F.W + n) * vol;
+            const double* Dn = F.D;
+            if (F.layout == AFB_COEF_PER_TET) Dn += (size_t)F.dlen * e;
+            else if (F.layout == AFB_COEF_PER_POINT) Dn += (size_t)F.dlen * (n + (size_t)F.q * e);
+            // band of ia: U[j0 + d], d < nb
+            int j0, nb;
+            if (F.opA == AFB_IDEN) { j0 = c; nb = 1; }
+            else if (F.opA == AFB_GRAD) { j0 = 3 * c; nb = 3; }
+            else { j0 = 0; nb = 1; }
+            double u[3];
+            if (F.opA == AFB_IDEN) u[0] = __ldg(F.phiA + (size_t)n * F.nfbA + a);
+            else if (F.opA == AFB_GRAD) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) u[d] = UbA[(d * F.qc + nl) * F.nfbA + a];
+            } else u[0] = UbA[(c * F.qc + nl) * F.nfbA + a];
+            double s;
+            if (F.ttype >= AFB_TENSOR_SYMMETRIC) {
+                s = 0.0;
+                for (int d = 0; d < nb; ++d) s += __ldg(Dn + k + F.jdim * (j0 + d)) * u[d];
+            } else {
+                const double sc = (F.ttype == AFB_TENSOR_SCALAR) ? __ldg(Dn) : 1.0;
+                if (F.jdim == F.idim) s = (k >= j0 && k < j0 + nb) ? sc * u[k - j0] : 0.0;
+                else s = sc * u[0];  // OpA = IDEN(P0) broadcast (rhs trick)
+            }
+            DU[(k * F.qc + nl) * nia + ial] = wv * s;
+        }
+        __syncwarp();
+        // ---- A(ib, ia) += sum_n sum_d Vb * DU
+#pragma unroll
+        for (int t = 0; t < ACC; ++t) {
+            const int idx = lane + 32 * t;
+            if (idx < nent) {
+                const int ib = idx / nia, ial = idx - ib * nia;
+                const int cb = ib / F.nfbB, b = ib - cb * F.nfbB;
+                double s = acc[t];
+                if (F.opB == AFB_IDEN) {
+                    for (int nl = 0; nl < qn; ++nl)
+                        s += __ldg(F.phiB + (size_t)(n0 + nl) * F.nfbB + b) * DU[(cb * F.qc + nl) * nia + ial];
+                } else if (F.opB == AFB_GRAD) {
+                    for (int nl = 0; nl < qn; ++nl)
+#pragma unroll
+                        for (int d = 0; d < 3; ++d)
+                            s += UbB[(d * F.qc + nl) * F.nfbB + b] * DU[((3 * cb + d) * F.qc + nl) * nia + ial];
+                } else {
+                    for (int nl = 0; nl < qn; ++nl) s += UbB[(cb * F.qc + nl) * F.nfbB + b] * DU[nl * nia + ial];
+                }
+                acc[t] = s;
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int t = 0; t < ACC; ++t) {
+        const int idx = lane + 32 * t;
+        if (idx < nent) {
+            const int ib = idx / nia, ial = idx - ib * nia;
+            double* o = out + e * F.s_e + (long long)(F.row_off + ib) * F.s_ib + (long long)(F.col_off + ia0 + ial) * F.s_ia;
+            const double v = F.alpha * acc[t];
+            if (F.add) *o += v; else *o = v;
+        }
+    }
+}
+
+template <int ACC>
+cudaError_t launch_generic(const FormDev& F, long long f, const GeomSrc& g, double* out, int ia0, int nia, int words, cudaStream_t st) {
+    const int warps = 4;
+    const size_t smem = (size_t)warps * words * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(k_element_generic<ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long long blocks = (f + warps - 1) / warps;
+    k_element_generic<ACC><<<(unsigned)blocks, warps * 32, smem, st>>>(F, f, g, out, ia0, nia, words);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+namespace afb {
+
+int form_dlen(const afb_form& form, const OpInfo& A, const OpInfo& B) {
+    if (form.tensor_type == AFB_TENSOR_NULL) return 0;
+    if (form.tensor_type == AFB_TENSOR_SCALAR) return 1;
+    return A.dim * B.dim;
+}
+
+int launch_form(afb_ctx* ctx, const afb_form& form, const OpInfo& A, const OpInfo& B, int64_t f,
+                const double* x, const double* y, const double* z,
+                const int32_t* v0, const int32_t* v1, const int32_t* v2, const int32_t* v3,
+                const double* XY, double* out, long long s_e, long long s_ib, long long s_ia, int add,
+                const double* Ddev) {
+    if (f <= 0) return 0;
+    const double *p, *w;
+    const int q = tet_rule(form.quad_order, &p, &w);
+    if (q < 0) { set_error(ctx, "quadrature order must be in 0..20"); return -7; }
+    const int tt = form.tensor_type;
+    if (tt < AFB_TENSOR_NULL || tt > AFB_TENSOR_GENERAL) { set_error(ctx, "bad tensor_type"); return -7; }
+    if ((tt == AFB_TENSOR_NULL || tt == AFB_TENSOR_SCALAR) && A.dim != B.dim && !(A.nfa == 1 && A.dim == 1)) {
+        set_error(ctx, "Identity tensor defined only for compatible (with same dimensions) operators A and B");
+        return -5;
+    }
+    if (tt == AFB_TENSOR_SYMMETRIC && A.dim != B.dim) { set_error(ctx, "TENSOR_SYMMETRIC should have equal dimensions"); return -5; }
+    if (form.coef_layout < AFB_COEF_CONST || form.coef_layout > AFB_COEF_PER_POINT) { set_error(ctx, "bad coef_layout"); return -7; }
+    // element-independent tables, cached on the device per (space, rule)
+    const double *dW, *dphiA, *dgrdA, *dphiB, *dgrdB;
+    int rc = get_tables(ctx, A.fem, form.quad_order, &dW, &dphiA, &dgrdA);
+    if (rc) return rc;
+    rc = get_tables(ctx, B.fem, form.quad_order, &dW, &dphiB, &dgrdB);
+    if (rc) return rc;
+
+    FormDev F;
+    F.opA = A.op; F.vecA = A.vec; F.nfbA = A.nf_base; F.nfa = A.nfa; F.idim = A.dim; F.dbA = A.dim_base;
+    F.opB = B.op; F.vecB = B.vec; F.nfbB = B.nf_base; F.nfb = B.nfa; F.jdim = B.dim; F.dbB = B.dim_base;
+    F.same = (A.op == B.op && A.fem == B.fem && A.vec == B.vec);
+    F.q = q;
+    F.W = dW; F.phiA = dphiA; F.grdA = dgrdA; F.phiB = dphiB; F.grdB = dgrdB;
+    F.ttype = tt; F.layout = form.coef_layout; F.dlen = form_dlen(form, A, B);
+    F.D = Ddev;
+    F.alpha = form.alpha;
+    F.s_e = s_e; F.s_ib = s_ib; F.s_ia = s_ia; F.row_off = form.row_off; F.col_off = form.col_off; F.add = add;
+
+    GeomSrc g;
+    g.x = x; g.y = y; g.z = z; g.v0 = v0; g.v1 = v1; g.v2 = v2; g.v3 = v3;
+    for (int k = 0; k < 4; ++k) g.XY[k] = XY ? XY + (size_t)3 * f * k : nullptr;
+
+    // split the trial dofs so that nfb*nia fits the accumulator budget (29 per lane)
+    const int max_ent = 32 * 29;
+    int nia_max = A.nfa;
+    while (B.nfa * nia_max > max_ent) nia_max = (nia_max + 1) / 2;
+    if (nia_max < 1) { set_error(ctx, "element block too large"); return -3; }
+    const int budget_words = 3072;  // 24 KiB of shared memory per warp
+    for (int ia0 = 0; ia0 < A.nfa; ia0 += nia_max) {
+        const int nia = std::min(nia_max, A.nfa - ia0);
+        const int per_pt = (A.op != AFB_IDEN ? 3 * A.nf_base : 0) + ((B.op != AFB_IDEN && !F.same) ? 3 * B.nf_base : 0) + B.dim * nia;
+        int qc = std::min(q, std::max(1, budget_words / per_pt));
+        if (per_pt > budget_words) { set_error(ctx, "element block does not fit shared memory"); return -3; }
+        F.qc = qc;
+        const int words = per_pt * qc;
+        const int nent = B.nfa * nia;
+        const int acc = (nent + 31) / 32;
+        cudaError_t e;
+        if (acc <= 1) e = launch_generic<1>(F, f, g, out, ia0, nia, words, ctx->stream);
+        else if (acc <= 2) e = launch_generic<2>(F, f, g, out, ia0, nia, words, ctx->stream);
+        else if (acc <= 4) e = launch_generic<4>(F, f, g, out, ia0, nia, words, ctx->stream);
+        else if (acc <= 7) e = launch_generic<7>(F, f, g, out, ia0, nia, words, ctx->stream);
+        else if (acc <= 13) e = launch_generic<13>(F, f, g, out, ia0, nia, words, ctx->stream);
+        else if (acc <= 19) e = launch_generic<19>(F, f, g, out, ia0, nia, words, ctx->stream);
+        else e = launch_generic<29>(F, f, g, out, ia0, nia, words, ctx->stream);
+        ctx->launches++;
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "k_element_generic launch");
+    }
+    return 0;
+}
+
+}  // namespace afb

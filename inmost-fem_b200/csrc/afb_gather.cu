@@ -1,0 +1,275 @@
+// Deterministic, atomic-free value scatter (K3) and the assembly driver.
+//
+// Replaces (reference): the scatter loops of AssemblerT::Assemble / AssembleMatrix / AssembleRHS
+// (inmost_interface/assembler.inl:397-481, :780-858, :555-573):
+//     rhs[r] += s_r F[i];  matrix[r][c] += s_r s_c A(i,j)  if |A(i,j)| > drop_val;  NaN/Inf -> status -1
+// The reference serialises row updates with INMOST's LockService and a find-or-insert per entry, so the summation
+// order depends on thread timing.  Here the scatter is turned inside out: a group of lanes owns one matrix row,
+// walks the row's adjacency list (element,local row) in ascending element order (plan built in afb_pattern.cu),
+// reads that row of the staged element matrix with coalesced loads and adds it into a shared-memory image of the
+// CSR row at the precomputed slots; the finished row is written once, coalesced.  No atomics, bit-reproducible.
+#include <algorithm>
+#include <cmath>
+
+#include "afb_internal.h"
+
+using namespace afb;
+
+namespace {
+
+template <int G, bool SIGNS>
+__global__ void __launch_bounds__(256) k_gather(long long nrows, long long ntet, int nrow_loc, int ncol_loc, int max_len,
+                                                const long long* __restrict__ rowptr, const long long* __restrict__ radj_ptr,
+                                                const unsigned* __restrict__ radj, const unsigned short* __restrict__ pos,
+                                                const int32_t* __restrict__ e2r, const int32_t* __restrict__ e2c,
+                                                const double* __restrict__ stageA, const double* __restrict__ stageF,
+                                                double* __restrict__ val, double* __restrict__ rhs, int accumulate, double drop_val,
+                                                int* __restrict__ status) {
+    extern __shared__ double sacc[];
+    const int gl = threadIdx.x % G;                    // lane inside the group
+    const int gib = threadIdx.x / G;                   // group inside the block
+    const int gpb = blockDim.x / G;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+    double* acc = sacc + (size_t)gib * max_len;
+    bool bad = false;
+    for (long long r = (long long)blockIdx.x * gpb + gib; r < nrows; r += (long long)gridDim.x * gpb) {
+        const long long p0 = rowptr[r];
+        const int len = (int)(rowptr[r + 1] - p0);
+        const long long a0 = radj_ptr[r], a1 = radj_ptr[r + 1];
+        double fsum = 0.0;
+        if (stageA) {
+            for (int s = gl; s < len; s += G) acc[s] = 0.0;
+            __syncwarp(gmask);
+        }
+        for (long long a = a0; a < a1; ++a) {
+            const unsigned t = __ldg(radj + a);
+            double sr = 1.0;
+            long long e = 0;
+            if (SIGNS) {
+                e = t / nrow_loc;
+                const int i = (int)(t - e * nrow_loc);
+                sr = e2r[(long long)i * ntet + e] < 0 ? -1.0 : 1.0;
+            }
+            if (stageF && gl == 0) {
+                const double fv = __ldg(stageF + t);
+                bad |= !isfinite(fv);
+                fsum += sr * fv;
+            }
+            if (stageA) {
+                const long long base = (long long)t * ncol_loc;
+                for (int j = gl; j < ncol_loc; j += G) {
+                    double v = __ldg(stageA + base + j);
+                    const int p = pos[base + j];
+                    bad |= !isfinite(v);
+                    if (SIGNS) v *= sr * (e2c[(long long)j * ntet + e] < 0 ? -1.0 : 1.0);
+                    if (fabs(v) > drop_val) acc[p] += v;
+                }
+                __syncwarp(gmask);
+            }
+        }
+        if (stageA) {
+            if (accumulate) for (int s = gl; s < len; s += G) val[p0 + s] += acc[s];
+            else for (int s = gl; s < len; s += G) val[p0 + s] = acc[s];
+            __syncwarp(gmask);
+        }
+        if (stageF && gl == 0) {
+            if (accumulate) rhs[r] += fsum; else rhs[r] = fsum;
+        }
+    }
+    if (bad) *status = 1;  // benign race: every writer stores the same value
+}
+
+template <int G>
+cudaError_t launch_g(afb_ctx* c, const double* sA, const double* sF, double* val, double* rhs, int accumulate, double drop, int* status) {
+    const long long nrows = c->row_end - c->row_begin;
+    const int gpb = 256 / G;
+    const size_t smem = (size_t)gpb * std::max(1, c->max_row_len) * sizeof(double);
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((nrows + gpb - 1) / gpb, 148LL * 64));
+    cudaError_t e;
+    if (c->has_signs) {
+        e = cudaFuncSetAttribute(k_gather<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k_gather<G, true><<<grid, 256, smem, c->stream>>>(nrows, c->ntet, c->nrow_loc, c->ncol_loc, std::max(1, c->max_row_len), c->rowptr.as<long long>(),
+                                                        c->radj_ptr.as<long long>(), c->radj.as<unsigned>(), c->pos.as<unsigned short>(), c->e2r.as<int32_t>(),
+                                                        c->e2c.as<int32_t>(), sA, sF, val, rhs, accumulate, drop, status);
+    } else {
+        e = cudaFuncSetAttribute(k_gather<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k_gather<G, false><<<grid, 256, smem, c->stream>>>(nrows, c->ntet, c->nrow_loc, c->ncol_loc, std::max(1, c->max_row_len), c->rowptr.as<long long>(),
+                                                         c->radj_ptr.as<long long>(), c->radj.as<unsigned>(), c->pos.as<unsigned short>(), c->e2r.as<int32_t>(),
+                                                         c->e2c.as<int32_t>(), sA, sF, val, rhs, accumulate, drop, status);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+namespace afb {
+
+int launch_gather(afb_ctx* ctx, const double* stageA, const double* stageF, double* val, double* rhs, int accumulate, double drop_val,
+                  int* status_flag) {
+    const size_t need = (size_t)(256 / 32) * std::max(1, ctx->max_row_len) * sizeof(double);
+    if (need > 200 * 1024) { set_error(ctx, "afb_assemble: matrix rows too long for the shared-memory row image"); return -3; }
+    cudaError_t e;
+    const int nc = ctx->ncol_loc;
+    if (nc <= 4) e = launch_g<4>(ctx, stageA, stageF, val, rhs, accumulate, drop_val, status_flag);
+    else if (nc <= 8) e = launch_g<8>(ctx, stageA, stageF, val, rhs, accumulate, drop_val, status_flag);
+    else if (nc <= 16) e = launch_g<16>(ctx, stageA, stageF, val, rhs, accumulate, drop_val, status_flag);
+    else e = launch_g<32>(ctx, stageA, stageF, val, rhs, accumulate, drop_val, status_flag);
+    ctx->launches++;
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "k_gather launch");
+    return 0;
+}
+
+}  // namespace afb
+
+extern "C" {
+
+int afb_assemble(afb_ctx* ctx, int nforms, const afb_form* forms, int nrhs, const afb_form* rhs_forms,
+                 double* csr_val, double* rhs, int accumulate, double drop_val, int mem_space) {
+    if (!ctx) return -7;
+    if (ctx->ntet <= 0) { set_error(ctx, "Mesh was not specified"); return -6; }
+    if (!ctx->has_pattern) { set_error(ctx, "pattern was not built: call afb_pattern_build first"); return -6; }
+    if ((nforms > 0 && !forms) || (nrhs > 0 && !rhs_forms) || nforms < 0 || nrhs < 0) { set_error(ctx, "afb_assemble: bad form arrays"); return -7; }
+    const bool doA = csr_val != nullptr, doF = rhs != nullptr;
+    if (!doA && !doF) return 0;
+    if (doA && nforms == 0 && doF && nrhs == 0) { set_error(ctx, "System local evaluator is not specified"); return -6; }
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    const long long ntet = ctx->ntet, nrows = ctx->row_end - ctx->row_begin;
+    const int nrl = ctx->nrow_loc, ncl = ctx->ncol_loc;
+    const int nfA = doA ? nforms : 0, nfF = doF ? nrhs : 0;
+
+    // ---- resolve + validate
+    std::vector<OpInfo> oa(nfA + nfF), ob(nfA + nfF);
+    std::vector<afb_form> fm(nfA + nfF);
+    for (int k = 0; k < nfA + nfF; ++k) {
+        fm[k] = k < nfA ? forms[k] : rhs_forms[k - nfA];
+        if (resolve_op(fm[k].opA, fm[k].femA, fm[k].vecA, &oa[k]) || resolve_op(fm[k].opB, fm[k].femB, fm[k].vecB, &ob[k])) {
+            set_error(ctx, "unsupported operator/space in form");
+            return -3;
+        }
+        if (k >= nfA) {
+            if (!(fm[k].opA == AFB_IDEN && fm[k].femA == AFB_FEM_P0 && fm[k].vecA == 1)) { set_error(ctx, "rhs form must use OpA = IDEN(P0)"); return -7; }
+            fm[k].col_off = 0;
+            if (fm[k].row_off < 0 || fm[k].row_off + ob[k].nfa > nrl) { set_error(ctx, "rhs form block outside the element vector"); return -7; }
+        } else if (fm[k].row_off < 0 || fm[k].col_off < 0 || fm[k].row_off + ob[k].nfa > nrl || fm[k].col_off + oa[k].nfa > ncl) {
+            set_error(ctx, "form block outside the element matrix");
+            return -7;
+        }
+    }
+    // ---- coefficients to the device
+    std::vector<const double*> Dd(nfA + nfF, nullptr);
+    {
+        size_t total = 0;
+        std::vector<size_t> offs(nfA + nfF, 0), sizes(nfA + nfF, 0);
+        for (int k = 0; k < nfA + nfF; ++k) {
+            const int dlen = form_dlen(fm[k], oa[k], ob[k]);
+            const int q = afb_tet_quadrature(fm[k].quad_order, nullptr, nullptr, 0);
+            if (q < 0) { set_error(ctx, "quadrature order must be in 0..20"); return -7; }
+            const size_t n = fm[k].coef_layout == AFB_COEF_CONST ? 1 : (fm[k].coef_layout == AFB_COEF_PER_TET ? (size_t)ntet : (size_t)ntet * q);
+            sizes[k] = dlen ? n * dlen : 0;
+            if (sizes[k] && !fm[k].D) { set_error(ctx, "tensor data missing"); return -7; }
+            if (sizes[k] && fm[k].coef_space == AFB_HOST) { offs[k] = total; total += (sizes[k] + 1) & ~(size_t)1; }
+        }
+        if (total) AFB_CUDA(ctx, ctx->coef.reserve(total * sizeof(double)));
+        cudaEventRecord(ctx->ev[0], st);
+        for (int k = 0; k < nfA + nfF; ++k) {
+            if (!sizes[k]) continue;
+            if (fm[k].coef_space == AFB_HOST) {
+                AFB_CUDA(ctx, cudaMemcpyAsync(ctx->coef.as<double>() + offs[k], fm[k].D, sizes[k] * sizeof(double), cudaMemcpyHostToDevice, st));
+                Dd[k] = ctx->coef.as<double>() + offs[k];
+            } else Dd[k] = fm[k].D;
+        }
+    }
+    // ---- staging
+    double *sA = nullptr, *sF = nullptr;
+    if (doA) {
+        const size_t bytes = (size_t)ntet * nrl * ncl * sizeof(double);
+        AFB_CUDA(ctx, ctx->stageA.reserve(bytes));
+        sA = ctx->stageA.as<double>();
+    }
+    if (doF) {
+        AFB_CUDA(ctx, ctx->stageF.reserve((size_t)ntet * nrl * sizeof(double)));
+        sF = ctx->stageF.as<double>();
+    }
+    // which launches may store and which must add: a block region already written -> add; uncovered area -> memset
+    auto plan = [&](int k0, int k1, bool matrix, std::vector<int>& add, bool& need_zero) {
+        long long covered = 0;
+        bool partial = false;
+        std::vector<int> seen;
+        for (int k = k0; k < k1; ++k) {
+            const int r0 = fm[k].row_off, r1 = r0 + ob[k].nfa, c0 = matrix ? fm[k].col_off : 0, c1 = matrix ? c0 + oa[k].nfa : 1;
+            bool same = false;
+            for (int s : seen) {
+                const int sr0 = fm[s].row_off, sr1 = sr0 + ob[s].nfa, sc0 = matrix ? fm[s].col_off : 0, sc1 = matrix ? sc0 + oa[s].nfa : 1;
+                if (sr0 == r0 && sr1 == r1 && sc0 == c0 && sc1 == c1) same = true;
+                else if (r0 < sr1 && sr0 < r1 && c0 < sc1 && sc0 < c1) partial = true;
+            }
+            add[k] = same ? 1 : 0;
+            if (!same) { covered += (long long)(r1 - r0) * (c1 - c0); seen.push_back(k); }
+        }
+        const long long area = (long long)nrl * (matrix ? ncl : 1);
+        need_zero = partial || covered < area;
+        if (partial) for (int k = k0; k < k1; ++k) add[k] = 1;
+    };
+    std::vector<int> add(nfA + nfF, 0);
+    bool zeroA = false, zeroF = false;
+    if (doA) plan(0, nfA, true, add, zeroA);
+    if (doF) plan(nfA, nfA + nfF, false, add, zeroF);
+    if (doA && zeroA) AFB_CUDA(ctx, cudaMemsetAsync(sA, 0, (size_t)ntet * nrl * ncl * sizeof(double), st));
+    if (doF && zeroF) AFB_CUDA(ctx, cudaMemsetAsync(sF, 0, (size_t)ntet * nrl * sizeof(double), st));
+
+    cudaEventRecord(ctx->ev[1], st);
+    // ---- K1: element blocks
+    for (int k = 0; k < nfA + nfF; ++k) {
+        const bool matrix = k < nfA;
+        int rc = launch_form(ctx, fm[k], oa[k], ob[k], ntet, ctx->x.as<double>(), ctx->y.as<double>(), ctx->z.as<double>(),
+                             ctx->v[0].as<int32_t>(), ctx->v[1].as<int32_t>(), ctx->v[2].as<int32_t>(), ctx->v[3].as<int32_t>(), nullptr,
+                             matrix ? sA : sF, matrix ? (long long)nrl * ncl : nrl, matrix ? ncl : 1, matrix ? 1 : 0, add[k], Dd[k]);
+        if (rc) return rc;
+    }
+    cudaEventRecord(ctx->ev[2], st);
+    // ---- K3: gather into CSR / rhs
+    double* dval = csr_val;
+    double* drhs = rhs;
+    if (mem_space == AFB_HOST) {
+        if (doA) {
+            AFB_CUDA(ctx, ctx->io_val.reserve(std::max<long long>(1, ctx->nnz) * sizeof(double)));
+            dval = ctx->io_val.as<double>();
+            if (accumulate) AFB_CUDA(ctx, cudaMemcpyAsync(dval, csr_val, ctx->nnz * sizeof(double), cudaMemcpyHostToDevice, st));
+        }
+        if (doF) {
+            AFB_CUDA(ctx, ctx->io_rhs.reserve(std::max<long long>(1, nrows) * sizeof(double)));
+            drhs = ctx->io_rhs.as<double>();
+            if (accumulate) AFB_CUDA(ctx, cudaMemcpyAsync(drhs, rhs, nrows * sizeof(double), cudaMemcpyHostToDevice, st));
+        }
+    }
+    AFB_CUDA(ctx, ctx->flag.reserve(64));
+    AFB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p, 0, 64, st));
+    int rc = launch_gather(ctx, doA ? sA : nullptr, doF ? sF : nullptr, dval, drhs, accumulate, drop_val, ctx->flag.as<int>());
+    if (rc) return rc;
+    cudaEventRecord(ctx->ev[3], st);
+    if (mem_space == AFB_HOST) {
+        if (doA && ctx->nnz) AFB_CUDA(ctx, cudaMemcpyAsync(csr_val, dval, ctx->nnz * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (doF && nrows) AFB_CUDA(ctx, cudaMemcpyAsync(rhs, drhs, nrows * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    int bad = 0;
+    AFB_CUDA(ctx, cudaMemcpyAsync(&bad, ctx->flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    AFB_CUDA(ctx, cudaStreamSynchronize(st));
+    float t01 = 0, t12 = 0, t23 = 0;
+    cudaEventElapsedTime(&t01, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&t12, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&t23, ctx->ev[2], ctx->ev[3]);
+    ctx->times[0] = t12; ctx->times[1] = t23; ctx->times[2] = t01;
+    if (bad) { set_error(ctx, "not a number in local matrix or rhs"); return -1; }
+    return 0;
+}
+
+int afb_last_times(afb_ctx* ctx, double* ms3) {
+    if (!ctx || !ms3) return -7;
+    for (int i = 0; i < 3; ++i) ms3[i] = ctx->times[i];
+    return 0;
+}
+
+}  // extern "C"

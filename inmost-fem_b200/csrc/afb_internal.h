@@ -1,0 +1,128 @@
+// Internal declarations shared by the .cu files of libanifem_b200.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/anifem_b200.h"
+
+#define AFB_MAX_BASE_NF 20
+
+namespace afb {
+
+void set_error(afb_ctx* ctx, const std::string& msg);
+int cuda_fail(afb_ctx* ctx, cudaError_t e, const char* what);
+
+#define AFB_CUDA(ctx, call)                                             \
+    do {                                                                \
+        cudaError_t _e = (call);                                        \
+        if (_e != cudaSuccess) return afb::cuda_fail(ctx, _e, #call);   \
+    } while (0)
+
+// growable device buffer
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes);
+    void release();
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+// description of Operator<op, FemFix|FemVec> resolved on the host
+struct OpInfo {
+    int op, fem, vec;
+    int nf_base;   // basis functions of the scalar base space
+    int nfa;       // Nfa of the operator
+    int dim;       // Dim of the operator
+    int dim_base;  // rows of the per-component base table: IDEN 1, GRAD/DIV 3
+};
+int resolve_op(int op, int fem, int vec, OpInfo* out);
+
+// host-side basis tables at the points of a rule (the product's own evaluation of the P0..P3
+// Lagrange bases; formulas documented in afb_tables.cpp)
+void basis_values(int fem, int q, const double* XYL, double* phi /*[n*nf + i]*/);
+void basis_ref_grads(int fem, int q, const double* XYL, double* G /*[(n*nf + i)*3 + d]*/);
+int tet_rule(int order, const double** p, const double** w);
+
+}  // namespace afb
+
+// device view of one volume form, passed by value to the element kernels
+struct FormDev {
+    int opA, vecA, nfbA, nfa, idim, dbA;   // dbA = dim_base of A
+    int opB, vecB, nfbB, nfb, jdim, dbB;
+    int same;            // OpA == OpB (V = U)
+    int q;               // quadrature points
+    int qc;              // points per shared-memory chunk
+    const double* W;     // [q]
+    const double* phiA;  // [q*nfbA]
+    const double* grdA;  // [q*nfbA*3]
+    const double* phiB;
+    const double* grdB;
+    int ttype, layout, dlen;
+    const double* D;
+    double alpha;
+    // output addressing: out[e*s_e + (row_off+ib)*s_ib + (col_off+ia)*s_ia]
+    long long s_e, s_ib, s_ia;
+    int row_off, col_off;
+    int add;             // 0: store, 1: add into out
+};
+
+struct TableEntry {
+    int fem, order;
+    double *W, *phi, *grd;  // device
+};
+
+struct afb_ctx {
+    int device = 0;
+    std::vector<TableEntry> table_cache;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    int64_t launches = 0;
+
+    // mesh (SoA)
+    int64_t nnode = 0, ntet = 0;
+    afb::DevBuf x, y, z;          // double[nnode]
+    afb::DevBuf v[4];             // int32[ntet]
+
+    // dof map: codes sign*(local+1), 0 = skipped; element-fastest SoA [i*ntet + e]
+    int nrow_loc = 0, ncol_loc = 0;
+    int64_t row_begin = 0, row_end = 0, ncols_global = 0;
+    afb::DevBuf e2r;              // int32[nrow_loc*ntet]  code of (row - row_begin)
+    afb::DevBuf e2c;              // int32[ncol_loc*ntet]  code of global column
+    bool has_dofmap = false;
+    bool has_signs = false;
+
+    // pattern + plan
+    bool has_pattern = false;
+    int64_t nnz = 0;
+    int max_row_len = 0;
+    afb::DevBuf rowptr;           // int64[nrows+1]
+    afb::DevBuf colind;           // int32[nnz]
+    afb::DevBuf radj_ptr;         // int64[nrows+1]
+    afb::DevBuf radj;             // uint32[n_adj]: e*nrow_loc + i, ascending per row
+    afb::DevBuf pos;              // uint16[ntet*nrow_loc*ncol_loc]: slot of (e,i,j) inside its row
+    int64_t n_adj = 0;
+
+    // work buffers
+    afb::DevBuf stageA, stageF, tables, coef, io_val, io_rhs, flag, tmp1, tmp2, tmp3, xy;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    double times[3] = {0, 0, 0};
+};
+
+namespace afb {
+// element kernels (afb_element.cu)
+int launch_form(afb_ctx* ctx, const afb_form& form, const OpInfo& A, const OpInfo& B, int64_t f,
+                const double* x, const double* y, const double* z,                 // SoA nodes (or NULL)
+                const int32_t* v0, const int32_t* v1, const int32_t* v2, const int32_t* v3,
+                const double* XY /* 4 arrays 3 x f, AoS variant, or NULL */,
+                double* out, long long s_e, long long s_ib, long long s_ia, int add, const double* Ddev);
+int form_dlen(const afb_form& form, const OpInfo& A, const OpInfo& B);
+// device tables W[q], phi[q*nf], G^[q*nf*3] of (space, rule); uploaded on first use (afb_ctx.cu)
+int get_tables(afb_ctx* ctx, int fem, int order, const double** W, const double** phi, const double** grd);
+// gather (afb_gather.cu)
+int launch_gather(afb_ctx* ctx, const double* stageA, const double* stageF, double* val, double* rhs,
+                  int accumulate, double drop_val, int* status_flag);
+}  // namespace afb

@@ -1,0 +1,272 @@
+"""TEST INFRASTRUCTURE ONLY: numpy restatement of the reference's global-assembly path
+(anifem++/inmost_interface + the cube generator of anifem++/utils).  Imported only by tests/,
+__graft_entry__.smoke() and bench.py's CPU-baseline legs -- never by the product.
+
+PARITY STATUS: **parity unpinned** at this level.  The reference's Assembler needs INMOST
+(un-vendored external pinned at INMOST-DEV/INMOST@f3392cef4cbb4d05b91c5cc94922040637bea4ee,
+cmake/Downloadinmost.cmake:4) which is absent here, and the reference holds no test for
+assembler.inl / global_enumerator.cpp / ordering.inl.  What INMOST decides (GlobalID of nodes /
+edges / faces, cell->node order, entity ownership) is replaced by the documented conventions
+below; everything AniFem++ itself decides is restated from its sources:
+
+  mesh          utils/mesh_utils.cpp:20-48 (6 tets per hex), :110-145 (node/hex loops)
+  orientation   inmost_interface/ordering.inl:8-26      (swap nodes 2,3 if det<0)
+  local edges   01,02,03,12,13,23; local face i = nodes (i,i+1,i+2)%4   (ordering.inl:84-116,
+                fem/fem_space.h:27-69)
+  local dofs    vertices, edges, faces, cell; vector = component-major; variables in order
+                (fem/tetdofmap.cpp:327-339,433-440,606-643)
+  P3 edge pair  slot flips with the global order of the edge's endpoints (tetdofmap.inl:98-104,
+                assembler.inl:160-164)
+  numbering     NATURAL = lexicographic (VAR, DIM, ELEM_TYPE, ELEM_ID, DOF_ID), per-rank contiguous
+                interval [BegInd,EndInd)  (global_enumerator.cpp:562-605, :702-777, :866-890)
+  index codes   sign*(id+1), 0 = row skipped (ghost)           (assembler.inl:49-55, :139-184)
+  pattern       AssembleTemplate: sorted rows, forced diagonal  (assembler.inl:114-136, :589-695)
+  values        matrix[r][c] += s_r s_c A(i,j) if |A|>drop_val; rhs[r] += s_r F[i]   (:397-425)
+
+Conventions replacing INMOST (ours, documented in DESIGN.md):
+  * cell->node order = order of first appearance in the face lists of CreateNWTetElements;
+  * canonical entity ids: nodes in (i,j,k) creation order; edges / faces numbered in
+    lexicographic order of their sorted node tuples;
+  * with R ranks: a cell belongs to the box block of mesh_utils.cpp:67-108; an entity is owned by
+    the lowest rank among its adjacent cells; GlobalID = BegElemID[owner] + position among the
+    owner's entities in canonical order.
+"""
+import numpy as np
+
+from . import oracle as O
+
+# nodes of the six tets of a hex, first-appearance order of the face lists (mesh_utils.cpp:22-40)
+HEX_TETS = np.array([[0, 1, 5, 3], [0, 3, 5, 7], [0, 7, 5, 4], [0, 3, 7, 2], [0, 7, 4, 2], [4, 6, 2, 7]])
+LOCAL_EDGES = np.array([[0, 1], [0, 2], [0, 3], [1, 2], [1, 3], [2, 3]])
+LOCAL_FACES = np.array([[0, 1, 2], [1, 2, 3], [2, 3, 0], [3, 0, 1]])
+
+# dofs per (node, edge, face, cell) of the scalar spaces (spaces/poly_*.h Dof<>::Map())
+NDOF = {O.P0: (0, 0, 0, 1), O.P1: (1, 0, 0, 0), O.P2: (1, 1, 0, 0), O.P3: (1, 2, 1, 0)}
+
+
+def proc_grid(nranks, sizes):
+    """process grid of GenerateParallelepiped (mesh_utils.cpp:67-86)"""
+    divs, d = [], nranks
+    while d > 1:
+        for k in range(2, d + 1):
+            if d % k == 0:
+                divs.append(k)
+                d //= k
+                break
+    ppa = [1, 1, 1]
+    epp = list(sizes)
+    for k in reversed(divs):
+        m = int(np.argmax(epp))  # std::max_element returns the first maximum
+        ppa[m] *= k
+        epp[m] //= k
+    return ppa
+
+
+def cube_mesh(nx, ny, nz, size=1.0, nranks=1):
+    """coords (nnode,3), tets (ntet,4) positively oriented, cell_rank (ntet,)"""
+    ii, jj, kk = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), np.arange(nz + 1), indexing="ij")
+    coords = np.stack([ii.ravel() * (size - 0.0) / nx + 0.0, jj.ravel() * (size - 0.0) / ny + 0.0,
+                       kk.ravel() * (size - 0.0) / nz + 0.0], axis=1)
+    vid = lambda i, j, k: (i * (ny + 1) + j) * (nz + 1) + k
+    hi, hj, hk = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    hi, hj, hk = hi.ravel(), hj.ravel(), hk.ravel()
+    # hex vertex v: bit0 -> +x, bit1 -> +y, bit2 -> +z  (mesh_utils.cpp:133-140)
+    hv = np.stack([vid(hi + (v & 1), hj + ((v >> 1) & 1), hk + ((v >> 2) & 1)) for v in range(8)], axis=1)
+    tets = hv[:, HEX_TETS].reshape(-1, 4)
+    # ordering.inl:8-26
+    p = coords[tets]
+    m = p[:, :3, :] - p[:, 3:4, :]
+    det = np.linalg.det(m)
+    neg = det < 0
+    tets[neg, 2], tets[neg, 3] = tets[neg, 3].copy(), tets[neg, 2].copy()
+    # box blocks (mesh_utils.cpp:88-108)
+    ppa = proc_grid(nranks, (nx, ny, nz))
+    avg = [int(np.ceil(s / p_)) for s, p_ in zip((nx, ny, nz), ppa)]
+    pc = [np.minimum(h // a, p_ - 1) for h, a, p_ in zip((hi, hj, hk), avg, ppa)]
+    hrank = pc[2] * ppa[0] * ppa[1] + pc[1] * ppa[0] + pc[0]
+    return coords, tets.astype(np.int64), np.repeat(hrank, 6)
+
+
+def _unique_rows(keys):
+    """ids of rows in lexicographic order of the rows"""
+    u, inv = np.unique(keys, axis=0, return_inverse=True)
+    return u, inv.reshape(-1)
+
+
+def connectivity(tets):
+    """edges (nedge,2), faces (nface,3) as sorted node tuples in canonical order,
+    tet_edges (ntet,6), tet_faces (ntet,4)"""
+    e = np.sort(tets[:, LOCAL_EDGES], axis=2).reshape(-1, 2)
+    edges, inv = _unique_rows(e)
+    f = np.sort(tets[:, LOCAL_FACES], axis=2).reshape(-1, 3)
+    faces, finv = _unique_rows(f)
+    return edges, faces, inv.reshape(-1, 6), finv.reshape(-1, 4)
+
+
+class DofMap:
+    """elem->dof tables for a list of variables [(fem, vecdim), ...] under NATURAL numbering."""
+
+    def __init__(self, tets, variables, cell_rank=None, nranks=1, nnode=None):
+        self.tets = tets
+        self.vars = list(variables)
+        ntet = tets.shape[0]
+        nnode = int(tets.max()) + 1 if nnode is None else nnode
+        cell_rank = np.zeros(ntet, dtype=np.int64) if cell_rank is None else cell_rank
+        self.cell_rank, self.nranks = cell_rank, nranks
+        edges, faces, te, tf = connectivity(tets)
+        ent_of_tet = [tets, te, tf, np.arange(ntet)[:, None]]
+        nent = [nnode, edges.shape[0], faces.shape[0], ntet]
+        # ownership: lowest rank among adjacent cells; GlobalID contiguous per owner
+        owner, gid, beg, num = [], [], [], []
+        for d in range(4):
+            ow = np.full(nent[d], nranks, dtype=np.int64)
+            np.minimum.at(ow, ent_of_tet[d].ravel(), np.repeat(cell_rank, ent_of_tet[d].shape[1]))
+            ow[ow == nranks] = 0  # isolated entity (cannot happen on the cube)
+            order = np.argsort(ow, kind="stable")  # canonical order inside each owner
+            g = np.empty(nent[d], dtype=np.int64)
+            g[order] = np.arange(nent[d])
+            cnt = np.bincount(ow, minlength=nranks)
+            owner.append(ow); gid.append(g); num.append(cnt); beg.append(np.concatenate([[0], np.cumsum(cnt)[:-1]]))
+        self.owner, self.gid, self.ent_of_tet, self.nent = owner, gid, ent_of_tet, nent
+        ndof_ent = np.zeros(4, dtype=np.int64)  # dofs per entity summed over vars and components
+        for fem, vec in self.vars:
+            ndof_ent += np.array(NDOF[fem]) * vec
+        # per-rank interval (global_enumerator.cpp:594-604)
+        self.beg_ind = np.array([sum(beg[d][r] * ndof_ent[d] for d in range(4)) for r in range(nranks)])
+        self.end_ind = np.array([self.beg_ind[r] + sum(num[d][r] * ndof_ent[d] for d in range(4)) for r in range(nranks)])
+        self.nrows = int(sum(nent[d] * ndof_ent[d] for d in range(4)))
+        # NATURAL: offsets of the (var, dim, etype) groups inside each rank's interval
+        cols, signs_unused = [], None
+        grp_off = {}
+        off = np.zeros(nranks, dtype=np.int64)
+        for v, (fem, vec) in enumerate(self.vars):
+            for c in range(vec):
+                for d in range(4):
+                    nd = NDOF[fem][d]
+                    if nd == 0:
+                        continue
+                    grp_off[(v, c, d)] = off.copy()
+                    off = off + num[d] * nd
+        self.grp_off = grp_off
+        # element -> global dof, local order: var-major, component-major, vertices/edges/faces/cell
+        gnode = gid[0][tets]  # global node ids (for the P3 edge-pair orientation)
+        for v, (fem, vec) in enumerate(self.vars):
+            for c in range(vec):
+                for d in range(4):
+                    nd = NDOF[fem][d]
+                    if nd == 0:
+                        continue
+                    ents = ent_of_tet[d]  # (ntet, nloc_ent)
+                    ow = owner[d][ents]
+                    base = self.beg_ind[ow] + grp_off[(v, c, d)][ow] + (gid[d][ents] - beg[d][ow]) * nd
+                    for le in range(ents.shape[1]):
+                        if d == 1 and nd == 2:  # S2 pair on an edge
+                            a, b = LOCAL_EDGES[le]
+                            flip = (gnode[:, a] > gnode[:, b]).astype(np.int64)
+                            cols.append(base[:, le] + flip)
+                            cols.append(base[:, le] + 1 - flip)
+                        else:
+                            for k in range(nd):
+                                cols.append(base[:, le] + k)
+        self.elem2dof = np.stack(cols, axis=1)  # (ntet, nloc) global ids
+        self.nloc = self.elem2dof.shape[1]
+        # owner rank of every local dof's entity (for row codes)
+        owc = []
+        for v, (fem, vec) in enumerate(self.vars):
+            for c in range(vec):
+                for d in range(4):
+                    nd = NDOF[fem][d]
+                    for le in range(ent_of_tet[d].shape[1] if nd else 0):
+                        for k in range(nd):
+                            owc.append(owner[d][ent_of_tet[d][:, le]])
+        self.dof_owner = np.stack(owc, axis=1)
+
+    def codes(self, rank=None):
+        """(rowcode, colcode) as assemble_index_encode: sign*(id+1); rows of entities not owned by
+        `rank` are CODE_UNDEF=0 (assembler.inl:174-181). rank=None: every row active."""
+        col = self.elem2dof + 1
+        row = col.copy()
+        if rank is not None:
+            row[self.dof_owner != rank] = 0
+        return row, col
+
+
+def template_pattern(rowcode, colcode, row_begin, row_end):
+    """AssembleTemplate: sorted CSR rows over [row_begin,row_end) incl. forced diagonal"""
+    ne, nrow = rowcode.shape
+    ncol = colcode.shape[1]
+    r = np.repeat(np.abs(rowcode) - 1, ncol, axis=1).ravel()
+    c = np.tile(np.abs(colcode) - 1, (1, nrow)).ravel()
+    act = np.repeat(rowcode != 0, ncol, axis=1).ravel()
+    r, c = r[act], c[act]
+    diag = np.arange(row_begin, row_end)
+    r = np.concatenate([r, diag]); c = np.concatenate([c, diag])
+    key = np.unique(r * (int(c.max()) + 1 if c.size else 1) + c)
+    m = int(c.max()) + 1 if c.size else 1
+    rr, cc = key // m, key % m
+    rowptr = np.zeros(row_end - row_begin + 1, dtype=np.int64)
+    np.add.at(rowptr, rr - row_begin + 1, 1)
+    return np.cumsum(rowptr), cc.astype(np.int32)
+
+
+class Problem:
+    """FemExprDescr-like description: variables + volume forms.
+    mat_forms: dicts(trial=var idx, test=var idx, opA, opB, order, ttype, layout, D, alpha)
+    rhs_forms: dicts(test=var idx, opB, order, ttype, layout, D, alpha)  -- IDEN(P0) trick (int_tet_test.cpp:448-501)"""
+
+    def __init__(self, variables, mat_forms=(), rhs_forms=()):
+        self.vars = list(variables)
+        self.mat_forms, self.rhs_forms = list(mat_forms), list(rhs_forms)
+        self.var_off, off = [], 0
+        for fem, vec in self.vars:
+            self.var_off.append(off)
+            off += O.op_dims(O.IDEN, fem, vec)[0]
+        self.nloc = off
+
+    @staticmethod
+    def _D(fm, idx):
+        D = fm.get("D")
+        if D is None or fm["layout"] == O.L_CONST or idx is None:
+            return D
+        return np.ascontiguousarray(np.asarray(D)[idx])  # per-tet / per-point data follow the element index
+
+    def element_matrices(self, XY, idx=None, impl="oracle", nthreads=1):
+        """A (f, nloc_col, nloc_row) [col-major per element like the reference's m_A], F (f, nloc).
+        idx: global element indices of the columns of XY (selects per-tet / per-point tensor data)."""
+        f = XY.shape[1]
+        A = np.zeros((f, self.nloc, self.nloc))
+        F = np.zeros((f, self.nloc))
+        for fm in self.mat_forms:
+            fa, va = self.vars[fm["trial"]]
+            fb, vb = self.vars[fm["test"]]
+            form = (fm["opA"], fa, va, fm["opB"], fb, vb, fm["order"], fm["ttype"], fm["layout"])
+            Ae = O.fem3dtet(form, XY, self._D(fm, idx), impl=impl, mode=1 if impl == "ref" else 0, nthreads=nthreads)
+            ca, rb = self.var_off[fm["trial"]], self.var_off[fm["test"]]
+            A[:, ca:ca + Ae.shape[1], rb:rb + Ae.shape[2]] += fm.get("alpha", 1.0) * Ae
+        for fm in self.rhs_forms:
+            fb, vb = self.vars[fm["test"]]
+            form = (O.IDEN, O.P0, 1, fm["opB"], fb, vb, fm["order"], fm["ttype"], fm["layout"])
+            Fe = O.fem3dtet(form, XY, self._D(fm, idx), impl=impl, mode=1 if impl == "ref" else 0, nthreads=nthreads)
+            rb = self.var_off[fm["test"]]
+            F[:, rb:rb + Fe.shape[2]] += fm.get("alpha", 1.0) * Fe[:, 0, :]
+        return A, F
+
+
+def assemble(problem, coords, tets, dofmap, rank=None, impl="oracle", drop_val=1e-100, chunk=200000):
+    """Full reference-style assembly on `rank`'s row interval: returns rowptr, colind, val, rhs"""
+    r = 0 if rank is None else rank
+    row_begin, row_end = (0, dofmap.nrows) if rank is None else (int(dofmap.beg_ind[r]), int(dofmap.end_ind[r]))
+    rowcode, colcode = dofmap.codes(rank)
+    sel = np.nonzero((rowcode != 0).any(axis=1))[0]  # has_active (assembler.inl:367)
+    rowcode, colcode = rowcode[sel], colcode[sel]
+    rowptr, colind = template_pattern(rowcode, colcode, row_begin, row_end)
+    val = np.zeros(colind.shape[0])
+    rhs = np.zeros(row_end - row_begin)
+    status = 0
+    for s in range(0, sel.shape[0], chunk):
+        idx = sel[s:s + chunk]
+        XY = coords[tets[idx]].transpose(1, 0, 2)  # (4, f, 3)
+        A, F = problem.element_matrices(XY, idx=idx, impl=impl)
+        st = O.scatter_csr(rowcode[s:s + chunk], colcode[s:s + chunk], A, F, row_begin, rowptr, colind, val, rhs, drop_val)
+        status = min(status, st)
+    return rowptr, colind, val, rhs, status

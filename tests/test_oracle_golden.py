@@ -1,0 +1,104 @@
+"""CPU tests (no GPU): the oracle restatement against the reference's own known-answer tables, the
+committed reference outputs, and -- when it was built here -- the reference itself."""
+import numpy as np
+import pytest
+
+import golden_cases as gc
+
+TET = np.array([[0, 0, 0], [2, 1, 1], [1, 2, 1], [2, 1, 2]], float)[:, None, :]  # (4,1,3)
+
+
+def poly_tensor(XYG, nrow, ncol):
+    """the polynomial GENERAL tensor of tests/fem/operations/int_tet_test.cpp:213-225 in user layout"""
+    f, q, _ = XYG.shape
+    D = np.zeros((f, q, ncol, nrow))  # memory [j][k] : K(k,j) at k + nrow*j
+    for i in range(nrow):
+        for j in range(ncol):
+            D[:, :, j, i] = (i * XYG[:, :, 0] + j * XYG[:, :, 1] + (i % 2) * XYG[:, :, 2]) * (i * ncol + j)
+    return np.ascontiguousarray(D.reshape(f * q, nrow * ncol))
+
+
+def test_int_tet_table_general(oracle, ref_tests):
+    """GRAD(P3) x GRAD(P1^3), 12x20 table /720 (int_tet_test.cpp:230-244), tol 10(1+|A|)eps"""
+    g = ref_tests["int_tet"]["grad_p3_x_grad_p1vec_general"]
+    exp = np.array(g["table_rows_test_cols_trial"]) / g["coef"]  # [ib][ia]
+    XYG = oracle.quad_points(5, TET)
+    D = poly_tensor(XYG, 9, 3)
+    form = (gc.GRAD, gc.P3, 1, gc.GRAD, gc.P1, 3, 5, gc.T_GENERAL, gc.L_PER_POINT)
+    A = oracle.fem3dtet(form, TET, D)[0]  # [ia][ib]
+    assert np.linalg.norm(A.T - exp) <= 10 * (1 + np.linalg.norm(A)) * np.finfo(float).eps * 4
+
+
+def test_int_tet_table_identity_all_tensor_kinds(oracle, ref_tests):
+    """GRAD(P1^3)^2 identity, 12x12 table /1440 for the trait variants (int_tet_test.cpp:332-389)"""
+    g = ref_tests["int_tet"]["grad_p1vec_sq_identity"]
+    exp = np.array(g["table"]) / g["coef"]
+    I9 = np.eye(9).reshape(1, 81)
+    for tt, lay, D in [(gc.T_GENERAL, gc.L_CONST, I9), (gc.T_SYMMETRIC, gc.L_CONST, I9), (gc.T_SCALAR, gc.L_CONST, np.ones((1, 1))),
+                       (gc.T_NULL, gc.L_CONST, None), (gc.T_GENERAL, gc.L_PER_TET, I9), (gc.T_SCALAR, gc.L_PER_POINT, np.ones((14, 1))),
+                       (gc.T_GENERAL, gc.L_PER_POINT, np.repeat(I9, 14, axis=0))]:
+        form = (gc.GRAD, gc.P1, 3, gc.GRAD, gc.P1, 3, 5, tt, lay)
+        A = oracle.fem3dtet(form, TET, D)[0]
+        assert np.linalg.norm(A.T - exp) <= 10 * (1 + np.linalg.norm(A)) * np.finfo(float).eps
+
+
+def test_rhs_trick(oracle, ref_tests):
+    """int (mu,mu,mu).phi_i, OpA = IDEN(P0), P2^3: {-1 x4, 4 x6} x3 * (mu |T| / 20) pattern (int_tet_test.cpp:448-501)"""
+    g = ref_tests["int_tet"]["rhs_p0_x_iden_p2vec"]
+    B = np.array(g["table"])
+    mu = g["mu"]
+    for tt, D, scale in [(gc.T_SCALAR, np.full((1, 1), mu), 1.0), (gc.T_NULL, None, 1.0 / mu)]:
+        form = (gc.IDEN, gc.P0, 1, gc.IDEN, gc.P2, 3, 2, tt, gc.L_CONST)
+        A = oracle.fem3dtet(form, TET, D)[0].ravel()
+        assert np.linalg.norm(A - scale * B) <= 10 * (1 + np.linalg.norm(A)) * np.finfo(float).eps
+
+
+def test_space_tables(oracle, ref_tests):
+    """U tables of IDEN/GRAD on P0..P3 at the 4-point rule on two fused tets (predefined_spaces_test.cpp:62-382)"""
+    s = ref_tests["spaces"]
+    XYL = np.array(s["XYL"])
+    XYZ = np.array(s["XYZ"]).reshape(4, 2, 3)  # [l][r][k]
+    fem = {"FEM_P0": gc.P0, "FEM_P1": gc.P1, "FEM_P2": gc.P2, "FEM_P3": gc.P3}
+    for name, t in s["tables"].items():
+        op = gc.IDEN if name.startswith("IDEN") else gc.GRAD
+        U = oracle.operator_apply(op, fem[name.split("_", 1)[1]], 1, XYL, XYZ)
+        exp = np.array(t["U"]).reshape(2, t["nfa"], 4, t["dim"])
+        assert np.linalg.norm(U - exp) <= 100 * (1 + np.linalg.norm(exp)) * np.finfo(float).eps * 50, name
+
+
+def test_quadrature_exactness(oracle):
+    """every rule integrates x + 10 y^(ord-1) + 1000 z^ord exactly on the unit tet, point counts
+    (quadrature_formulas_test.cpp:7-45)"""
+    from math import factorial
+    for order in range(1, 21):
+        p, w = oracle.tet_quadrature(order)
+        assert p.shape[0] == gc.NPTS[order]
+        assert abs(w.sum() - 1) < 1e-14 and (p > 0).all()
+        x, y, z = p[:, 1], p[:, 2], p[:, 3]
+        num = (w * (x + 10 * y ** (order - 1) + 1000 * z ** order)).sum() / 6
+        mono = lambda k: factorial(k) / factorial(k + 3)  # int_T z^k
+        exact = mono(1) + 10 * mono(order - 1) + 1000 * mono(order)
+        assert abs(num - exact) <= max(1e-10, 1e-15 * abs(exact))
+
+
+def test_oracle_vs_committed_reference_outputs(oracle, ref_outputs):
+    for name, form, XY, D in gc.cases():
+        A = oracle.fem3dtet(form, XY, D)
+        ref = ref_outputs[name]
+        assert np.abs(A - ref).max() <= 1e-13 * (1 + np.abs(ref).max()), name
+
+
+def test_oracle_vs_live_reference(oracle):
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    for name, form, XY, D in gc.cases():
+        a = oracle.fem3dtet(form, XY, D)
+        b = oracle.fem3dtet(form, XY, D, impl="ref", mode=1, fuse=3, nthreads=2)
+        assert np.abs(a - b).max() <= 1e-13 * (1 + np.abs(b).max()), name
+
+
+def test_identity_tensor_incompatible_dims(oracle):
+    """TENSOR_NULL with Dim(OpA) != Dim(OpB) is an error (diff_tensor.h:315-317)"""
+    form = (gc.GRAD, gc.P1, 1, gc.IDEN, gc.P1, 1, 2, gc.T_NULL, gc.L_CONST)
+    with pytest.raises(RuntimeError):
+        oracle.fem3dtet(form, TET, None)
