@@ -54,16 +54,16 @@ __device__ __forceinline__ double jacobian_inverse(const double P[4][3], double 
     const double c02 = m[1] * m[5] - m[4] * m[2];
     const double det = m[0] * c00 + m[3] * c01 + m[6] * c02;
     const double id = 1.0 / det;
-    // inv(j,k) = cof(k,j)/det ; stored at PSI[j + 3k]
-    PSI[0] = c00 * id;                           // inv(0,0)
-    PSI[3] = c01 * id;                           // inv(0,1)
-    PSI[6] = c02 * id;                           // inv(0,2)
-    PSI[1] = (m[6] * m[5] - m[3] * m[8]) * id;   // inv(1,0)
-    PSI[4] = (m[0] * m[8] - m[6] * m[2]) * id;   // inv(1,1)
-    PSI[7] = (m[3] * m[2] - m[0] * m[5]) * id;   // inv(1,2)
-    PSI[2] = (m[3] * m[7] - m[6] * m[4]) * id;   // inv(2,0)
-    PSI[5] = (m[6] * m[1] - m[0] * m[7]) * id;   // inv(2,1)
-    PSI[8] = (m[0] * m[4] - m[3] * m[1]) * id;   // inv(2,2)
+    // PSI[j + 3k] = inv(j,k) = cof(k,j)/det  (adjugate; same entries as geometry.h:25-45)
+    PSI[0] = c00 * id;
+    PSI[1] = c01 * id;
+    PSI[2] = c02 * id;
+    PSI[3] = (m[6] * m[5] - m[3] * m[8]) * id;
+    PSI[4] = (m[0] * m[8] - m[6] * m[2]) * id;
+    PSI[5] = (m[3] * m[2] - m[0] * m[5]) * id;
+    PSI[6] = (m[3] * m[7] - m[6] * m[4]) * id;
+    PSI[7] = (m[6] * m[1] - m[0] * m[7]) * id;
+    PSI[8] = (m[0] * m[4] - m[3] * m[1]) * id;
     return det;
 }
 

@@ -65,8 +65,8 @@ def c2_p2_aniso(pkg, M, coords, tets):
 def c3_p3_react_diff(pkg, M, coords, tets, xyg4=None, xyg6=None):
     """C3: P3, scalar K(x) stiffness at order 4 (q=14) + reaction A(x) mass at order 6 (q=24), per point
     (examples/tutorials/react_diff1.cpp:125-131 pattern with UFem = FEM_P3)"""
-    Kx = np.ascontiguousarray((1 + xyg4[..., 0] ** 2).reshape(-1, 1))
-    Ax = np.ascontiguousarray((1 + xyg6[..., 1]).reshape(-1, 1))
+    Kx = np.ascontiguousarray(1 + xyg4[..., 0] ** 2)  # (ntet, q): one scalar per quadrature point
+    Ax = np.ascontiguousarray(1 + xyg6[..., 1])
     return _mk(pkg, M, [(gc.P3, 1)],
                [(0, 0, gc.GRAD, gc.GRAD, 4, gc.T_SCALAR, gc.L_PER_POINT, Kx, 1.0), (0, 0, gc.IDEN, gc.IDEN, 6, gc.T_SCALAR, gc.L_PER_POINT, Ax, 1.0)],
                [(0, gc.IDEN, 4, gc.T_NULL, gc.L_CONST, None, 1.0)])
