@@ -171,3 +171,45 @@ def scatter_csr(rowcode, colcode, A, F, row_begin, rowptr, colind, val, rhs, dro
         ne, nrow, ncol, rowcode.ctypes.data_as(_lp), colcode.ctypes.data_as(_lp),
         _P(None if A is None else np.ascontiguousarray(A)), _P(None if F is None else np.ascontiguousarray(F)),
         row_begin, rowptr.ctypes.data_as(_lp), colind.ctypes.data_as(_ip), _P(val), _P(rhs), drop_val)
+
+
+class _RefForm(ctypes.Structure):
+    _fields_ = [("opA", ctypes.c_int), ("femA", ctypes.c_int), ("vecA", ctypes.c_int),
+                ("opB", ctypes.c_int), ("femB", ctypes.c_int), ("vecB", ctypes.c_int),
+                ("order", ctypes.c_int), ("ttype", ctypes.c_int), ("layout", ctypes.c_int), ("is_rhs", ctypes.c_int),
+                ("D", _dp), ("alpha", ctypes.c_double), ("row_off", ctypes.c_int), ("col_off", ctypes.c_int)]
+
+
+def ref_assemble_csr(problem, coords, tets, codes, row_begin, rowptr, colind, val, rhs, drop_val=1e-100, nthreads=1):
+    """CPU baseline: reference element code (one cell per call) + restated scatter, threaded over cell ranges
+    (oracle/ref_driver.cpp::ref_assemble_csr).  `problem` is an asm_oracle.Problem."""
+    L = ref()
+    L.ref_assemble_csr.restype = ctypes.c_int
+    L.ref_assemble_csr.argtypes = [ctypes.c_int, ctypes.POINTER(_RefForm), ctypes.c_long, _dp, _lp, ctypes.c_int, _lp,
+                                   ctypes.c_long, ctypes.c_long, _lp, _ip, _dp, _dp, ctypes.c_double, ctypes.c_int]
+    forms, keep = [], []
+    for fm in problem.mat_forms:
+        fa, va = problem.vars[fm["trial"]]
+        fb, vb = problem.vars[fm["test"]]
+        D = None if fm.get("D") is None else np.ascontiguousarray(fm["D"], dtype=np.float64)
+        keep.append(D)
+        forms.append(_RefForm(fm["opA"], fa, va, fm["opB"], fb, vb, fm["order"], fm["ttype"], fm["layout"], 0, _P(D),
+                              fm.get("alpha", 1.0), problem.var_off[fm["test"]], problem.var_off[fm["trial"]]))
+    for fm in problem.rhs_forms:
+        fb, vb = problem.vars[fm["test"]]
+        D = None if fm.get("D") is None else np.ascontiguousarray(fm["D"], dtype=np.float64)
+        keep.append(D)
+        forms.append(_RefForm(IDEN, P0, 1, fm["opB"], fb, vb, fm["order"], fm["ttype"], fm["layout"], 1, _P(D),
+                              fm.get("alpha", 1.0), problem.var_off[fm["test"]], 0))
+    arr = (_RefForm * len(forms))(*forms)
+    coords = np.ascontiguousarray(coords, dtype=np.float64)
+    tets = np.ascontiguousarray(tets, dtype=np.int64)
+    codes = np.ascontiguousarray(codes, dtype=np.int64)
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+    colind = np.ascontiguousarray(colind, dtype=np.int32)
+    rc = L.ref_assemble_csr(len(forms), arr, tets.shape[0], _P(coords), tets.ctypes.data_as(_lp), codes.shape[1],
+                            codes.ctypes.data_as(_lp), row_begin, rowptr.size - 1, rowptr.ctypes.data_as(_lp),
+                            colind.ctypes.data_as(_ip), _P(val), _P(rhs), drop_val, nthreads)
+    if rc not in (0, -1):
+        raise RuntimeError("ref_assemble_csr failed rc=%d: %s" % (rc, L.ref_last_error().decode()))
+    return rc

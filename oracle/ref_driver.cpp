@@ -15,7 +15,10 @@
 #include "anifem++/fem/spaces/spaces.h"
 #include "anifem++/fem/quadrature_formulas.h"
 
+#include <atomic>
+#include <cmath>
 #include <cstring>
+#include <algorithm>
 #include <memory>
 #include <thread>
 #include <vector>
@@ -199,6 +202,90 @@ int try_template(int opA, int femA, int vecA, int opB, int femB, int vecB, int o
     return 0;
 }
 
+
+// ---- per-thread single-cell evaluators for the CPU-baseline assembler ---------------------------
+struct CellRunner {
+    virtual ~CellRunner() {}
+    virtual void run(const double* X0, const double* X1, const double* X2, const double* X3, long e, double* A) = 0;
+    long nfa = 0, nfb = 0;
+};
+
+template <typename OpA, typename OpB, typename Traits>
+struct TemplateRunner : CellRunner {
+    TensorData td;
+    int order;
+    std::vector<char> raw;
+    PlainMemory<> req;
+    TemplateRunner(int order_, int ttype, int layout, const double* D) : order(order_) {
+        nfa = OpA::Nfa::value; nfb = OpB::Nfa::value;
+        td = TensorData{ttype, layout, D, tetrahedron_quadrature_formulas(order).GetNumPoints(), 0, 0};
+        req = fem3Dtet_memory_requirements<OpA, OpB>(order, 1);
+        raw.resize(req.enoughRawSize());
+        req.allocateFromRaw(raw.data(), raw.size());
+    }
+    void run(const double* X0, const double* X1, const double* X2, const double* X3, long e, double* A) override {
+        td.base_tet = e; td.calls = 0;
+        TensorFunctor fn{&td};
+        DenseMatrix<> x0(const_cast<double*>(X0), 3, 1), x1(const_cast<double*>(X1), 3, 1), x2(const_cast<double*>(X2), 3, 1), x3(const_cast<double*>(X3), 3, 1);
+        DenseMatrix<> Am(A, nfb, nfa, nfa * nfb);
+        fem3Dtet<OpA, OpB, Traits>(x0, x1, x2, x3, fn, Am, req, order, nullptr);
+    }
+};
+
+struct RuntimeRunner : CellRunner {
+    std::shared_ptr<ApplyOpBase> oa, ob;
+    TensorData td;
+    int order, layout;
+    std::vector<char> raw;
+    PlainMemoryX<> req;
+    RuntimeRunner(std::shared_ptr<ApplyOpBase> a, std::shared_ptr<ApplyOpBase> b, int order_, int ttype, int layout_, const double* D)
+        : oa(a), ob(b), order(order_), layout(layout_) {
+        nfa = oa->Nfa(); nfb = ob->Nfa();
+        td = TensorData{ttype, layout, D, tetrahedron_quadrature_formulas(order).GetNumPoints(), 0, 0};
+        if (layout == 0) req = fem3Dtet_memory_requirements<DfuncTraits<PerPoint, true>>(*oa, *ob, order, 1);
+        else req = fem3Dtet_memory_requirements<DfuncTraits<PerPoint, false>>(*oa, *ob, order, 1);
+        raw.resize(req.enoughRawSize());
+        req.allocateFromRaw(raw.data(), raw.size());
+    }
+    void run(const double* X0, const double* X1, const double* X2, const double* X3, long e, double* A) override {
+        td.base_tet = e; td.calls = 0;
+        TensorFunctor fn{&td};
+        auto XYZ = make_tetras(X0, X1, X2, X3, 1);
+        DenseMatrix<> Am(A, nfb, nfa, nfa * nfb);
+        if (layout == 0) fem3Dtet<DfuncTraits<PerPoint, true>>(XYZ, *oa, *ob, fn, Am, req, order, nullptr);
+        else fem3Dtet<DfuncTraits<PerPoint, false>>(XYZ, *oa, *ob, fn, Am, req, order, nullptr);
+    }
+};
+
+std::unique_ptr<CellRunner> make_runner(int opA, int femA, int vecA, int opB, int femB, int vecB, int order, int ttype, int layout, const double* D) {
+    auto K = [](int oa, int fa, int va, int ob, int fb, int vb) { return (((((long)oa * 8 + fa) * 4 + va) * 8 + ob) * 8 + fb) * 4 + vb; };
+    const long key = K(opA, femA, vecA, opB, femB, vecB);
+#define MK(OA, OB)                                                                                                   \
+    {                                                                                                                \
+        if (layout == 0) return std::unique_ptr<CellRunner>(new TemplateRunner<OA, OB, DfuncTraits<PerPoint, true>>(order, ttype, layout, D)); \
+        if (ttype == TENSOR_SYMMETRIC) return std::unique_ptr<CellRunner>(new TemplateRunner<OA, OB, DfuncTraits<TENSOR_SYMMETRIC, false>>(order, ttype, layout, D)); \
+        if (ttype == TENSOR_SCALAR) return std::unique_ptr<CellRunner>(new TemplateRunner<OA, OB, DfuncTraits<TENSOR_SCALAR, false>>(order, ttype, layout, D)); \
+        return std::unique_ptr<CellRunner>(new TemplateRunner<OA, OB, DfuncTraits<PerPoint, false>>(order, ttype, layout, D)); \
+    }
+    if (key == K(GRAD, FEM_P1, 1, GRAD, FEM_P1, 1)) MK(GP1, GP1)
+    if (key == K(IDEN, FEM_P1, 1, IDEN, FEM_P1, 1)) MK(IP1, IP1)
+    if (key == K(GRAD, FEM_P2, 1, GRAD, FEM_P2, 1)) MK(GP2, GP2)
+    if (key == K(IDEN, FEM_P2, 1, IDEN, FEM_P2, 1)) MK(IP2, IP2)
+    if (key == K(GRAD, FEM_P3, 1, GRAD, FEM_P3, 1)) MK(GP3, GP3)
+    if (key == K(IDEN, FEM_P3, 1, IDEN, FEM_P3, 1)) MK(IP3, IP3)
+    if (key == K(GRAD, FEM_P2, 3, GRAD, FEM_P2, 3)) MK(GP2v, GP2v)
+    if (key == K(IDEN, FEM_P1, 1, DIV, FEM_P2, 3)) MK(IP1, DP2v)
+    if (key == K(DIV, FEM_P2, 3, IDEN, FEM_P1, 1)) MK(DP2v, IP1)
+    if (key == K(IDEN, FEM_P0, 1, IDEN, FEM_P1, 1)) MK(IP0, IP1)
+    if (key == K(IDEN, FEM_P0, 1, IDEN, FEM_P2, 1)) MK(IP0, IP2)
+    if (key == K(IDEN, FEM_P0, 1, IDEN, FEM_P3, 1)) MK(IP0, IP3)
+    if (key == K(IDEN, FEM_P0, 1, IDEN, FEM_P2, 3)) MK(IP0, IP2v)
+#undef MK
+    auto oa = make_op(opA, femA, vecA), ob = make_op(opB, femB, vecB);
+    if (!oa || !ob) return nullptr;
+    return std::unique_ptr<CellRunner>(new RuntimeRunner(oa, ob, order, ttype, layout, D));
+}
+
 }  // namespace
 
 extern "C" {
@@ -302,6 +389,89 @@ int ref_operator_apply(int op, int fem, int vec, int q, const double* XYL, const
         }
         return 0;
     } catch (std::exception& e) { g_err = e.what(); return -4; }
+}
+
+// One form of the CPU-baseline assembler (mirrors struct afb_form; is_rhs: OpA = IDEN(P0) trick)
+struct RefForm {
+    int opA, femA, vecA, opB, femB, vecB, order, ttype, layout, is_rhs;
+    const double* D;
+    double alpha;
+    int row_off, col_off;
+};
+
+// CPU baseline = the reference's element code (unmodified, one cell per call exactly like
+// AssemblerT::Assemble, assembler.inl:353-381) + the restated scatter of assembler.inl:397-481 into a
+// pre-built sorted CSR (binary search = the is_mtx_include_template branch :428-438), cell ranges split
+// over std::thread like ThreadPar::ParallelFor<STD> (fem/mutex_type.h:110-131), row updates serialised by
+// a per-row spin lock standing in for INMOST::Sparse::LockService (assembler.inl:339-340,406,474).
+// NOTE: this is FASTER than the true reference scatter (INMOST Row linear find-or-append + reallocs).
+int ref_assemble_csr(int nforms, const RefForm* forms, long ntet, const double* coords /*nnode x 3*/, const long* tets /*ntet x 4*/,
+                     int nloc, const long* codes /*ntet x nloc, sign*(id+1)*/, long row_begin, long nrows,
+                     const long* rowptr, const int* colind, double* val, double* rhs, double drop_val, int nthreads) {
+    if (nthreads < 1) nthreads = 1;
+    std::vector<std::atomic_flag> locks(nthreads > 1 ? nrows : 0);
+    for (auto& l : locks) l.clear();
+    std::vector<int> status(nthreads, 0);
+    std::vector<std::string> errs(nthreads);
+    auto work = [&](int th) {
+        try {
+            std::vector<std::unique_ptr<CellRunner>> runners;
+            for (int k = 0; k < nforms; ++k) {
+                const RefForm& f = forms[k];
+                runners.push_back(make_runner(f.opA, f.femA, f.vecA, f.opB, f.femB, f.vecB, f.order, f.ttype, f.layout, f.D));
+                if (!runners.back()) { status[th] = -3; errs[th] = "unsupported operator/space"; return; }
+            }
+            std::vector<double> A((size_t)nloc * nloc), F(nloc), blk((size_t)nloc * nloc);
+            const long t0 = ntet * th / nthreads, t1 = ntet * (th + 1) / nthreads;
+            for (long e = t0; e < t1; ++e) {
+                const long* nd = tets + 4 * e;
+                const double *X0 = coords + 3 * nd[0], *X1 = coords + 3 * nd[1], *X2 = coords + 3 * nd[2], *X3 = coords + 3 * nd[3];
+                std::fill(A.begin(), A.end(), 0.0);  // ElementalAssembler::update (elemental_assembler.cpp:105-117)
+                std::fill(F.begin(), F.end(), 0.0);
+                for (int k = 0; k < nforms; ++k) {
+                    const RefForm& f = forms[k];
+                    CellRunner& r = *runners[k];
+                    r.run(X0, X1, X2, X3, e, blk.data());
+                    if (f.is_rhs) for (long ib = 0; ib < r.nfb; ++ib) F[f.row_off + ib] += f.alpha * blk[ib];
+                    else
+                        for (long ia = 0; ia < r.nfa; ++ia)
+                            for (long ib = 0; ib < r.nfb; ++ib) A[(f.row_off + ib) + (size_t)nloc * (f.col_off + ia)] += f.alpha * blk[ib + r.nfb * ia];
+                }
+                const long* cd = codes + (size_t)nloc * e;
+                for (int i = 0; i < nloc; ++i) {
+                    if (cd[i] == 0) continue;
+                    const long rid = std::labs(cd[i]) - 1 - row_begin;
+                    if (rid < 0 || rid >= nrows) continue;  // ghost row
+                    const int rs = cd[i] < 0 ? -1 : 1;
+                    if (nthreads > 1) while (locks[rid].test_and_set(std::memory_order_acquire)) {}
+                    if (rhs) rhs[rid] += rs * F[i];
+                    if (val) {
+                        const long b = rowptr[rid], en = rowptr[rid + 1];
+                        for (int j = 0; j < nloc; ++j) {
+                            const double a = A[i + (size_t)nloc * j];
+                            if (!std::isfinite(a)) { status[th] = -1; continue; }
+                            if (!(std::fabs(a) > drop_val)) continue;
+                            const long cid = std::labs(cd[j]) - 1;
+                            const int cs = cd[j] < 0 ? -1 : 1;
+                            const int* it = std::lower_bound(colind + b, colind + en, (int)cid);
+                            if (it != colind + en && *it == cid) val[it - colind] += rs * cs * a;
+                        }
+                    }
+                    if (nthreads > 1) locks[rid].clear(std::memory_order_release);
+                    if (!std::isfinite(F[i])) status[th] = -1;
+                }
+            }
+        } catch (std::exception& ex) { status[th] = -4; errs[th] = ex.what(); }
+    };
+    if (nthreads == 1) work(0);
+    else {
+        std::vector<std::thread> ths;
+        for (int i = 0; i < nthreads; ++i) ths.emplace_back(work, i);
+        for (auto& t : ths) t.join();
+    }
+    int st = 0;
+    for (int i = 0; i < nthreads; ++i) if (status[i] < st) { st = status[i]; g_err = errs[i]; }
+    return st;
 }
 
 }  // extern "C"
