@@ -200,7 +200,7 @@ def main():
     for _ in range(args.steps):
         assert ctx.assemble(forms_d, rhsf_d, val_dev, rhs_dev) == 0
         t = ctx.last_times()
-        el_ms += t["element_ms"]; ga_ms += t["gather_ms"]
+        el_ms += t["element_ms"]; ga_ms += t["gather_ms"]; fused = t["fused_path"]
     ev1.record(stream)
     torch.cuda.synchronize()
     launches = ctx.launch_count()
@@ -233,7 +233,8 @@ def main():
     peak_gbs = peaks.get("hbm_gbs", 6650.0)
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
     alg_bytes = 4 * 10 * ntet + 24 * nnode + 72 * ntet + 8 * nnz + 8 * nrows
-    dom_name, dom_ms = ("k_element_generic", el_ms) if el_ms >= ga_ms else ("k_gather", ga_ms)
+    names = ("k_geom", "k_gather_tensor") if fused else ("k_element_generic", "k_gather")
+    dom_name, dom_ms = (names[0], el_ms) if el_ms >= ga_ms else (names[1], ga_ms)
     traffic = None
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
@@ -244,7 +245,7 @@ def main():
     step_gbs = alg_bytes / (ms_dev * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic,
                 "kernel": dom_name, "kernel_ms": dom_ms, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                "step": {"achieved": step_gbs, "frac": step_gbs / peak_gbs, "element_ms": el_ms, "gather_ms": ga_ms,
+                "step": {"achieved": step_gbs, "frac": step_gbs / peak_gbs, "element_ms": el_ms, "gather_ms": ga_ms, "path": "fused tensor-representation" if fused else "generic staged",
                          "note": "whole step = element kernels + gather; frac of the step is the honest end figure"}}
 
     line = {"metric": METRIC, "value": ntet / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,

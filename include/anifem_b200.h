@@ -128,9 +128,10 @@ int afb_assemble(afb_ctx* ctx, int nforms, const afb_form* forms, int nrhs_forms
                  double* csr_val, double* rhs, int accumulate, double drop_val, int mem_space);
 
 /* phase times of the last afb_assemble in ms (CUDA events on the context stream):
- * [0] element kernels, [1] gather/scatter, [2] copies; mirrors GetTimeEvalLocFunc / GetTimeFillMapTemplate
- * style getters (assembler.inl:949-964) */
-int afb_last_times(afb_ctx* ctx, double* ms3);
+ * [0] element kernels (k_element_generic / k_geom), [1] gather/scatter (k_gather / k_gather_tensor),
+ * [2] coefficient copies, [3] = 1 if the fused tensor-representation path ran, 0 for the generic staged path;
+ * mirrors the GetTimeEvalLocFunc / GetTimeFillMapTemplate style getters (assembler.inl:949-964) */
+int afb_last_times(afb_ctx* ctx, double* ms4);
 
 #ifdef __cplusplus
 }

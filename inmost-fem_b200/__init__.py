@@ -273,6 +273,6 @@ class Context:
                                            drop_val, space), allow=(-1,))
 
     def last_times(self):
-        t = (ctypes.c_double * 3)()
+        t = (ctypes.c_double * 4)()
         lib().afb_last_times(self._h, t)
-        return {"element_ms": t[0], "gather_ms": t[1], "copy_ms": t[2]}
+        return {"element_ms": t[0], "gather_ms": t[1], "copy_ms": t[2], "fused_path": bool(t[3])}

@@ -109,7 +109,7 @@ struct afb_ctx {
     // work buffers
     afb::DevBuf stageA, stageF, tables, coef, io_val, io_rhs, flag, tmp1, tmp2, tmp3, xy;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    double times[3] = {0, 0, 0};
+    double times[4] = {0, 0, 0, 0};
 };
 
 namespace afb {

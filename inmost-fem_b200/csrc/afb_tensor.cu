@@ -1,0 +1,407 @@
+// Fused fast path of afb_assemble for affine elements with element-wise constant coefficients:
+// "tensor representation" of the element matrix, expanded inside the row gather.
+//
+// Reference semantics being reproduced (AniFem++): fem3Dtet<Operator<GRAD|IDEN,FemFix<P0..P3>>, ...> with a
+// CONST / per-tetrahedron tensor (fem/operations/core.inl:277-367, fem/diff_tensor.h:276-549) summed over the forms
+// of the user's local assembler and scattered by AssemblerT::Assemble (inmost_interface/assembler.inl:397-481).
+//
+// Algebra.  With the coefficient K constant on a tet, physical gradients (grad phi)_k = sum_a PSI[a+3k] G^_a and
+// |T| constant, the reference's quadrature sum factors exactly (for ANY rule, no exactness assumption):
+//   A_e(i,j) = sum_n w_n |T| (K grad phi_j).grad phi_i = sum_{ab} M_e[ab] * S^{ab}_{ij},
+//   M_e[ab]  = |T| sum_{kl} PSI[a+3k] K(k,l) PSI[b+3l]          (per element: 6 or 9 doubles)
+//   S^{ab}_{ij} = sum_n w_n G^B_{ia}(n) G^A_{jb}(n)             (element independent, built once on the host)
+// and likewise IDEN x IDEN (1 number per element), GRAD x IDEN / IDEN x GRAD (3 numbers), and the rhs trick.
+// All forms of one Assemble are concatenated: A_e(i,j) = sum_alpha T[alpha][i][j] * g_e[alpha].
+//
+// Kernels.
+//   k_geom          one thread per tet: coordinates + coefficient -> g_e[alpha] (coalesced 16-byte stores).  This
+//                   replaces the 100-entry element matrix that the generic path stages through HBM by <= 8 doubles.
+//   k_gather_tensor a group of G lanes owns a CSR row, walks the row's (element, local row) adjacency in ascending
+//                   element order, lane j evaluates A_e(i,j) from g_e (broadcast load) and the shared-memory table T,
+//                   and adds it into the shared-memory row image at the precomputed slot; the row is written once.
+//                   Deterministic, no atomics.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "afb_internal.h"
+
+using namespace afb;
+
+namespace {
+
+constexpr int MAX_TFORMS = 8;
+
+struct TFormDev {
+    int kind;      // 0 GRADxGRAD, 1 IDENxIDEN, 2 GRAD(A)xIDEN(B), 3 IDEN(A)xGRAD(B)
+    int ttype;     // AFB_TENSOR_*
+    int layout;    // CONST / PER_TET
+    int dlen;
+    int goff, ng;  // components [goff, goff+ng) of g_e
+    double alpha;
+    const double* D;
+};
+struct GeomParams {
+    int nforms;
+    int ngpad;  // doubles per element in gbuf (even)
+    TFormDev f[MAX_TFORMS];
+};
+
+__device__ __forceinline__ double jac_inv(const double P[4][3], double PSI[9]) {
+    double m[9];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) m[i + 3 * c] = P[c + 1][i] - P[0][i];
+    const double c00 = m[4] * m[8] - m[7] * m[5];
+    const double c01 = m[7] * m[2] - m[1] * m[8];
+    const double c02 = m[1] * m[5] - m[4] * m[2];
+    const double det = m[0] * c00 + m[3] * c01 + m[6] * c02;
+    const double id = 1.0 / det;
+    PSI[0] = c00 * id; PSI[1] = c01 * id; PSI[2] = c02 * id;
+    PSI[3] = (m[6] * m[5] - m[3] * m[8]) * id;
+    PSI[4] = (m[0] * m[8] - m[6] * m[2]) * id;
+    PSI[5] = (m[3] * m[2] - m[0] * m[5]) * id;
+    PSI[6] = (m[3] * m[7] - m[6] * m[4]) * id;
+    PSI[7] = (m[6] * m[1] - m[0] * m[7]) * id;
+    PSI[8] = (m[0] * m[4] - m[3] * m[1]) * id;
+    return det;
+}
+
+__global__ void __launch_bounds__(256) k_geom(long long ntet, GeomParams gp, const double* __restrict__ x, const double* __restrict__ y,
+                                              const double* __restrict__ z, const int32_t* __restrict__ v0, const int32_t* __restrict__ v1,
+                                              const int32_t* __restrict__ v2, const int32_t* __restrict__ v3, double* __restrict__ gbuf) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= ntet) return;
+    const int nn[4] = {__ldg(v0 + e), __ldg(v1 + e), __ldg(v2 + e), __ldg(v3 + e)};
+    double P[4][3], PSI[9];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { P[k][0] = __ldg(x + nn[k]); P[k][1] = __ldg(y + nn[k]); P[k][2] = __ldg(z + nn[k]); }
+    const double vol = fabs(jac_inv(P, PSI)) * (1.0 / 6.0);
+    double* g = gbuf + e * gp.ngpad;
+    for (int f = 0; f < gp.nforms; ++f) {
+        const TFormDev& F = gp.f[f];
+        const double* D = F.D;
+        if (F.layout == AFB_COEF_PER_TET) D += (size_t)F.dlen * e;
+        const double s = vol * F.alpha;
+        double* o = g + F.goff;
+        if (F.kind == 0) {
+            if (F.ttype >= AFB_TENSOR_SYMMETRIC) {
+                double K[9];
+#pragma unroll
+                for (int t = 0; t < 9; ++t) K[t] = __ldg(D + t);   // K(k,l) at k + 3l
+                // R[k][b] = sum_l K(k,l) PSI[b+3l];  M[a][b] = sum_k PSI[a+3k] R[k][b]
+                double R[3][3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) R[k][b] = K[k] * PSI[b] + K[k + 3] * PSI[b + 3] + K[k + 6] * PSI[b + 6];
+                double M[3][3];
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) M[a][b] = s * (PSI[a] * R[0][b] + PSI[a + 3] * R[1][b] + PSI[a + 6] * R[2][b]);
+                if (F.ng == 6) { o[0] = M[0][0]; o[1] = M[1][1]; o[2] = M[2][2]; o[3] = M[0][1]; o[4] = M[0][2]; o[5] = M[1][2]; }
+                else {
+#pragma unroll
+                    for (int a = 0; a < 3; ++a)
+#pragma unroll
+                        for (int b = 0; b < 3; ++b) o[3 * a + b] = M[a][b];
+                }
+            } else {
+                const double c = s * (F.ttype == AFB_TENSOR_SCALAR ? __ldg(D) : 1.0);
+                // M = c * PSI PSI^T (rows a of the inverse Jacobian dotted)
+                o[0] = c * (PSI[0] * PSI[0] + PSI[3] * PSI[3] + PSI[6] * PSI[6]);
+                o[1] = c * (PSI[1] * PSI[1] + PSI[4] * PSI[4] + PSI[7] * PSI[7]);
+                o[2] = c * (PSI[2] * PSI[2] + PSI[5] * PSI[5] + PSI[8] * PSI[8]);
+                o[3] = c * (PSI[0] * PSI[1] + PSI[3] * PSI[4] + PSI[6] * PSI[7]);
+                o[4] = c * (PSI[0] * PSI[2] + PSI[3] * PSI[5] + PSI[6] * PSI[8]);
+                o[5] = c * (PSI[1] * PSI[2] + PSI[4] * PSI[5] + PSI[7] * PSI[8]);
+            }
+        } else if (F.kind == 1) {
+            o[0] = s * (F.ttype >= AFB_TENSOR_SCALAR ? __ldg(D) : 1.0);
+        } else {
+            // kind 2: K(0,l) = D[l] -> o[b] = s sum_l K(0,l) PSI[b+3l];  kind 3: K(k,0) = D[k] -> o[a] = s sum_k PSI[a+3k] K(k,0)
+            double k0, k1, k2;
+            if (F.ttype >= AFB_TENSOR_SYMMETRIC) { k0 = __ldg(D); k1 = __ldg(D + 1); k2 = __ldg(D + 2); }
+            else { k0 = k1 = k2 = (F.ttype == AFB_TENSOR_SCALAR ? __ldg(D) : 1.0); }
+#pragma unroll
+            for (int a = 0; a < 3; ++a) o[a] = s * (PSI[a] * k0 + PSI[a + 3] * k1 + PSI[a + 6] * k2);
+        }
+    }
+}
+
+struct GatherT {
+    long long nrows, ntet;
+    int nrow_loc, ncol_loc, max_len;
+    int G, gpw, passes;        // lanes per row, rows per warp, column passes per visit
+    int nga, ngf, ngpad;       // matrix / rhs components, stride of gbuf
+    unsigned long long divM;   // ceil(2^40 / nrow_loc)
+    const long long* rowptr;
+    const long long* radj_ptr;
+    const unsigned* radj;
+    const unsigned short* pos;
+    const double* gbuf;
+    const double* TA;          // [nga][nrow_loc][ncol_loc]
+    const double* TF;          // [ngf][nrow_loc]
+    double* val;
+    double* rhs;
+    int accumulate;
+    double drop_val;
+    int* status;
+};
+
+template <int NGMAX>
+__global__ void __launch_bounds__(256) k_gather_tensor(GatherT p) {
+    extern __shared__ double sm[];
+    const int tabA = p.nga * p.nrow_loc * p.ncol_loc, tabF = p.ngf * p.nrow_loc;
+    double* sTA = sm;
+    double* sTF = sTA + tabA;
+    double* sacc = sTF + tabF;
+    for (int t = threadIdx.x; t < tabA; t += blockDim.x) sTA[t] = p.TA[t];
+    for (int t = threadIdx.x; t < tabF; t += blockDim.x) sTF[t] = p.TF[t];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int g = lane / p.G;           // group inside the warp
+    if (g >= p.gpw) return;             // idle tail lanes
+    const int gl = lane - g * p.G;
+    const unsigned gmask = (p.G == 32) ? 0xffffffffu : (((1u << p.G) - 1u) << (g * p.G));
+    double* acc = sacc + (size_t)(warp * p.gpw + g) * p.max_len;
+    const int rpb = wpb * p.gpw;
+    const bool doA = p.val != nullptr, doF = p.rhs != nullptr;
+    bool bad = false;
+    for (long long r = (long long)blockIdx.x * rpb + warp * p.gpw + g; r < p.nrows; r += (long long)gridDim.x * rpb) {
+        const long long p0 = p.rowptr[r];
+        const int len = (int)(p.rowptr[r + 1] - p0);
+        const long long a0 = p.radj_ptr[r], a1 = p.radj_ptr[r + 1];
+        if (doA) {
+            for (int s = gl; s < len; s += p.G) acc[s] = 0.0;
+            __syncwarp(gmask);
+        }
+        double fsum = 0.0;
+        for (long long a = a0; a < a1; ++a) {
+            const unsigned t = __ldg(p.radj + a);
+            const unsigned e = (unsigned)(((unsigned long long)t * p.divM) >> 40);
+            const int i = (int)(t - e * (unsigned)p.nrow_loc);
+            const double2* ge = reinterpret_cast<const double2*>(p.gbuf + (size_t)e * p.ngpad);
+            double gv[NGMAX];
+#pragma unroll
+            for (int c = 0; c < NGMAX / 2; ++c) {
+                if (2 * c < p.nga + p.ngf) { const double2 d = __ldg(ge + c); gv[2 * c] = d.x; gv[2 * c + 1] = d.y; }
+                else { gv[2 * c] = 0.0; gv[2 * c + 1] = 0.0; }
+            }
+            if (doF && gl == 0) {
+                double f = 0.0;
+#pragma unroll
+                for (int c = 0; c < NGMAX; ++c)
+                    if (c >= p.nga && c < p.nga + p.ngf) f += sTF[(c - p.nga) * p.nrow_loc + i] * gv[c];
+                bad |= !isfinite(f);
+                fsum += f;
+            }
+            if (doA) {
+                const size_t base = (size_t)t * p.ncol_loc;
+                for (int ps = 0; ps < p.passes; ++ps) {
+                    const int j = gl + ps * p.G;
+                    if (j < p.ncol_loc) {
+                        const double* T = sTA + i * p.ncol_loc + j;
+                        const int stride = p.nrow_loc * p.ncol_loc;
+                        double v = 0.0;
+#pragma unroll
+                        for (int c = 0; c < NGMAX; ++c)
+                            if (c < p.nga) v += T[c * stride] * gv[c];
+                        const int sl = p.pos[base + j];
+                        bad |= !isfinite(v);
+                        if (fabs(v) > p.drop_val) acc[sl] += v;
+                    }
+                }
+                __syncwarp(gmask);
+            }
+        }
+        if (doA) {
+            if (p.accumulate) for (int s = gl; s < len; s += p.G) p.val[p0 + s] += acc[s];
+            else for (int s = gl; s < len; s += p.G) p.val[p0 + s] = acc[s];
+            __syncwarp(gmask);
+        }
+        if (doF && gl == 0) {
+            if (p.accumulate) p.rhs[r] += fsum; else p.rhs[r] = fsum;
+        }
+    }
+    if (bad) *p.status = 1;
+}
+
+// S tables on the host
+struct HostForm {
+    int kind, ng;
+    std::vector<double> T;  // [ng][nfb][nfa]
+};
+
+void build_form_table(const afb_form& fm, const OpInfo& A, const OpInfo& B, int kind, int ng, std::vector<double>& T) {
+    const double *pq, *wq;
+    const int q = tet_rule(fm.quad_order, &pq, &wq);
+    const int nfa = A.nf_base, nfb = B.nf_base;
+    std::vector<double> phiA((size_t)q * nfa), phiB((size_t)q * nfb), GA((size_t)q * nfa * 3), GB((size_t)q * nfb * 3);
+    basis_values(A.fem, q, pq, phiA.data());
+    basis_values(B.fem, q, pq, phiB.data());
+    basis_ref_grads(A.fem, q, pq, GA.data());
+    basis_ref_grads(B.fem, q, pq, GB.data());
+    T.assign((size_t)ng * nfb * nfa, 0.0);
+    auto S = [&](int a, int b, int i, int j) {  // sum_n w_n GB[i][a] GA[j][b]
+        double s = 0;
+        for (int n = 0; n < q; ++n) s += wq[n] * GB[((size_t)n * nfb + i) * 3 + a] * GA[((size_t)n * nfa + j) * 3 + b];
+        return s;
+    };
+    for (int i = 0; i < nfb; ++i)
+        for (int j = 0; j < nfa; ++j) {
+            auto at = [&](int c) -> double& { return T[((size_t)c * nfb + i) * nfa + j]; };
+            if (kind == 0) {
+                if (ng == 9) { for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) at(3 * a + b) = S(a, b, i, j); }
+                else {
+                    at(0) = S(0, 0, i, j); at(1) = S(1, 1, i, j); at(2) = S(2, 2, i, j);
+                    at(3) = S(0, 1, i, j) + S(1, 0, i, j); at(4) = S(0, 2, i, j) + S(2, 0, i, j); at(5) = S(1, 2, i, j) + S(2, 1, i, j);
+                }
+            } else if (kind == 1) {
+                double s = 0;
+                for (int n = 0; n < q; ++n) s += wq[n] * phiB[(size_t)n * nfb + i] * phiA[(size_t)n * nfa + j];
+                at(0) = s;
+            } else if (kind == 2) {
+                for (int b = 0; b < 3; ++b) {
+                    double s = 0;
+                    for (int n = 0; n < q; ++n) s += wq[n] * phiB[(size_t)n * nfb + i] * GA[((size_t)n * nfa + j) * 3 + b];
+                    at(b) = s;
+                }
+            } else {
+                for (int a = 0; a < 3; ++a) {
+                    double s = 0;
+                    for (int n = 0; n < q; ++n) s += wq[n] * GB[((size_t)n * nfb + i) * 3 + a] * phiA[(size_t)n * nfa + j];
+                    at(a) = s;
+                }
+            }
+        }
+}
+
+template <int NGMAX>
+cudaError_t launch_gt(const GatherT& p, unsigned grid, size_t smem, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(k_gather_tensor<NGMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_gather_tensor<NGMAX><<<grid, 256, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+namespace afb {
+
+// Returns 1 if the call was handled by the fused path, 0 if it does not apply (caller falls back to the generic
+// staged path), < 0 on error.
+int assemble_tensor_path(afb_ctx* ctx, int nfA, int nfF, const std::vector<afb_form>& fm, const std::vector<OpInfo>& oa,
+                         const std::vector<OpInfo>& ob, const std::vector<const double*>& Dd, double* dval, double* drhs,
+                         int accumulate, double drop_val, int* status_flag) {
+    const int nforms = nfA + nfF;
+    if (nforms == 0 || nforms > MAX_TFORMS) return 0;
+    if (getenv("AFB_DISABLE_TENSOR_PATH")) return 0;
+    const int nrl = ctx->nrow_loc, ncl = ctx->ncol_loc;
+    if (ctx->has_signs) return 0;
+    std::vector<int> kind(nforms), ng(nforms);
+    int nga = 0, ngf = 0;
+    for (int k = 0; k < nforms; ++k) {
+        const afb_form& f = fm[k];
+        if (oa[k].vec != 1 || ob[k].vec != 1) return 0;
+        if (f.coef_layout == AFB_COEF_PER_POINT) return 0;
+        const bool gA = f.opA == AFB_GRAD, gB = f.opB == AFB_GRAD;
+        if ((f.opA != AFB_IDEN && !gA) || (f.opB != AFB_IDEN && !gB)) return 0;
+        kind[k] = gA ? (gB ? 0 : 2) : (gB ? 3 : 1);
+        const int tt = f.tensor_type;
+        if (kind[k] == 0) ng[k] = (tt == AFB_TENSOR_GENERAL) ? 9 : 6;
+        else if (kind[k] == 1) ng[k] = 1;
+        else {
+            ng[k] = 3;
+            // scalar / identity tensors are only legal here through the IDEN(P0) broadcast (diff_tensor.h:333-338)
+            if (tt < AFB_TENSOR_SYMMETRIC && !(kind[k] == 3 && oa[k].nfa == 1)) return 0;
+        }
+        if (tt == AFB_TENSOR_SYMMETRIC && oa[k].dim != ob[k].dim) return 0;
+        (k < nfA ? nga : ngf) += ng[k];
+    }
+    const int ngtot = nga + ngf;
+    if (ngtot > 32) return 0;
+    const size_t tabA = (size_t)nga * nrl * ncl, tabF = (size_t)ngf * nrl;
+    if ((tabA + tabF) * 8 > 96 * 1024) return 0;
+    const int ngpad = (ngtot + 1) & ~1;
+
+    // ---- host tables T[alpha][i][j] over the whole element matrix, rhs table TF[beta][i]
+    std::vector<double> TA(tabA, 0.0), TF(tabF, 0.0);
+    GeomParams gp;
+    std::memset(&gp, 0, sizeof(gp));
+    gp.nforms = nforms; gp.ngpad = ngpad;
+    int offA = 0, offF = nga;
+    for (int k = 0; k < nforms; ++k) {
+        std::vector<double> T;
+        build_form_table(fm[k], oa[k], ob[k], kind[k], ng[k], T);
+        const bool mat = k < nfA;
+        const int goff = mat ? offA : offF;
+        for (int c = 0; c < ng[k]; ++c)
+            for (int i = 0; i < ob[k].nfa; ++i)
+                for (int j = 0; j < oa[k].nfa; ++j) {
+                    const double v = T[((size_t)c * ob[k].nfa + i) * oa[k].nfa + j];
+                    if (mat) TA[((size_t)(goff + c) * nrl + fm[k].row_off + i) * ncl + fm[k].col_off + j] = v;
+                    else TF[(size_t)(goff - nga + c) * nrl + fm[k].row_off + i] = v;
+                }
+        TFormDev& d = gp.f[k];
+        d.kind = kind[k]; d.ttype = fm[k].tensor_type; d.layout = fm[k].coef_layout; d.dlen = form_dlen(fm[k], oa[k], ob[k]);
+        d.goff = goff; d.ng = ng[k]; d.alpha = fm[k].alpha; d.D = Dd[k];
+        (mat ? offA : offF) += ng[k];
+    }
+    cudaStream_t st = ctx->stream;
+    // tables: small, uploaded through a per-context device buffer; stream-ordered so reuse across calls is safe
+    AFB_CUDA(ctx, ctx->tables.reserve((tabA + tabF + 2) * sizeof(double)));
+    if (tabA) AFB_CUDA(ctx, cudaMemcpyAsync(ctx->tables.p, TA.data(), tabA * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (tabF) AFB_CUDA(ctx, cudaMemcpyAsync(ctx->tables.as<double>() + tabA, TF.data(), tabF * sizeof(double), cudaMemcpyHostToDevice, st));
+    AFB_CUDA(ctx, ctx->stageF.reserve((size_t)ctx->ntet * ngpad * sizeof(double)));  // g_e buffer
+    double* gbuf = ctx->stageF.as<double>();
+
+    cudaEventRecord(ctx->ev[1], st);
+    const unsigned gridg = (unsigned)((ctx->ntet + 255) / 256);
+    k_geom<<<gridg, 256, 0, st>>>(ctx->ntet, gp, ctx->x.as<double>(), ctx->y.as<double>(), ctx->z.as<double>(), ctx->v[0].as<int32_t>(),
+                                 ctx->v[1].as<int32_t>(), ctx->v[2].as<int32_t>(), ctx->v[3].as<int32_t>(), gbuf);
+    ctx->launches++;
+    AFB_CUDA(ctx, cudaGetLastError());
+    cudaEventRecord(ctx->ev[2], st);
+
+    // ---- gather geometry: lanes per row
+    int bestG = 1; double bestU = -1;
+    for (int G = 1; G <= 32; ++G) {
+        const int passes = (ncl + G - 1) / G;
+        if (passes > 4) continue;
+        const double util = (double)ncl / (passes * G) * ((32 / G) * G / 32.0);
+        if (util > bestU + 1e-9) { bestU = util; bestG = G; }
+    }
+    GatherT p;
+    p.nrows = ctx->row_end - ctx->row_begin; p.ntet = ctx->ntet;
+    p.nrow_loc = nrl; p.ncol_loc = ncl; p.max_len = std::max(1, ctx->max_row_len);
+    p.G = bestG; p.gpw = 32 / bestG; p.passes = (ncl + bestG - 1) / bestG;
+    p.nga = dval ? nga : 0; p.ngf = ngf; p.ngpad = ngpad;
+    p.divM = ((1ULL << 40) + nrl - 1) / nrl;
+    p.rowptr = ctx->rowptr.as<long long>(); p.radj_ptr = ctx->radj_ptr.as<long long>(); p.radj = ctx->radj.as<unsigned>();
+    p.pos = ctx->pos.as<unsigned short>(); p.gbuf = gbuf;
+    p.TA = ctx->tables.as<double>(); p.TF = ctx->tables.as<double>() + tabA;
+    p.val = dval; p.rhs = drhs; p.accumulate = accumulate; p.drop_val = drop_val; p.status = status_flag;
+    // note: p.nga = 0 when only the rhs is wanted, but the component offsets inside g_e stay the same
+    if (!dval) { p.nga = nga; }
+    const int rpb = 8 * p.gpw;
+    const size_t smem = (tabA + tabF + (size_t)rpb * p.max_len) * sizeof(double);
+    if (smem > 200 * 1024) return 0;
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((p.nrows + rpb - 1) / rpb, 148LL * 32));
+    cudaError_t e;
+    if (ngtot <= 2) e = launch_gt<2>(p, grid, smem, st);
+    else if (ngtot <= 6) e = launch_gt<6>(p, grid, smem, st);
+    else if (ngtot <= 8) e = launch_gt<8>(p, grid, smem, st);
+    else if (ngtot <= 12) e = launch_gt<12>(p, grid, smem, st);
+    else if (ngtot <= 16) e = launch_gt<16>(p, grid, smem, st);
+    else if (ngtot <= 24) e = launch_gt<24>(p, grid, smem, st);
+    else e = launch_gt<32>(p, grid, smem, st);
+    ctx->launches++;
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "k_gather_tensor launch");
+    cudaEventRecord(ctx->ev[3], st);
+    return 1;
+}
+
+}  // namespace afb

@@ -1,6 +1,8 @@
 """GPU parity tests of the global-assembly path through the C ABI: mesh generator, NATURAL dof map,
 CSR pattern (bit-exact against the restated AssembleTemplate), values and RHS (1e-12 relative),
 status codes, accumulate semantics, explicit dof tables with ghost rows (multi-rank layout)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -34,9 +36,22 @@ def _check(ctx, M, prob, forms, rhsf, co, te, dm, tag):
     rp, ci, v, r, st = M.assemble(prob, co, te, dm)
     assert np.array_equal(rowptr, rp), tag + ": rowptr not bit-exact"
     assert np.array_equal(colind, ci), tag + ": colind not bit-exact"
-    val, rhs = np.full(nnz, np.nan), np.full(rp.size - 1, np.nan)
-    status = ctx.assemble(forms, rhsf, val, rhs)
-    assert status == 0 and st == 0
+    assert st == 0
+    # both product paths: the fused tensor-representation path (when it applies) and the generic staged path
+    for env in ("", "1"):
+        if env:
+            os.environ["AFB_DISABLE_TENSOR_PATH"] = env
+        else:
+            os.environ.pop("AFB_DISABLE_TENSOR_PATH", None)
+        val, rhs = np.full(nnz, np.nan), np.full(rp.size - 1, np.nan)
+        status = ctx.assemble(forms, rhsf, val, rhs)
+        os.environ.pop("AFB_DISABLE_TENSOR_PATH", None)
+        assert status == 0
+        _compare(val, rhs, v, r, rp, te, nnz, tag + (" [generic path]" if env else " [default path]"))
+    return val, rhs, v, r
+
+
+def _compare(val, rhs, v, r, rp, te, nnz, tag):
     # H7 tolerance: relative to the largest element contribution ~ largest |entry| of the row
     rowmax = np.maximum.reduceat(np.abs(v), rp[:-1])
     scale = np.repeat(rowmax, np.diff(rp))
@@ -44,7 +59,6 @@ def _check(ctx, M, prob, forms, rhsf, co, te, dm, tag):
     rerr = np.abs(rhs - r).max() / np.abs(r).max()
     print("%s: ntet=%d nnz=%d max rel err A %.2e rhs %.2e" % (tag, te.shape[0], nnz, err, rerr))
     assert err <= RTOL and rerr <= RTOL, (tag, err, rerr)
-    return val, rhs, v, r
 
 
 def test_c1_p1_diffusion(pkg, ctx, asm_oracle):
