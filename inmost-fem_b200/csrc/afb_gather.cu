@@ -17,10 +17,10 @@ using namespace afb;
 
 namespace {
 
-template <int G, bool SIGNS>
+template <int G, bool SIGNS, typename PosT>
 __global__ void __launch_bounds__(256) k_gather(long long nrows, long long ntet, int nrow_loc, int ncol_loc, int max_len,
                                                 const long long* __restrict__ rowptr, const long long* __restrict__ radj_ptr,
-                                                const unsigned* __restrict__ radj, const unsigned short* __restrict__ pos,
+                                                const unsigned* __restrict__ radj, const PosT* __restrict__ pos,
                                                 const int32_t* __restrict__ e2r, const int32_t* __restrict__ e2c,
                                                 const double* __restrict__ stageA, const double* __restrict__ stageF,
                                                 double* __restrict__ val, double* __restrict__ rhs, int accumulate, double drop_val,
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256) k_gather(long long nrows, long long ntet,
                 const long long base = (long long)t * ncol_loc;
                 for (int j = gl; j < ncol_loc; j += G) {
                     double v = __ldg(stageA + base + j);
-                    const int p = pos[base + j];
+                    const int p = pos[a * ncol_loc + j];
                     bad |= !isfinite(v);
                     if (SIGNS) v *= sr * (e2c[(long long)j * ntet + e] < 0 ? -1.0 : 1.0);
                     if (fabs(v) > drop_val) acc[p] += v;
@@ -79,27 +79,28 @@ __global__ void __launch_bounds__(256) k_gather(long long nrows, long long ntet,
     if (bad) *status = 1;  // benign race: every writer stores the same value
 }
 
-template <int G>
-cudaError_t launch_g(afb_ctx* c, const double* sA, const double* sF, double* val, double* rhs, int accumulate, double drop, int* status) {
+template <int G, bool SIGNS, typename PosT>
+cudaError_t launch_g2(afb_ctx* c, const double* sA, const double* sF, double* val, double* rhs, int accumulate, double drop, int* status) {
     const long long nrows = c->row_end - c->row_begin;
     const int gpb = 256 / G;
     const size_t smem = (size_t)gpb * std::max(1, c->max_row_len) * sizeof(double);
     const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((nrows + gpb - 1) / gpb, 148LL * 64));
-    cudaError_t e;
-    if (c->has_signs) {
-        e = cudaFuncSetAttribute(k_gather<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        k_gather<G, true><<<grid, 256, smem, c->stream>>>(nrows, c->ntet, c->nrow_loc, c->ncol_loc, std::max(1, c->max_row_len), c->rowptr.as<long long>(),
-                                                        c->radj_ptr.as<long long>(), c->radj.as<unsigned>(), c->pos.as<unsigned short>(), c->e2r.as<int32_t>(),
-                                                        c->e2c.as<int32_t>(), sA, sF, val, rhs, accumulate, drop, status);
-    } else {
-        e = cudaFuncSetAttribute(k_gather<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        k_gather<G, false><<<grid, 256, smem, c->stream>>>(nrows, c->ntet, c->nrow_loc, c->ncol_loc, std::max(1, c->max_row_len), c->rowptr.as<long long>(),
-                                                         c->radj_ptr.as<long long>(), c->radj.as<unsigned>(), c->pos.as<unsigned short>(), c->e2r.as<int32_t>(),
-                                                         c->e2c.as<int32_t>(), sA, sF, val, rhs, accumulate, drop, status);
-    }
+    cudaError_t e = cudaFuncSetAttribute(k_gather<G, SIGNS, PosT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_gather<G, SIGNS, PosT><<<grid, 256, smem, c->stream>>>(nrows, c->ntet, c->nrow_loc, c->ncol_loc, std::max(1, c->max_row_len), c->rowptr.as<long long>(),
+                                                             c->radj_ptr.as<long long>(), c->radj.as<unsigned>(), c->pos.as<PosT>(), c->e2r.as<int32_t>(),
+                                                             c->e2c.as<int32_t>(), sA, sF, val, rhs, accumulate, drop, status);
     return cudaGetLastError();
+}
+
+template <int G>
+cudaError_t launch_g(afb_ctx* c, const double* sA, const double* sF, double* val, double* rhs, int accumulate, double drop, int* status) {
+    if (c->has_signs) {
+        if (c->pos_bytes == 1) return launch_g2<G, true, unsigned char>(c, sA, sF, val, rhs, accumulate, drop, status);
+        return launch_g2<G, true, unsigned short>(c, sA, sF, val, rhs, accumulate, drop, status);
+    }
+    if (c->pos_bytes == 1) return launch_g2<G, false, unsigned char>(c, sA, sF, val, rhs, accumulate, drop, status);
+    return launch_g2<G, false, unsigned short>(c, sA, sF, val, rhs, accumulate, drop, status);
 }
 
 }  // namespace

@@ -103,7 +103,8 @@ struct afb_ctx {
     afb::DevBuf colind;           // int32[nnz]
     afb::DevBuf radj_ptr;         // int64[nrows+1]
     afb::DevBuf radj;             // uint32[n_adj]: e*nrow_loc + i, ascending per row
-    afb::DevBuf pos;              // uint16[ntet*nrow_loc*ncol_loc]: slot of (e,i,j) inside its row
+    afb::DevBuf pos;              // uint8|uint16[n_adj*ncol_loc]: slot of column j of adjacency entry a inside its row
+    int pos_bytes = 2;
     int64_t n_adj = 0;
 
     // work buffers

@@ -7,7 +7,8 @@
 //      element index inside a row: this fixes the summation order of the assembly once and for all;
 //   2. one warp per row gathers the candidate columns of the adjacent elements (+ the forced diagonal) into shared
 //      memory, bitonic-sorts and uniques them: pass 1 counts (-> rowptr by prefix sum), pass 2 writes colind;
-//   3. every (element,i,j) looks up the slot of its column inside its row (binary search) -> 16-bit `pos` table.
+//   3. every (element,i) pair of the row lists looks up the slots of the element's columns inside the row (binary
+//      search) -> `pos` table in adjacency order (8-bit when all rows have <= 256 entries, else 16-bit).
 // The plan (radj, pos) is what makes the value scatter atomic-free and deterministic (afb_gather.cu).
 #include <cub/cub.cuh>
 
@@ -105,18 +106,16 @@ __global__ void k_row_columns(long long nrows, long long row_begin, long long nt
     }
 }
 
-__global__ void k_pos(long long ntet, int nrow_loc, int ncol_loc, const int32_t* e2r, const int32_t* e2c, const long long* rowptr,
-                      const int32_t* colind, unsigned short* pos) {
-    const long long n = ntet * nrow_loc;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+// slot table in adjacency order: for the a-th (element, local row) pair of the row lists, the slot of each of the
+// element's columns inside that row.  8-bit when every row has <= 256 entries, else 16-bit.
+template <typename PosT>
+__global__ void k_pos(long long n_adj, long long ntet, int nrow_loc, int ncol_loc, const unsigned* radj, const int32_t* e2r,
+                      const int32_t* e2c, const long long* rowptr, const int32_t* colind, PosT* pos) {
+    for (long long a = blockIdx.x * (long long)blockDim.x + threadIdx.x; a < n_adj; a += (long long)gridDim.x * blockDim.x) {
+        const unsigned t = radj[a];
         const long long e = t / nrow_loc;
         const int i = (int)(t - e * nrow_loc);
-        const int rc = e2r[(long long)i * ntet + e];
-        if (rc == 0) {
-            for (int j = 0; j < ncol_loc; ++j) pos[t * ncol_loc + j] = 0;
-            continue;
-        }
-        const long long r = abs(rc) - 1;
+        const long long r = abs(e2r[(long long)i * ntet + e]) - 1;
         const long long b = rowptr[r], en = rowptr[r + 1];
         for (int j = 0; j < ncol_loc; ++j) {
             const int c = abs(e2c[(long long)j * ntet + e]) - 1;
@@ -125,7 +124,7 @@ __global__ void k_pos(long long ntet, int nrow_loc, int ncol_loc, const int32_t*
                 const long long mid = (lo + hi) >> 1;
                 if (colind[mid] < c) lo = mid + 1; else hi = mid;
             }
-            pos[t * ncol_loc + j] = (unsigned short)(lo - b);
+            pos[a * ncol_loc + j] = (PosT)(lo - b);
         }
     }
 }
@@ -207,9 +206,14 @@ int afb_pattern_build(afb_ctx* ctx, int64_t* nnz_out) {
     P_CUDA(cudaStreamSynchronize(st));
     if (max_len > 65535) { cleanup(); set_error(ctx, "afb_pattern_build: row longer than 65535 entries"); return -3; }
     // 3. slot table
-    P_CUDA(ctx->pos.reserve((size_t)nitem * ncl * sizeof(unsigned short)));
-    k_pos<<<grid_for(nitem), 256, 0, st>>>(ntet, nrl, ncl, ctx->e2r.as<int32_t>(), ctx->e2c.as<int32_t>(), ctx->rowptr.as<long long>(),
-                                         ctx->colind.as<int32_t>(), ctx->pos.as<unsigned short>());
+    ctx->pos_bytes = max_len <= 256 ? 1 : 2;
+    P_CUDA(ctx->pos.reserve((size_t)std::max<long long>(1, n_adj) * ncl * ctx->pos_bytes));
+    if (ctx->pos_bytes == 1)
+        k_pos<unsigned char><<<grid_for(n_adj), 256, 0, st>>>(n_adj, ntet, nrl, ncl, ctx->radj.as<unsigned>(), ctx->e2r.as<int32_t>(), ctx->e2c.as<int32_t>(),
+                                                             ctx->rowptr.as<long long>(), ctx->colind.as<int32_t>(), ctx->pos.as<unsigned char>());
+    else
+        k_pos<unsigned short><<<grid_for(n_adj), 256, 0, st>>>(n_adj, ntet, nrl, ncl, ctx->radj.as<unsigned>(), ctx->e2r.as<int32_t>(), ctx->e2c.as<int32_t>(),
+                                                              ctx->rowptr.as<long long>(), ctx->colind.as<int32_t>(), ctx->pos.as<unsigned short>());
     P_CUDA(cudaGetLastError());
     P_CUDA(cudaStreamSynchronize(st));
     ctx->launches += 5;

@@ -44,6 +44,7 @@ struct TFormDev {
 struct GeomParams {
     int nforms;
     int ngpad;  // doubles per element in gbuf (even)
+    int ngtot;  // components actually used; the pad slot is zeroed
     TFormDev f[MAX_TFORMS];
 };
 
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(256) k_geom(long long ntet, GeomParams gp, con
     for (int k = 0; k < 4; ++k) { P[k][0] = __ldg(x + nn[k]); P[k][1] = __ldg(y + nn[k]); P[k][2] = __ldg(z + nn[k]); }
     const double vol = fabs(jac_inv(P, PSI)) * (1.0 / 6.0);
     double* g = gbuf + e * gp.ngpad;
+    if (gp.ngpad > gp.ngtot) g[gp.ngtot] = 0.0;
     for (int f = 0; f < gp.nforms; ++f) {
         const TFormDev& F = gp.f[f];
         const double* D = F.D;
@@ -140,7 +142,8 @@ struct GatherT {
     const long long* rowptr;
     const long long* radj_ptr;
     const unsigned* radj;
-    const unsigned short* pos;
+    const void* pos;           // uint8 | uint16, adjacency order
+    int pos_bytes;
     const double* gbuf;
     const double* TA;          // [nga][nrow_loc][ncol_loc]
     const double* TF;          // [ngf][nrow_loc]
@@ -199,7 +202,7 @@ __global__ void __launch_bounds__(256) k_gather_tensor(GatherT p) {
                 fsum += f;
             }
             if (doA) {
-                const size_t base = (size_t)t * p.ncol_loc;
+                const size_t base = (size_t)a * p.ncol_loc;
                 for (int ps = 0; ps < p.passes; ++ps) {
                     const int j = gl + ps * p.G;
                     if (j < p.ncol_loc) {
@@ -209,7 +212,8 @@ __global__ void __launch_bounds__(256) k_gather_tensor(GatherT p) {
 #pragma unroll
                         for (int c = 0; c < NGMAX; ++c)
                             if (c < p.nga) v += T[c * stride] * gv[c];
-                        const int sl = p.pos[base + j];
+                        const int sl = p.pos_bytes == 1 ? (int)static_cast<const unsigned char*>(p.pos)[base + j]
+                                                        : (int)static_cast<const unsigned short*>(p.pos)[base + j];
                         bad |= !isfinite(v);
                         if (fabs(v) > p.drop_val) acc[sl] += v;
                     }
@@ -227,6 +231,143 @@ __global__ void __launch_bounds__(256) k_gather_tensor(GatherT p) {
         }
     }
     if (bad) *p.status = 1;
+}
+
+// Specialisation for square element matrices with compile-time sizes (NLOC = 4, 10, 20), NGA matrix components and
+// NGF rhs components: no predicates in the inner loop, shared memory addressed through 32-bit shared-window
+// addresses with immediate offsets, the slot bytes of a visit read before the FMA chain, the adjacency entry of the
+// next visit prefetched, one warp-uniform trip count (max degree of the warp's rows) so that the per-visit barrier is a
+// plain full-mask __syncwarp, and NaN/Inf detection folded into one FMA per entry (v*0 accumulates NaN).
+__device__ __forceinline__ double lds64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts64(unsigned addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
+
+template <int NLOC, int G, int NGA, int NGF, typename PosT>
+__global__ void __launch_bounds__(256) k_gather_tensor_sq(GatherT p) {
+    // G = lanes per row
+    constexpr int PASSES = (NLOC + G - 1) / G;    // columns per lane
+    constexpr int GPW = 32 / G;                   // rows per warp
+    constexpr int TAB = NLOC * NLOC;
+    constexpr int NG = NGA + NGF;
+    constexpr int NGP = (NG + 1) & ~1;
+    static_assert(PASSES * G == NLOC, "columns must tile the lane group");
+    extern __shared__ double sm[];
+    double* sTA = sm;                   // [NGA][NLOC][NLOC]
+    double* sTF = sTA + NGA * TAB;      // [NGF][NLOC]
+    double* sacc = sTF + NGF * NLOC;
+    for (int t = threadIdx.x; t < NGA * TAB; t += 256) sTA[t] = p.TA[t];
+    for (int t = threadIdx.x; t < NGF * NLOC; t += 256) sTF[t] = p.TF[t];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = min(lane / G, GPW - 1);
+    const bool lane_on = lane < GPW * G;          // the tail lanes of a warp idle but keep the warp converged
+    const int gl = lane_on ? lane - g * G : 0;
+    constexpr int RPB = 8 * GPW;
+    const bool doA = p.val != nullptr, doF = p.rhs != nullptr;
+    const PosT* __restrict__ pos = static_cast<const PosT*>(p.pos);
+    const unsigned* __restrict__ radj = p.radj;
+    const double* __restrict__ gbuf = p.gbuf;
+    const double drop = p.drop_val;
+    const unsigned sTA_a = (unsigned)__cvta_generic_to_shared(sTA) + gl * 8;
+    const unsigned sTF_a = (unsigned)__cvta_generic_to_shared(sTF);
+    const unsigned acc_a = (unsigned)__cvta_generic_to_shared(sacc) + (unsigned)(warp * GPW + g) * p.max_len * 8;
+    double chk = 0.0;
+    const long long nrows_pad = ((p.nrows + RPB - 1) / RPB) * RPB;
+    for (long long r0 = (long long)blockIdx.x * RPB + warp * GPW; r0 < nrows_pad; r0 += (long long)gridDim.x * RPB) {
+        const long long r = r0 + g;
+        const bool row_on = lane_on && r < p.nrows;
+        long long p0 = 0, a0 = 0;
+        int len = 0, deg = 0;
+        if (row_on) {
+            p0 = p.rowptr[r];
+            len = (int)(p.rowptr[r + 1] - p0);
+            a0 = p.radj_ptr[r];
+            deg = (int)(p.radj_ptr[r + 1] - a0);
+        }
+        const int degmax = __reduce_max_sync(0xffffffffu, deg);
+        if (doA) {
+            for (int s = gl; s < len; s += G) sts64(acc_a + s * 8, 0.0);
+            __syncwarp();
+        }
+        double fsum = 0.0;
+        const unsigned* ra = radj + a0;
+        const PosT* pa = pos + a0 * NLOC + gl;
+        unsigned tn = deg > 0 ? __ldg(ra) : 0u;
+        for (int k = 0; k < degmax; ++k) {
+            const bool on = k < deg;
+            const unsigned t = tn;
+            if (k + 1 < deg) tn = __ldg(ra + k + 1);
+            const unsigned e = t / (unsigned)NLOC;
+            const int i = (int)(t - e * (unsigned)NLOC);
+            int sl[PASSES];
+#pragma unroll
+            for (int ps = 0; ps < PASSES; ++ps) sl[ps] = on ? (int)pa[k * NLOC + ps * G] : 0;
+            double gv[NGP];
+            if (on) {
+                const double2* ge = reinterpret_cast<const double2*>(gbuf + (size_t)e * NGP);
+#pragma unroll
+                for (int c = 0; c < NGP / 2; ++c) { const double2 d = __ldg(ge + c); gv[2 * c] = d.x; gv[2 * c + 1] = d.y; }
+            } else {
+#pragma unroll
+                for (int c = 0; c < NGP; ++c) gv[c] = 0.0;
+            }
+            if (NGF > 0 && doF && gl == 0) {
+                double f = 0.0;
+#pragma unroll
+                for (int c = 0; c < NGF; ++c) f = fma(lds64(sTF_a + (c * NLOC + i) * 8), gv[NGA + c], f);
+                chk = fma(f, 0.0, chk);
+                fsum += f;
+            }
+            if (NGA > 0 && doA) {
+                const unsigned Ta = sTA_a + i * (NLOC * 8);
+#pragma unroll
+                for (int ps = 0; ps < PASSES; ++ps) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int c = 0; c < NGA; ++c) v = fma(lds64(Ta + (c * TAB + ps * G) * 8), gv[c], v);
+                    chk = fma(v, 0.0, chk);
+                    if (on && fabs(v) > drop) {
+                        const unsigned sa = acc_a + sl[ps] * 8;
+                        sts64(sa, lds64(sa) + v);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        if (doA) {
+            if (p.accumulate) for (int s = gl; s < len; s += G) p.val[p0 + s] += lds64(acc_a + s * 8);
+            else for (int s = gl; s < len; s += G) p.val[p0 + s] = lds64(acc_a + s * 8);
+            __syncwarp();
+        }
+        if (doF && row_on && gl == 0) {
+            if (p.accumulate) p.rhs[r] += fsum; else p.rhs[r] = fsum;
+        }
+    }
+    if (chk != chk) *p.status = 1;   // NaN <=> some local value was NaN or +-Inf
+}
+
+template <int NLOC, int G, int NGA, int NGF, typename PosT>
+cudaError_t launch_sq(const GatherT& p, cudaStream_t st) {
+    constexpr int RPB = 8 * (32 / G);
+    const size_t smem = ((size_t)NGA * NLOC * NLOC + (size_t)NGF * NLOC + (size_t)RPB * p.max_len) * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(k_gather_tensor_sq<NLOC, G, NGA, NGF, PosT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((p.nrows + RPB - 1) / RPB, 148LL * 32));
+    k_gather_tensor_sq<NLOC, G, NGA, NGF, PosT><<<grid, 256, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+template <int NLOC, int G, typename PosT>
+cudaError_t launch_sq_ng(const GatherT& p, int nga, int ngf, cudaStream_t st, bool* done) {
+    *done = true;
+#define SQ(A, F) if (nga == A && ngf == F) return launch_sq<NLOC, G, A, F, PosT>(p, st);
+    SQ(6, 1) SQ(6, 0) SQ(7, 1) SQ(7, 0) SQ(1, 1) SQ(1, 0) SQ(0, 1) SQ(9, 1) SQ(9, 0) SQ(10, 1) SQ(10, 0) SQ(3, 0) SQ(3, 1)
+#undef SQ
+    *done = false;
+    return cudaSuccess;
 }
 
 // S tables on the host
@@ -331,7 +472,7 @@ int assemble_tensor_path(afb_ctx* ctx, int nfA, int nfF, const std::vector<afb_f
     std::vector<double> TA(tabA, 0.0), TF(tabF, 0.0);
     GeomParams gp;
     std::memset(&gp, 0, sizeof(gp));
-    gp.nforms = nforms; gp.ngpad = ngpad;
+    gp.nforms = nforms; gp.ngpad = ngpad; gp.ngtot = ngtot;
     int offA = 0, offF = nga;
     for (int k = 0; k < nforms; ++k) {
         std::vector<double> T;
@@ -381,7 +522,7 @@ int assemble_tensor_path(afb_ctx* ctx, int nfA, int nfF, const std::vector<afb_f
     p.nga = dval ? nga : 0; p.ngf = ngf; p.ngpad = ngpad;
     p.divM = ((1ULL << 40) + nrl - 1) / nrl;
     p.rowptr = ctx->rowptr.as<long long>(); p.radj_ptr = ctx->radj_ptr.as<long long>(); p.radj = ctx->radj.as<unsigned>();
-    p.pos = ctx->pos.as<unsigned short>(); p.gbuf = gbuf;
+    p.pos = ctx->pos.p; p.pos_bytes = ctx->pos_bytes; p.gbuf = gbuf;
     p.TA = ctx->tables.as<double>(); p.TF = ctx->tables.as<double>() + tabA;
     p.val = dval; p.rhs = drhs; p.accumulate = accumulate; p.drop_val = drop_val; p.status = status_flag;
     // note: p.nga = 0 when only the rhs is wanted, but the component offsets inside g_e stay the same
@@ -390,8 +531,27 @@ int assemble_tensor_path(afb_ctx* ctx, int nfA, int nfF, const std::vector<afb_f
     const size_t smem = (tabA + tabF + (size_t)rpb * p.max_len) * sizeof(double);
     if (smem > 200 * 1024) return 0;
     const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((p.nrows + rpb - 1) / rpb, 148LL * 32));
-    cudaError_t e;
-    if (ngtot <= 2) e = launch_gt<2>(p, grid, smem, st);
+    cudaError_t e = cudaSuccess;
+    bool done = false;
+    if (nrl == ncl && (nrl == 4 || nrl == 10 || nrl == 20) && !getenv("AFB_DISABLE_SQ_KERNEL")) {
+        // lanes per row: fewer lanes -> more rows (independent load chains) per warp and less per-visit overhead
+        int G = nrl == 4 ? 2 : 5;
+        if (const char* gs = getenv("AFB_SQ_G")) G = atoi(gs);
+        if (nrl == 4 && G != 2 && G != 4) G = 2;
+        if (nrl != 4 && G != 5 && G != 10) G = 5;
+        const size_t smem_sq = ((size_t)nga * nrl * nrl + (size_t)ngf * nrl + (size_t)8 * (32 / G) * p.max_len) * sizeof(double);
+        if (smem_sq <= 200 * 1024) {
+#define DISPATCH(NL, GG)                                                                                  \
+    if (nrl == NL && G == GG) {                                                                           \
+        if (ctx->pos_bytes == 1) e = launch_sq_ng<NL, GG, unsigned char>(p, nga, ngf, st, &done);         \
+        else e = launch_sq_ng<NL, GG, unsigned short>(p, nga, ngf, st, &done);                            \
+    }
+            DISPATCH(4, 2) DISPATCH(4, 4) DISPATCH(10, 5) DISPATCH(10, 10) DISPATCH(20, 5) DISPATCH(20, 10)
+#undef DISPATCH
+        }
+    }
+    if (done) { /* specialised kernel launched */ }
+    else if (ngtot <= 2) e = launch_gt<2>(p, grid, smem, st);
     else if (ngtot <= 6) e = launch_gt<6>(p, grid, smem, st);
     else if (ngtot <= 8) e = launch_gt<8>(p, grid, smem, st);
     else if (ngtot <= 12) e = launch_gt<12>(p, grid, smem, st);
