@@ -1,0 +1,111 @@
+"""N>1 leg of bench.py: one rank per GPU (torchrun), the cube split into box blocks like GenerateParallelepiped
+(utils/mesh_utils.cpp:67-108), every GPU assembles its own elements and the contributions to interface rows are
+exchanged over NCCL (owner-computes + exchange, inmost-fem_b200/parallel.py).  Weak scaling: the per-GPU block is
+the N=1 workload (n^3 hexes), so the global mesh grows with the number of GPUs."""
+import importlib
+import json
+import os
+import time
+
+import torch
+import torch.distributed as dist
+
+import bench
+
+
+def run(args, pkg, rank, world, local_rank):
+    par = importlib.import_module("inmost_fem_b200.parallel")
+    n = args.n
+    ppa = par.proc_grid(world, (n, n, n))
+    dims = (n * ppa[0], n * ppa[1], n * ppa[2])
+    assert par.proc_grid(world, dims) == ppa
+    stream = torch.cuda.current_stream()
+    ctx = pkg.Context(local_rank, stream.cuda_stream)
+    t0 = time.perf_counter()
+    da = par.DistributedAssembler(ctx, dims, [(pkg.P2, 1)])
+    torch.cuda.synchronize()
+    setup_ms = (time.perf_counter() - t0) * 1e3
+    ntet = da.ntet
+    xc = da.coords[da.tets.long()].mean(dim=1)
+    K_dev = torch.zeros((ntet, 9), dtype=torch.float64, device="cuda")
+    K_dev[:, 0] = 2 + xc[:, 0]; K_dev[:, 4] = 1; K_dev[:, 8] = 3
+    K_dev[:, 1] = K_dev[:, 3] = 0.5
+    K_dev[:, 5] = K_dev[:, 7] = -0.25
+    K_host = K_dev.cpu().pin_memory()
+    mk = lambda K: ([pkg.make_form(pkg.GRAD, pkg.P2, 1, pkg.GRAD, pkg.P2, 1, 2, pkg.TENSOR_SYMMETRIC, pkg.COEF_PER_TET, K)],
+                    [pkg.make_form(pkg.IDEN, pkg.P0, 1, pkg.IDEN, pkg.P2, 1, 2, pkg.TENSOR_NULL, pkg.COEF_CONST)])
+    forms_d, rhsf_d = mk(K_dev)
+    forms_h, rhsf_h = mk(K_host)
+    for _ in range(args.warmup):
+        assert da.assemble(forms_d, rhsf_d) == 0
+    sampler = bench.ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    ctx.launch_count(reset=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        assert da.assemble(forms_d, rhsf_d) == 0
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    launches = ctx.launch_count()
+    ms = torch.tensor([ev0.elapsed_time(ev1) / args.steps], device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    # end to end: host coefficient in, owned values + rhs out, every step
+    nnz_own, n_own = da.plan.nnz_own, da.plan.n_own
+    val_host = torch.zeros(nnz_own, dtype=torch.float64).pin_memory()
+    rhs_host = torch.zeros(n_own, dtype=torch.float64).pin_memory()
+    e2e_steps = max(2, min(args.steps, 5))
+
+    def e2e_step():
+        assert da.assemble(forms_h, rhsf_h) == 0
+        val_host.copy_(da.val[:nnz_own], non_blocking=True)
+        rhs_host.copy_(da.rhs[:n_own], non_blocking=True)
+    e2e_step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    for _ in range(e2e_steps):
+        e2e_step()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms_e2e = torch.tensor([ev0.elapsed_time(ev1) / e2e_steps], device="cuda")
+    dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
+    tot = torch.tensor([ntet, n_own, nnz_own, da.plan.n_for, sum(da.plan.send_nnz)], dtype=torch.int64, device="cuda")
+    dist.all_reduce(tot)
+    if rank == 0:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+        ntet_all, nrows_all, nnz_all, nfor_all, nsend_all = [int(v) for v in tot.tolist()]
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(bench.ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_gbs = peaks.get("hbm_gbs", 6650.0)
+        nn_all = (dims[0] + 1) * (dims[1] + 1) * (dims[2] + 1)
+        alg_bytes = 4 * 10 * ntet_all + 24 * nn_all + 72 * ntet_all + 8 * nnz_all + 8 * nrows_all
+        gbs = alg_bytes / (ms.item() * 1e-3) / 1e9
+        line = {"metric": bench.METRIC, "value": ntet_all / (ms.item() * 1e-3), "unit": bench.UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms.item(), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": bench.config_dict(n, {"global_hexes": list(dims), "proc_grid": ppa, "ntet": ntet_all, "nrows": nrows_all, "nnz": nnz_all,
+                                                "interface_rows_sent": nfor_all, "interface_values_sent_per_step": nsend_all,
+                                                "exchange": "NCCL all_to_all_single of packed FP64 interface contributions + afb_halo_add in rank order",
+                                                "setup_ms_rank0": setup_ms}),
+                "dof_per_s": nrows_all / (ms.item() * 1e-3),
+                "e2e": {"value": ntet_all / (ms_e2e.item() * 1e-3), "unit": bench.UNIT, "ms_per_step": ms_e2e.item(), "steps": e2e_steps,
+                        "h2d_bytes_per_step": int(K_host.numel() * 8) * world, "d2h_bytes_per_step": int((nnz_all + nrows_all) * 8)},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "achieved": gbs / world, "peak": peak_gbs, "unit": "GB/s", "frac": gbs / world / peak_gbs, "traffic": None,
+                             "kernel": "whole step per GPU (k_geom + k_gather_tensor + exchange)", "algorithmic_bytes_per_launch": alg_bytes // world},
+                "clocks": sampler.summary()}
+        print(json.dumps(line))
+    ctx.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0

@@ -107,6 +107,10 @@ int afb_dofmap_set(afb_ctx* ctx, int nrow_loc, int ncol_loc, const int64_t* elem
  * lexicographic order of their sorted node pairs/triples (our stand-in for INMOST GlobalIDs).
  * Same trial and test space. Builds the tables on the device. */
 int afb_dofmap_natural(afb_ctx* ctx, int nvars, const int* fem, const int* vec);
+/* Optional: the column of the forced diagonal entry of every row (set_elements_on_matrix_diagonal,
+ * assembler.inl:114-136) when rows are not numbered like columns (multi-GPU: owned rows followed by the
+ * interface rows of other ranks); -1 = no forced entry.  Default: row_begin + r. */
+int afb_dofmap_set_diag(afb_ctx* ctx, const int64_t* diag_col /*nrows*/, int mem_space);
 int afb_dofmap_get(afb_ctx* ctx, int* nrow_loc, int* ncol_loc, int64_t* row_begin, int64_t* row_end,
                    int64_t* ncols_global, int64_t* elem2row, int64_t* elem2col, int mem_space);
 
@@ -115,6 +119,10 @@ int afb_dofmap_get(afb_ctx* ctx, int* nrow_loc, int* ncol_loc, int64_t* row_begi
  * also builds the gather plan (row -> contributing element rows, slot table) used by afb_assemble. */
 int afb_pattern_build(afb_ctx* ctx, int64_t* nnz);
 int afb_pattern_get(afb_ctx* ctx, int64_t* rowptr /*nrows+1*/, int32_t* colind /*nnz*/, int mem_space);
+/* Use a caller-supplied sorted pattern instead (it must contain every structural entry of the dof map): this is
+ * "Assemble into a matrix that already includes the template" (opts.is_mtx_include_template, assembler.h:214-220),
+ * e.g. the union with the columns that other ranks contribute to interface rows. Rebuilds the gather plan. */
+int afb_pattern_set(afb_ctx* ctx, const int64_t* rowptr /*nrows+1*/, const int32_t* colind /*nnz*/, int64_t nnz, int mem_space);
 
 /* ---- assembly: AssemblerT::Assemble / AssembleMatrix / AssembleRHS (assembler.inl:313-488,
  * 497-580, 704-865) with is_mtx_include_template = use_ordered_insert = true ------------------ */
@@ -126,6 +134,11 @@ int afb_pattern_get(afb_ctx* ctx, int64_t* rowptr /*nrows+1*/, int32_t* colind /
  * (ascending element index per row), no atomics. */
 int afb_assemble(afb_ctx* ctx, int nforms, const afb_form* forms, int nrhs_forms, const afb_form* rhs_forms,
                  double* csr_val, double* rhs, int accumulate, double drop_val, int mem_space);
+
+/* Multi-GPU interface rows: dst[slot[k]] += contrib[k] for the n contributions received from ONE peer (device
+ * pointers; the slots of one call are distinct, peers are applied in rank order => deterministic, no atomics).
+ * Replaces the value exchange the reference avoids by recomputing ghost cells (assembler.inl:162-183). */
+int afb_halo_add(afb_ctx* ctx, int64_t n, const int64_t* slot, const double* contrib, double* dst);
 
 /* phase times of the last afb_assemble in ms (CUDA events on the context stream):
  * [0] element kernels (k_element_generic / k_geom), [1] gather/scatter (k_gather / k_gather_tensor),

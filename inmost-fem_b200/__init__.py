@@ -39,8 +39,8 @@ class AfbForm(ctypes.Structure):
 EXPORTS = ["afb_ctx_create", "afb_ctx_destroy", "afb_last_error", "afb_sync", "afb_launch_count",
            "afb_fem3dtet_batched", "afb_op_dims", "afb_tet_quadrature", "afb_quad_points",
            "afb_mesh_set", "afb_mesh_cube", "afb_mesh_orient", "afb_mesh_get",
-           "afb_dofmap_set", "afb_dofmap_natural", "afb_dofmap_get",
-           "afb_pattern_build", "afb_pattern_get", "afb_assemble", "afb_last_times"]
+           "afb_dofmap_set", "afb_dofmap_set_diag", "afb_dofmap_natural", "afb_dofmap_get",
+           "afb_pattern_build", "afb_pattern_get", "afb_pattern_set", "afb_assemble", "afb_halo_add", "afb_last_times"]
 
 
 def build(verbose=False):
@@ -81,6 +81,9 @@ def lib():
         L.afb_dofmap_set.argtypes = [vp, ci, ci, vp, vp, c64, c64, c64, ci]
         L.afb_dofmap_natural.argtypes = [vp, ci, ctypes.POINTER(ci), ctypes.POINTER(ci)]
         L.afb_dofmap_get.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(ci), _i64p, _i64p, _i64p, vp, vp, ci]
+        L.afb_dofmap_set_diag.argtypes = [vp, vp, ci]
+        L.afb_pattern_set.argtypes = [vp, vp, vp, c64, ci]
+        L.afb_halo_add.argtypes = [vp, c64, vp, vp, vp]
         L.afb_pattern_build.argtypes = [vp, _i64p]
         L.afb_pattern_get.argtypes = [vp, vp, vp, ci]
         L.afb_assemble.argtypes = [vp, ci, ctypes.POINTER(AfbForm), ci, ctypes.POINTER(AfbForm), vp, vp, ci, cd, ci]
@@ -216,12 +219,50 @@ class Context:
         self._ck(lib().afb_mesh_get(self._h, None, None, xyz.ctypes.data, v.ctypes.data, HOST))
         return np.ascontiguousarray(xyz.T), np.ascontiguousarray(v.T)
 
+    def mesh_get_torch(self):
+        """coords (nnode,3) float64 and tets (ntet,4) int32 as torch tensors on this context's GPU"""
+        import torch
+        nn, nt = self.mesh_sizes()
+        xyz = torch.empty((3, nn), dtype=torch.float64, device="cuda")
+        v = torch.empty((4, nt), dtype=torch.int32, device="cuda")
+        self._ck(lib().afb_mesh_get(self._h, None, None, xyz.data_ptr(), v.data_ptr(), DEVICE))
+        return xyz.t().contiguous(), v.t().contiguous()
+
+    def pattern_get_torch(self):
+        import torch
+        _, _, rb, re, _ = self.dofmap_info()
+        rowptr = torch.empty(re - rb + 1, dtype=torch.int64, device="cuda")
+        colind = torch.empty(max(self.nnz, 1), dtype=torch.int32, device="cuda")
+        self._ck(lib().afb_pattern_get(self._h, rowptr.data_ptr(), colind.data_ptr(), DEVICE))
+        return rowptr, colind[:self.nnz]
+
     # ---- dof map -------------------------------------------------------------------------------
     def dofmap_set(self, rowcode, colcode, row_begin, row_end, ncols_global):
         rowcode = np.ascontiguousarray(rowcode, dtype=np.int64)
         colcode = np.ascontiguousarray(colcode, dtype=np.int64)
         self._ck(lib().afb_dofmap_set(self._h, rowcode.shape[1], colcode.shape[1], rowcode.ctypes.data, colcode.ctypes.data,
                                       row_begin, row_end, ncols_global, HOST))
+
+    def dofmap_set_any(self, rowcode, colcode, row_begin, row_end, ncols_global, diag_col=None):
+        """like dofmap_set but accepts numpy arrays or torch tensors (host or cuda); optional forced-diagonal columns"""
+        pr, sr = _ptr(rowcode)
+        pc, sc = _ptr(colcode)
+        assert sr == sc
+        self._ck(lib().afb_dofmap_set(self._h, rowcode.shape[1], colcode.shape[1], pr, pc, row_begin, row_end, ncols_global, sr))
+        if diag_col is not None:
+            pd, sd = _ptr(diag_col)
+            self._ck(lib().afb_dofmap_set_diag(self._h, pd, sd))
+
+    def pattern_set(self, rowptr, colind):
+        pr, sr = _ptr(rowptr)
+        pc, sc = _ptr(colind)
+        assert sr == sc
+        self.nnz = int(colind.shape[0])
+        self._ck(lib().afb_pattern_set(self._h, pr, pc, self.nnz, sr))
+
+    def halo_add(self, slot, contrib, dst):
+        """dst[slot] += contrib for the contributions of one peer (torch cuda tensors; slot int64, distinct)"""
+        self._ck(lib().afb_halo_add(self._h, int(slot.shape[0]), slot.data_ptr(), contrib.data_ptr(), dst.data_ptr()))
 
     def dofmap_natural(self, variables):
         n = len(variables)

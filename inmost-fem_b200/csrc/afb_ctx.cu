@@ -264,6 +264,11 @@ inline unsigned grid_for(long long n, int block = 256) {
     return (unsigned)std::max<long long>(1, std::min<long long>(g, 148LL * 32));
 }
 
+// dst[slot[k]] += src[k]; the slots of one call are distinct, so no atomics are needed
+__global__ void k_halo_add(long long n, const long long* __restrict__ slot, const double* __restrict__ src, double* __restrict__ dst) {
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) dst[slot[k]] += src[k];
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -302,7 +307,7 @@ void afb_ctx_destroy(afb_ctx* c) {
     cudaStreamSynchronize(c->stream);
     afb::DevBuf* bufs[] = {&c->x, &c->y, &c->z, &c->v[0], &c->v[1], &c->v[2], &c->v[3], &c->e2r, &c->e2c, &c->rowptr, &c->colind,
                            &c->radj_ptr, &c->radj, &c->pos, &c->stageA, &c->stageF, &c->tables, &c->coef, &c->io_val, &c->io_rhs,
-                           &c->flag, &c->tmp1, &c->tmp2, &c->tmp3, &c->xy};
+                           &c->flag, &c->tmp1, &c->tmp2, &c->tmp3, &c->xy, &c->diag_col};
     for (auto* b : bufs) b->release();
     for (auto& t : c->table_cache) cudaFree(t.W);
     for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -427,7 +432,27 @@ int afb_dofmap_set(afb_ctx* ctx, int nrow_loc, int ncol_loc, const int64_t* elem
     ctx->has_signs = neg != 0;
     ctx->nrow_loc = nrow_loc; ctx->ncol_loc = ncol_loc;
     ctx->row_begin = row_begin; ctx->row_end = row_end; ctx->ncols_global = ncols_global;
-    ctx->has_dofmap = true; ctx->has_pattern = false;
+    ctx->has_dofmap = true; ctx->has_pattern = false; ctx->has_diag = false;
+    return 0;
+}
+
+int afb_dofmap_set_diag(afb_ctx* ctx, const int64_t* diag_col, int mem_space) {
+    if (!ctx) return -7;
+    if (!ctx->has_dofmap) { set_error(ctx, "dof map was not specified"); return -6; }
+    cudaSetDevice(ctx->device);
+    const long long nrows = ctx->row_end - ctx->row_begin;
+    if (!diag_col) { ctx->has_diag = false; ctx->has_pattern = false; return 0; }
+    std::vector<long long> h(nrows);
+    if (mem_space == AFB_DEVICE) AFB_CUDA(ctx, cudaMemcpy(h.data(), diag_col, nrows * sizeof(long long), cudaMemcpyDeviceToHost));
+    else std::memcpy(h.data(), diag_col, nrows * sizeof(long long));
+    std::vector<int32_t> d(nrows);
+    for (long long r = 0; r < nrows; ++r) {
+        if (h[r] >= ctx->ncols_global) { set_error(ctx, "afb_dofmap_set_diag: column out of range"); return -7; }
+        d[r] = h[r] < 0 ? -1 : (int32_t)h[r];
+    }
+    AFB_CUDA(ctx, ctx->diag_col.reserve(std::max<long long>(1, nrows) * sizeof(int32_t)));
+    AFB_CUDA(ctx, cudaMemcpy(ctx->diag_col.p, d.data(), nrows * sizeof(int32_t), cudaMemcpyHostToDevice));
+    ctx->has_diag = true; ctx->has_pattern = false;
     return 0;
 }
 
@@ -561,8 +586,19 @@ int afb_dofmap_natural(afb_ctx* ctx, int nvars, const int* fem, const int* vec) 
     cleanup();
     ctx->nrow_loc = ctx->ncol_loc = nloc;
     ctx->row_begin = 0; ctx->row_end = off; ctx->ncols_global = off;
-    ctx->has_signs = false;
+    ctx->has_signs = false; ctx->has_diag = false;
     ctx->has_dofmap = true; ctx->has_pattern = false;
+    return 0;
+}
+
+int afb_halo_add(afb_ctx* ctx, int64_t n, const int64_t* slot, const double* contrib, double* dst) {
+    if (!ctx) return -7;
+    if (n <= 0) return 0;
+    if (!slot || !contrib || !dst) { set_error(ctx, "afb_halo_add: null buffer"); return -7; }
+    cudaSetDevice(ctx->device);
+    k_halo_add<<<grid_for(n), 256, 0, ctx->stream>>>(n, reinterpret_cast<const long long*>(slot), contrib, dst);
+    ctx->launches++;
+    AFB_CUDA(ctx, cudaGetLastError());
     return 0;
 }
 

@@ -94,6 +94,8 @@ struct afb_ctx {
     afb::DevBuf e2c;              // int32[ncol_loc*ntet]  code of global column
     bool has_dofmap = false;
     bool has_signs = false;
+    bool has_diag = false;        // explicit forced-diagonal columns (afb_dofmap_set_diag)
+    afb::DevBuf diag_col;         // int32[nrows], -1 = none
 
     // pattern + plan
     bool has_pattern = false;

@@ -59,23 +59,25 @@ __global__ void k_max_deg(long long nrows, const long long* ptr, int* max_deg) {
 template <bool FILL>
 __global__ void k_row_columns(long long nrows, long long row_begin, long long ntet, int nrow_loc, int ncol_loc,
                               const long long* radj_ptr, const unsigned* radj, const int32_t* e2c, int cap,
-                              long long* rowcnt /* [nrows+1], counts at r+1 */, const long long* rowptr, int32_t* colind) {
+                              long long* rowcnt /* [nrows+1], counts at r+1 */, const long long* rowptr, int32_t* colind,
+                              const int32_t* diag_col /* NULL: row_begin + r; else per row, -1 = no forced diagonal */) {
     extern __shared__ int sbuf[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     int* buf = sbuf + (size_t)wib * cap;
     for (long long r = (long long)blockIdx.x * wpb + wib; r < nrows; r += (long long)gridDim.x * wpb) {
         const long long a0 = radj_ptr[r], a1 = radj_ptr[r + 1];
-        const int ncand = (int)(a1 - a0) * ncol_loc + 1;
+        const int dcol = diag_col ? diag_col[r] : (int)(row_begin + r);
+        const int ncand = (int)(a1 - a0) * ncol_loc + (dcol >= 0 ? 1 : 0);
         int n2 = 32;
         while (n2 < ncand) n2 <<= 1;
         for (int t = lane; t < n2; t += 32) {
             int c = 0x7fffffff;
-            if (t < ncand - 1) {
+            if (t < (int)(a1 - a0) * ncol_loc) {
                 const unsigned ei = radj[a0 + t / ncol_loc];
                 const long long e = ei / nrow_loc;
                 const int j = t % ncol_loc;
                 c = abs(e2c[(long long)j * ntet + e]) - 1;
-            } else if (t == ncand - 1) c = (int)(row_begin + r);  // forced diagonal
+            } else if (t < ncand) c = dcol;  // forced diagonal
             buf[t] = c;
         }
         __syncwarp();
@@ -110,7 +112,7 @@ __global__ void k_row_columns(long long nrows, long long row_begin, long long nt
 // element's columns inside that row.  8-bit when every row has <= 256 entries, else 16-bit.
 template <typename PosT>
 __global__ void k_pos(long long n_adj, long long ntet, int nrow_loc, int ncol_loc, const unsigned* radj, const int32_t* e2r,
-                      const int32_t* e2c, const long long* rowptr, const int32_t* colind, PosT* pos) {
+                      const int32_t* e2c, const long long* rowptr, const int32_t* colind, PosT* pos, int* missing) {
     for (long long a = blockIdx.x * (long long)blockDim.x + threadIdx.x; a < n_adj; a += (long long)gridDim.x * blockDim.x) {
         const unsigned t = radj[a];
         const long long e = t / nrow_loc;
@@ -124,6 +126,7 @@ __global__ void k_pos(long long n_adj, long long ntet, int nrow_loc, int ncol_lo
                 const long long mid = (lo + hi) >> 1;
                 if (colind[mid] < c) lo = mid + 1; else hi = mid;
             }
+            if (lo >= en || colind[lo] != c) *missing = 1;  // the pattern does not contain this structural entry
             pos[a * ncol_loc + j] = (PosT)(lo - b);
         }
     }
@@ -141,7 +144,16 @@ __global__ void k_max_len(long long nrows, const long long* rowptr, int* out) {
 
 extern "C" {
 
-int afb_pattern_build(afb_ctx* ctx, int64_t* nnz_out) {
+static int pattern_impl(afb_ctx* ctx, int64_t* nnz_out, const int64_t* user_rowptr, const int32_t* user_colind, int64_t user_nnz, int mem_space);
+
+int afb_pattern_build(afb_ctx* ctx, int64_t* nnz_out) { return pattern_impl(ctx, nnz_out, nullptr, nullptr, 0, AFB_HOST); }
+
+int afb_pattern_set(afb_ctx* ctx, const int64_t* rowptr, const int32_t* colind, int64_t nnz, int mem_space) {
+    if (!rowptr || (nnz > 0 && !colind) || nnz < 0) { afb::set_error(ctx, "afb_pattern_set: bad arguments"); return -7; }
+    return pattern_impl(ctx, nullptr, rowptr, colind, nnz, mem_space);
+}
+
+static int pattern_impl(afb_ctx* ctx, int64_t* nnz_out, const int64_t* user_rowptr, const int32_t* user_colind, int64_t user_nnz, int mem_space) {
     if (!ctx) return -7;
     if (ctx->ntet <= 0) { set_error(ctx, "Mesh was not specified"); return -6; }
     if (!ctx->has_dofmap) { set_error(ctx, "dof map was not specified (afb_dofmap_set / afb_dofmap_natural)"); return -6; }
@@ -178,6 +190,16 @@ int afb_pattern_build(afb_ctx* ctx, int64_t* nnz_out) {
     P_CUDA(cudaStreamSynchronize(st));
     ctx->n_adj = n_adj;
     key.release(); val.release();
+    const int32_t* diag = ctx->has_diag ? ctx->diag_col.as<int32_t>() : nullptr;
+    long long nnz = 0;
+    if (user_rowptr) {
+        // caller-supplied (superset) pattern, e.g. the union with columns contributed by other ranks
+        const cudaMemcpyKind kin = mem_space == AFB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        nnz = user_nnz;
+        P_CUDA(ctx->colind.reserve(std::max<long long>(nnz, 1) * sizeof(int32_t)));
+        P_CUDA(cudaMemcpyAsync(ctx->rowptr.p, user_rowptr, (nrows + 1) * sizeof(long long), kin, st));
+        if (nnz) P_CUDA(cudaMemcpyAsync(ctx->colind.p, user_colind, nnz * sizeof(int32_t), kin, st));
+    } else {
     // 2. rows: count, scan, fill
     int cap = 32;
     while (cap < max_deg * ncl + 1) cap <<= 1;
@@ -189,16 +211,16 @@ int afb_pattern_build(afb_ctx* ctx, int64_t* nnz_out) {
     const unsigned gridr = (unsigned)std::max<long long>(1, std::min<long long>((nrows + wpb - 1) / wpb, 148LL * 64));
     P_CUDA(cudaMemsetAsync(ctx->rowptr.p, 0, sizeof(long long), st));
     k_row_columns<false><<<gridr, wpb * 32, smem, st>>>(nrows, ctx->row_begin, ntet, nrl, ncl, ctx->radj_ptr.as<long long>(), ctx->radj.as<unsigned>(),
-                                                      ctx->e2c.as<int32_t>(), cap, ctx->rowptr.as<long long>(), nullptr, nullptr);
+                                                      ctx->e2c.as<int32_t>(), cap, ctx->rowptr.as<long long>(), nullptr, nullptr, diag);
     P_CUDA(cudaGetLastError());
     P_CUDA(cub::DeviceScan::InclusiveSum(cubtmp.p, tb2, ctx->rowptr.as<long long>(), ctx->rowptr.as<long long>(), nrows + 1, st));
-    long long nnz = 0;
     P_CUDA(cudaMemcpyAsync(&nnz, ctx->rowptr.as<long long>() + nrows, sizeof(long long), cudaMemcpyDeviceToHost, st));
     P_CUDA(cudaStreamSynchronize(st));
     P_CUDA(ctx->colind.reserve(std::max<long long>(nnz, 1) * sizeof(int32_t)));
     k_row_columns<true><<<gridr, wpb * 32, smem, st>>>(nrows, ctx->row_begin, ntet, nrl, ncl, ctx->radj_ptr.as<long long>(), ctx->radj.as<unsigned>(),
-                                                     ctx->e2c.as<int32_t>(), cap, nullptr, ctx->rowptr.as<long long>(), ctx->colind.as<int32_t>());
+                                                     ctx->e2c.as<int32_t>(), cap, nullptr, ctx->rowptr.as<long long>(), ctx->colind.as<int32_t>(), diag);
     P_CUDA(cudaGetLastError());
+    }
     P_CUDA(cudaMemsetAsync(ctx->flag.p, 0, 64, st));
     k_max_len<<<grid_for(nrows), 256, 0, st>>>(nrows, ctx->rowptr.as<long long>(), ctx->flag.as<int>());
     int max_len = 0;
@@ -210,13 +232,16 @@ int afb_pattern_build(afb_ctx* ctx, int64_t* nnz_out) {
     P_CUDA(ctx->pos.reserve((size_t)std::max<long long>(1, n_adj) * ncl * ctx->pos_bytes));
     if (ctx->pos_bytes == 1)
         k_pos<unsigned char><<<grid_for(n_adj), 256, 0, st>>>(n_adj, ntet, nrl, ncl, ctx->radj.as<unsigned>(), ctx->e2r.as<int32_t>(), ctx->e2c.as<int32_t>(),
-                                                             ctx->rowptr.as<long long>(), ctx->colind.as<int32_t>(), ctx->pos.as<unsigned char>());
+                                                             ctx->rowptr.as<long long>(), ctx->colind.as<int32_t>(), ctx->pos.as<unsigned char>(), ctx->flag.as<int>() + 1);
     else
         k_pos<unsigned short><<<grid_for(n_adj), 256, 0, st>>>(n_adj, ntet, nrl, ncl, ctx->radj.as<unsigned>(), ctx->e2r.as<int32_t>(), ctx->e2c.as<int32_t>(),
-                                                              ctx->rowptr.as<long long>(), ctx->colind.as<int32_t>(), ctx->pos.as<unsigned short>());
+                                                              ctx->rowptr.as<long long>(), ctx->colind.as<int32_t>(), ctx->pos.as<unsigned short>(), ctx->flag.as<int>() + 1);
     P_CUDA(cudaGetLastError());
+    int missing = 0;
+    P_CUDA(cudaMemcpyAsync(&missing, ctx->flag.as<int>() + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
     P_CUDA(cudaStreamSynchronize(st));
     ctx->launches += 5;
+    if (missing) { cleanup(); set_error(ctx, "afb_pattern_set: the pattern does not contain every structural entry of the dof map"); return -7; }
 #undef P_CUDA
     cleanup();
     ctx->nnz = nnz;

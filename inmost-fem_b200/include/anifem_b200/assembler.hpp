@@ -1,0 +1,172 @@
+// anifem_b200/assembler.hpp -- C++ mirror of the AniFem++ global assembler on top of the C ABI.
+//
+// Mirrors inmost_interface/assembler.h:210-456 (AssemblerT / AssmOpts) for the path in scope.  What the reference pulls
+// out of an INMOST mesh per cell is passed in as flat arrays; what the reference's user lambda computes with
+// fem3Dtet calls is described as a list of volume forms (one entry = one fem3Dtet<OpA,OpB>(..) call whose result
+// the lambda adds into the block (row_off, col_off) of the local matrix, e.g. examples/Fem/Ani/stokes.cpp:138-185).
+//
+//   reference                                    here
+//   -------------------------------------------  --------------------------------------------------------------
+//   SetMesh(INMOST::Mesh*)                       SetMesh(nnode, x, y, z, ntet, v0..v3)  |  SetCubeMesh(nx, ny, nz)
+//   SetProbDescr(FemExprDescr) + m_enum(NATURAL) SetProbDescr({{FEM_P2, 1}, ...})  or  SetDofMap(explicit index codes)
+//   SetMatRHSFunc(GenerateElemMatRhs(lambda))    AddMatForm<OpA,OpB>(...), AddRhsForm<OpB>(...)
+//   PrepareProblem()                             PrepareProblem()   (numbering + pattern + gather plan on the device)
+//   AssembleTemplate(Matrix&)                    AssembleTemplate(CsrMatrix&)
+//   Assemble(Matrix&, Vector&, AssmOpts)         Assemble(CsrMatrix&, std::vector<double>&, AssmOpts)  -> 0 / -1
+//   AssembleMatrix / AssembleRHS                 AssembleMatrix / AssembleRHS
+//   getBegInd() / getEndInd()                    getBegInd() / getEndInd()
+// The matrix always has the structural pattern of AssembleTemplate with rows sorted ascending, i.e. the reference's
+// opts.is_mtx_include_template = opts.use_ordered_insert = true mode (assembler.inl:428-438); Assemble ADDS into it.
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "fem.hpp"
+
+namespace Ani {
+
+/// assembler.h:210-231
+struct AssmOpts {
+    double drop_val = 1e-100;
+    bool is_mtx_sorted = true;
+    bool is_mtx_include_template = true;
+    bool use_ordered_insert = true;
+    AssmOpts& SetDropVal(double v) { drop_val = v; return *this; }
+};
+
+/// stand-in for INMOST::Sparse::Matrix over [BegInd, EndInd): sorted CSR
+struct CsrMatrix {
+    int64_t row_begin = 0, row_end = 0;
+    std::vector<int64_t> rowptr;
+    std::vector<int32_t> colind;
+    std::vector<double> val;
+    bool empty() const { return rowptr.empty(); }
+};
+
+struct FemVarDescr { int fem; int vec; };
+
+class Assembler {
+public:
+    explicit Assembler(int device = 0) {
+        if (afb_ctx_create(device, nullptr, &m_ctx) != 0) throw std::runtime_error(std::string("anifem_b200: ") + afb_last_error(nullptr));
+    }
+    ~Assembler() { afb_ctx_destroy(m_ctx); }
+    Assembler(const Assembler&) = delete;
+    Assembler& operator=(const Assembler&) = delete;
+
+    Assembler& SetMesh(int64_t nnode, const double* x, const double* y, const double* z, int64_t ntet, const int32_t* v0, const int32_t* v1,
+                       const int32_t* v2, const int32_t* v3, bool reorder_nodes = true) {
+        ck(afb_mesh_set(m_ctx, nnode, x, y, z, ntet, v0, v1, v2, v3, AFB_HOST));
+        if (reorder_nodes) ck(afb_mesh_orient(m_ctx));  // AssembleMode::reorder_nodes (assembler.h:297-302)
+        m_has_mesh = true; m_prepared = false;
+        return *this;
+    }
+    /// utils/mesh_utils.h:11-17 GenerateCube
+    Assembler& SetCubeMesh(int nx, int ny, int nz, double size = 1.0) {
+        ck(afb_mesh_cube(m_ctx, nx, ny, nz, size, 0, 0, 0, nx, ny, nz));
+        m_has_mesh = true; m_prepared = false;
+        return *this;
+    }
+    Assembler& SetProbDescr(std::vector<FemVarDescr> vars) { m_vars = std::move(vars); m_explicit = false; m_prepared = false; return *this; }
+    /// explicit elem -> global index codes (m_indexesR / m_indexesC, assembler.inl:49-55,139-184)
+    Assembler& SetDofMap(int nrow_loc, int ncol_loc, const int64_t* rowcode, const int64_t* colcode, int64_t row_begin, int64_t row_end, int64_t ncols) {
+        if (!m_has_mesh) throw std::runtime_error("Mesh was not specified");
+        ck(afb_dofmap_set(m_ctx, nrow_loc, ncol_loc, rowcode, colcode, row_begin, row_end, ncols, AFB_HOST));
+        m_explicit = true; m_prepared = false;
+        return *this;
+    }
+    /// local offset of variable v inside the element vector (variable-major order, fem/tetdofmap.cpp:606-643)
+    int VarOffset(int v) const {
+        int o = 0;
+        for (int k = 0; k < v; ++k) o += b200_detail::base_nf(m_vars[k].fem) * m_vars[k].vec;
+        return o;
+    }
+    /// one fem3Dtet<OpA,OpB> term of the local matrix; D in the user-callback layout (col-major Dim(OpB) x Dim(OpA))
+    template <typename OpA, typename OpB>
+    Assembler& AddMatForm(int trial_var, int test_var, int order, TensorType ttype, int coef_layout, const double* D, double alpha = 1.0,
+                          int coef_space = AFB_HOST) {
+        m_forms.push_back(afb_form{OpA::op, OpA::fem, OpA::vec, OpB::op, OpB::fem, OpB::vec, order, ttype, coef_layout, coef_space, D, alpha,
+                                   VarOffset(test_var), VarOffset(trial_var)});
+        return *this;
+    }
+    /// rhs term int f . OpB(v): the reference's fem3Dtet<Operator<IDEN,FemFix<FEM_P0>>, OpB> idiom (ex1.cpp:92-95)
+    template <typename OpB>
+    Assembler& AddRhsForm(int test_var, int order, TensorType ttype, int coef_layout, const double* D, double alpha = 1.0, int coef_space = AFB_HOST) {
+        m_rhs.push_back(afb_form{IDEN, FEM_P0, 1, OpB::op, OpB::fem, OpB::vec, order, ttype, coef_layout, coef_space, D, alpha, VarOffset(test_var), 0});
+        return *this;
+    }
+    void ClearForms() { m_forms.clear(); m_rhs.clear(); }
+
+    /// assembler.inl:193-275
+    void PrepareProblem() {
+        if (!m_has_mesh) throw std::runtime_error("Mesh was not specified");
+        if (!m_explicit) {
+            if (m_vars.empty()) throw std::runtime_error("Description of fem expression is empty, try SetProbDescr(...)");
+            std::vector<int> fem, vec;
+            for (auto& v : m_vars) { fem.push_back(v.fem); vec.push_back(v.vec); }
+            ck(afb_dofmap_natural(m_ctx, static_cast<int>(fem.size()), fem.data(), vec.data()));
+        }
+        ck(afb_pattern_build(m_ctx, &m_nnz));
+        int nr, nc; int64_t ng;
+        ck(afb_dofmap_get(m_ctx, &nr, &nc, &m_beg, &m_end, &ng, nullptr, nullptr, AFB_HOST));
+        m_prepared = true;
+    }
+    int64_t getBegInd() const { return m_beg; }
+    int64_t getEndInd() const { return m_end; }
+    int64_t getNnz() const { return m_nnz; }
+
+    /// assembler.inl:589-695: adds the zero matrix of structural non-zeros (here: defines the pattern)
+    int AssembleTemplate(CsrMatrix& matrix) {
+        need_prepared();
+        matrix.row_begin = m_beg; matrix.row_end = m_end;
+        matrix.rowptr.assign(m_end - m_beg + 1, 0);
+        matrix.colind.assign(m_nnz, 0);
+        ck(afb_pattern_get(m_ctx, matrix.rowptr.data(), matrix.colind.data(), AFB_HOST));
+        matrix.val.assign(m_nnz, 0.0);
+        return 0;
+    }
+    /// assembler.inl:313-488. matrix <- matrix + assembled, rhs <- rhs + assembled. Returns 0, or -1 on NaN/Inf.
+    int Assemble(CsrMatrix& matrix, std::vector<double>& rhs, const AssmOpts& opts = AssmOpts()) {
+        if (m_forms.empty() && m_rhs.empty()) throw std::runtime_error("System local evaluator is not specified");
+        prepare_outputs(&matrix, &rhs);
+        return ck(afb_assemble(m_ctx, (int)m_forms.size(), m_forms.data(), (int)m_rhs.size(), m_rhs.data(), matrix.val.data(), rhs.data(), 1,
+                               opts.drop_val, AFB_HOST));
+    }
+    int AssembleMatrix(CsrMatrix& matrix, const AssmOpts& opts = AssmOpts()) {
+        if (m_forms.empty()) throw std::runtime_error("Matrix local evaluator is not specified");
+        prepare_outputs(&matrix, nullptr);
+        return ck(afb_assemble(m_ctx, (int)m_forms.size(), m_forms.data(), 0, nullptr, matrix.val.data(), nullptr, 1, opts.drop_val, AFB_HOST));
+    }
+    int AssembleRHS(std::vector<double>& rhs, const AssmOpts& opts = AssmOpts()) {
+        if (m_rhs.empty()) throw std::runtime_error("Right-hand side local evaluator is not specified");
+        prepare_outputs(nullptr, &rhs);
+        return ck(afb_assemble(m_ctx, 0, nullptr, (int)m_rhs.size(), m_rhs.data(), nullptr, rhs.data(), 1, opts.drop_val, AFB_HOST));
+    }
+    /// GetTimeEvalLocFunc-style getters (assembler.inl:949-964): ms of the last Assemble
+    double GetTimeEvalLocFunc() const { double t[4]; afb_last_times(m_ctx, t); return t[0]; }
+    double GetTimeFillGlobalStructs() const { double t[4]; afb_last_times(m_ctx, t); return t[1]; }
+    afb_ctx* context() { return m_ctx; }
+
+private:
+    int ck(int rc) {
+        if (rc < 0 && rc != -1) throw std::runtime_error(afb_last_error(m_ctx));
+        return rc;
+    }
+    void need_prepared() {
+        if (!m_prepared) PrepareProblem();
+    }
+    void prepare_outputs(CsrMatrix* m, std::vector<double>* rhs) {
+        need_prepared();
+        if (m && (m->empty() || m->row_begin != m_beg || m->row_end != m_end || (int64_t)m->colind.size() != m_nnz)) AssembleTemplate(*m);
+        if (rhs && (int64_t)rhs->size() != m_end - m_beg) rhs->assign(m_end - m_beg, 0.0);  // rhs.SetInterval (assembler.inl:323)
+    }
+    afb_ctx* m_ctx = nullptr;
+    std::vector<FemVarDescr> m_vars;
+    std::vector<afb_form> m_forms, m_rhs;
+    bool m_has_mesh = false, m_explicit = false, m_prepared = false;
+    int64_t m_nnz = 0, m_beg = 0, m_end = 0;
+};
+
+}  // namespace Ani

@@ -1,0 +1,169 @@
+// anifem_b200/fem.hpp -- C++ mirror of the AniFem++ element API on top of the C ABI (include/anifem_b200.h).
+//
+// Same names, template arguments, argument meaning, layouts and error behaviour as the reference so that a user's
+// local assembler compiles against it unchanged for the operators in scope:
+//   Ani::fem3Dtet<OpA, OpB, FuncTraits>(XYZ | XY0..XY3, Dfnc, A, order, user_data)   fem/operations/int_tet.h:17-78
+//   Ani::Operator<GRAD|IDEN|DIV, FemFix<FEM_P0..P3> | FemVec<3,FEM_Pk>>               fem/operators.h:50-67,127-155,320-353
+//   Ani::DfuncTraits<...>, TensorType, DenseMatrix<>, Tetras<>, make_tetras            fem/diff_tensor.h:17-53, fem_memory.h:55-130, geometry.h:96-200
+// The arithmetic runs on the GPU (afb_fem3dtet_batched); `fusion` (XYZ.fusion tets per call) is the batch axis.
+// Tensor callbacks are host functors exactly like the reference's; the shim evaluates them at the quadrature points
+// (afb_quad_points) into the FusiveTensor data layout and ships the data (compatibility path, not the
+// timed path -- hot loops should pass coefficient arrays through the C ABI directly).
+#pragma once
+#include <array>
+#include <cstddef>
+#include <functional>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+#include "../../../include/anifem_b200.h"
+
+namespace Ani {
+
+enum FiniteElement { FEM_P0 = 1, FEM_P1 = 2, FEM_P2 = 3, FEM_P3 = 4 };
+enum OperatorType { IDEN = 1, GRAD = 2, DIV = 3 };
+enum TensorType { TENSOR_NULL = 1, TENSOR_SCALAR = 2, TENSOR_SYMMETRIC = 3, TENSOR_GENERAL = 4 };
+enum TensorTypeSparsity { PerPoint = 0, PerTetra = -1, PerSelection = -2 };
+
+template <int OP> using FemFix = std::integral_constant<int, OP>;
+template <int DIM, int OP> struct FemVec { using Dim = std::integral_constant<int, DIM>; using Base = FemFix<OP>; };
+
+namespace b200_detail {
+constexpr int base_nf(int fem) { return fem == FEM_P0 ? 1 : fem == FEM_P1 ? 4 : fem == FEM_P2 ? 10 : 20; }
+template <typename FEM> struct FemInfo;
+template <int F> struct FemInfo<FemFix<F>> { static constexpr int fem = F, vec = 1; };
+template <int D, int F> struct FemInfo<FemVec<D, F>> { static constexpr int fem = F, vec = D; static_assert(D == 3, "only FemVec<3,.> is supported"); };
+}  // namespace b200_detail
+
+template <int OPERATOR, typename FEMTYPE>
+struct Operator {
+    static constexpr int op = OPERATOR, fem = b200_detail::FemInfo<FEMTYPE>::fem, vec = b200_detail::FemInfo<FEMTYPE>::vec;
+    static_assert(OPERATOR == IDEN || OPERATOR == GRAD || (OPERATOR == DIV && vec == 3), "operator out of scope of the B200 path");
+    using Nfa = std::integral_constant<int, vec * b200_detail::base_nf(fem)>;
+    using Dim = std::integral_constant<int, OPERATOR == IDEN ? vec : (OPERATOR == GRAD ? 3 * vec : 1)>;
+};
+
+template <int TensorTypeSparse = PerPoint, bool isConstant = false, long idim = -1, long jdim = -1>
+struct DfuncTraits {
+    using IsConstant = std::integral_constant<bool, isConstant>;
+    using TensorSparsity = std::integral_constant<int, TensorTypeSparse>;
+};
+
+using TensorDims = std::pair<std::size_t, std::size_t>;
+template <typename Scalar = double> using Coord = std::array<Scalar, 3>;
+
+// column-major dense matrix view (fem/fem_memory.h:55-130)
+template <typename ScalarType = double>
+struct DenseMatrix {
+    ScalarType* data = nullptr;
+    std::size_t nRow = 0, nCol = 0, size = 0;
+    DenseMatrix() = default;
+    DenseMatrix(ScalarType* d, std::size_t r, std::size_t c) : data(d), nRow(r), nCol(c), size(r * c) {}
+    DenseMatrix(ScalarType* d, std::size_t r, std::size_t c, std::size_t sz) : data(d), nRow(r), nCol(c), size(sz) {}
+    ScalarType& operator()(std::size_t i, std::size_t j) { return data[i + nRow * j]; }
+    const ScalarType& operator()(std::size_t i, std::size_t j) const { return data[i + nRow * j]; }
+    void SetZero() { for (std::size_t i = 0; i < nRow * nCol; ++i) data[i] = 0; }
+};
+
+// coordinates of `fusion` tetrahedra: XYk is 3 x fusion col-major (fem/geometry.h:96-200)
+template <typename ScalarType = const double>
+struct Tetras {
+    ScalarType *XY0, *XY1, *XY2, *XY3;
+    int fusion = 0;
+};
+inline Tetras<const double> make_tetras(const double* XY0, const double* XY1, const double* XY2, const double* XY3, int count = 1) {
+    return Tetras<const double>{XY0, XY1, XY2, XY3, count};
+}
+
+namespace b200 {
+// process-wide context used by the free functions (one GPU, device 0 unless ANIFEM_B200_DEVICE is set)
+inline afb_ctx* default_context() {
+    static afb_ctx* ctx = [] {
+        afb_ctx* c = nullptr;
+        int dev = 0;
+        if (const char* s = std::getenv("ANIFEM_B200_DEVICE")) dev = std::atoi(s);
+        if (afb_ctx_create(dev, nullptr, &c) != 0) throw std::runtime_error(std::string("anifem_b200: ") + afb_last_error(nullptr));
+        return c;
+    }();
+    return ctx;
+}
+inline void check(afb_ctx* c, int rc) {
+    if (rc < 0 && rc != -1) throw std::runtime_error(afb_last_error(c));
+}
+}  // namespace b200
+
+/// Elemental matrix of int_T (D OpA(u)) . OpB(v) dx for XYZ.fusion tetrahedra; A is nfB x (nfA*fusion) col-major.
+/// Dfnc: TensorType(const std::array<double,3>& x, double* Dmem, TensorDims Ddims, void* user_data, int iTet) with
+/// Dmem a col-major (Ddims.first x Ddims.second) = (Dim(OpB) x Dim(OpA)) matrix (fem/operations/int_tet.h:31-47).
+template <typename OpA, typename OpB, typename FuncTraits = DfuncTraits<>, typename Functor>
+void fem3Dtet(const Tetras<const double>& XYZ, const Functor& Dfnc, DenseMatrix<double>& A, int order = 5, void* user_data = nullptr) {
+    const int f = XYZ.fusion;
+    if (f <= 0) return;
+    constexpr int nfa = OpA::Nfa::value, nfb = OpB::Nfa::value, idim = OpA::Dim::value, jdim = OpB::Dim::value;
+    if (A.size < static_cast<std::size_t>(nfa) * nfb * f)
+        throw std::runtime_error("Not enough memory for local matrix, expected size = " + std::to_string(nfa * nfb * f) +
+                                 " but A has size = " + std::to_string(A.size));
+    A.nRow = nfb; A.nCol = static_cast<std::size_t>(nfa) * f;
+    afb_ctx* ctx = b200::default_context();
+    const int q = afb_tet_quadrature(order, nullptr, nullptr, 0);
+    if (q < 0) throw std::runtime_error("Numerical tetrahedron integration formula implemented only for 0 <= order <= 20");
+    // evaluate the callback: once (constant tensor) or per quadrature point of every tet, r-major / n-minor like the
+    // reference (fem/diff_tensor.h:492-520)
+    const TensorDims dims{static_cast<std::size_t>(jdim), static_cast<std::size_t>(idim)};
+    const std::size_t dl = static_cast<std::size_t>(idim) * jdim;
+    std::vector<double> D;
+    std::vector<int> types;
+    int layout;
+    if (FuncTraits::IsConstant::value) {
+        layout = AFB_COEF_CONST;
+        D.assign(dl, 0.0);
+        types.push_back(Dfnc(std::array<double, 3>{0, 0, 0}, D.data(), dims, user_data, 0));
+    } else {
+        layout = AFB_COEF_PER_POINT;
+        std::vector<double> XYG(static_cast<std::size_t>(3) * q * f);
+        b200::check(ctx, afb_quad_points(ctx, order, f, XYZ.XY0, XYZ.XY1, XYZ.XY2, XYZ.XY3, XYG.data(), AFB_HOST));
+        D.assign(dl * q * f, 0.0);
+        types.reserve(static_cast<std::size_t>(q) * f);
+        for (int r = 0; r < f; ++r)
+            for (int n = 0; n < q; ++n) {
+                const std::size_t p = n + static_cast<std::size_t>(q) * r;
+                types.push_back(Dfnc(std::array<double, 3>{XYG[3 * p], XYG[3 * p + 1], XYG[3 * p + 2]}, D.data() + dl * p, dims, user_data, r));
+            }
+    }
+    bool uniform = true;
+    for (int t : types) uniform = uniform && t == types[0];
+    int ttype = types[0];
+    if (!uniform || ttype == TENSOR_SCALAR) {
+        // SCALAR data are compacted to 1 value per point; mixed types are densified to GENERAL
+        const std::size_t np = types.size();
+        if (uniform) {
+            std::vector<double> S(np);
+            for (std::size_t p = 0; p < np; ++p) S[p] = D[dl * p];
+            D.swap(S);
+        } else {
+            if (jdim != idim && !(nfa == 1 && idim == 1))
+                for (int t : types) if (t <= TENSOR_SCALAR)
+                    throw std::runtime_error("Identity tensor defined only for compatible (with same dimensions) operators A and B");
+            for (std::size_t p = 0; p < np; ++p) if (types[p] <= TENSOR_SCALAR) {
+                const double s = types[p] == TENSOR_SCALAR ? D[dl * p] : 1.0;
+                for (std::size_t k = 0; k < dl; ++k) D[dl * p + k] = 0;
+                if (jdim == idim) for (int k = 0; k < jdim; ++k) D[dl * p + k + jdim * k] = s;
+                else for (int k = 0; k < jdim; ++k) D[dl * p + k] = s;  // OpA = IDEN(P0) broadcast
+            }
+            ttype = TENSOR_GENERAL;
+        }
+    }
+    afb_form fm{OpA::op, OpA::fem, OpA::vec, OpB::op, OpB::fem, OpB::vec, order, ttype, layout, AFB_HOST, D.data(), 1.0, 0, 0};
+    b200::check(ctx, afb_fem3dtet_batched(ctx, &fm, f, XYZ.XY0, XYZ.XY1, XYZ.XY2, XYZ.XY3, A.data, AFB_HOST));
+}
+
+template <typename OpA, typename OpB, typename FuncTraits = DfuncTraits<>, typename Functor>
+void fem3Dtet(const DenseMatrix<double>& XY0, const DenseMatrix<double>& XY1, const DenseMatrix<double>& XY2, const DenseMatrix<double>& XY3,
+              const Functor& Dfnc, DenseMatrix<double>& A, int order = 5, void* user_data = nullptr) {
+    fem3Dtet<OpA, OpB, FuncTraits>(make_tetras(XY0.data, XY1.data, XY2.data, XY3.data, static_cast<int>(XY0.nCol)), Dfnc, A, order, user_data);
+}
+
+}  // namespace Ani

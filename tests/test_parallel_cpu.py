@@ -1,0 +1,124 @@
+"""CPU tests (gloo, world_size 2 and 3) of the multi-GPU host logic in inmost-fem_b200/parallel.py: block partition,
+ownership, NATURAL numbering with per-rank intervals, interface pattern union and the value/rhs exchange.  The
+numerics (element matrices, local scatter) come from the CPU oracle here; on the GPU the same plan drives
+afb_assemble + afb_halo_add (tests/test_multi_gpu.py)."""
+import os
+import sys
+import traceback
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+import golden_cases as gc
+
+
+def _local_pattern(rowcode, colcode, n_own, n_ext, row_begin):
+    """sorted local pattern of the extended rows: structural entries of the local cells + forced diagonal of owned rows"""
+    nrow, ncol = rowcode.shape[1], colcode.shape[1]
+    r = np.repeat(rowcode - 1, ncol, axis=1).ravel()
+    c = np.tile(colcode - 1, (1, nrow)).ravel()
+    r = np.concatenate([r, np.arange(n_own)])
+    c = np.concatenate([c, row_begin + np.arange(n_own)])
+    NC = int(c.max()) + 1
+    key = np.unique(r * NC + c)
+    rowptr = np.zeros(n_ext + 1, dtype=np.int64)
+    np.add.at(rowptr, key // NC + 1, 1)
+    return np.cumsum(rowptr), (key % NC).astype(np.int32)
+
+
+def _worker(rank, world, port, dims, variables, errq):
+    try:
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        sys.path.insert(0, ROOT)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import __graft_entry__ as entry
+        import problems
+        pkg = entry.load_package()
+        O, M = entry.load_oracle()
+        import importlib
+        par = importlib.import_module("inmost_fem_b200.parallel")
+        co, te, cr = M.cube_mesh(*dims, nranks=world)
+        dm = M.DofMap(te, variables, cr, world, nnode=co.shape[0])
+        # block / grid restatement agrees with the oracle's cell -> rank map
+        bx, by, bz, lx, ly, lz = par.block_of_rank(rank, world, dims)
+        assert 6 * lx * ly * lz == int((cr == rank).sum())
+        mine = np.nonzero(cr == rank)[0]
+        lt = te[mine]
+        gn, inv = np.unique(lt, return_inverse=True)
+        ltl = inv.reshape(-1, 4)
+        # nodes that also belong to cells of another rank
+        other = np.zeros(co.shape[0], dtype=bool)
+        other[np.unique(te[cr != rank])] = True
+        nb = par.Numbering(torch.from_numpy(ltl), torch.from_numpy(gn), torch.from_numpy(other[gn]), variables, co.shape[0])
+        assert np.array_equal(nb.elem2dof.numpy(), dm.elem2dof[mine]), "global numbering differs from the oracle"
+        assert nb.row_begin == dm.beg_ind[rank] and nb.row_end == dm.end_ind[rank] and nb.nrows_global == dm.nrows
+        plan = par.InterfacePlan(nb)
+        n_ext = plan.n_own + plan.n_for
+        rp_l, ci_l = _local_pattern(plan.rowcode.numpy(), plan.colcode.numpy(), plan.n_own, n_ext, nb.row_begin)
+        rp_e, ci_e = plan.finalize_pattern(torch.from_numpy(rp_l), torch.from_numpy(ci_l))
+        # problem: stiffness (+ mass on variable 0) with per-tet coefficients, rhs load
+        xc = co[te].mean(axis=1)
+        v0 = variables[0]
+        if v0[1] == 1:
+            mats = [(0, 0, gc.GRAD, gc.GRAD, 2, gc.T_SYMMETRIC, gc.L_PER_TET, problems.sym_K(xc), 1.0)]
+            rhss = [(0, gc.IDEN, 2, gc.T_NULL, gc.L_CONST, None, 1.0)]
+            _, _, _, prob = problems._mk(pkg, M, variables, mats, rhss)
+        else:
+            _, _, _, prob = problems.c5_stokes(pkg, M, co, te)
+        rp_o, ci_o, v_o, r_o, st = M.assemble(prob, co, te, dm, rank=rank)
+        assert np.array_equal(rp_e.numpy()[:plan.n_own + 1], rp_o), "owned rowptr differs from the oracle"
+        assert np.array_equal(ci_e.numpy()[:plan.nnz_own], ci_o), "owned colind differs from the oracle"
+        # local (owner-computes) contributions into the extended CSR, then the exchange
+        XY = co[lt].transpose(1, 0, 2)
+        A, F = prob.element_matrices(XY, idx=mine)
+        val = np.zeros(plan.nnz_ext)
+        rhs = np.zeros(n_ext)
+        assert O.scatter_csr(plan.rowcode.numpy(), plan.colcode.numpy(), A, F, 0, rp_e.numpy(), ci_e.numpy(), val, rhs) == 0
+        tv, tr = torch.from_numpy(val), torch.from_numpy(rhs)
+
+        def add(slots, contrib, dst):
+            assert torch.unique(slots).numel() == slots.numel()
+            dst[slots] += contrib
+        plan.exchange(tv, tr, add)
+        scale = np.abs(v_o).max()
+        assert np.abs(tv.numpy()[:plan.nnz_own] - v_o).max() <= 1e-13 * scale
+        assert np.abs(tr.numpy()[:plan.n_own] - r_o).max() <= 1e-13 * np.abs(r_o).max()
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        errq.put("rank %d:\n%s" % (rank, traceback.format_exc()))
+
+
+def _run(world, dims, variables):
+    ctx = mp.get_context("spawn")
+    errq = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, dims, variables, errq)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=600)
+    errs = []
+    while not errq.empty():
+        errs.append(errq.get())
+    assert not errs, "\n".join(errs)
+    assert all(p.exitcode == 0 for p in procs)
+
+
+def test_two_ranks_p2(pkg, oracle):
+    _run(2, (4, 3, 3), [(gc.P2, 1)])
+
+
+def test_three_ranks_p1(pkg, oracle):
+    _run(3, (5, 3, 2), [(gc.P1, 1)])
+
+
+def test_two_ranks_taylor_hood(pkg, oracle):
+    _run(2, (3, 2, 2), [(gc.P2, 3), (gc.P1, 1)])
