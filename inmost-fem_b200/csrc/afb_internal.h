@@ -108,6 +108,18 @@ struct afb_ctx {
     afb::DevBuf pos;              // uint8|uint16[n_adj*ncol_loc]: slot of column j of adjacency entry a inside its row
     int pos_bytes = 2;
     int64_t n_adj = 0;
+    bool pos_has_dup = false;     // some element maps two local columns to the same global column
+
+    // class-sorted sliced-ELL plan of the thread-per-row gather (afb_rows.cu)
+    bool has_rows_plan = false;
+    int rp_nloc = 0;
+    long long rp_steps = 0;
+    afb::DevBuf rp_order;         // uint32[nrows]: rows in plan order (32 per slice)
+    afb::DevBuf rp_cnt;           // uint16[nslices*nloc]: visit-steps of class i in slice s
+    afb::DevBuf rp_sptr;          // int64[nslices+1]: first visit-step of a slice
+    afb::DevBuf rp_ell;           // uint32[steps*NW*32]: slot bytes + element id per (step, lane)
+    struct RowsBucket { long long s0, s1; int L; };
+    std::vector<RowsBucket> rp_buckets;
 
     // work buffers
     afb::DevBuf stageA, stageF, tables, coef, io_val, io_rhs, flag, tmp1, tmp2, tmp3, xy;
@@ -125,6 +137,10 @@ int launch_form(afb_ctx* ctx, const afb_form& form, const OpInfo& A, const OpInf
 int form_dlen(const afb_form& form, const OpInfo& A, const OpInfo& B);
 // device tables W[q], phi[q*nf], G^[q*nf*3] of (space, rule); uploaded on first use (afb_ctx.cu)
 int get_tables(afb_ctx* ctx, int fem, int order, const double** W, const double** phi, const double** grd);
+// thread-per-row gather + its plan (afb_rows.cu)
+int build_rows_plan(afb_ctx* ctx);
+int launch_rows(afb_ctx* ctx, int nga, int ngf, const double* TA, const double* TF, const double* gbuf, double* val, double* rhs,
+                int accumulate, double drop_val, int* status);
 // gather (afb_gather.cu)
 int launch_gather(afb_ctx* ctx, const double* stageA, const double* stageF, double* val, double* rhs,
                   int accumulate, double drop_val, int* status_flag);

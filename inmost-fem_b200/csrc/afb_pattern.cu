@@ -129,6 +129,10 @@ __global__ void k_pos(long long n_adj, long long ntet, int nrow_loc, int ncol_lo
             if (lo >= en || colind[lo] != c) *missing = 1;  // the pattern does not contain this structural entry
             pos[a * ncol_loc + j] = (PosT)(lo - b);
         }
+        // two local columns on one global column (collapsed dofs): the batched row update of afb_rows.cu must not be used
+        for (int j = 1; j < ncol_loc; ++j)
+            for (int j2 = 0; j2 < j; ++j2)
+                if (pos[a * ncol_loc + j] == pos[a * ncol_loc + j2]) missing[1] = 1;
     }
 }
 
@@ -237,9 +241,11 @@ static int pattern_impl(afb_ctx* ctx, int64_t* nnz_out, const int64_t* user_rowp
         k_pos<unsigned short><<<grid_for(n_adj), 256, 0, st>>>(n_adj, ntet, nrl, ncl, ctx->radj.as<unsigned>(), ctx->e2r.as<int32_t>(), ctx->e2c.as<int32_t>(),
                                                               ctx->rowptr.as<long long>(), ctx->colind.as<int32_t>(), ctx->pos.as<unsigned short>(), ctx->flag.as<int>() + 1);
     P_CUDA(cudaGetLastError());
-    int missing = 0;
-    P_CUDA(cudaMemcpyAsync(&missing, ctx->flag.as<int>() + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    int missing2[2] = {0, 0};
+    P_CUDA(cudaMemcpyAsync(missing2, ctx->flag.as<int>() + 1, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     P_CUDA(cudaStreamSynchronize(st));
+    const int missing = missing2[0];
+    ctx->pos_has_dup = missing2[1] != 0;
     ctx->launches += 5;
     if (missing) { cleanup(); set_error(ctx, "afb_pattern_set: the pattern does not contain every structural entry of the dof map"); return -7; }
 #undef P_CUDA
@@ -248,7 +254,7 @@ static int pattern_impl(afb_ctx* ctx, int64_t* nnz_out, const int64_t* user_rowp
     ctx->max_row_len = max_len;
     ctx->has_pattern = true;
     if (nnz_out) *nnz_out = nnz;
-    return 0;
+    return build_rows_plan(ctx);
 }
 
 int afb_pattern_get(afb_ctx* ctx, int64_t* rowptr, int32_t* colind, int mem_space) {

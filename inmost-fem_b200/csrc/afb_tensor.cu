@@ -533,6 +533,12 @@ int assemble_tensor_path(afb_ctx* ctx, int nfA, int nfF, const std::vector<afb_f
     const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((p.nrows + rpb - 1) / rpb, 148LL * 32));
     cudaError_t e = cudaSuccess;
     bool done = false;
+    {
+        // thread-per-row gather over the class-sorted ELL plan (afb_rows.cu) when the plan exists and covers this case
+        const int rc = launch_rows(ctx, nga, ngf, TA.data(), TF.data(), gbuf, dval, drhs, accumulate, drop_val, status_flag);
+        if (rc < 0) return rc;
+        if (rc == 1) { cudaEventRecord(ctx->ev[3], st); return 1; }
+    }
     if (nrl == ncl && (nrl == 4 || nrl == 10 || nrl == 20) && !getenv("AFB_DISABLE_SQ_KERNEL")) {
         // lanes per row: fewer lanes -> more rows (independent load chains) per warp and less per-visit overhead
         int G = nrl == 4 ? 2 : 5;
