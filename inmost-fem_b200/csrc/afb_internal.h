@@ -110,16 +110,19 @@ struct afb_ctx {
     int64_t n_adj = 0;
     bool pos_has_dup = false;     // some element maps two local columns to the same global column
 
-    // class-sorted sliced-ELL plan of the thread-per-row gather (afb_rows.cu)
+    // cluster plan of the thread-per-row gather (afb_rows.cu)
     bool has_rows_plan = false;
-    int rp_nloc = 0;
-    long long rp_steps = 0;
-    afb::DevBuf rp_order;         // uint32[nrows]: rows in plan order (32 per slice)
+    int rp_nloc = 0, rp_gcap = 0, rp_maxlen = 0;
+    long long rp_steps = 0, rp_ncl = 0, rp_nslices = 0;
+    afb::DevBuf rp_new2old, rp_old2new;  // uint32[ntet]: Morton order of the elements
+    afb::DevBuf rp_cs;            // int32[ncl+1]: slices of a cluster
+    afb::DevBuf rp_eptr;          // int32[ncl+1]: element list of a cluster
+    afb::DevBuf rp_elist;         // uint32: Morton ids of the elements a cluster touches
+    afb::DevBuf rp_order;         // uint32[nslices*32]: rows of a slice (0xFFFFFFFF = empty lane)
+    afb::DevBuf rp_p0, rp_len, rp_smax;  // int64 / uint16 [nslices*32]: first CSR entry and length of the row; uint16[nslices] longest row
     afb::DevBuf rp_cnt;           // uint16[nslices*nloc]: visit-steps of class i in slice s
     afb::DevBuf rp_sptr;          // int64[nslices+1]: first visit-step of a slice
-    afb::DevBuf rp_ell;           // uint32[steps*NW*32]: slot bytes + element id per (step, lane)
-    struct RowsBucket { long long s0, s1; int L; };
-    std::vector<RowsBucket> rp_buckets;
+    afb::DevBuf rp_ell;           // uint32[steps*NW*32]: slot bytes + local element per (step, lane)
 
     // work buffers
     afb::DevBuf stageA, stageF, tables, coef, io_val, io_rhs, flag, tmp1, tmp2, tmp3, xy;
@@ -139,6 +142,7 @@ int form_dlen(const afb_form& form, const OpInfo& A, const OpInfo& B);
 int get_tables(afb_ctx* ctx, int fem, int order, const double** W, const double** phi, const double** grd);
 // thread-per-row gather + its plan (afb_rows.cu)
 int build_rows_plan(afb_ctx* ctx);
+bool rows_supports(const afb_ctx* ctx, int nga, int ngf);
 int launch_rows(afb_ctx* ctx, int nga, int ngf, const double* TA, const double* TF, const double* gbuf, double* val, double* rhs,
                 int accumulate, double drop_val, int* status);
 // gather (afb_gather.cu)

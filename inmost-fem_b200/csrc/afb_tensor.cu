@@ -71,7 +71,8 @@ __device__ __forceinline__ double jac_inv(const double P[4][3], double PSI[9]) {
 
 __global__ void __launch_bounds__(256) k_geom(long long ntet, GeomParams gp, const double* __restrict__ x, const double* __restrict__ y,
                                               const double* __restrict__ z, const int32_t* __restrict__ v0, const int32_t* __restrict__ v1,
-                                              const int32_t* __restrict__ v2, const int32_t* __restrict__ v3, double* __restrict__ gbuf) {
+                                              const int32_t* __restrict__ v2, const int32_t* __restrict__ v3, double* __restrict__ gbuf,
+                                              const unsigned* __restrict__ old2new /* NULL or the Morton id of every element */) {
     const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (e >= ntet) return;
     const int nn[4] = {__ldg(v0 + e), __ldg(v1 + e), __ldg(v2 + e), __ldg(v3 + e)};
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(256) k_geom(long long ntet, GeomParams gp, con
 #pragma unroll
     for (int k = 0; k < 4; ++k) { P[k][0] = __ldg(x + nn[k]); P[k][1] = __ldg(y + nn[k]); P[k][2] = __ldg(z + nn[k]); }
     const double vol = fabs(jac_inv(P, PSI)) * (1.0 / 6.0);
-    double* g = gbuf + e * gp.ngpad;
+    double* g = gbuf + (old2new ? (long long)old2new[e] : e) * gp.ngpad;
     if (gp.ngpad > gp.ngtot) g[gp.ngtot] = 0.0;
     for (int f = 0; f < gp.nforms; ++f) {
         const TFormDev& F = gp.f[f];
@@ -499,10 +500,13 @@ int assemble_tensor_path(afb_ctx* ctx, int nfA, int nfF, const std::vector<afb_f
     AFB_CUDA(ctx, ctx->stageF.reserve((size_t)ctx->ntet * ngpad * sizeof(double)));  // g_e buffer
     double* gbuf = ctx->stageF.as<double>();
 
+    // the cluster gather reads the coefficients in the Morton order of its plan, the lane-group gather in mesh order
+    const bool use_rows = nrl == ncl && rows_supports(ctx, nga, ngf) && (nga == 0 || dval) && (ngf == 0 || drhs);
     cudaEventRecord(ctx->ev[1], st);
     const unsigned gridg = (unsigned)((ctx->ntet + 255) / 256);
     k_geom<<<gridg, 256, 0, st>>>(ctx->ntet, gp, ctx->x.as<double>(), ctx->y.as<double>(), ctx->z.as<double>(), ctx->v[0].as<int32_t>(),
-                                 ctx->v[1].as<int32_t>(), ctx->v[2].as<int32_t>(), ctx->v[3].as<int32_t>(), gbuf);
+                                 ctx->v[1].as<int32_t>(), ctx->v[2].as<int32_t>(), ctx->v[3].as<int32_t>(), gbuf,
+                                 use_rows ? ctx->rp_old2new.as<unsigned>() : nullptr);
     ctx->launches++;
     AFB_CUDA(ctx, cudaGetLastError());
     cudaEventRecord(ctx->ev[2], st);
@@ -533,11 +537,13 @@ int assemble_tensor_path(afb_ctx* ctx, int nfA, int nfF, const std::vector<afb_f
     const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((p.nrows + rpb - 1) / rpb, 148LL * 32));
     cudaError_t e = cudaSuccess;
     bool done = false;
-    {
-        // thread-per-row gather over the class-sorted ELL plan (afb_rows.cu) when the plan exists and covers this case
+    if (use_rows) {
+        // cluster-tiled thread-per-row gather (afb_rows.cu)
         const int rc = launch_rows(ctx, nga, ngf, TA.data(), TF.data(), gbuf, dval, drhs, accumulate, drop_val, status_flag);
         if (rc < 0) return rc;
-        if (rc == 1) { cudaEventRecord(ctx->ev[3], st); return 1; }
+        if (rc != 1) { set_error(ctx, "internal: cluster gather refused a case it advertised"); return -4; }
+        cudaEventRecord(ctx->ev[3], st);
+        return 1;
     }
     if (nrl == ncl && (nrl == 4 || nrl == 10 || nrl == 20) && !getenv("AFB_DISABLE_SQ_KERNEL")) {
         // lanes per row: fewer lanes -> more rows (independent load chains) per warp and less per-visit overhead
