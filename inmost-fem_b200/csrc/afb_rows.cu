@@ -320,22 +320,10 @@ __device__ __forceinline__ void cp_async16(unsigned dst, const void* src) { asm 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// rotation of the 16-byte parts of an element record inside shared memory: spreads the records of a warp's 32 random
-// elements over all eight 16-byte bank groups (without it a 64-byte record pitch puts them on two groups: 16-way conflicts)
-template <int PARTS>
-__device__ __forceinline__ unsigned part_rot(unsigned el) {
-    if (PARTS == 4) return (el >> 1) & 3u;
-    if (PARTS == 2) return (el >> 2) & 1u;
-    if (PARTS == 8) return el & 7u;
-    if (PARTS == 6) return (el >> 2) & 1u;
-    return 0u;
-}
-template <int PARTS>
-__device__ __forceinline__ unsigned part_pos(unsigned q, unsigned rot) {
-    if ((PARTS & (PARTS - 1)) == 0) return q ^ rot;
-    const unsigned t = q + rot;
-    return t >= PARTS ? t - PARTS : t;
-}
+// slot of an element record inside a coefficient plane: the low three bits (= the 16-byte bank group) are hashed with
+// the next three, so that the regular element strides of structured meshes (6 tets per hex, ...) still spread a warp's
+// 32 records over all eight bank groups
+__device__ __forceinline__ unsigned rec_slot(unsigned el1) { return el1 ^ (((el1 >> 3) ^ (el1 >> 6) ^ (el1 >> 9)) & 7u); }
 
 template <int NLOC>
 struct SliceMeta {
@@ -359,15 +347,19 @@ __global__ void __launch_bounds__(256, 1) k_rows_cl(const __grid_constant__ RowT
     const int e0 = p.eptr[c], ne = p.eptr[c + 1] - e0;
     const int sl0 = p.cs[c], sl1 = p.cs[c + 1];
     const unsigned g_a = (unsigned)__cvta_generic_to_shared(smraw);
-    // ---- stage the coefficients of the cluster's elements: record 0 stays zero (padding visits read it), element el of
-    //      the cluster's list lands in record el+1; asynchronous 16-byte copies, parts XOR-rotated (part_rot)
+    // ---- stage the coefficients of the cluster's elements as PARTS planes of 16-byte pieces (SoA): record 0 stays zero
+    //      (padding visits read it), element el of the cluster's list lands in slot rec_slot(el+1) of every plane
+    const unsigned plane = (((unsigned)p.gcap + 8u) & ~7u) * 16u;  // rec_slot permutes inside blocks of 8 slots
     {
         const char* gsrc = reinterpret_cast<const char*>(p.gbuf);
         if (threadIdx.x < PARTS) {
             double2 zz; zz.x = 0.0; zz.y = 0.0;
-            reinterpret_cast<double2*>(smraw)[threadIdx.x] = zz;
+            *reinterpret_cast<double2*>(smraw + (size_t)threadIdx.x * plane) = zz;
         }
-        constexpr int U = 4;  // element ids in flight per thread
+        // one thread per element: its id, then PARTS asynchronous 16-byte copies (fire and forget; a batch of ids is loaded
+        // first so that their latencies overlap).  Measured alternatives: lane-per-piece cp.async and LDG.128+STS.128 are
+        // 5-8 % slower end to end -- the phase is latency-bound (one CTA per SM), not LSU-bound.
+        constexpr int U = 4;
         for (int base = 0; base < ne; base += U * (int)blockDim.x) {
             unsigned id[U];
 #pragma unroll
@@ -379,10 +371,9 @@ __global__ void __launch_bounds__(256, 1) k_rows_cl(const __grid_constant__ RowT
             for (int u = 0; u < U; ++u) {
                 const unsigned el1 = (unsigned)(base + u * (int)blockDim.x + (int)threadIdx.x) + 1u;
                 if ((int)el1 <= ne) {
-                    const unsigned rot = part_rot<PARTS>(el1);
+                    const unsigned dst = g_a + rec_slot(el1) * 16;
 #pragma unroll
-                    for (int part = 0; part < PARTS; ++part)
-                        cp_async16(g_a + (el1 * PARTS + part_pos<PARTS>(part, rot)) * 16, gsrc + ((size_t)id[u] * PARTS + part) * 16);
+                    for (int part = 0; part < PARTS; ++part) cp_async16(dst + part * plane, gsrc + ((size_t)id[u] * PARTS + part) * 16);
                 }
             }
         }
@@ -402,7 +393,7 @@ __global__ void __launch_bounds__(256, 1) k_rows_cl(const __grid_constant__ RowT
     const int sb = s_sb;
     const bool isbig = warp < p.nbig;
     const int L16 = isbig ? p.L16b : p.L16s;
-    const size_t goff = ((size_t)(p.gcap + 1) * NGP * 8 + 127) & ~(size_t)127;
+    const size_t goff = (size_t)plane * PARTS;
     unsigned char* wraw = smraw + goff +
                           (isbig ? (size_t)warp * rows_warp_bytes(p.L16b, NW)
                                  : (size_t)p.nbig * rows_warp_bytes(p.L16b, NW) + (size_t)(warp - p.nbig) * rows_warp_bytes(p.L16s, NW));
@@ -492,11 +483,10 @@ __global__ void __launch_bounds__(256, 1) k_rows_cl(const __grid_constant__ RowT
                 const unsigned el1 = w[NW - 1] >> 16;  // 0 = padding visit -> the zero record
                 double g[NGP];
                 {
-                    const unsigned rec = g_a + el1 * (NGP * 8);
-                    const unsigned rot = part_rot<PARTS>(el1);
+                    const unsigned rec = g_a + rec_slot(el1) * 16;
 #pragma unroll
                     for (int q = 0; q < PARTS; ++q) {
-                        const double2 d = lds128(rec + part_pos<PARTS>(q, rot) * 16);
+                        const double2 d = lds128(rec + q * plane);
                         g[2 * q] = d.x; g[2 * q + 1] = d.y;
                     }
                 }
@@ -616,7 +606,7 @@ RowsShape rows_shape(const afb_ctx* ctx, int ngp) {
     RowsShape r{};
     const int nw = (ctx->rp_nloc + 2 + 3) / 4;
     const size_t budget = 225 * 1024;
-    const size_t gbytes = ((size_t)(ctx->rp_gcap + 1) * ngp * 8 + 127) & ~(size_t)127;  // + the zero record
+    const size_t gbytes = (((size_t)ctx->rp_gcap + 8) & ~(size_t)7) * 16 * (ngp / 2);  // planes of 16-byte pieces, + the zero record
     const int L16 = (ctx->rp_maxlen + 15) & ~15;
     int maxw = 8;
     if (const char* wv = getenv("AFB_ROWS_WARPS")) maxw = std::max(1, std::min(8, atoi(wv)));
