@@ -200,7 +200,7 @@ def main():
     for _ in range(args.steps):
         assert ctx.assemble(forms_d, rhsf_d, val_dev, rhs_dev) == 0
         t = ctx.last_times()
-        el_ms += t["element_ms"]; ga_ms += t["gather_ms"]; fused = t["fused_path"]
+        el_ms += t["element_ms"]; ga_ms += t["gather_ms"]; fused = t["fused_path"]; names = (t["element_kernel"], t["gather_kernel"])
     ev1.record(stream)
     torch.cuda.synchronize()
     launches = ctx.launch_count()
@@ -233,7 +233,6 @@ def main():
     peak_gbs = peaks.get("hbm_gbs", 6650.0)
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
     alg_bytes = 4 * 10 * ntet + 24 * nnode + 72 * ntet + 8 * nnz + 8 * nrows
-    names = ("k_geom", "k_gather_tensor") if fused else ("k_element_generic", "k_gather")
     dom_name, dom_ms = (names[0], el_ms) if el_ms >= ga_ms else (names[1], ga_ms)
     traffic = None
     try:

@@ -102,7 +102,7 @@ def run(args, pkg, rank, world, local_rank):
                         "h2d_bytes_per_step": int(K_host.numel() * 8) * world, "d2h_bytes_per_step": int((nnz_all + nrows_all) * 8)},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": gbs / world, "peak": peak_gbs, "unit": "GB/s", "frac": gbs / world / peak_gbs, "traffic": None,
-                             "kernel": "whole step per GPU (k_geom + k_gather_tensor + exchange)", "algorithmic_bytes_per_launch": alg_bytes // world},
+                             "kernel": "whole step per GPU (k_geom + k_rows_cl + exchange)", "algorithmic_bytes_per_launch": alg_bytes // world},
                 "clocks": sampler.summary()}
         print(json.dumps(line))
     ctx.close()

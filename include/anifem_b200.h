@@ -141,8 +141,9 @@ int afb_assemble(afb_ctx* ctx, int nforms, const afb_form* forms, int nrhs_forms
 int afb_halo_add(afb_ctx* ctx, int64_t n, const int64_t* slot, const double* contrib, double* dst);
 
 /* phase times of the last afb_assemble in ms (CUDA events on the context stream):
- * [0] element kernels (k_element_generic / k_geom), [1] gather/scatter (k_gather / k_gather_tensor),
- * [2] coefficient copies, [3] = 1 if the fused tensor-representation path ran, 0 for the generic staged path;
+ * [0] element kernels (k_element_generic / k_geom), [1] gather/scatter (k_gather / k_gather_tensor / k_rows_cl),
+ * [2] coefficient copies, [3] = path: 0 generic staged (k_element_generic + k_gather), 1 fused tensor representation with the
+ * lane-group gather (k_geom + k_gather_tensor), 2 fused with the cluster-tiled thread-per-row gather (k_geom + k_rows_cl);
  * mirrors the GetTimeEvalLocFunc / GetTimeFillMapTemplate style getters (assembler.inl:949-964) */
 int afb_last_times(afb_ctx* ctx, double* ms4);
 

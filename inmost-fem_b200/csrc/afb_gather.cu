@@ -274,7 +274,7 @@ int afb_assemble(afb_ctx* ctx, int nforms, const afb_form* forms, int nrhs, cons
     cudaEventElapsedTime(&t01, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&t12, ctx->ev[1], ctx->ev[2]);
     cudaEventElapsedTime(&t23, ctx->ev[2], ctx->ev[3]);
-    ctx->times[0] = t12; ctx->times[1] = t23; ctx->times[2] = t01; ctx->times[3] = handled ? 1.0 : 0.0;
+    ctx->times[0] = t12; ctx->times[1] = t23; ctx->times[2] = t01; ctx->times[3] = (double)handled;
     if (bad) { set_error(ctx, "not a number in local matrix or rhs"); return -1; }
     return 0;
 }

@@ -433,7 +433,7 @@ cudaError_t launch_gt(const GatherT& p, unsigned grid, size_t smem, cudaStream_t
 
 namespace afb {
 
-// Returns 1 if the call was handled by the fused path, 0 if it does not apply (caller falls back to the generic
+// Returns 1 (lane-group gather) or 2 (cluster gather k_rows_cl) if the call was handled by the fused path, 0 if it does not apply (caller falls back to the generic
 // staged path), < 0 on error.
 int assemble_tensor_path(afb_ctx* ctx, int nfA, int nfF, const std::vector<afb_form>& fm, const std::vector<OpInfo>& oa,
                          const std::vector<OpInfo>& ob, const std::vector<const double*>& Dd, double* dval, double* drhs,
@@ -543,7 +543,7 @@ int assemble_tensor_path(afb_ctx* ctx, int nfA, int nfF, const std::vector<afb_f
         if (rc < 0) return rc;
         if (rc != 1) { set_error(ctx, "internal: cluster gather refused a case it advertised"); return -4; }
         cudaEventRecord(ctx->ev[3], st);
-        return 1;
+        return 2;
     }
     if (nrl == ncl && (nrl == 4 || nrl == 10 || nrl == 20) && !getenv("AFB_DISABLE_SQ_KERNEL")) {
         // lanes per row: fewer lanes -> more rows (independent load chains) per warp and less per-visit overhead
