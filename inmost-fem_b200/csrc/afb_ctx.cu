@@ -26,15 +26,16 @@ int cuda_fail(afb_ctx* ctx, cudaError_t e, const char* what) {
 }
 cudaError_t DevBuf::reserve(size_t bytes) {
     if (bytes <= cap && p) return cudaSuccess;
-    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    if (p && !borrowed) cudaFree(p);
+    p = nullptr; cap = 0; borrowed = false;
     if (bytes == 0) bytes = 16;
     cudaError_t e = cudaMalloc(&p, bytes);
     if (e == cudaSuccess) cap = bytes; else p = nullptr;
     return e;
 }
 void DevBuf::release() {
-    if (p) cudaFree(p);
-    p = nullptr; cap = 0;
+    if (p && !borrowed) cudaFree(p);
+    p = nullptr; cap = 0; borrowed = false;
 }
 
 int get_tables(afb_ctx* ctx, int fem, int order, const double** W, const double** phi, const double** grd) {
@@ -305,6 +306,7 @@ void afb_ctx_destroy(afb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    afb::blocks_clear(c);
     afb::DevBuf* bufs[] = {&c->x, &c->y, &c->z, &c->v[0], &c->v[1], &c->v[2], &c->v[3], &c->e2r, &c->e2c, &c->rowptr, &c->colind,
                            &c->radj_ptr, &c->radj, &c->pos, &c->stageA, &c->stageF, &c->tables, &c->coef, &c->io_val, &c->io_rhs,
                            &c->flag, &c->tmp1, &c->tmp2, &c->tmp3, &c->xy, &c->diag_col, &c->rp_order, &c->rp_cnt, &c->rp_sptr, &c->rp_ell, &c->rp_new2old, &c->rp_old2new, &c->rp_cs, &c->rp_eptr, &c->rp_elist, &c->rp_p0, &c->rp_len, &c->rp_smax};
@@ -349,6 +351,7 @@ int afb_mesh_set(afb_ctx* ctx, int64_t nnode, const double* x, const double* y, 
     AFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->nnode = nnode; ctx->ntet = ntet;
     ctx->has_dofmap = false; ctx->has_pattern = false;
+    ctx->fields.clear(); afb::blocks_clear(ctx);
     return 0;
 }
 
@@ -369,6 +372,7 @@ int afb_mesh_cube(afb_ctx* ctx, int nx, int ny, int nz, double size, int bx, int
     AFB_CUDA(ctx, cudaGetLastError());
     ctx->nnode = nnode; ctx->ntet = ntet;
     ctx->has_dofmap = false; ctx->has_pattern = false;
+    ctx->fields.clear(); afb::blocks_clear(ctx);
     return afb_mesh_orient(ctx);
 }
 
@@ -433,6 +437,7 @@ int afb_dofmap_set(afb_ctx* ctx, int nrow_loc, int ncol_loc, const int64_t* elem
     ctx->nrow_loc = nrow_loc; ctx->ncol_loc = ncol_loc;
     ctx->row_begin = row_begin; ctx->row_end = row_end; ctx->ncols_global = ncols_global;
     ctx->has_dofmap = true; ctx->has_pattern = false; ctx->has_diag = false;
+    ctx->fields.clear(); afb::blocks_clear(ctx);
     return 0;
 }
 
@@ -562,15 +567,21 @@ int afb_dofmap_natural(afb_ctx* ctx, int nvars, const int* fem, const int* vec) 
     long long off = 0;
     int nloc = 0;
     const long long nent[4] = {ctx->nnode, nedge, nface, ntet};
+    std::vector<Field> fields;
     for (int v = 0; v < nvars; ++v) {
         nd.var[v].fem = fem[v]; nd.var[v].vec = vec[v];
         const int ndof[4] = {fem[v] == AFB_FEM_P0 ? 0 : 1, fem[v] == AFB_FEM_P2 ? 1 : (fem[v] == AFB_FEM_P3 ? 2 : 0), fem[v] == AFB_FEM_P3 ? 1 : 0, fem[v] == AFB_FEM_P0 ? 1 : 0};
-        for (int c = 0; c < vec[v]; ++c)
+        const int nl1 = 4 * ndof[0] + 6 * ndof[1] + 4 * ndof[2] + ndof[3];
+        for (int c = 0; c < vec[v]; ++c) {
+            Field f{fem[v], nl1, nloc + c * nl1, off, 0};
             for (int d = 0; d < 4; ++d) {
                 nd.off[v][c][d] = off;
                 off += nent[d] * ndof[d];
             }
-        nloc += vec[v] * (4 * ndof[0] + 6 * ndof[1] + 4 * ndof[2] + ndof[3]);
+            f.count = off - f.goff;
+            fields.push_back(f);
+        }
+        nloc += vec[v] * nl1;
     }
     nd.nloc = nloc;
     if (off > 2147483000LL) { cleanup(); set_error(ctx, "afb_dofmap_natural: more than 2^31 dofs per context"); return -7; }
@@ -588,6 +599,8 @@ int afb_dofmap_natural(afb_ctx* ctx, int nvars, const int* fem, const int* vec) 
     ctx->row_begin = 0; ctx->row_end = off; ctx->ncols_global = off;
     ctx->has_signs = false; ctx->has_diag = false;
     ctx->has_dofmap = true; ctx->has_pattern = false;
+    afb::blocks_clear(ctx);
+    ctx->fields = fields;
     return 0;
 }
 

@@ -206,7 +206,12 @@ int afb_assemble(afb_ctx* ctx, int nforms, const afb_form* forms, int nrhs, cons
     AFB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p, 0, 64, st));
 
     // ---- fused fast path (afb_tensor.cu): element-wise constant coefficients on scalar P0..P3 spaces
-    int handled = assemble_tensor_path(ctx, nfA, nfF, fm, oa, ob, Dd, doA ? dval : nullptr, doF ? drhs : nullptr, accumulate, drop_val,
+    //      and, for vector / mixed spaces numbered by afb_dofmap_natural, the same path block by block (afb_blocks.cu)
+    int handled = assemble_block_path(ctx, nfA, nfF, fm, oa, ob, Dd, doA ? dval : nullptr, doF ? drhs : nullptr, accumulate, drop_val,
+                                      ctx->flag.as<int>());
+    if (handled < 0) return handled;
+    if (!handled)
+        handled = assemble_tensor_path(ctx, nfA, nfF, fm, oa, ob, Dd, doA ? dval : nullptr, doF ? drhs : nullptr, accumulate, drop_val,
                                        ctx->flag.as<int>());
     if (handled < 0) return handled;
     if (!handled) {

@@ -25,6 +25,7 @@ int cuda_fail(afb_ctx* ctx, cudaError_t e, const char* what);
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
+    bool borrowed = false;  // view of a buffer owned by another context (pair sub-contexts share the mesh)
     cudaError_t reserve(size_t bytes);
     void release();
     template <typename T> T* as() const { return static_cast<T*>(p); }
@@ -74,8 +75,17 @@ struct TableEntry {
     double *W, *phi, *grd;  // device
 };
 
+// scalar field (variable, component) of a NATURAL dof map: base space, local and global offsets
+struct Field { int fem, nloc, loff; long long goff, count; };
+struct PairPlan { int femR, femC; afb_ctx* sub; };
+
 struct afb_ctx {
     int device = 0;
+    bool is_sub = false;          // pair sub-context of afb_blocks.cu
+    std::vector<Field> fields;    // set by afb_dofmap_natural
+    std::vector<PairPlan> pairs;  // gather plans of (row space, column space) pairs
+    std::vector<afb::DevBuf> block_dst;   // [fR*nf + fC]: first CSR entry of block (fR,fC) per (slice, lane) of its pair plan
+    bool blocks_ready = false;
     std::vector<TableEntry> table_cache;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
@@ -112,7 +122,7 @@ struct afb_ctx {
 
     // cluster plan of the thread-per-row gather (afb_rows.cu)
     bool has_rows_plan = false;
-    int rp_nloc = 0, rp_gcap = 0, rp_maxlen = 0;
+    int rp_nloc = 0, rp_ncol = 0, rp_gcap = 0, rp_maxlen = 0;
     long long rp_steps = 0, rp_ncl = 0, rp_nslices = 0;
     afb::DevBuf rp_new2old, rp_old2new;  // uint32[ntet]: Morton order of the elements
     afb::DevBuf rp_cs;            // int32[ncl+1]: slices of a cluster
@@ -130,7 +140,24 @@ struct afb_ctx {
     double times[4] = {0, 0, 0, 0};
 };
 
+// one scalar block form of the tensor representation (afb_tensor.cu): A_e(i,j) = sum_c T[c][i][j] g_e[c]
+struct SForm {
+    int kind;             // 0 GRADxGRAD, 1 IDENxIDEN, 2 GRAD(A)xIDEN(B), 3 IDEN(A)xGRAD(B)
+    int ng;               // components of g_e it uses
+    int full;             // kind 0: a 3x3 tensor is given (else c * identity)
+    int layout, dstride;  // AFB_COEF_CONST / PER_TET, doubles per element record of D
+    int kidx[9];          // where the tensor values sit in the record; -1 = 0, -2 = 1
+    double alpha;
+    const double* D;      // device
+    int femA, femB, nfa, nfb;   // base spaces (trial, test) and their sizes
+    int quad_order;
+    int row_off, col_off;       // inside the local matrix of the plan it is assembled with
+};
+
 namespace afb {
+bool make_sform(const afb_form& f, const OpInfo& oa, const OpInfo& ob, const double* Ddev, SForm* out);
+int fused_group(afb_ctx* ctx, afb_ctx* plan, const std::vector<SForm>& mat, const std::vector<SForm>& rhsf, double* dval, double* drhs,
+                const long long* p0_override, int accumulate, double drop_val, int* status_flag, bool record_events);
 // element kernels (afb_element.cu)
 int launch_form(afb_ctx* ctx, const afb_form& form, const OpInfo& A, const OpInfo& B, int64_t f,
                 const double* x, const double* y, const double* z,                 // SoA nodes (or NULL)
@@ -140,11 +167,17 @@ int launch_form(afb_ctx* ctx, const afb_form& form, const OpInfo& A, const OpInf
 int form_dlen(const afb_form& form, const OpInfo& A, const OpInfo& B);
 // device tables W[q], phi[q*nf], G^[q*nf*3] of (space, rule); uploaded on first use (afb_ctx.cu)
 int get_tables(afb_ctx* ctx, int fem, int order, const double** W, const double** phi, const double** grd);
+// block-decomposed fused path of vector / mixed spaces (afb_blocks.cu)
+void blocks_clear(afb_ctx* ctx);
+int blocks_build(afb_ctx* ctx);
+int assemble_block_path(afb_ctx* ctx, int nfA, int nfF, const std::vector<afb_form>& fm, const std::vector<OpInfo>& oa,
+                        const std::vector<OpInfo>& ob, const std::vector<const double*>& Dd, double* dval, double* drhs, int accumulate,
+                        double drop_val, int* status_flag);
 // thread-per-row gather + its plan (afb_rows.cu)
 int build_rows_plan(afb_ctx* ctx);
 bool rows_supports(const afb_ctx* ctx, int nga, int ngf);
 int launch_rows(afb_ctx* ctx, int nga, int ngf, const double* TA, const double* TF, const double* gbuf, double* val, double* rhs,
-                int accumulate, double drop_val, int* status);
+                int accumulate, double drop_val, int* status, const long long* p0_override = nullptr);
 // gather (afb_gather.cu)
 int launch_gather(afb_ctx* ctx, const double* stageA, const double* stageF, double* val, double* rhs,
                   int accumulate, double drop_val, int* status_flag);

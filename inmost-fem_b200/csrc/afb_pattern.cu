@@ -162,6 +162,7 @@ static int pattern_impl(afb_ctx* ctx, int64_t* nnz_out, const int64_t* user_rowp
     if (ctx->ntet <= 0) { set_error(ctx, "Mesh was not specified"); return -6; }
     if (!ctx->has_dofmap) { set_error(ctx, "dof map was not specified (afb_dofmap_set / afb_dofmap_natural)"); return -6; }
     cudaSetDevice(ctx->device);
+    blocks_clear(ctx);
     const long long ntet = ctx->ntet, nrows = ctx->row_end - ctx->row_begin;
     const int nrl = ctx->nrow_loc, ncl = ctx->ncol_loc;
     const long long nitem = ntet * nrl;
@@ -254,7 +255,9 @@ static int pattern_impl(afb_ctx* ctx, int64_t* nnz_out, const int64_t* user_rowp
     ctx->max_row_len = max_len;
     ctx->has_pattern = true;
     if (nnz_out) *nnz_out = nnz;
-    return build_rows_plan(ctx);
+    const int rcp = build_rows_plan(ctx);
+    if (rcp) return rcp;
+    return user_rowptr ? 0 : blocks_build(ctx);  // pair plans of vector / mixed spaces (structural pattern only)
 }
 
 int afb_pattern_get(afb_ctx* ctx, int64_t* rowptr, int32_t* colind, int mem_space) {

@@ -217,14 +217,14 @@ __global__ void k_slice_info(long long nslices, const unsigned* __restrict__ sro
     }
 }
 
-// fills the ELL stream: word w of visit-step t of lane l at ell[(t*NW + w)*32 + l]; bytes 0..NLOC-1 = slots of the NLOC
-// columns, the last two bytes = local element index + 1 inside the cluster (0 = padding visit; buffer pre-set to 0)
-template <int NLOC>
+// fills the ELL stream: word w of visit-step t of lane l at ell[(t*NW + w)*32 + l]; bytes 0..NC-1 = slots of the NC local
+// columns (NLOC = local rows = visit classes), the last two bytes = local element index + 1 inside the cluster (0 = padding visit; buffer pre-set to 0)
+template <int NLOC, int NC>
 __global__ void k_ell_fill(long long nslices, const unsigned* __restrict__ srow, const unsigned* __restrict__ scl,
                            const long long* __restrict__ radj_ptr, const unsigned* __restrict__ radj, const unsigned char* __restrict__ pos,
                            const unsigned short* __restrict__ cntS, const long long* __restrict__ sptr, const unsigned* __restrict__ old2new,
                            const int* __restrict__ eptr, const unsigned* __restrict__ elist, unsigned* ell) {
-    constexpr int NW = (NLOC + 2 + 3) / 4;
+    constexpr int NW = (NC + 2 + 3) / 4;
     const int lane = threadIdx.x & 31;
     const long long wglob = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long s = wglob; s < nslices; s += nw) {
@@ -244,13 +244,13 @@ __global__ void k_ell_fill(long long nslices, const unsigned* __restrict__ srow,
                 while (lo < hi) { const int mid = (lo + hi) >> 1; if (elist[mid] < en) lo = mid + 1; else hi = mid; }
                 const unsigned eloc = (unsigned)(lo - e0) + 1u;
                 unsigned* dst = ell + (size_t)(base + k) * NW * 32 + lane;
-                const unsigned char* pa = pos + (size_t)a * NLOC;
+                const unsigned char* pa = pos + (size_t)a * NC;
 #pragma unroll
                 for (int w = 0; w < NW; ++w) {
                     unsigned word = 0;
 #pragma unroll
                     for (int b = 0; b < 4; ++b)
-                        if (4 * w + b < NLOC) word |= (unsigned)pa[4 * w + b] << (8 * b);
+                        if (4 * w + b < NC) word |= (unsigned)pa[4 * w + b] << (8 * b);
                     if (w == NW - 1) word |= eloc << 16;
                     dst[w * 32] = word;
                 }
@@ -264,10 +264,10 @@ __global__ void k_ell_fill(long long nslices, const unsigned* __restrict__ srow,
 // ---------------------------------------------------------------------------------------------------------------------
 // the gather
 // ---------------------------------------------------------------------------------------------------------------------
-template <int NLOC, int NGA, int NGF>
+template <int NLOC, int NC, int NGA, int NGF>
 struct alignas(16) RowTab {
-    static constexpr int NGAP = NGA + (NGA & 1);      // even pitch: every (i,j) group is 16-byte aligned -> LDCU.128
-    double A[NGA > 0 ? NLOC * NLOC * NGAP : 2];       // [(i*NLOC + j)*NGAP + c]
+    static constexpr int NGAP = NGA + (NGA & 1);      // even pitch: every (i,j) group is 16-byte aligned
+    double A[NGA > 0 ? NLOC * NC * NGAP : 2];         // [(i*NC + j)*NGAP + c], i = local row (test), j = local column (trial)
     double F[NGF > 0 ? NLOC * NGF + 2 : 2];           // [i*NGF + c]
 };
 
@@ -334,11 +334,11 @@ struct SliceMeta {
     int cn[NLOC];
 };
 
-template <int NLOC, int NGA, int NGF>
-__global__ void __launch_bounds__(256, 1) k_rows_cl(const __grid_constant__ RowTab<NLOC, NGA, NGF> T, const RowsArgs p) {
-    constexpr int NW = (NLOC + 2 + 3) / 4;
+template <int NLOC, int NC, int NGA, int NGF>
+__global__ void __launch_bounds__(256, 1) k_rows_cl(const __grid_constant__ RowTab<NLOC, NC, NGA, NGF> T, const RowsArgs p) {
+    constexpr int NW = (NC + 2 + 3) / 4;
     constexpr int NG = NGA + NGF, NGP = (NG + 1) & ~1, PARTS = NGP / 2;
-    constexpr int NGAP = RowTab<NLOC, NGA, NGF>::NGAP;
+    constexpr int NGAP = RowTab<NLOC, NC, NGA, NGF>::NGAP;
     extern __shared__ __align__(128) unsigned char smraw[];
     __shared__ int s_q[2];  // slices handed out: [0] long ones, [1] short ones
     __shared__ int s_sb;    // first long slice of the cluster
@@ -501,15 +501,15 @@ __global__ void __launch_bounds__(256, 1) k_rows_cl(const __grid_constant__ RowT
                     // The volatile shared-memory accesses fence the groups, which keeps the number of live table values small
                     // enough for ptxas to use uniform constant loads (LDCU) instead of per-thread LDC (ADU pipe, 8x slower).
                     constexpr int NGA1 = NGA > 0 ? NGA : 1;
-                    constexpr int GJ = NGA1 >= 30 ? 1 : (30 / NGA1 > NLOC ? NLOC : 30 / NGA1);
+                    constexpr int GJ = NGA1 >= 30 ? 1 : (30 / NGA1 > NC ? NC : 30 / NGA1);
 #pragma unroll
-                    for (int j0 = 0; j0 < NLOC; j0 += GJ) {
+                    for (int j0 = 0; j0 < NC; j0 += GJ) {
                         double v[GJ], o[GJ];
                         unsigned sa[GJ];
 #pragma unroll
                         for (int jj = 0; jj < GJ; ++jj) {
                             const int j = j0 + jj;
-                            if (j < NLOC) {
+                            if (j < NC) {
                                 // slot byte -> byte offset slot*256 in one PRMT
                                 sa[jj] = acc_a + __byte_perm(w[j >> 2], 0u, 0x4404u | ((unsigned)(j & 3) << 4));
                                 o[jj] = lds64(sa[jj]);  // the slots of one visit are distinct (checked by the plan)
@@ -518,17 +518,17 @@ __global__ void __launch_bounds__(256, 1) k_rows_cl(const __grid_constant__ RowT
 #pragma unroll
                         for (int jj = 0; jj < GJ; ++jj) {
                             const int j = j0 + jj;
-                            if (j < NLOC) {
+                            if (j < NC) {
                                 double x = 0.0;
 #pragma unroll
-                                for (int q = 0; q < NGA; ++q) x = fma(T.A[(i * NLOC + j) * NGAP + q + z2], g[q], x);
+                                for (int q = 0; q < NGA; ++q) x = fma(T.A[(i * NC + j) * NGAP + q + z2], g[q], x);
                                 v[jj] = x;
                             }
                         }
 #pragma unroll
                         for (int jj = 0; jj < GJ; ++jj) {
                             const int j = j0 + jj;
-                            if (j < NLOC) {
+                            if (j < NC) {
                                 // |A_e(i,j)| > drop_val is the reference's rule (assembler.inl:416); written as !(<=) so that a NaN
                                 // IS added and poisons the row sum, which the write-out reports as status -1
                                 if (!(fabs(v[jj]) <= drop)) sts64(sa[jj], o[jj] + v[jj]);
@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(256, 1) k_rows_cl(const __grid_constant__ RowT
 struct RowsShape { int nwarps, nbig, L16b, L16s, small_len; size_t smem; bool ok; };
 RowsShape rows_shape(const afb_ctx* ctx, int ngp) {
     RowsShape r{};
-    const int nw = (ctx->rp_nloc + 2 + 3) / 4;
+    const int nw = (ctx->rp_ncol + 2 + 3) / 4;
     const size_t budget = 225 * 1024;
     const size_t gbytes = (((size_t)ctx->rp_gcap + 8) & ~(size_t)7) * 16 * (ngp / 2);  // planes of 16-byte pieces, + the zero record
     const int L16 = (ctx->rp_maxlen + 15) & ~15;
@@ -636,15 +636,15 @@ RowsShape rows_shape(const afb_ctx* ctx, int ngp) {
     return r;
 }
 
-template <int NLOC, int NGA, int NGF>
+template <int NLOC, int NC, int NGA, int NGF>
 int launch_rows_t(afb_ctx* ctx, const double* TA, const double* TF, const double* gbuf, double* val, double* rhs, int accumulate,
-                  double drop_val, int* status) {
+                  double drop_val, int* status, const long long* p0_override) {
     constexpr int NGP = (NGA + NGF + 1) & ~1;
-    static RowTab<NLOC, NGA, NGF> T;  // host staging of the parameter (copied by value at launch)
+    static RowTab<NLOC, NC, NGA, NGF> T;  // host staging of the parameter (copied by value at launch)
     // TA is [c][i][j], TF is [c][i]
     for (int i = 0; i < NLOC; ++i)
-        for (int j = 0; j < NLOC; ++j)
-            for (int c = 0; c < NGA; ++c) T.A[(i * NLOC + j) * RowTab<NLOC, NGA, NGF>::NGAP + c] = TA[((size_t)c * NLOC + i) * NLOC + j];
+        for (int j = 0; j < NC; ++j)
+            for (int c = 0; c < NGA; ++c) T.A[(i * NC + j) * RowTab<NLOC, NC, NGA, NGF>::NGAP + c] = TA[((size_t)c * NLOC + i) * NC + j];
     for (int i = 0; i < NLOC; ++i)
         for (int c = 0; c < NGF; ++c) T.F[i * NGF + c] = TF[(size_t)c * NLOC + i];
     const RowsShape sh = rows_shape(ctx, NGP);
@@ -654,13 +654,13 @@ int launch_rows_t(afb_ctx* ctx, const double* TA, const double* TF, const double
     p.gcap = ctx->rp_gcap;
     p.zero = 0;
     p.cs = ctx->rp_cs.as<int>(); p.eptr = ctx->rp_eptr.as<int>(); p.elist = ctx->rp_elist.as<unsigned>();
-    p.srow = ctx->rp_order.as<unsigned>(); p.sp0 = ctx->rp_p0.as<long long>(); p.slen = ctx->rp_len.as<unsigned short>();
+    p.srow = ctx->rp_order.as<unsigned>(); p.sp0 = p0_override ? p0_override : ctx->rp_p0.as<long long>(); p.slen = ctx->rp_len.as<unsigned short>();
     p.smax = ctx->rp_smax.as<unsigned short>();
     p.cnt = ctx->rp_cnt.as<unsigned short>(); p.sptr = ctx->rp_sptr.as<long long>();
     p.ell = ctx->rp_ell.as<unsigned>(); p.gbuf = gbuf;
     p.val = val; p.rhs = rhs; p.accumulate = accumulate; p.status = status;
     p.drop = drop_val;
-    auto kern = k_rows_cl<NLOC, NGA, NGF>;
+    auto kern = k_rows_cl<NLOC, NC, NGA, NGF>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaFuncSetAttribute(k_rows_cl)");
     kern<<<(unsigned)ctx->rp_ncl, sh.nwarps * 32, sh.smem, ctx->stream>>>(T, p);
@@ -670,11 +670,11 @@ int launch_rows_t(afb_ctx* ctx, const double* TA, const double* TF, const double
     return 1;
 }
 
-template <int NLOC>
+template <int NLOC, int NC>
 int launch_rows_n(afb_ctx* ctx, int nga, int ngf, const double* TA, const double* TF, const double* gbuf, double* val, double* rhs,
-                  int accumulate, double drop_val, int* status) {
-#define RW(A, F) if (nga == A && ngf == F) return launch_rows_t<NLOC, A, F>(ctx, TA, TF, gbuf, val, rhs, accumulate, drop_val, status);
-    RW(6, 1) RW(6, 0) RW(7, 1) RW(7, 0) RW(1, 1) RW(1, 0) RW(0, 1)
+                  int accumulate, double drop_val, int* status, const long long* p0_override) {
+#define RW(A, F) if (nga == A && ngf == F) return launch_rows_t<NLOC, NC, A, F>(ctx, TA, TF, gbuf, val, rhs, accumulate, drop_val, status, p0_override);
+    RW(6, 1) RW(6, 0) RW(7, 1) RW(7, 0) RW(1, 1) RW(1, 0) RW(0, 1) RW(3, 0) RW(3, 1)
     if constexpr (NLOC <= 10) { RW(9, 1) RW(9, 0) RW(10, 1) RW(10, 0) }
 #undef RW
     return 0;
@@ -685,9 +685,9 @@ int launch_rows_n(afb_ctx* ctx, int nga, int ngf, const double* TA, const double
 namespace afb {
 
 bool rows_supports(const afb_ctx* ctx, int nga, int ngf) {
-    if (!ctx->has_rows_plan || ctx->rp_nloc != ctx->nrow_loc) return false;
+    if (!ctx->has_rows_plan || ctx->rp_nloc != ctx->nrow_loc || ctx->rp_ncol != ctx->ncol_loc) return false;
     if (getenv("AFB_DISABLE_ROWS_KERNEL")) return false;
-    const bool base = (ngf == 0 || ngf == 1) && (nga == 6 || nga == 7 || nga == 1 || (nga == 0 && ngf == 1));
+    const bool base = (ngf == 0 || ngf == 1) && (nga == 6 || nga == 7 || nga == 1 || nga == 3 || (nga == 0 && ngf == 1));
     const bool wide = ctx->rp_nloc <= 10 && (ngf == 0 || ngf == 1) && (nga == 9 || nga == 10);
     if (!(base || wide)) return false;
     return rows_shape(ctx, (nga + ngf + 1) & ~1).ok;
@@ -697,9 +697,10 @@ bool rows_supports(const afb_ctx* ctx, int nga, int ngf) {
 // absent (has_rows_plan = false -> lane-group gather) when the dof map is not one of the supported shapes.
 int build_rows_plan(afb_ctx* ctx) {
     ctx->has_rows_plan = false;
-    const int nl = ctx->nrow_loc;
+    const int nl = ctx->nrow_loc, nc = ctx->ncol_loc;
     if (getenv("AFB_DISABLE_ROWS_PLAN")) return 0;
-    if (ctx->nrow_loc != ctx->ncol_loc || !(nl == 4 || nl == 10 || nl == 20)) return 0;
+    // shapes: square P1/P2/P3 blocks and the rectangular P2 x P1 / P1 x P2 blocks of mixed spaces
+    if (!((nl == nc && (nl == 4 || nl == 10 || nl == 20)) || (nl == 10 && nc == 4) || (nl == 4 && nc == 10))) return 0;
     if (ctx->pos_bytes != 1 || ctx->has_signs || ctx->pos_has_dup) return 0;
     const long long nrows = ctx->row_end - ctx->row_begin, ntet = ctx->ntet, nadj = ctx->n_adj;
     if (nrows <= 0 || nadj <= 0 || ctx->nnode <= 0) return 0;
@@ -846,14 +847,20 @@ int build_rows_plan(afb_ctx* ctx) {
     R_CUDA(cudaMemcpyAsync(hflags, ctx->flag.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
     R_CUDA(cudaStreamSynchronize(st));
     if (hflags[0]) { cleanup(); return 0; }
-    const int nw = (nl + 2 + 3) / 4;
+    const int nw = (nc + 2 + 3) / 4;
     const size_t ell_bytes = (size_t)std::max<long long>(1, total) * nw * 32 * sizeof(unsigned);
     R_CUDA(ctx->rp_ell.reserve(ell_bytes));
     R_CUDA(cudaMemsetAsync(ctx->rp_ell.p, 0, ell_bytes, st));
-    BY_NLOC(k_ell_fill, <<<grid_for(nslices * 32), 256, 0, st>>>(nslices, ctx->rp_order.as<unsigned>(), scl.as<unsigned>(), radj_ptr, radj,
-                                                               ctx->pos.as<unsigned char>(), ctx->rp_cnt.as<unsigned short>(),
-                                                               ctx->rp_sptr.as<long long>(), old2new, ctx->rp_eptr.as<int>(),
-                                                               ctx->rp_elist.as<unsigned>(), ctx->rp_ell.as<unsigned>()));
+#define ELL_FILL(NRr, NCc) k_ell_fill<NRr, NCc><<<grid_for(nslices * 32), 256, 0, st>>>(nslices, ctx->rp_order.as<unsigned>(), scl.as<unsigned>(), radj_ptr, radj, \
+                                                               ctx->pos.as<unsigned char>(), ctx->rp_cnt.as<unsigned short>(),                            \
+                                                               ctx->rp_sptr.as<long long>(), old2new, ctx->rp_eptr.as<int>(),                           \
+                                                               ctx->rp_elist.as<unsigned>(), ctx->rp_ell.as<unsigned>())
+    if (nl == 4 && nc == 4) ELL_FILL(4, 4);
+    else if (nl == 10 && nc == 10) ELL_FILL(10, 10);
+    else if (nl == 20 && nc == 20) ELL_FILL(20, 20);
+    else if (nl == 10 && nc == 4) ELL_FILL(10, 4);
+    else ELL_FILL(4, 10);
+#undef ELL_FILL
     R_CUDA(cudaGetLastError());
     R_CUDA(cudaStreamSynchronize(st));
     ctx->launches += 2;
@@ -861,6 +868,7 @@ int build_rows_plan(afb_ctx* ctx) {
 #undef R_CUDA
     cleanup();
     ctx->rp_nloc = nl;
+    ctx->rp_ncol = nc;
     ctx->rp_steps = total;
     ctx->rp_ncl = ncl;
     ctx->rp_gcap = gcap;
@@ -876,14 +884,14 @@ int build_rows_plan(afb_ctx* ctx) {
 }
 
 // 1 = launched, 0 = combination not covered (caller uses the lane-group gather), < 0 error.  gbuf must be in Morton order.
+// p0_override: first CSR entry of every (slice, lane) row when the rows of this plan are sub-blocks of longer rows (afb_blocks.cu).
 int launch_rows(afb_ctx* ctx, int nga, int ngf, const double* TA, const double* TF, const double* gbuf, double* val, double* rhs,
-                int accumulate, double drop_val, int* status) {
+                int accumulate, double drop_val, int* status, const long long* p0_override) {
     if (!rows_supports(ctx, nga, ngf)) return 0;
-    switch (ctx->rp_nloc) {
-        case 4: return launch_rows_n<4>(ctx, nga, ngf, TA, TF, gbuf, val, rhs, accumulate, drop_val, status);
-        case 10: return launch_rows_n<10>(ctx, nga, ngf, TA, TF, gbuf, val, rhs, accumulate, drop_val, status);
-        case 20: return launch_rows_n<20>(ctx, nga, ngf, TA, TF, gbuf, val, rhs, accumulate, drop_val, status);
-    }
+    const int nl = ctx->rp_nloc, nc = ctx->rp_ncol;
+#define RWD(NRr, NCc) if (nl == NRr && nc == NCc) return launch_rows_n<NRr, NCc>(ctx, nga, ngf, TA, TF, gbuf, val, rhs, accumulate, drop_val, status, p0_override);
+    RWD(4, 4) RWD(10, 10) RWD(20, 20) RWD(10, 4) RWD(4, 10)
+#undef RWD
     return 0;
 }
 

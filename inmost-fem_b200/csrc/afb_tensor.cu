@@ -34,9 +34,10 @@ constexpr int MAX_TFORMS = 8;
 
 struct TFormDev {
     int kind;      // 0 GRADxGRAD, 1 IDENxIDEN, 2 GRAD(A)xIDEN(B), 3 IDEN(A)xGRAD(B)
-    int ttype;     // AFB_TENSOR_*
+    int full;      // kind 0: 1 = a 3x3 tensor K is given (9 values through kidx), 0 = c * identity (value kidx[0])
     int layout;    // CONST / PER_TET
-    int dlen;
+    int dstride;   // doubles per element record of D (PER_TET)
+    int kidx[9];   // position of every tensor value inside the record; -1 = the value 0, -2 = the value 1
     int goff, ng;  // components [goff, goff+ng) of g_e
     double alpha;
     const double* D;
@@ -69,6 +70,10 @@ __device__ __forceinline__ double jac_inv(const double P[4][3], double PSI[9]) {
     return det;
 }
 
+__device__ __forceinline__ double coef_value(const double* __restrict__ D, int idx) {
+    return idx >= 0 ? __ldg(D + idx) : (idx == -2 ? 1.0 : 0.0);
+}
+
 __global__ void __launch_bounds__(256) k_geom(long long ntet, GeomParams gp, const double* __restrict__ x, const double* __restrict__ y,
                                               const double* __restrict__ z, const int32_t* __restrict__ v0, const int32_t* __restrict__ v1,
                                               const int32_t* __restrict__ v2, const int32_t* __restrict__ v3, double* __restrict__ gbuf,
@@ -85,14 +90,14 @@ __global__ void __launch_bounds__(256) k_geom(long long ntet, GeomParams gp, con
     for (int f = 0; f < gp.nforms; ++f) {
         const TFormDev& F = gp.f[f];
         const double* D = F.D;
-        if (F.layout == AFB_COEF_PER_TET) D += (size_t)F.dlen * e;
+        if (F.layout == AFB_COEF_PER_TET) D += (size_t)F.dstride * e;
         const double s = vol * F.alpha;
         double* o = g + F.goff;
         if (F.kind == 0) {
-            if (F.ttype >= AFB_TENSOR_SYMMETRIC) {
+            if (F.full) {
                 double K[9];
 #pragma unroll
-                for (int t = 0; t < 9; ++t) K[t] = __ldg(D + t);   // K(k,l) at k + 3l
+                for (int t = 0; t < 9; ++t) K[t] = coef_value(D, F.kidx[t]);   // K(k,l) at k + 3l
                 // R[k][b] = sum_l K(k,l) PSI[b+3l];  M[a][b] = sum_k PSI[a+3k] R[k][b]
                 double R[3][3];
 #pragma unroll
@@ -112,7 +117,7 @@ __global__ void __launch_bounds__(256) k_geom(long long ntet, GeomParams gp, con
                         for (int b = 0; b < 3; ++b) o[3 * a + b] = M[a][b];
                 }
             } else {
-                const double c = s * (F.ttype == AFB_TENSOR_SCALAR ? __ldg(D) : 1.0);
+                const double c = s * coef_value(D, F.kidx[0]);
                 // M = c * PSI PSI^T (rows a of the inverse Jacobian dotted)
                 o[0] = c * (PSI[0] * PSI[0] + PSI[3] * PSI[3] + PSI[6] * PSI[6]);
                 o[1] = c * (PSI[1] * PSI[1] + PSI[4] * PSI[4] + PSI[7] * PSI[7]);
@@ -122,12 +127,10 @@ __global__ void __launch_bounds__(256) k_geom(long long ntet, GeomParams gp, con
                 o[5] = c * (PSI[1] * PSI[2] + PSI[4] * PSI[5] + PSI[7] * PSI[8]);
             }
         } else if (F.kind == 1) {
-            o[0] = s * (F.ttype >= AFB_TENSOR_SCALAR ? __ldg(D) : 1.0);
+            o[0] = s * coef_value(D, F.kidx[0]);
         } else {
-            // kind 2: K(0,l) = D[l] -> o[b] = s sum_l K(0,l) PSI[b+3l];  kind 3: K(k,0) = D[k] -> o[a] = s sum_k PSI[a+3k] K(k,0)
-            double k0, k1, k2;
-            if (F.ttype >= AFB_TENSOR_SYMMETRIC) { k0 = __ldg(D); k1 = __ldg(D + 1); k2 = __ldg(D + 2); }
-            else { k0 = k1 = k2 = (F.ttype == AFB_TENSOR_SCALAR ? __ldg(D) : 1.0); }
+            // kind 2: K(0,l) = k_l -> o[b] = s sum_l k_l PSI[b+3l];  kind 3: K(k,0) = k_k -> o[a] = s sum_k PSI[a+3k] k_k
+            const double k0 = coef_value(D, F.kidx[0]), k1 = coef_value(D, F.kidx[1]), k2 = coef_value(D, F.kidx[2]);
 #pragma unroll
             for (int a = 0; a < 3; ++a) o[a] = s * (PSI[a] * k0 + PSI[a + 3] * k1 + PSI[a + 6] * k2);
         }
@@ -377,15 +380,15 @@ struct HostForm {
     std::vector<double> T;  // [ng][nfb][nfa]
 };
 
-void build_form_table(const afb_form& fm, const OpInfo& A, const OpInfo& B, int kind, int ng, std::vector<double>& T) {
+void build_form_table(const SForm& f, std::vector<double>& T) {
     const double *pq, *wq;
-    const int q = tet_rule(fm.quad_order, &pq, &wq);
-    const int nfa = A.nf_base, nfb = B.nf_base;
+    const int q = tet_rule(f.quad_order, &pq, &wq);
+    const int nfa = f.nfa, nfb = f.nfb, kind = f.kind, ng = f.ng;
     std::vector<double> phiA((size_t)q * nfa), phiB((size_t)q * nfb), GA((size_t)q * nfa * 3), GB((size_t)q * nfb * 3);
-    basis_values(A.fem, q, pq, phiA.data());
-    basis_values(B.fem, q, pq, phiB.data());
-    basis_ref_grads(A.fem, q, pq, GA.data());
-    basis_ref_grads(B.fem, q, pq, GB.data());
+    basis_values(f.femA, q, pq, phiA.data());
+    basis_values(f.femB, q, pq, phiB.data());
+    basis_ref_grads(f.femA, q, pq, GA.data());
+    basis_ref_grads(f.femB, q, pq, GB.data());
     T.assign((size_t)ng * nfb * nfa, 0.0);
     auto S = [&](int a, int b, int i, int j) {  // sum_n w_n GB[i][a] GA[j][b]
         double s = 0;
@@ -433,85 +436,82 @@ cudaError_t launch_gt(const GatherT& p, unsigned grid, size_t smem, cudaStream_t
 
 namespace afb {
 
-// Returns 1 (lane-group gather) or 2 (cluster gather k_rows_cl) if the call was handled by the fused path, 0 if it does not apply (caller falls back to the generic
-// staged path), < 0 on error.
-int assemble_tensor_path(afb_ctx* ctx, int nfA, int nfF, const std::vector<afb_form>& fm, const std::vector<OpInfo>& oa,
-                         const std::vector<OpInfo>& ob, const std::vector<const double*>& Dd, double* dval, double* drhs,
-                         int accumulate, double drop_val, int* status_flag) {
-    const int nforms = nfA + nfF;
+// The fused path for a group of scalar block forms that share one gather plan.  `ctx` owns the mesh and the work buffers,
+// `plan` the dof map / pattern / gather plan the forms are assembled with (== ctx for single-field problems, a pair
+// sub-context of afb_blocks.cu for the blocks of vector and mixed spaces; then p0_override gives the first CSR entry of every
+// plan row inside the caller's matrix).  Returns 1 (lane-group gather) or 2 (cluster gather k_rows_cl), 0 if the group
+// cannot be handled (nothing was launched), < 0 on error.
+int fused_group(afb_ctx* ctx, afb_ctx* plan, const std::vector<SForm>& mat, const std::vector<SForm>& rhsf, double* dval, double* drhs,
+                const long long* p0_override, int accumulate, double drop_val, int* status_flag, bool record_events) {
+    const int nfA = (int)mat.size(), nfF = (int)rhsf.size(), nforms = nfA + nfF;
     if (nforms == 0 || nforms > MAX_TFORMS) return 0;
-    if (getenv("AFB_DISABLE_TENSOR_PATH")) return 0;
-    const int nrl = ctx->nrow_loc, ncl = ctx->ncol_loc;
-    if (ctx->has_signs) return 0;
-    std::vector<int> kind(nforms), ng(nforms);
+    const int nrl = plan->nrow_loc, ncl = plan->ncol_loc;
     int nga = 0, ngf = 0;
-    for (int k = 0; k < nforms; ++k) {
-        const afb_form& f = fm[k];
-        if (oa[k].vec != 1 || ob[k].vec != 1) return 0;
-        if (f.coef_layout == AFB_COEF_PER_POINT) return 0;
-        const bool gA = f.opA == AFB_GRAD, gB = f.opB == AFB_GRAD;
-        if ((f.opA != AFB_IDEN && !gA) || (f.opB != AFB_IDEN && !gB)) return 0;
-        kind[k] = gA ? (gB ? 0 : 2) : (gB ? 3 : 1);
-        const int tt = f.tensor_type;
-        if (kind[k] == 0) ng[k] = (tt == AFB_TENSOR_GENERAL) ? 9 : 6;
-        else if (kind[k] == 1) ng[k] = 1;
-        else {
-            ng[k] = 3;
-            // scalar / identity tensors are only legal here through the IDEN(P0) broadcast (diff_tensor.h:333-338)
-            if (tt < AFB_TENSOR_SYMMETRIC && !(kind[k] == 3 && oa[k].nfa == 1)) return 0;
-        }
-        if (tt == AFB_TENSOR_SYMMETRIC && oa[k].dim != ob[k].dim) return 0;
-        (k < nfA ? nga : ngf) += ng[k];
-    }
+    for (const SForm& f : mat) nga += f.ng;
+    for (const SForm& f : rhsf) ngf += f.ng;
     const int ngtot = nga + ngf;
     if (ngtot > 32) return 0;
     const size_t tabA = (size_t)nga * nrl * ncl, tabF = (size_t)ngf * nrl;
     if ((tabA + tabF) * 8 > 96 * 1024) return 0;
     const int ngpad = (ngtot + 1) & ~1;
+    // the cluster gather reads the coefficients in the Morton order of its plan, the lane-group gather in mesh order
+    const bool use_rows = rows_supports(plan, nga, ngf) && (nga == 0 || dval) && (ngf == 0 || drhs);
+    if (!use_rows && (plan != ctx || p0_override)) return 0;
 
-    // ---- host tables T[alpha][i][j] over the whole element matrix, rhs table TF[beta][i]
+    // ---- host tables T[alpha][i][j] over the whole local matrix of the plan, rhs table TF[beta][i]
     std::vector<double> TA(tabA, 0.0), TF(tabF, 0.0);
     GeomParams gp;
     std::memset(&gp, 0, sizeof(gp));
     gp.nforms = nforms; gp.ngpad = ngpad; gp.ngtot = ngtot;
     int offA = 0, offF = nga;
     for (int k = 0; k < nforms; ++k) {
+        const bool ismat = k < nfA;
+        const SForm& f = ismat ? mat[k] : rhsf[k - nfA];
         std::vector<double> T;
-        build_form_table(fm[k], oa[k], ob[k], kind[k], ng[k], T);
-        const bool mat = k < nfA;
-        const int goff = mat ? offA : offF;
-        for (int c = 0; c < ng[k]; ++c)
-            for (int i = 0; i < ob[k].nfa; ++i)
-                for (int j = 0; j < oa[k].nfa; ++j) {
-                    const double v = T[((size_t)c * ob[k].nfa + i) * oa[k].nfa + j];
-                    if (mat) TA[((size_t)(goff + c) * nrl + fm[k].row_off + i) * ncl + fm[k].col_off + j] = v;
-                    else TF[(size_t)(goff - nga + c) * nrl + fm[k].row_off + i] = v;
+        build_form_table(f, T);
+        const int goff = ismat ? offA : offF;
+        for (int c = 0; c < f.ng; ++c)
+            for (int i = 0; i < f.nfb; ++i)
+                for (int j = 0; j < f.nfa; ++j) {
+                    const double v = T[((size_t)c * f.nfb + i) * f.nfa + j];
+                    if (ismat) TA[((size_t)(goff + c) * nrl + f.row_off + i) * ncl + f.col_off + j] = v;
+                    else TF[(size_t)(goff - nga + c) * nrl + f.row_off + i] = v;
                 }
         TFormDev& d = gp.f[k];
-        d.kind = kind[k]; d.ttype = fm[k].tensor_type; d.layout = fm[k].coef_layout; d.dlen = form_dlen(fm[k], oa[k], ob[k]);
-        d.goff = goff; d.ng = ng[k]; d.alpha = fm[k].alpha; d.D = Dd[k];
-        (mat ? offA : offF) += ng[k];
+        d.kind = f.kind; d.full = f.full; d.layout = f.layout; d.dstride = f.dstride;
+        for (int t = 0; t < 9; ++t) d.kidx[t] = f.kidx[t];
+        d.goff = goff; d.ng = f.ng; d.alpha = f.alpha; d.D = f.D;
+        (ismat ? offA : offF) += f.ng;
     }
     cudaStream_t st = ctx->stream;
+    AFB_CUDA(ctx, ctx->stageF.reserve((size_t)ctx->ntet * ngpad * sizeof(double)));  // g_e buffer
+    double* gbuf = ctx->stageF.as<double>();
+
+    if (record_events) cudaEventRecord(ctx->ev[1], st);
+    const unsigned gridg = (unsigned)((ctx->ntet + 255) / 256);
+    k_geom<<<gridg, 256, 0, st>>>(ctx->ntet, gp, ctx->x.as<double>(), ctx->y.as<double>(), ctx->z.as<double>(), ctx->v[0].as<int32_t>(),
+                                 ctx->v[1].as<int32_t>(), ctx->v[2].as<int32_t>(), ctx->v[3].as<int32_t>(), gbuf,
+                                 use_rows ? plan->rp_old2new.as<unsigned>() : nullptr);
+    ctx->launches++;
+    AFB_CUDA(ctx, cudaGetLastError());
+    if (record_events) cudaEventRecord(ctx->ev[2], st);
+
+    if (use_rows) {
+        // cluster-tiled thread-per-row gather (afb_rows.cu)
+        plan->stream = ctx->stream;
+        const int rc = launch_rows(plan, nga, ngf, TA.data(), TF.data(), gbuf, dval, drhs, accumulate, drop_val, status_flag, p0_override);
+        if (plan != ctx) { ctx->launches += plan->launches; plan->launches = 0; if (rc < 0) set_error(ctx, plan->err); }
+        if (rc < 0) return rc;
+        if (rc != 1) { set_error(ctx, "internal: cluster gather refused a case it advertised"); return -4; }
+        if (record_events) cudaEventRecord(ctx->ev[3], st);
+        return 2;
+    }
+
+    // ---- lane-group gather (single-field plans only)
     // tables: small, uploaded through a per-context device buffer; stream-ordered so reuse across calls is safe
     AFB_CUDA(ctx, ctx->tables.reserve((tabA + tabF + 2) * sizeof(double)));
     if (tabA) AFB_CUDA(ctx, cudaMemcpyAsync(ctx->tables.p, TA.data(), tabA * sizeof(double), cudaMemcpyHostToDevice, st));
     if (tabF) AFB_CUDA(ctx, cudaMemcpyAsync(ctx->tables.as<double>() + tabA, TF.data(), tabF * sizeof(double), cudaMemcpyHostToDevice, st));
-    AFB_CUDA(ctx, ctx->stageF.reserve((size_t)ctx->ntet * ngpad * sizeof(double)));  // g_e buffer
-    double* gbuf = ctx->stageF.as<double>();
-
-    // the cluster gather reads the coefficients in the Morton order of its plan, the lane-group gather in mesh order
-    const bool use_rows = nrl == ncl && rows_supports(ctx, nga, ngf) && (nga == 0 || dval) && (ngf == 0 || drhs);
-    cudaEventRecord(ctx->ev[1], st);
-    const unsigned gridg = (unsigned)((ctx->ntet + 255) / 256);
-    k_geom<<<gridg, 256, 0, st>>>(ctx->ntet, gp, ctx->x.as<double>(), ctx->y.as<double>(), ctx->z.as<double>(), ctx->v[0].as<int32_t>(),
-                                 ctx->v[1].as<int32_t>(), ctx->v[2].as<int32_t>(), ctx->v[3].as<int32_t>(), gbuf,
-                                 use_rows ? ctx->rp_old2new.as<unsigned>() : nullptr);
-    ctx->launches++;
-    AFB_CUDA(ctx, cudaGetLastError());
-    cudaEventRecord(ctx->ev[2], st);
-
-    // ---- gather geometry: lanes per row
     int bestG = 1; double bestU = -1;
     for (int G = 1; G <= 32; ++G) {
         const int passes = (ncl + G - 1) / G;
@@ -523,28 +523,18 @@ int assemble_tensor_path(afb_ctx* ctx, int nfA, int nfF, const std::vector<afb_f
     p.nrows = ctx->row_end - ctx->row_begin; p.ntet = ctx->ntet;
     p.nrow_loc = nrl; p.ncol_loc = ncl; p.max_len = std::max(1, ctx->max_row_len);
     p.G = bestG; p.gpw = 32 / bestG; p.passes = (ncl + bestG - 1) / bestG;
-    p.nga = dval ? nga : 0; p.ngf = ngf; p.ngpad = ngpad;
+    p.nga = nga; p.ngf = ngf; p.ngpad = ngpad;
     p.divM = ((1ULL << 40) + nrl - 1) / nrl;
     p.rowptr = ctx->rowptr.as<long long>(); p.radj_ptr = ctx->radj_ptr.as<long long>(); p.radj = ctx->radj.as<unsigned>();
     p.pos = ctx->pos.p; p.pos_bytes = ctx->pos_bytes; p.gbuf = gbuf;
     p.TA = ctx->tables.as<double>(); p.TF = ctx->tables.as<double>() + tabA;
     p.val = dval; p.rhs = drhs; p.accumulate = accumulate; p.drop_val = drop_val; p.status = status_flag;
-    // note: p.nga = 0 when only the rhs is wanted, but the component offsets inside g_e stay the same
-    if (!dval) { p.nga = nga; }
     const int rpb = 8 * p.gpw;
     const size_t smem = (tabA + tabF + (size_t)rpb * p.max_len) * sizeof(double);
-    if (smem > 200 * 1024) return 0;
+    if (smem > 200 * 1024) { set_error(ctx, "afb_assemble: matrix rows too long for the shared-memory row image"); return -3; }
     const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((p.nrows + rpb - 1) / rpb, 148LL * 32));
     cudaError_t e = cudaSuccess;
     bool done = false;
-    if (use_rows) {
-        // cluster-tiled thread-per-row gather (afb_rows.cu)
-        const int rc = launch_rows(ctx, nga, ngf, TA.data(), TF.data(), gbuf, dval, drhs, accumulate, drop_val, status_flag);
-        if (rc < 0) return rc;
-        if (rc != 1) { set_error(ctx, "internal: cluster gather refused a case it advertised"); return -4; }
-        cudaEventRecord(ctx->ev[3], st);
-        return 2;
-    }
     if (nrl == ncl && (nrl == 4 || nrl == 10 || nrl == 20) && !getenv("AFB_DISABLE_SQ_KERNEL")) {
         // lanes per row: fewer lanes -> more rows (independent load chains) per warp and less per-visit overhead
         int G = nrl == 4 ? 2 : 5;
@@ -572,8 +562,60 @@ int assemble_tensor_path(afb_ctx* ctx, int nfA, int nfF, const std::vector<afb_f
     else e = launch_gt<32>(p, grid, smem, st);
     ctx->launches++;
     if (e != cudaSuccess) return cuda_fail(ctx, e, "k_gather_tensor launch");
-    cudaEventRecord(ctx->ev[3], st);
+    if (record_events) cudaEventRecord(ctx->ev[3], st);
     return 1;
+}
+
+// Scalar form (vecA = vecB = 1, operators IDEN / GRAD, CONST or PER_TET coefficient) -> SForm.  false: not representable.
+bool make_sform(const afb_form& f, const OpInfo& oa, const OpInfo& ob, const double* Ddev, SForm* out) {
+    if (oa.vec != 1 || ob.vec != 1) return false;
+    if (f.coef_layout == AFB_COEF_PER_POINT) return false;
+    const bool gA = f.opA == AFB_GRAD, gB = f.opB == AFB_GRAD;
+    if ((f.opA != AFB_IDEN && !gA) || (f.opB != AFB_IDEN && !gB)) return false;
+    SForm s;
+    std::memset(&s, 0, sizeof(s));
+    s.kind = gA ? (gB ? 0 : 2) : (gB ? 3 : 1);
+    const int tt = f.tensor_type;
+    if (tt == AFB_TENSOR_SYMMETRIC && oa.dim != ob.dim) return false;
+    const int dlen = form_dlen(f, oa, ob);
+    s.layout = f.coef_layout; s.dstride = dlen; s.D = Ddev; s.alpha = f.alpha;
+    for (int t = 0; t < 9; ++t) s.kidx[t] = -1;
+    if (s.kind == 0) {
+        s.full = tt >= AFB_TENSOR_SYMMETRIC;
+        s.ng = tt == AFB_TENSOR_GENERAL ? 9 : 6;
+        if (s.full) for (int t = 0; t < 9; ++t) s.kidx[t] = t;
+        else s.kidx[0] = tt == AFB_TENSOR_SCALAR ? 0 : -2;
+    } else if (s.kind == 1) {
+        s.ng = 1;
+        s.kidx[0] = tt >= AFB_TENSOR_SCALAR ? 0 : -2;
+    } else {
+        s.ng = 3;
+        if (tt >= AFB_TENSOR_SYMMETRIC) { s.kidx[0] = 0; s.kidx[1] = 1; s.kidx[2] = 2; }
+        else {
+            // scalar / identity tensors are only legal here through the IDEN(P0) broadcast (diff_tensor.h:333-338)
+            if (!(s.kind == 3 && oa.nfa == 1)) return false;
+            s.kidx[0] = s.kidx[1] = s.kidx[2] = tt == AFB_TENSOR_SCALAR ? 0 : -2;
+        }
+    }
+    s.femA = oa.fem; s.femB = ob.fem; s.nfa = oa.nf_base; s.nfb = ob.nf_base;
+    s.quad_order = f.quad_order; s.row_off = f.row_off; s.col_off = f.col_off;
+    *out = s;
+    return true;
+}
+
+// Single-field entry: every form is a scalar form on the context's own plan.
+int assemble_tensor_path(afb_ctx* ctx, int nfA, int nfF, const std::vector<afb_form>& fm, const std::vector<OpInfo>& oa,
+                         const std::vector<OpInfo>& ob, const std::vector<const double*>& Dd, double* dval, double* drhs,
+                         int accumulate, double drop_val, int* status_flag) {
+    if (getenv("AFB_DISABLE_TENSOR_PATH")) return 0;
+    if (ctx->has_signs) return 0;
+    std::vector<SForm> mat, rhsf;
+    for (int k = 0; k < nfA + nfF; ++k) {
+        SForm s;
+        if (!make_sform(fm[k], oa[k], ob[k], Dd[k], &s)) return 0;
+        (k < nfA ? mat : rhsf).push_back(s);
+    }
+    return fused_group(ctx, ctx, mat, rhsf, dval, drhs, nullptr, accumulate, drop_val, status_flag, true);
 }
 
 }  // namespace afb
