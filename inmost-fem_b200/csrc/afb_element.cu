@@ -11,6 +11,7 @@
 //                 accumulators in registers, quadrature points processed in shared-memory chunks
 // The reference tables phi / G^ are element independent and come from afb_tables.cpp.
 #include <cstdio>
+#include <vector>
 
 #include "afb_internal.h"
 
@@ -187,6 +188,115 @@ __global__ void __launch_bounds__(128) k_element_generic(FormDev F, long long f,
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_element_sq: register-tiled element kernel for the contraction-bound case: all forms of one Assemble that
+// are square on one scalar space with the same operator on both sides,
+//     A(i,j) = sum_forms sum_n sum_d V[d][n][i] * DU[d][n][j],   V = GRAD or IDEN of P1/P2/P3,  DU = w_n |T| alpha K_n V
+// with any tensor kind and layout (CONST / PER_TET / PER_POINT).  Same arithmetic as internalFem3Dtet + fusive_AT_mul_B
+// (fem/operations/core.inl:28-60,277-367), organised as a rank-1-update GEMM: one warp per tetrahedron, lane (li, lj) of an
+// 8 x 4 grid owns the entries i = li + 8t, j = lj + 4u in registers (3 x 5 for P3), V and DU of a chunk of quadrature
+// points sit in shared memory, and every quadrature point / direction costs TR + TC shared loads for TR*TC DFMAs per lane
+// (the generic kernel needs two loads per DFMA).  All forms accumulate into the same registers: the staged element matrix
+// is written once.
+constexpr int SQ_MAXF = 4;
+constexpr int SQ_QC = 8;  // quadrature points per shared-memory chunk
+struct SqForm {
+    int grad;            // 1: GRAD x GRAD, 0: IDEN x IDEN
+    int q;
+    const double *W, *phi, *grd;
+    int ttype, layout, dlen;
+    const double* D;
+    double alpha;
+};
+struct SqParams { int nforms; SqForm f[SQ_MAXF]; };
+
+template <int NF>
+__global__ void __launch_bounds__(128) k_element_sq(SqParams P, long long ntet, GeomSrc g, double* __restrict__ out, long long s_e) {
+    constexpr int TR = (NF + 7) / 8, TC = (NF + 3) / 4;
+    __shared__ double sU[4][3 * SQ_QC * NF];
+    __shared__ double sDU[4][3 * SQ_QC * NF];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long e = (long long)blockIdx.x * 4 + wib;
+    if (e >= ntet) return;
+    double* U = sU[wib];
+    double* DU = sDU[wib];
+    const int li = lane >> 2, lj = lane & 3;
+    double Pt[4][3], PSI[9];
+    load_tet(g, e, Pt);
+    const double vol = fabs(jacobian_inverse(Pt, PSI)) * (1.0 / 6.0);
+    double acc[TR][TC];
+#pragma unroll
+    for (int t = 0; t < TR; ++t)
+#pragma unroll
+        for (int u = 0; u < TC; ++u) acc[t][u] = 0.0;
+
+    for (int fi = 0; fi < P.nforms; ++fi) {
+        const SqForm& F = P.f[fi];
+        const int nd = F.grad ? 3 : 1;
+        for (int n0 = 0; n0 < F.q; n0 += SQ_QC) {
+            const int qn = min(SQ_QC, F.q - n0);
+            // ---- V and DU of this chunk
+            for (int it = lane; it < qn * NF; it += 32) {
+                const int nl = it / NF, a = it - nl * NF;
+                const int n = n0 + nl;
+                const double wv = __ldg(F.W + n) * vol * F.alpha;
+                const double* Dn = F.D;
+                if (F.layout == AFB_COEF_PER_TET) Dn += (size_t)F.dlen * e;
+                else if (F.layout == AFB_COEF_PER_POINT) Dn += (size_t)F.dlen * (n + (size_t)F.q * e);
+                if (F.grad) {
+                    const double* G = F.grd + ((size_t)n * NF + a) * 3;
+                    const double g0 = __ldg(G), g1 = __ldg(G + 1), g2 = __ldg(G + 2);
+                    double u[3];
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) u[d] = PSI[0 + 3 * d] * g0 + PSI[1 + 3 * d] * g1 + PSI[2 + 3 * d] * g2;
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) U[(d * SQ_QC + nl) * NF + a] = u[d];
+                    if (F.ttype >= AFB_TENSOR_SYMMETRIC) {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k)  // DU[k] = sum_l K(k,l) u[l], K(k,l) at k + 3l
+                            DU[(k * SQ_QC + nl) * NF + a] = wv * (__ldg(Dn + k) * u[0] + __ldg(Dn + k + 3) * u[1] + __ldg(Dn + k + 6) * u[2]);
+                    } else {
+                        const double c = wv * (F.ttype == AFB_TENSOR_SCALAR ? __ldg(Dn) : 1.0);
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) DU[(d * SQ_QC + nl) * NF + a] = c * u[d];
+                    }
+                } else {
+                    const double ph = __ldg(F.phi + (size_t)n * NF + a);
+                    const double c = wv * (F.ttype >= AFB_TENSOR_SCALAR ? __ldg(Dn) : 1.0);
+                    U[nl * NF + a] = ph;
+                    DU[nl * NF + a] = c * ph;
+                }
+            }
+            __syncwarp();
+            // ---- rank-1 updates
+            for (int d = 0; d < nd; ++d)
+                for (int nl = 0; nl < qn; ++nl) {
+                    const double* ur = U + (d * SQ_QC + nl) * NF;
+                    const double* dr = DU + (d * SQ_QC + nl) * NF;
+                    double vr[TR], dc[TC];
+#pragma unroll
+                    for (int t = 0; t < TR; ++t) vr[t] = (li + 8 * t < NF) ? ur[li + 8 * t] : 0.0;
+#pragma unroll
+                    for (int u = 0; u < TC; ++u) dc[u] = (lj + 4 * u < NF) ? dr[lj + 4 * u] : 0.0;
+#pragma unroll
+                    for (int t = 0; t < TR; ++t)
+#pragma unroll
+                        for (int u = 0; u < TC; ++u) acc[t][u] = fma(vr[t], dc[u], acc[t][u]);
+                }
+            __syncwarp();
+        }
+    }
+    double* o = out + e * s_e;
+#pragma unroll
+    for (int t = 0; t < TR; ++t)
+#pragma unroll
+        for (int u = 0; u < TC; ++u) {
+            const int i = li + 8 * t, j = lj + 4 * u;
+            if (i < NF && j < NF) o[i * NF + j] = acc[t][u];
+        }
+}
+
 template <int ACC>
 cudaError_t launch_generic(const FormDev& F, long long f, const GeomSrc& g, double* out, int ia0, int nia, int words, cudaStream_t st) {
     const int warps = 4;
@@ -273,6 +383,42 @@ int launch_form(afb_ctx* ctx, const afb_form& form, const OpInfo& A, const OpInf
         ctx->launches++;
         if (e != cudaSuccess) return cuda_fail(ctx, e, "k_element_generic launch");
     }
+    return 0;
+}
+
+// Launches k_element_sq for the forms sel[] (all square on one scalar space, same operator on both sides, full local
+// matrix): out[e*s_e + i*nf + j] = sum of the selected forms (store).  Returns 0 ok, < 0 error.
+int launch_forms_sq(afb_ctx* ctx, const std::vector<afb_form>& fm, const std::vector<OpInfo>& oa, const std::vector<const double*>& Dd,
+                    const std::vector<int>& sel, int64_t ntet, double* out, long long s_e) {
+    if (sel.empty() || (int)sel.size() > SQ_MAXF) return -7;
+    SqParams P;
+    P.nforms = (int)sel.size();
+    const int nf = oa[sel[0]].nf_base;
+    for (size_t k = 0; k < sel.size(); ++k) {
+        const afb_form& f = fm[sel[k]];
+        const OpInfo& A = oa[sel[k]];
+        SqForm& F = P.f[k];
+        const double *p, *w;
+        F.q = tet_rule(f.quad_order, &p, &w);
+        if (F.q < 0) { set_error(ctx, "quadrature order must be in 0..20"); return -7; }
+        int rc = get_tables(ctx, A.fem, f.quad_order, &F.W, &F.phi, &F.grd);
+        if (rc) return rc;
+        F.grad = A.op == AFB_GRAD;
+        F.ttype = f.tensor_type; F.layout = f.coef_layout; F.dlen = form_dlen(f, A, A);
+        F.D = Dd[sel[k]]; F.alpha = f.alpha;
+    }
+    GeomSrc g;
+    g.x = ctx->x.as<double>(); g.y = ctx->y.as<double>(); g.z = ctx->z.as<double>();
+    g.v0 = ctx->v[0].as<int32_t>(); g.v1 = ctx->v[1].as<int32_t>(); g.v2 = ctx->v[2].as<int32_t>(); g.v3 = ctx->v[3].as<int32_t>();
+    for (int k = 0; k < 4; ++k) g.XY[k] = nullptr;
+    const unsigned blocks = (unsigned)((ntet + 3) / 4);
+    if (nf == 4) k_element_sq<4><<<blocks, 128, 0, ctx->stream>>>(P, ntet, g, out, s_e);
+    else if (nf == 10) k_element_sq<10><<<blocks, 128, 0, ctx->stream>>>(P, ntet, g, out, s_e);
+    else if (nf == 20) k_element_sq<20><<<blocks, 128, 0, ctx->stream>>>(P, ntet, g, out, s_e);
+    else return -7;
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "k_element_sq launch");
     return 0;
 }
 

@@ -248,14 +248,37 @@ int afb_assemble(afb_ctx* ctx, int nforms, const afb_form* forms, int nrhs, cons
     };
     std::vector<int> add(nfA + nfF, 0);
     bool zeroA = false, zeroF = false;
-    if (doA) plan(0, nfA, true, add, zeroA);
+    // forms that are square on one scalar space with the same operator on both sides and cover the whole local matrix go
+    // through the register-tiled kernel k_element_sq in one launch (the FP64 contraction-bound case: P3, many points)
+    std::vector<int> sq;
+    if (doA && nrl == ncl && (nrl == 4 || nrl == 10 || nrl == 20) && !getenv("AFB_DISABLE_SQ_ELEMENT")) {
+        for (int k = 0; k < nfA && (int)sq.size() < 4; ++k) {
+            const afb_form& f = fm[k];
+            const int dl = form_dlen(f, oa[k], ob[k]);
+            const bool same = oa[k].vec == 1 && ob[k].vec == 1 && oa[k].fem == ob[k].fem && f.opA == f.opB && (f.opA == AFB_GRAD || f.opA == AFB_IDEN);
+            const bool dims_ok = f.tensor_type < AFB_TENSOR_SYMMETRIC || dl == (f.opA == AFB_GRAD ? 9 : 1);
+            if (same && dims_ok && oa[k].nfa == nrl && f.row_off == 0 && f.col_off == 0 && (sq.empty() || oa[k].fem == oa[sq[0]].fem)) sq.push_back(k);
+        }
+    }
+    if (doA) {
+        plan(0, nfA, true, add, zeroA);
+        if (!sq.empty()) {  // the tiled launch stores the full matrix first; every other matrix form adds to it
+            zeroA = false;
+            for (int k = 0; k < nfA; ++k) add[k] = 1;
+        }
+    }
     if (doF) plan(nfA, nfA + nfF, false, add, zeroF);
     if (doA && zeroA) AFB_CUDA(ctx, cudaMemsetAsync(sA, 0, (size_t)ntet * nrl * ncl * sizeof(double), st));
     if (doF && zeroF) AFB_CUDA(ctx, cudaMemsetAsync(sF, 0, (size_t)ntet * nrl * sizeof(double), st));
 
     cudaEventRecord(ctx->ev[1], st);
     // ---- K1: element blocks
+    if (!sq.empty()) {
+        int rc = launch_forms_sq(ctx, fm, oa, Dd, sq, ntet, sA, (long long)nrl * ncl);
+        if (rc) return rc;
+    }
     for (int k = 0; k < nfA + nfF; ++k) {
+        if (std::find(sq.begin(), sq.end(), k) != sq.end()) continue;
         const bool matrix = k < nfA;
         int rc = launch_form(ctx, fm[k], oa[k], ob[k], ntet, ctx->x.as<double>(), ctx->y.as<double>(), ctx->z.as<double>(),
                              ctx->v[0].as<int32_t>(), ctx->v[1].as<int32_t>(), ctx->v[2].as<int32_t>(), ctx->v[3].as<int32_t>(), nullptr,
