@@ -207,13 +207,17 @@ int afb_assemble(afb_ctx* ctx, int nforms, const afb_form* forms, int nrhs, cons
 
     // ---- fused fast path (afb_tensor.cu): element-wise constant coefficients on scalar P0..P3 spaces
     //      and, for vector / mixed spaces numbered by afb_dofmap_natural, the same path block by block (afb_blocks.cu)
-    int handled = assemble_block_path(ctx, nfA, nfF, fm, oa, ob, Dd, doA ? dval : nullptr, doF ? drhs : nullptr, accumulate, drop_val,
-                                      ctx->flag.as<int>());
+    // an output without forms (e.g. Assemble(A, b) of a problem without load) is not touched by the fused kernels
+    double* fval = (doA && nfA > 0) ? dval : nullptr;
+    double* frhs = (doF && nfF > 0) ? drhs : nullptr;
+    int handled = assemble_block_path(ctx, nfA, nfF, fm, oa, ob, Dd, fval, frhs, accumulate, drop_val, ctx->flag.as<int>());
     if (handled < 0) return handled;
-    if (!handled)
-        handled = assemble_tensor_path(ctx, nfA, nfF, fm, oa, ob, Dd, doA ? dval : nullptr, doF ? drhs : nullptr, accumulate, drop_val,
-                                       ctx->flag.as<int>());
+    if (!handled) handled = assemble_tensor_path(ctx, nfA, nfF, fm, oa, ob, Dd, fval, frhs, accumulate, drop_val, ctx->flag.as<int>());
     if (handled < 0) return handled;
+    if (handled && !accumulate) {
+        if (doA && !fval && ctx->nnz) AFB_CUDA(ctx, cudaMemsetAsync(dval, 0, ctx->nnz * sizeof(double), st));
+        if (doF && !frhs && nrows) AFB_CUDA(ctx, cudaMemsetAsync(drhs, 0, nrows * sizeof(double), st));
+    }
     if (!handled) {
     // ---- generic path: stage full element matrices, then gather
     double *sA = nullptr, *sF = nullptr;

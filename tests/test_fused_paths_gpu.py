@@ -1,0 +1,227 @@
+"""GPU parity tests aimed at the fused assembly paths added after the first slice:
+  * cluster-tiled gather k_rows_cl with several clusters per mesh, long / short row regions, ragged slices, padding visits;
+  * block-decomposed assembly of vector / mixed spaces (afb_blocks.cu) incl. per-tet tensors, accumulate, matrix-only, rhs-only;
+  * register-tiled element kernel k_element_sq (all tensor kinds and layouts) through the generic staged path;
+  * size-independent properties at a larger size: symmetry of the matrix, constant null space of the stiffness rows,
+    sum of the load vector = volume, bit-reproducibility.
+All comparisons go through the C ABI against the CPU oracle (CSR pattern bit-exact, values within 1e-12 of the row scale)."""
+import os
+
+import numpy as np
+import pytest
+
+import golden_cases as gc
+import problems
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+
+
+def _oracle_compare(ctx, M, prob, forms, rhsf, co, te, dm, tag, env=None):
+    env = env or {}
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        nnz = ctx.pattern_build()
+        rowptr, colind = ctx.pattern_get()
+        val, rhs = np.full(nnz, np.nan), np.full(rowptr.size - 1, np.nan)
+        assert ctx.assemble(forms, rhsf, val, rhs) == 0
+        path = ctx.last_times()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    rp, ci, v, r, st = M.assemble(prob, co, te, dm)
+    assert st == 0
+    assert np.array_equal(rowptr, rp) and np.array_equal(colind, ci), tag + ": pattern not bit-exact"
+    rowmax = np.maximum.reduceat(np.abs(v), rp[:-1])
+    rowmax[rowmax == 0] = 1.0
+    err = (np.abs(val - v) / np.repeat(rowmax, np.diff(rp))).max()
+    rs = np.abs(r).max()
+    rerr = np.abs(rhs - r).max() / (rs if rs > 0 else 1.0)
+    print("%s [%s + %s]: ntet=%d nnz=%d err A %.2e rhs %.2e" % (tag, path["element_kernel"], path["gather_kernel"], te.shape[0], nnz, err, rerr))
+    assert err <= RTOL and rerr <= RTOL, (tag, err, rerr)
+    return val, rhs, path
+
+
+def _mesh(pkg, ctx, M, n, variables, jitter=0.0, seed=0):
+    co, te, _ = M.cube_mesh(*n)
+    if jitter:
+        rng = np.random.default_rng(seed)
+        co = co + jitter * rng.standard_normal(co.shape) / max(n)
+        p = co[te]
+        det = np.linalg.det(p[:, :3, :] - p[:, 3:4, :])
+        te[det < 0] = te[det < 0][:, [0, 1, 3, 2]]
+        ctx.mesh_set(co, te)
+    else:
+        ctx.mesh_cube(*n)
+    ctx.dofmap_natural(variables)
+    dm = M.DofMap(te, variables, nnode=co.shape[0])
+    return co, te, dm
+
+
+@pytest.mark.parametrize("chunk", [32, 96, 512])
+@pytest.mark.parametrize("space", ["p1", "p2", "p3"])
+def test_cluster_gather_many_clusters(pkg, ctx, asm_oracle, chunk, space):
+    """small chunks force many clusters, partially filled slices and halo elements on a mesh the oracle finishes quickly"""
+    M = asm_oracle
+    fem = {"p1": gc.P1, "p2": gc.P2, "p3": gc.P3}[space]
+    n = {"p1": (7, 6, 5), "p2": (5, 4, 4), "p3": (3, 3, 3)}[space]
+    co, te, dm = _mesh(pkg, ctx, M, n, [(fem, 1)], jitter=0.08, seed=chunk)
+    rng = np.random.default_rng(chunk + fem)
+    K = gc.tensor(rng, gc.T_SYMMETRIC, gc.L_PER_TET, 3, 3, te.shape[0], 4)
+    c = gc.tensor(rng, gc.T_SCALAR, gc.L_PER_TET, 1, 1, te.shape[0], 4)
+    _, forms, rhsf, prob = problems._mk(pkg, M, [(fem, 1)],
+                                        [(0, 0, gc.GRAD, gc.GRAD, 2, gc.T_SYMMETRIC, gc.L_PER_TET, K, 1.0),
+                                         (0, 0, gc.IDEN, gc.IDEN, 3, gc.T_SCALAR, gc.L_PER_TET, c, 0.5)],
+                                        [(0, gc.IDEN, 2, gc.T_SCALAR, gc.L_PER_TET, c, 2.0)])
+    _, _, path = _oracle_compare(ctx, M, prob, forms, rhsf, co, te, dm, "%s chunk %d" % (space, chunk), {"AFB_ROWS_CHUNK": str(chunk)})
+    assert path["gather_kernel"] == "k_rows_cl"
+
+
+def test_cluster_gather_general_tensor_and_drop(pkg, ctx, asm_oracle):
+    """GENERAL (non-symmetric) 3x3 tensor = 9 components; drop_val larger than some entries changes values, not the pattern"""
+    M = asm_oracle
+    co, te, dm = _mesh(pkg, ctx, M, (4, 4, 3), [(gc.P2, 1)])
+    rng = np.random.default_rng(3)
+    K = gc.tensor(rng, gc.T_GENERAL, gc.L_PER_TET, 3, 3, te.shape[0], 4)
+    _, forms, rhsf, prob = problems._mk(pkg, M, [(gc.P2, 1)], [(0, 0, gc.GRAD, gc.GRAD, 2, gc.T_GENERAL, gc.L_PER_TET, K, 1.0)], [])
+    val, _, path = _oracle_compare(ctx, M, prob, forms, [], co, te, dm, "general tensor")
+    assert path["gather_kernel"] == "k_rows_cl"
+    # drop_val: contributions with |A_e(i,j)| <= drop are skipped (assembler.inl:416); compare with the oracle run with the same drop
+    drop = 0.02 * np.abs(val).max()
+    nnz = ctx.pattern_build()
+    v2 = np.zeros(nnz)
+    assert ctx.assemble(forms, [], v2, None, drop_val=drop) == 0
+    rp, ci, v, r, st = M.assemble(prob, co, te, dm, drop_val=drop)
+    rowmax = np.maximum.reduceat(np.abs(v), rp[:-1])
+    rowmax[rowmax == 0] = 1.0
+    # entries within rounding of the threshold may flip: allow a handful of element contributions of size drop
+    bad = np.abs(v2 - v) / np.repeat(rowmax, np.diff(rp)) > RTOL
+    assert bad.mean() < 1e-3 and (np.abs(v2 - v)[bad] <= 1.001 * drop * 4).all()
+    assert not np.array_equal(v2, val)
+
+
+@pytest.mark.parametrize("problem", ["c4", "c5"])
+def test_block_path_accumulate_and_partial(pkg, ctx, asm_oracle, problem):
+    M = asm_oracle
+    variables = [(gc.P2, 3)] if problem == "c4" else [(gc.P2, 3), (gc.P1, 1)]
+    co, te, dm = _mesh(pkg, ctx, M, (3, 3, 2), variables)
+    _, forms, rhsf, prob = (problems.c4_p2_elasticity if problem == "c4" else problems.c5_stokes)(pkg, M, co, te)
+    a, fa, path = _oracle_compare(ctx, M, prob, forms, rhsf, co, te, dm, problem + " blocks")
+    assert path["gather_kernel"] == "k_rows_cl", "the block path did not run"
+    nnz, nrows = a.size, fa.size
+    b, fb = a.copy(), fa.copy()
+    assert ctx.assemble(forms, rhsf, b, fb, accumulate=True) == 0
+    assert np.array_equal(b, 2 * a) and np.array_equal(fb, 2 * fa), "Assemble must add into the existing contents"
+    c = np.full(nnz, np.nan)
+    assert ctx.assemble(forms, [], c, None) == 0 and np.array_equal(c, a)       # AssembleMatrix
+    fc = np.full(nrows, np.nan)
+    assert ctx.assemble([], rhsf, None, fc) == 0 and np.array_equal(fc, fa)     # AssembleRHS
+    # same numbers as the generic staged path up to rounding
+    os.environ["AFB_DISABLE_TENSOR_PATH"] = "1"
+    try:
+        d, fd = np.zeros(nnz), np.zeros(nrows)
+        assert ctx.assemble(forms, rhsf, d, fd) == 0
+        assert ctx.last_times()["gather_kernel"] == "k_gather"
+    finally:
+        os.environ.pop("AFB_DISABLE_TENSOR_PATH")
+    assert np.abs(d - a).max() <= 1e-12 * np.abs(a).max() and np.abs(fd - fa).max() <= 1e-12 * np.abs(fa).max()
+
+
+def test_block_path_per_tet_elasticity_tensor(pkg, ctx, asm_oracle):
+    """FemVec<3,P2>: symmetric 9x9 tensor varying per tet + vector mass with a 3x3 tensor + body force per tet"""
+    M = asm_oracle
+    variables = [(gc.P2, 3)]
+    co, te, dm = _mesh(pkg, ctx, M, (3, 2, 3), variables, jitter=0.05, seed=11)
+    rng = np.random.default_rng(12)
+    nt = te.shape[0]
+    C = gc.tensor(rng, gc.T_SYMMETRIC, gc.L_PER_TET, 9, 9, nt, 4)
+    Mm = gc.tensor(rng, gc.T_SYMMETRIC, gc.L_PER_TET, 3, 3, nt, 4)
+    f = np.ascontiguousarray(rng.standard_normal((nt, 3)))
+    _, forms, rhsf, prob = problems._mk(pkg, M, variables,
+                                        [(0, 0, gc.GRAD, gc.GRAD, 2, gc.T_SYMMETRIC, gc.L_PER_TET, C, 1.0),
+                                         (0, 0, gc.IDEN, gc.IDEN, 2, gc.T_SYMMETRIC, gc.L_PER_TET, Mm, 0.3)],
+                                        [(0, gc.IDEN, 2, gc.T_GENERAL, gc.L_PER_TET, f, 1.0)])
+    _, _, path = _oracle_compare(ctx, M, prob, forms, rhsf, co, te, dm, "per-tet elasticity")
+    assert path["gather_kernel"] == "k_rows_cl"
+
+
+def test_block_path_mixed_p2_p1_scalars(pkg, ctx, asm_oracle):
+    """two scalar variables P2 and P1 coupled by mass-like and convection-like blocks (rectangular pair plans)"""
+    M = asm_oracle
+    variables = [(gc.P2, 1), (gc.P1, 1)]
+    co, te, dm = _mesh(pkg, ctx, M, (3, 3, 3), variables)
+    rng = np.random.default_rng(5)
+    nt = te.shape[0]
+    b = np.ascontiguousarray(rng.standard_normal((nt, 3)))  # GRAD(A) x IDEN(B): K is 1 x 3
+    c = gc.tensor(rng, gc.T_SCALAR, gc.L_PER_TET, 1, 1, nt, 4)
+    _, forms, rhsf, prob = problems._mk(pkg, M, variables,
+                                        [(0, 0, gc.GRAD, gc.GRAD, 2, gc.T_NULL, gc.L_CONST, None, 1.0),
+                                         (1, 1, gc.GRAD, gc.GRAD, 2, gc.T_SCALAR, gc.L_PER_TET, c, 1.0),
+                                         (1, 0, gc.IDEN, gc.IDEN, 2, gc.T_SCALAR, gc.L_PER_TET, c, -2.0),
+                                         (0, 1, gc.GRAD, gc.IDEN, 2, gc.T_GENERAL, gc.L_PER_TET, b, 1.5)],
+                                        [(1, gc.IDEN, 2, gc.T_NULL, gc.L_CONST, None, 1.0)])
+    _, _, path = _oracle_compare(ctx, M, prob, forms, rhsf, co, te, dm, "mixed scalars")
+    assert path["gather_kernel"] == "k_rows_cl"
+
+
+@pytest.mark.parametrize("ttype", [gc.T_NULL, gc.T_SCALAR, gc.T_SYMMETRIC, gc.T_GENERAL])
+@pytest.mark.parametrize("layout", [gc.L_CONST, gc.L_PER_TET, gc.L_PER_POINT])
+def test_tiled_element_kernel_all_tensor_kinds(pkg, ctx, asm_oracle, ttype, layout):
+    """k_element_sq through the generic staged path: P3 stiffness (order 4) + P3 mass (order 6)"""
+    if ttype == gc.T_NULL and layout != gc.L_CONST:
+        pytest.skip("no data for TENSOR_NULL")
+    M = asm_oracle
+    variables = [(gc.P3, 1)]
+    co, te, dm = _mesh(pkg, ctx, M, (2, 2, 2), variables, jitter=0.05, seed=7)
+    rng = np.random.default_rng(100 * ttype + layout)
+    nt = te.shape[0]
+    K = gc.tensor(rng, ttype, layout, 3, 3, nt, 14)
+    mt = gc.T_NULL if ttype == gc.T_NULL else gc.T_SCALAR
+    c = gc.tensor(rng, mt, layout, 1, 1, nt, 24)
+    if layout == gc.L_PER_POINT:  # one record per element: (ntet, q * dlen), the FusiveTensor layout D[dlen*(n + q*r)]
+        K, c = K.reshape(nt, -1), c.reshape(nt, -1)
+    _, forms, rhsf, prob = problems._mk(pkg, M, variables,
+                                        [(0, 0, gc.GRAD, gc.GRAD, 4, ttype, layout, K, 1.0), (0, 0, gc.IDEN, gc.IDEN, 6, mt, layout, c, 0.7)],
+                                        [(0, gc.IDEN, 3, gc.T_NULL, gc.L_CONST, None, 1.0)])
+    _, _, path = _oracle_compare(ctx, M, prob, forms, rhsf, co, te, dm, "tiled ttype %d layout %d" % (ttype, layout), {"AFB_DISABLE_TENSOR_PATH": "1"})
+    assert path["element_kernel"] == "k_element_generic"  # generic staged path (k_element_sq + k_element_generic for the rhs)
+
+
+def test_properties_at_scale(pkg, asm_oracle):
+    """C2 at 48^3 x 6 = 663,552 tets (too large for the numpy oracle): properties that do not need one"""
+    c = pkg.Context(0)
+    n = 48
+    c.mesh_cube(n, n, n)
+    c.dofmap_natural([(gc.P2, 1)])
+    nnz = c.pattern_build()
+    rowptr, colind = c.pattern_get()
+    coords, tets = c.mesh_get()
+    _, forms, rhsf, _ = problems.c2_p2_aniso(pkg, None, coords, tets)
+    nrows = rowptr.size - 1
+    a, fa = np.zeros(nnz), np.zeros(nrows)
+    assert c.assemble(forms, rhsf, a, fa) == 0
+    assert c.last_times()["gather_kernel"] == "k_rows_cl"
+    b, fb = np.zeros(nnz), np.zeros(nrows)
+    assert c.assemble(forms, rhsf, b, fb) == 0
+    assert np.array_equal(a, b) and np.array_equal(fa, fb), "not bit-reproducible"
+    rows = np.repeat(np.arange(nrows), np.diff(rowptr))
+    scale = np.abs(a).max()
+    # stiffness rows annihilate constants; the load vector integrates 1 over the unit cube
+    assert np.abs(np.bincount(rows, weights=a, minlength=nrows)).max() <= 1e-12 * scale * 70
+    assert abs(fa.sum() - 1.0) <= 1e-12
+    # symmetric tensor => symmetric matrix: compare with the transpose through a sort of (col,row) keys
+    key = colind.astype(np.int64) * nrows + rows
+    perm = np.argsort(key, kind="stable")
+    assert np.array_equal(rows[perm], colind) and np.array_equal(colind[perm], rows), "pattern not structurally symmetric"
+    assert np.abs(a[perm] - a).max() <= 1e-12 * scale
+    # columns ascending inside every row, diagonal present
+    d = np.diff(colind.astype(np.int64))
+    starts = rowptr[1:-1] - 1
+    d[starts] = 1
+    assert (d > 0).all()
+    assert np.isin(np.arange(nrows, dtype=np.int64) * nrows + np.arange(nrows), rows * np.int64(nrows) + colind).all()
+    c.close()
