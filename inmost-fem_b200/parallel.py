@@ -258,16 +258,32 @@ class InterfacePlan:
 
     def exchange(self, val_ext, rhs_ext, add):
         """send the foreign-row values / rhs entries to their owners and add what arrives, peers in rank order.
-        add(slots, contrib, dst) performs dst[slots] += contrib (afb_halo_add on the GPU)."""
+        add(slots, contrib, dst) performs dst[slots] += contrib (afb_halo_add on the GPU).
+        The foreign rows are sorted by global id = grouped by owner, so the tail of val_ext / rhs_ext IS the send buffer;
+        all sizes are known from the plan: one all_to_all_single per array, no size exchange, no host synchronisation."""
         nb = self.nb
+        fixed = val_ext.is_cuda if val_ext is not None else (rhs_ext is not None and rhs_ext.is_cuda)
         if val_ext is not None:
-            parts = list(torch.split(val_ext[self.nnz_own:], self.send_nnz))
-            for p, r in enumerate(_all_to_all_var(parts, nb.group)):
+            if fixed:
+                if getattr(self, "_vrecv", None) is None:
+                    self._vrecv = torch.empty(sum(self.recv_nnz), dtype=val_ext.dtype, device=val_ext.device)
+                dist.all_to_all_single(self._vrecv, val_ext[self.nnz_own:], self.recv_nnz, self.send_nnz, group=nb.group)
+                got = torch.split(self._vrecv, self.recv_nnz)
+            else:
+                got = _all_to_all_var(list(torch.split(val_ext[self.nnz_own:], self.send_nnz)), nb.group)
+            for p, r in enumerate(got):
                 if r.numel():
                     add(self.val_slots[p], r.contiguous(), val_ext)
         if rhs_ext is not None:
-            parts = list(torch.split(rhs_ext[self.n_own:], self.for_per_peer))
-            for p, r in enumerate(_all_to_all_var(parts, nb.group)):
+            if fixed:
+                sizes = [int(r.numel()) for r in self.rhs_slots]
+                if getattr(self, "_rrecv", None) is None:
+                    self._rrecv = torch.empty(sum(sizes), dtype=rhs_ext.dtype, device=rhs_ext.device)
+                dist.all_to_all_single(self._rrecv, rhs_ext[self.n_own:], sizes, self.for_per_peer, group=nb.group)
+                got = torch.split(self._rrecv, sizes)
+            else:
+                got = _all_to_all_var(list(torch.split(rhs_ext[self.n_own:], self.for_per_peer)), nb.group)
+            for p, r in enumerate(got):
                 if r.numel():
                     add(self.rhs_slots[p], r.contiguous(), rhs_ext)
 
