@@ -123,7 +123,7 @@ struct afb_ctx {
     // cluster plan of the thread-per-row gather (afb_rows.cu)
     bool has_rows_plan = false;
     int rp_nloc = 0, rp_ncol = 0, rp_gcap = 0, rp_maxlen = 0;
-    long long rp_steps = 0, rp_ncl = 0, rp_nslices = 0;
+    long long rp_steps = 0, rp_ncl = 0, rp_nslices = 0, rp_long_steps[2] = {0, 0};
     afb::DevBuf rp_new2old, rp_old2new;  // uint32[ntet]: Morton order of the elements
     afb::DevBuf rp_cs;            // int32[ncl+1]: slices of a cluster
     afb::DevBuf rp_eptr;          // int32[ncl+1]: element list of a cluster

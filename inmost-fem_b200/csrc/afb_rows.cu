@@ -335,7 +335,7 @@ struct SliceMeta {
 };
 
 template <int NLOC, int NC, int NGA, int NGF>
-__global__ void __launch_bounds__(256, 1) k_rows_cl(const __grid_constant__ RowTab<NLOC, NC, NGA, NGF> T, const RowsArgs p) {
+__global__ void __launch_bounds__(384, 1) k_rows_cl(const __grid_constant__ RowTab<NLOC, NC, NGA, NGF> T, const RowsArgs p) {
     constexpr int NW = (NC + 2 + 3) / 4;
     constexpr int NG = NGA + NGF, NGP = (NG + 1) & ~1, PARTS = NGP / 2;
     constexpr int NGAP = RowTab<NLOC, NC, NGA, NGF>::NGAP;
@@ -608,25 +608,29 @@ RowsShape rows_shape(const afb_ctx* ctx, int ngp) {
     const size_t budget = 225 * 1024;
     const size_t gbytes = (((size_t)ctx->rp_gcap + 8) & ~(size_t)7) * 16 * (ngp / 2);  // planes of 16-byte pieces, + the zero record
     const int L16 = (ctx->rp_maxlen + 15) & ~15;
-    int maxw = 8;
-    if (const char* wv = getenv("AFB_ROWS_WARPS")) maxw = std::max(1, std::min(8, atoi(wv)));
+    int maxw = 12;
+    if (const char* wv = getenv("AFB_ROWS_WARPS")) maxw = std::max(1, std::min(12, atoi(wv)));
     r.L16b = L16; r.ok = false;
     // candidates: uniform regions, or short regions (rows <= 48 / <= 28 entries) + a few long ones
     const int small_lens[3] = {1 << 30, 48, 28};
-    int best = 0;
+    double best = 1e300;
     for (int k = 0; k < 3; ++k) {
         const int sl = small_lens[k];
         if (k > 0 && ctx->rp_maxlen <= sl) continue;
         const int L16s = k == 0 ? L16 : ((sl + 15) & ~15);
         const size_t big = rows_warp_bytes(L16, nw), small = rows_warp_bytes(L16s, nw);
-        for (int nbig = (k == 0 ? 0 : 1); nbig <= (k == 0 ? 0 : 3); ++nbig) {
+        // visit-steps in slices that need a long-row region; the long-region warps also serve short slices afterwards
+        const double longs = k == 0 ? 0.0 : (double)ctx->rp_long_steps[k - 1], total = (double)std::max<long long>(1, ctx->rp_steps);
+        for (int nbig = (k == 0 ? 0 : 1); nbig <= (k == 0 ? 0 : 6); ++nbig) {
             if (gbytes + big * nbig > budget) break;
-            int nsm = (int)std::min<size_t>(maxw - nbig, (budget - gbytes - big * nbig) / small);
+            const int nsm = (int)std::min<size_t>(maxw - nbig, (budget - gbytes - big * nbig) / small);
             if (nsm < 0) continue;
             const int tot = nbig + nsm;
-            // prefer more warps; among equal counts more long-row regions
-            if (tot > best || (tot == best && nbig > r.nbig)) {
-                best = tot;
+            if (tot < 1) continue;
+            // time model: the cluster is done when the long slices are done and when all slices are done
+            const double t = std::max(nbig ? longs / nbig : 0.0, total / tot);
+            if (t < best * 0.999) {
+                best = t;
                 r.nwarps = tot; r.nbig = nbig; r.L16s = L16s; r.small_len = k == 0 ? (1 << 30) : sl;
                 r.smem = gbytes + big * nbig + small * nsm;
                 r.ok = tot >= 2;
@@ -874,7 +878,25 @@ int build_rows_plan(afb_ctx* ctx) {
     ctx->rp_gcap = gcap;
     ctx->rp_maxlen = std::max(1, hflags[2]);
     ctx->rp_nslices = nslices;
+    {   // visit-steps in slices whose longest row exceeds 48 / 28 entries (launch shape model, rows_shape)
+        std::vector<long long> hs(nslices + 1);
+        std::vector<unsigned short> hm(nslices);
+        if (cudaMemcpy(hs.data(), ctx->rp_sptr.p, (nslices + 1) * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(hm.data(), ctx->rp_smax.p, nslices * sizeof(unsigned short), cudaMemcpyDeviceToHost) != cudaSuccess)
+            return cuda_fail(ctx, cudaGetLastError(), "plan statistics");
+        ctx->rp_long_steps[0] = ctx->rp_long_steps[1] = 0;
+        for (long long s2 = 0; s2 < nslices; ++s2) {
+            const long long st2 = hs[s2 + 1] - hs[s2];
+            if (hm[s2] > 48) ctx->rp_long_steps[0] += st2;
+            if (hm[s2] > 28) ctx->rp_long_steps[1] += st2;
+        }
+    }
     ctx->has_rows_plan = true;
+    if (getenv("AFB_VERBOSE")) {
+        const RowsShape sh = rows_shape(ctx, 8);
+        fprintf(stderr, "[afb] launch shape for 8 coefficient doubles: %d warps (%d long-row regions of %d slots, short ones %d slots for rows <= %d), %zu B shared\n",
+                sh.nwarps, sh.nbig, sh.L16b, sh.L16s, sh.small_len, sh.smem);
+    }
     if (getenv("AFB_VERBOSE"))
         fprintf(stderr, "[afb] cluster plan: nloc %d, %lld clusters, %lld slices (%.1f%% lanes filled), %lld visit-steps (%.1f%% real visits), "
                         "%lld staged elements (x%.2f), gcap %d, max row length %d\n",
