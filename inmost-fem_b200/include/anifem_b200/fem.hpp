@@ -95,19 +95,63 @@ inline void check(afb_ctx* c, int rc) {
 }
 }  // namespace b200
 
-/// Elemental matrix of int_T (D OpA(u)) . OpB(v) dx for XYZ.fusion tetrahedra; A is nfB x (nfA*fusion) col-major.
-/// Dfnc: TensorType(const std::array<double,3>& x, double* Dmem, TensorDims Ddims, void* user_data, int iTet) with
-/// Dmem a col-major (Ddims.first x Ddims.second) = (Dim(OpB) x Dim(OpA)) matrix (fem/operations/int_tet.h:31-47).
-template <typename OpA, typename OpB, typename FuncTraits = DfuncTraits<>, typename Functor>
-void fem3Dtet(const Tetras<const double>& XYZ, const Functor& Dfnc, DenseMatrix<double>& A, int order = 5, void* user_data = nullptr) {
+// ---- memory arguments of the reference overloads ----------------------------------------------------------------------
+// The reference carves its scratch (XYG, PSI, U, V, DU, ...) out of caller memory (fem/fem_memory.h:195-520; sizes from
+// fem3Dtet_memory_requirements, int_tet.h:154-160).  Here the scratch lives on the device, so the requirement is zero and
+// the overloads that take a memory argument accept and ignore it: reference call sites compile unchanged.
+template <typename ScalarType = double, typename IndexType = int>
+struct PlainMemory {
+    ScalarType* ddata = nullptr;
+    IndexType* idata = nullptr;
+    std::size_t dSize = 0, iSize = 0;
+    bool ge(const PlainMemory& o) const { return dSize >= o.dSize && iSize >= o.iSize; }
+    void allocateFromPlainMemory(ScalarType* d, IndexType* i) { ddata = d; idata = i; }
+};
+template <typename ScalarType = double, typename IndexType = int>
+struct PlainMemoryX : public PlainMemory<ScalarType, IndexType> {
+    void** pdata = nullptr;
+    std::size_t pSize = 0;
+};
+template <typename ScalarType = double, typename IndexType = int>
+struct DynMem {  // fem/fem_memory.h:262-520: pool of chunks; nothing is drawn from it here
+    void defragment() {}
+    void clear() {}
+};
+
+// ---- runtime twins of the operators (fem/fem_space.h:170-306, ApplyOpBase / FemSpace::getOP) -------------------------
+struct ApplyOpBase {
+    int op = IDEN, fem = FEM_P1, vec = 1;
+    ApplyOpBase() = default;
+    ApplyOpBase(int op_, int fem_, int vec_ = 1) : op(op_), fem(fem_), vec(vec_) {
+        int nfa = 0, dim = 0;
+        if (afb_op_dims(op, fem, vec, &nfa, &dim) != 0) throw std::runtime_error("operator / space out of scope of the B200 path");
+    }
+    unsigned Nfa() const { int nfa = 0, dim = 0; afb_op_dims(op, fem, vec, &nfa, &dim); return static_cast<unsigned>(nfa); }
+    unsigned Dim() const { int nfa = 0, dim = 0; afb_op_dims(op, fem, vec, &nfa, &dim); return static_cast<unsigned>(dim); }
+};
+/// runtime description of a space: FemSpace{FEM_P2} (scalar) or FemSpace{FEM_P2, 3} (= P2^3); getOP mirrors fem_space.h:502
+struct FemSpace {
+    int fem = FEM_P1, vec = 1;
+    FemSpace() = default;
+    FemSpace(int fem_, int vec_ = 1) : fem(fem_), vec(vec_) {}
+    ApplyOpBase getOP(OperatorType op) const { return ApplyOpBase(op, fem, vec); }
+    unsigned dofMapSize() const { return static_cast<unsigned>(vec * b200_detail::base_nf(fem)); }
+    FemSpace operator^(int k) const { return FemSpace(fem, vec * k); }
+};
+
+namespace b200 {
+/// core shared by the compile-time and the runtime front ends
+template <typename Functor>
+void fem3Dtet_core(const ApplyOpBase& oa, const ApplyOpBase& ob, bool is_constant, const Tetras<const double>& XYZ, const Functor& Dfnc,
+                   DenseMatrix<double>& A, int order, void* user_data) {
     const int f = XYZ.fusion;
     if (f <= 0) return;
-    constexpr int nfa = OpA::Nfa::value, nfb = OpB::Nfa::value, idim = OpA::Dim::value, jdim = OpB::Dim::value;
+    const int nfa = static_cast<int>(oa.Nfa()), nfb = static_cast<int>(ob.Nfa()), idim = static_cast<int>(oa.Dim()), jdim = static_cast<int>(ob.Dim());
     if (A.size < static_cast<std::size_t>(nfa) * nfb * f)
         throw std::runtime_error("Not enough memory for local matrix, expected size = " + std::to_string(nfa * nfb * f) +
                                  " but A has size = " + std::to_string(A.size));
     A.nRow = nfb; A.nCol = static_cast<std::size_t>(nfa) * f;
-    afb_ctx* ctx = b200::default_context();
+    afb_ctx* ctx = default_context();
     const int q = afb_tet_quadrature(order, nullptr, nullptr, 0);
     if (q < 0) throw std::runtime_error("Numerical tetrahedron integration formula implemented only for 0 <= order <= 20");
     // evaluate the callback: once (constant tensor) or per quadrature point of every tet, r-major / n-minor like the
@@ -117,14 +161,14 @@ void fem3Dtet(const Tetras<const double>& XYZ, const Functor& Dfnc, DenseMatrix<
     std::vector<double> D;
     std::vector<int> types;
     int layout;
-    if (FuncTraits::IsConstant::value) {
+    if (is_constant) {
         layout = AFB_COEF_CONST;
         D.assign(dl, 0.0);
         types.push_back(Dfnc(std::array<double, 3>{0, 0, 0}, D.data(), dims, user_data, 0));
     } else {
         layout = AFB_COEF_PER_POINT;
         std::vector<double> XYG(static_cast<std::size_t>(3) * q * f);
-        b200::check(ctx, afb_quad_points(ctx, order, f, XYZ.XY0, XYZ.XY1, XYZ.XY2, XYZ.XY3, XYG.data(), AFB_HOST));
+        check(ctx, afb_quad_points(ctx, order, f, XYZ.XY0, XYZ.XY1, XYZ.XY2, XYZ.XY3, XYG.data(), AFB_HOST));
         D.assign(dl * q * f, 0.0);
         types.reserve(static_cast<std::size_t>(q) * f);
         for (int r = 0; r < f; ++r)
@@ -156,8 +200,18 @@ void fem3Dtet(const Tetras<const double>& XYZ, const Functor& Dfnc, DenseMatrix<
             ttype = TENSOR_GENERAL;
         }
     }
-    afb_form fm{OpA::op, OpA::fem, OpA::vec, OpB::op, OpB::fem, OpB::vec, order, ttype, layout, AFB_HOST, D.data(), 1.0, 0, 0};
-    b200::check(ctx, afb_fem3dtet_batched(ctx, &fm, f, XYZ.XY0, XYZ.XY1, XYZ.XY2, XYZ.XY3, A.data, AFB_HOST));
+    afb_form fm{oa.op, oa.fem, oa.vec, ob.op, ob.fem, ob.vec, order, ttype, layout, AFB_HOST, D.data(), 1.0, 0, 0};
+    check(ctx, afb_fem3dtet_batched(ctx, &fm, f, XYZ.XY0, XYZ.XY1, XYZ.XY2, XYZ.XY3, A.data, AFB_HOST));
+}
+}  // namespace b200
+
+/// Elemental matrix of int_T (D OpA(u)) . OpB(v) dx for XYZ.fusion tetrahedra; A is nfB x (nfA*fusion) col-major.
+/// Dfnc: TensorType(const std::array<double,3>& x, double* Dmem, TensorDims Ddims, void* user_data, int iTet) with
+/// Dmem a col-major (Ddims.first x Ddims.second) = (Dim(OpB) x Dim(OpA)) matrix (fem/operations/int_tet.h:31-47).
+template <typename OpA, typename OpB, typename FuncTraits = DfuncTraits<>, typename Functor>
+void fem3Dtet(const Tetras<const double>& XYZ, const Functor& Dfnc, DenseMatrix<double>& A, int order = 5, void* user_data = nullptr) {
+    b200::fem3Dtet_core(ApplyOpBase(OpA::op, OpA::fem, OpA::vec), ApplyOpBase(OpB::op, OpB::fem, OpB::vec), FuncTraits::IsConstant::value, XYZ, Dfnc, A,
+                        order, user_data);
 }
 
 template <typename OpA, typename OpB, typename FuncTraits = DfuncTraits<>, typename Functor>
@@ -165,5 +219,38 @@ void fem3Dtet(const DenseMatrix<double>& XY0, const DenseMatrix<double>& XY1, co
               const Functor& Dfnc, DenseMatrix<double>& A, int order = 5, void* user_data = nullptr) {
     fem3Dtet<OpA, OpB, FuncTraits>(make_tetras(XY0.data, XY1.data, XY2.data, XY3.data, static_cast<int>(XY0.nCol)), Dfnc, A, order, user_data);
 }
+
+/// reference overloads with caller memory (int_tet.h:17-29,111-122; dyn_ops.h:18-20): the memory argument is not used
+template <typename OpA, typename OpB, typename FuncTraits = DfuncTraits<>, typename Functor, typename ScalarType, typename IndexType>
+void fem3Dtet(const Tetras<const double>& XYZ, const Functor& Dfnc, DenseMatrix<double>& A, PlainMemory<ScalarType, IndexType>, int order = 5,
+              void* user_data = nullptr) {
+    fem3Dtet<OpA, OpB, FuncTraits>(XYZ, Dfnc, A, order, user_data);
+}
+template <typename OpA, typename OpB, typename FuncTraits = DfuncTraits<>, typename Functor, typename ScalarType, typename IndexType>
+void fem3Dtet(const DenseMatrix<double>& XY0, const DenseMatrix<double>& XY1, const DenseMatrix<double>& XY2, const DenseMatrix<double>& XY3,
+              const Functor& Dfnc, DenseMatrix<double>& A, PlainMemory<ScalarType, IndexType>, int order = 5, void* user_data = nullptr) {
+    fem3Dtet<OpA, OpB, FuncTraits>(make_tetras(XY0.data, XY1.data, XY2.data, XY3.data, static_cast<int>(XY0.nCol)), Dfnc, A, order, user_data);
+}
+template <typename OpA, typename OpB, typename FuncTraits = DfuncTraits<>, typename Functor, typename ScalarType, typename IndexType>
+void fem3Dtet(const Tetras<const double>& XYZ, const Functor& Dfnc, DenseMatrix<double>& A, DynMem<ScalarType, IndexType>&, int order = 5,
+              void* user_data = nullptr) {
+    fem3Dtet<OpA, OpB, FuncTraits>(XYZ, Dfnc, A, order, user_data);
+}
+/// runtime operators (dyn_ops.h:21-23, int_tet.h:144-160)
+template <typename FuncTraits = DfuncTraits<>, typename Functor>
+void fem3Dtet(const Tetras<const double>& XYZ, const ApplyOpBase& applyOpU, const ApplyOpBase& applyOpV, const Functor& Dfnc, DenseMatrix<double>& A,
+              DynMem<>& /*wmem*/, int order = 5, void* user_data = nullptr) {
+    b200::fem3Dtet_core(applyOpU, applyOpV, FuncTraits::IsConstant::value, XYZ, Dfnc, A, order, user_data);
+}
+template <typename FuncTraits = DfuncTraits<>, typename Functor>
+void fem3Dtet(const Tetras<const double>& XYZ, const ApplyOpBase& applyOpU, const ApplyOpBase& applyOpV, const Functor& Dfnc, DenseMatrix<double>& A,
+              PlainMemoryX<> /*mem*/, int order = 5, void* user_data = nullptr) {
+    b200::fem3Dtet_core(applyOpU, applyOpV, FuncTraits::IsConstant::value, XYZ, Dfnc, A, order, user_data);
+}
+/// no host scratch is needed: both sizes are zero (int_tet.h:154-160)
+template <typename OpA, typename OpB, typename ScalarType = double, typename IndexType = int>
+PlainMemory<ScalarType, IndexType> fem3Dtet_memory_requirements(int /*order*/, int /*fusion*/ = 1) { return PlainMemory<ScalarType, IndexType>(); }
+template <typename FuncTraits = DfuncTraits<>>
+PlainMemoryX<> fem3Dtet_memory_requirements(const ApplyOpBase&, const ApplyOpBase&, int /*order*/, int /*fusion*/ = 1) { return PlainMemoryX<>(); }
 
 }  // namespace Ani

@@ -57,6 +57,31 @@ int main() {
         fem3Dtet<Operator<IDEN, FemFix<FEM_P0>>, Operator<IDEN, FemVec<3, FEM_P2>>, DfuncTraits<PerPoint, false>>(XY1, XY2, XY3, XY4, scal, A, 2);
         EXPECT(norm_diff(1, A, -1, Bp) <= 100 * (1 + norm(A)) * DBL_EPSILON);
     }
+    // --- reference overloads with caller memory and the runtime twin (dyn_ops.h:18-23, int_tet.h:111-160): same numbers
+    {
+        using Op = Operator<GRAD, FemFix<FEM_P2>>;
+        auto Kfn = [](const std::array<double, 3>& x, double* Dmem, TensorDims d, void*, int) {
+            for (std::size_t i = 0; i < d.first; ++i) for (std::size_t j = 0; j < d.second; ++j) Dmem[i + d.first * j] = (i == j) * (1 + x[0]) + 0.1 * (i + j);
+            return TENSOR_SYMMETRIC;
+        };
+        double A0[100], A1[100], A2[100], A3[100];
+        DenseMatrix<> M0(A0, 10, 10), M1(A1, 10, 10), M2(A2, 10, 10), M3(A3, 10, 10);
+        fem3Dtet<Op, Op>(XY1, XY2, XY3, XY4, Kfn, M0, 4);
+        auto req = fem3Dtet_memory_requirements<Op, Op>(4, 1);
+        EXPECT(req.dSize == 0 && req.iSize == 0);
+        fem3Dtet<Op, Op>(XY1, XY2, XY3, XY4, Kfn, M1, req, 4);
+        DynMem<> wmem;
+        fem3Dtet<Op, Op>(make_tetras(XY1p, XY2p, XY3p, XY4p, 1), Kfn, M2, wmem, 4);
+        FemSpace P2s{FEM_P2};
+        fem3Dtet(make_tetras(XY1p, XY2p, XY3p, XY4p, 1), P2s.getOP(GRAD), P2s.getOP(GRAD), Kfn, M3, wmem, 4);
+        EXPECT(P2s.getOP(GRAD).Nfa() == 10 && P2s.getOP(GRAD).Dim() == 3 && (P2s ^ 3).getOP(GRAD).Dim() == 9 && (P2s ^ 3).dofMapSize() == 30);
+        double d = 0;
+        for (int i = 0; i < 100; ++i) d = std::fmax(d, std::fmax(std::fabs(A1[i] - A0[i]), std::fmax(std::fabs(A2[i] - A0[i]), std::fabs(A3[i] - A0[i]))));
+        EXPECT(d == 0.0 && norm(M0) > 0);
+        bool thrown = false;
+        try { ApplyOpBase bad(DIV, FEM_P1, 1); (void)bad; } catch (std::runtime_error&) { thrown = true; }
+        EXPECT(thrown);
+    }
     // --- fusive mass matrix with D = x^2 per point (int_tet_test.cpp:395-446): fusion of 2 equals two single calls
     {
         double X0[6] = {0, 0, 0, 1, 1, 1}, X1[6] = {2, 1, 1, 2, 1, 1}, X2[6] = {1, 2, 1, 1, 2, 1}, X3[6] = {2, 1, 2, 1, 1, 2};
