@@ -14,7 +14,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libanifem_b200.so")
+LIB_PATH = os.environ.get("AFB_LIB", os.path.join(HERE, "libanifem_b200.so"))  # AFB_LIB: A/B runs of two builds in one session
 
 HOST, DEVICE = 0, 1
 IDEN, GRAD, DIV = 1, 2, 3
