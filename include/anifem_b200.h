@@ -135,6 +135,13 @@ int afb_pattern_set(afb_ctx* ctx, const int64_t* rowptr /*nrows+1*/, const int32
 int afb_assemble(afb_ctx* ctx, int nforms, const afb_form* forms, int nrhs_forms, const afb_form* rhs_forms,
                  double* csr_val, double* rhs, int accumulate, double drop_val, int mem_space);
 
+/* Essential (Dirichlet) boundary conditions = applyDir(A, F, k, bc) on every Dirichlet dof of every cell, as the reference's local
+ * assemblers do (fem/operations/dc_on_dof.h:27-45; examples/tutorials/ex1.cpp:96-105).  is_dirichlet[ncols_global] (0/1) and
+ * value[ncols_global] are indexed by the global dof; NULL clears.  Every following afb_assemble then returns constrained rows:
+ * a Dirichlet row r is deg(r) on the diagonal (deg = cells containing the dof) and deg(r)*bc_r in the rhs, free rows lose their
+ * Dirichlet columns to the rhs (b_r -= A_rc bc_c).  The setting is dropped when the dof map changes. */
+int afb_dirichlet_set(afb_ctx* ctx, const unsigned char* is_dirichlet, const double* value, int mem_space);
+
 /* Multi-GPU interface rows: dst[slot[k]] += contrib[k] for the n contributions received from ONE peer (device
  * pointers; the slots of one call are distinct, peers are applied in rank order => deterministic, no atomics).
  * Replaces the value exchange the reference avoids by recomputing ghost cells (assembler.inl:162-183). */

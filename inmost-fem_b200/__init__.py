@@ -40,7 +40,8 @@ EXPORTS = ["afb_ctx_create", "afb_ctx_destroy", "afb_last_error", "afb_sync", "a
            "afb_fem3dtet_batched", "afb_op_dims", "afb_tet_quadrature", "afb_quad_points",
            "afb_mesh_set", "afb_mesh_cube", "afb_mesh_orient", "afb_mesh_get",
            "afb_dofmap_set", "afb_dofmap_set_diag", "afb_dofmap_natural", "afb_dofmap_get",
-           "afb_pattern_build", "afb_pattern_get", "afb_pattern_set", "afb_assemble", "afb_halo_add", "afb_last_times"]
+           "afb_pattern_build", "afb_pattern_get", "afb_pattern_set", "afb_assemble", "afb_halo_add", "afb_last_times",
+           "afb_dirichlet_set"]
 
 
 def build(verbose=False):
@@ -88,6 +89,7 @@ def lib():
         L.afb_pattern_get.argtypes = [vp, vp, vp, ci]
         L.afb_assemble.argtypes = [vp, ci, ctypes.POINTER(AfbForm), ci, ctypes.POINTER(AfbForm), vp, vp, ci, cd, ci]
         L.afb_last_times.argtypes = [vp, _dp]
+        L.afb_dirichlet_set.argtypes = [vp, vp, vp, ci]
         _lib = L
     return _lib
 
@@ -284,6 +286,20 @@ class Context:
         col = np.zeros((nt, nc), dtype=np.int64)
         self._ck(lib().afb_dofmap_get(self._h, None, None, None, None, None, row.ctypes.data, col.ctypes.data, HOST))
         return row, col
+
+    def dirichlet_set(self, is_dirichlet, value):
+        """essential BCs per global dof (numpy uint8 / float64 or torch tensors); None clears (afb_dirichlet_set)"""
+        if is_dirichlet is None:
+            self._ck(lib().afb_dirichlet_set(self._h, None, None, HOST))
+            return
+        if isinstance(is_dirichlet, np.ndarray):
+            is_dirichlet = np.ascontiguousarray(is_dirichlet, dtype=np.uint8)
+            value = np.ascontiguousarray(value, dtype=np.float64)
+        pf, sf = _ptr(is_dirichlet)
+        pv, sv = _ptr(value)
+        assert sf == sv
+        self._keep_dir = (is_dirichlet, value)
+        self._ck(lib().afb_dirichlet_set(self._h, pf, pv, sf))
 
     # ---- pattern -------------------------------------------------------------------------------
     def pattern_build(self):

@@ -309,7 +309,7 @@ void afb_ctx_destroy(afb_ctx* c) {
     afb::blocks_clear(c);
     afb::DevBuf* bufs[] = {&c->x, &c->y, &c->z, &c->v[0], &c->v[1], &c->v[2], &c->v[3], &c->e2r, &c->e2c, &c->rowptr, &c->colind,
                            &c->radj_ptr, &c->radj, &c->pos, &c->stageA, &c->stageF, &c->tables, &c->coef, &c->io_val, &c->io_rhs,
-                           &c->flag, &c->tmp1, &c->tmp2, &c->tmp3, &c->xy, &c->diag_col, &c->rp_order, &c->rp_cnt, &c->rp_sptr, &c->rp_ell, &c->rp_new2old, &c->rp_old2new, &c->rp_cs, &c->rp_eptr, &c->rp_elist, &c->rp_p0, &c->rp_len, &c->rp_smax};
+                           &c->flag, &c->tmp1, &c->tmp2, &c->tmp3, &c->xy, &c->diag_col, &c->rp_order, &c->rp_cnt, &c->rp_sptr, &c->rp_ell, &c->rp_new2old, &c->rp_old2new, &c->rp_cs, &c->rp_eptr, &c->rp_elist, &c->rp_p0, &c->rp_len, &c->rp_smax, &c->dir_flag, &c->dir_val, &c->dir_rows};
     for (auto* b : bufs) b->release();
     for (auto& t : c->table_cache) cudaFree(t.W);
     for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -438,6 +438,7 @@ int afb_dofmap_set(afb_ctx* ctx, int nrow_loc, int ncol_loc, const int64_t* elem
     ctx->row_begin = row_begin; ctx->row_end = row_end; ctx->ncols_global = ncols_global;
     ctx->has_dofmap = true; ctx->has_pattern = false; ctx->has_diag = false;
     ctx->fields.clear(); afb::blocks_clear(ctx);
+    ctx->has_dirichlet = false; ctx->dir_rows_valid = false;
     return 0;
 }
 
@@ -601,6 +602,7 @@ int afb_dofmap_natural(afb_ctx* ctx, int nvars, const int* fem, const int* vec) 
     ctx->has_dofmap = true; ctx->has_pattern = false;
     afb::blocks_clear(ctx);
     ctx->fields = fields;
+    ctx->has_dirichlet = false; ctx->dir_rows_valid = false;
     return 0;
 }
 

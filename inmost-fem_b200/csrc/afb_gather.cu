@@ -105,6 +105,19 @@ cudaError_t launch_g(afb_ctx* c, const double* sA, const double* sF, double* val
 
 }  // namespace
 
+namespace {
+__global__ void k_axpy(long long n, const double* __restrict__ x, double* __restrict__ y) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] += x[i];
+}
+int launch_axpy(afb_ctx* ctx, long long n, const double* x, double* y) {
+    if (n <= 0) return 0;
+    k_axpy<<<(unsigned)std::max<long long>(1, std::min<long long>((n + 255) / 256, 148LL * 32)), 256, 0, ctx->stream>>>(n, x, y);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : afb::cuda_fail(ctx, e, "k_axpy launch");
+}
+}  // namespace
+
 namespace afb {
 
 int assemble_tensor_path(afb_ctx* ctx, int nfA, int nfF, const std::vector<afb_form>& fm, const std::vector<OpInfo>& oa,
@@ -136,8 +149,15 @@ int afb_assemble(afb_ctx* ctx, int nforms, const afb_form* forms, int nrhs, cons
     if (ctx->ntet <= 0) { set_error(ctx, "Mesh was not specified"); return -6; }
     if (!ctx->has_pattern) { set_error(ctx, "pattern was not built: call afb_pattern_build first"); return -6; }
     if ((nforms > 0 && !forms) || (nrhs > 0 && !rhs_forms) || nforms < 0 || nrhs < 0) { set_error(ctx, "afb_assemble: bad form arrays"); return -7; }
-    const bool doA = csr_val != nullptr, doF = rhs != nullptr;
-    if (!doA && !doF) return 0;
+    const bool userA = csr_val != nullptr, doF = rhs != nullptr;
+    if (!userA && !doF) return 0;
+    // essential boundary conditions (afb_dirichlet_set): the rhs of free rows needs the matrix entries of the Dirichlet
+    // columns, so a rhs-only call assembles the matrix into scratch; an accumulating call assembles this call's contribution
+    // into scratch, constrains it, then adds it (the reference adds constrained element matrices, assembler.inl:397-425)
+    const bool dir = ctx->has_dirichlet;
+    const bool doA = userA || (dir && doF && nforms > 0);
+    const int user_accumulate = accumulate;
+    if (dir) accumulate = 0;
     if (doA && nforms == 0 && doF && nrhs == 0) { set_error(ctx, "System local evaluator is not specified"); return -6; }
     cudaSetDevice(ctx->device);
     cudaStream_t st = ctx->stream;
@@ -190,16 +210,29 @@ int afb_assemble(afb_ctx* ctx, int nforms, const afb_form* forms, int nrhs, cons
     // ---- output buffers (device images of csr_val / rhs when the caller's live on the host)
     double* dval = csr_val;
     double* drhs = rhs;
+    double *uval = nullptr, *urhs = nullptr;  // device images of the caller's arrays when this call's contribution goes to scratch
     if (mem_space == AFB_HOST) {
-        if (doA) {
+        if (userA) {
             AFB_CUDA(ctx, ctx->io_val.reserve(std::max<long long>(1, ctx->nnz) * sizeof(double)));
             dval = ctx->io_val.as<double>();
-            if (accumulate) AFB_CUDA(ctx, cudaMemcpyAsync(dval, csr_val, ctx->nnz * sizeof(double), cudaMemcpyHostToDevice, st));
+            if (user_accumulate) AFB_CUDA(ctx, cudaMemcpyAsync(dval, csr_val, ctx->nnz * sizeof(double), cudaMemcpyHostToDevice, st));
         }
         if (doF) {
             AFB_CUDA(ctx, ctx->io_rhs.reserve(std::max<long long>(1, nrows) * sizeof(double)));
             drhs = ctx->io_rhs.as<double>();
-            if (accumulate) AFB_CUDA(ctx, cudaMemcpyAsync(drhs, rhs, nrows * sizeof(double), cudaMemcpyHostToDevice, st));
+            if (user_accumulate) AFB_CUDA(ctx, cudaMemcpyAsync(drhs, rhs, nrows * sizeof(double), cudaMemcpyHostToDevice, st));
+        }
+    }
+    if (dir && (user_accumulate || !userA)) {
+        if (doA) {
+            AFB_CUDA(ctx, ctx->tmp2.reserve(std::max<long long>(1, ctx->nnz) * sizeof(double)));
+            uval = userA ? dval : nullptr;
+            dval = ctx->tmp2.as<double>();
+        }
+        if (doF && user_accumulate) {
+            AFB_CUDA(ctx, ctx->tmp3.reserve(std::max<long long>(1, nrows) * sizeof(double)));
+            urhs = drhs;
+            drhs = ctx->tmp3.as<double>();
         }
     }
     AFB_CUDA(ctx, ctx->flag.reserve(64));
@@ -295,8 +328,14 @@ int afb_assemble(afb_ctx* ctx, int nforms, const afb_form* forms, int nrhs, cons
     if (rc) return rc;
     cudaEventRecord(ctx->ev[3], st);
     }
+    if (dir) {
+        int rcd = dirichlet_apply(ctx, doA ? dval : nullptr, doF ? drhs : nullptr);
+        if (rcd) return rcd;
+        if (uval) { rcd = launch_axpy(ctx, ctx->nnz, dval, uval); if (rcd) return rcd; dval = uval; }
+        if (urhs) { rcd = launch_axpy(ctx, nrows, drhs, urhs); if (rcd) return rcd; drhs = urhs; }
+    }
     if (mem_space == AFB_HOST) {
-        if (doA && ctx->nnz) AFB_CUDA(ctx, cudaMemcpyAsync(csr_val, dval, ctx->nnz * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (userA && ctx->nnz) AFB_CUDA(ctx, cudaMemcpyAsync(csr_val, dval, ctx->nnz * sizeof(double), cudaMemcpyDeviceToHost, st));
         if (doF && nrows) AFB_CUDA(ctx, cudaMemcpyAsync(rhs, drhs, nrows * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
     int bad = 0;

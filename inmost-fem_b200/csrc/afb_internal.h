@@ -134,6 +134,11 @@ struct afb_ctx {
     afb::DevBuf rp_sptr;          // int64[nslices+1]: first visit-step of a slice
     afb::DevBuf rp_ell;           // uint32[steps*NW*32]: slot bytes + local element per (step, lane)
 
+    // essential boundary conditions (afb_dirichlet.cu): per global dof flag + value, list of affected rows
+    bool has_dirichlet = false, dir_rows_valid = false;
+    afb::DevBuf dir_flag, dir_val, dir_rows;
+    long long n_dir_rows = 0;
+
     // work buffers
     afb::DevBuf stageA, stageF, tables, coef, io_val, io_rhs, flag, tmp1, tmp2, tmp3, xy;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -175,6 +180,8 @@ int blocks_build(afb_ctx* ctx);
 int assemble_block_path(afb_ctx* ctx, int nfA, int nfF, const std::vector<afb_form>& fm, const std::vector<OpInfo>& oa,
                         const std::vector<OpInfo>& ob, const std::vector<const double*>& Dd, double* dval, double* drhs, int accumulate,
                         double drop_val, int* status_flag);
+// essential boundary conditions (afb_dirichlet.cu)
+int dirichlet_apply(afb_ctx* ctx, double* val, double* rhs);
 // thread-per-row gather + its plan (afb_rows.cu)
 int build_rows_plan(afb_ctx* ctx);
 bool rows_supports(const afb_ctx* ctx, int nga, int ngf);

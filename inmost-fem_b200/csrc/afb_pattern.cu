@@ -163,6 +163,7 @@ static int pattern_impl(afb_ctx* ctx, int64_t* nnz_out, const int64_t* user_rowp
     if (!ctx->has_dofmap) { set_error(ctx, "dof map was not specified (afb_dofmap_set / afb_dofmap_natural)"); return -6; }
     cudaSetDevice(ctx->device);
     blocks_clear(ctx);
+    ctx->dir_rows_valid = false;
     const long long ntet = ctx->ntet, nrows = ctx->row_end - ctx->row_begin;
     const int nrl = ctx->nrow_loc, ncl = ctx->ncol_loc;
     const long long nitem = ntet * nrl;

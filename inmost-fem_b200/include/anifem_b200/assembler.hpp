@@ -15,6 +15,7 @@
 //   Assemble(Matrix&, Vector&, AssmOpts)         Assemble(CsrMatrix&, std::vector<double>&, AssmOpts)  -> 0 / -1
 //   AssembleMatrix / AssembleRHS                 AssembleMatrix / AssembleRHS
 //   getBegInd() / getEndInd()                    getBegInd() / getEndInd()
+//   applyDir(A, F, k, bc) inside the lambda      SetDirichlet(flag per dof, value per dof)
 // The matrix always has the structural pattern of AssembleTemplate with rows sorted ascending, i.e. the reference's
 // opts.is_mtx_include_template = opts.use_ordered_insert = true mode (assembler.inl:428-438); Assemble ADDS into it.
 #pragma once
@@ -98,6 +99,17 @@ public:
         return *this;
     }
     void ClearForms() { m_forms.clear(); m_rhs.clear(); }
+
+    /// Essential boundary conditions: what the reference's local assemblers do with applyDir(A, F, k, bc) on every Dirichlet
+    /// dof of every cell (fem/operations/dc_on_dof.h:27-45, examples/tutorials/ex1.cpp:96-105).  is_dirichlet / value are
+    /// indexed by the global dof; call after PrepareProblem (the numbering must exist).  Empty vectors clear the setting.
+    Assembler& SetDirichlet(const std::vector<unsigned char>& is_dirichlet, const std::vector<double>& value) {
+        if (!m_prepared) throw std::runtime_error("SetDirichlet: call PrepareProblem first");
+        if (is_dirichlet.empty()) { ck(afb_dirichlet_set(m_ctx, nullptr, nullptr, AFB_HOST)); return *this; }
+        if (is_dirichlet.size() != value.size()) throw std::runtime_error("SetDirichlet: flag and value arrays differ in size");
+        ck(afb_dirichlet_set(m_ctx, is_dirichlet.data(), value.data(), AFB_HOST));
+        return *this;
+    }
 
     /// assembler.inl:193-275
     void PrepareProblem() {

@@ -252,8 +252,24 @@ class Problem:
         return A, F
 
 
-def assemble(problem, coords, tets, dofmap, rank=None, impl="oracle", drop_val=1e-100, chunk=200000):
-    """Full reference-style assembly on `rank`'s row interval: returns rowptr, colind, val, rhs"""
+def apply_dir(A, F, colcode, flag, value):
+    """applyDir(A, F, k, bc) of fem/operations/dc_on_dof.h:27-45 for every Dirichlet local dof k of every element, as the
+    reference's local assemblers do (examples/tutorials/ex1.cpp:96-105): F(i) -= A(i,k) bc; F(k) = bc; row and column k
+    of A zeroed; A(k,k) = 1.  A is (f, ncol, nrow) with A[e, k, i] = A_e(i, k).  The result does not depend on the order of k."""
+    g = np.abs(colcode) - 1
+    d = flag[g].astype(bool)
+    bcv = np.where(d, value[g], 0.0)
+    F -= np.einsum("eki,ek->ei", A, bcv)
+    F[d] = bcv[d]
+    A[d, :] = 0.0                                    # column k
+    A[np.broadcast_to(d[:, None, :], A.shape)] = 0.0  # row k
+    e, k = np.nonzero(d)
+    A[e, k, k] = 1.0
+
+
+def assemble(problem, coords, tets, dofmap, rank=None, impl="oracle", drop_val=1e-100, chunk=200000, dirichlet=None):
+    """Full reference-style assembly on `rank`'s row interval: returns rowptr, colind, val, rhs.
+    dirichlet = (flag[ndof], value[ndof]): essential BCs applied to every element matrix like the reference's examples."""
     r = 0 if rank is None else rank
     row_begin, row_end = (0, dofmap.nrows) if rank is None else (int(dofmap.beg_ind[r]), int(dofmap.end_ind[r]))
     rowcode, colcode = dofmap.codes(rank)
@@ -267,6 +283,8 @@ def assemble(problem, coords, tets, dofmap, rank=None, impl="oracle", drop_val=1
         idx = sel[s:s + chunk]
         XY = coords[tets[idx]].transpose(1, 0, 2)  # (4, f, 3)
         A, F = problem.element_matrices(XY, idx=idx, impl=impl)
+        if dirichlet is not None:
+            apply_dir(A, F, colcode[s:s + chunk], np.asarray(dirichlet[0]), np.asarray(dirichlet[1], dtype=float))
         st = O.scatter_csr(rowcode[s:s + chunk], colcode[s:s + chunk], A, F, row_begin, rowptr, colind, val, rhs, drop_val)
         status = min(status, st)
     return rowptr, colind, val, rhs, status

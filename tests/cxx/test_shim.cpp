@@ -144,6 +144,19 @@ int main() {
         }
         std::vector<double> v1 = A.val;
         EXPECT(discr.Assemble(A, b) == 0);   // Assemble accumulates (assembler.inl:305-306)
+        {   // Dirichlet dof 0 with value 2 (applyDir, dc_on_dof.h:27-45): row 0 = deg * e_0, rhs_0 = deg * 2, column 0 empty elsewhere
+            std::vector<unsigned char> flag(125, 0); std::vector<double> bc(125, 0.0);
+            flag[0] = 1; bc[0] = 2.0;
+            discr.SetDirichlet(flag, bc);
+            CsrMatrix Ad; std::vector<double> bd;
+            EXPECT(discr.Assemble(Ad, bd) == 0);
+            double diag = 0, off = 0, col0 = 0;
+            for (int64_t k = Ad.rowptr[0]; k < Ad.rowptr[1]; ++k) (Ad.colind[k] == 0 ? diag : off) += std::fabs(Ad.val[k]);
+            for (int64_t r = 1; r + 1 < (int64_t)Ad.rowptr.size(); ++r)
+                for (int64_t k = Ad.rowptr[r]; k < Ad.rowptr[r + 1]; ++k) if (Ad.colind[k] == 0) col0 += std::fabs(Ad.val[k]);
+            EXPECT(diag >= 1.0 && off == 0.0 && col0 == 0.0 && std::fabs(bd[0] - 2.0 * diag) < 1e-13);
+            discr.SetDirichlet({}, {});
+        }
         double d = 0;
         for (std::size_t k = 0; k < v1.size(); ++k) d = std::fmax(d, std::fabs(A.val[k] - 2 * v1[k]));
         EXPECT(d == 0.0);

@@ -191,6 +191,68 @@ def test_tiled_element_kernel_all_tensor_kinds(pkg, ctx, asm_oracle, ttype, layo
     assert path["element_kernel"] == "k_element_generic"  # generic staged path (k_element_sq + k_element_generic for the rhs)
 
 
+@pytest.mark.parametrize("case", ["p2_fused", "p2_generic", "p1", "th_blocks"])
+def test_dirichlet_conditions(pkg, ctx, asm_oracle, case):
+    """afb_dirichlet_set = applyDir on every Dirichlet dof of every cell (dc_on_dof.h:27-45), all product paths; accumulate
+    and rhs-only semantics with constraints"""
+    M = asm_oracle
+    variables = {"p1": [(gc.P1, 1)], "th_blocks": [(gc.P2, 3), (gc.P1, 1)]}.get(case, [(gc.P2, 1)])
+    co, te, dm = _mesh(pkg, ctx, M, (3, 3, 2) if case == "th_blocks" else (4, 3, 3), variables)
+    if case == "th_blocks":
+        _, forms, rhsf, prob = problems.c5_stokes(pkg, M, co, te)
+    elif case == "p1":
+        _, forms, rhsf, prob = problems.c1_p1_diffusion(pkg, M, co, te)
+    else:
+        _, forms, rhsf, prob = problems.c2_p2_aniso(pkg, M, co, te)
+    rng = np.random.default_rng(9)
+    ndof = dm.nrows
+    flag = (rng.random(ndof) < 0.3).astype(np.uint8)
+    if case == "th_blocks":
+        flag[-(co.shape[0]):] = 0   # pressure dofs stay free (velocity Dirichlet only, stokes.cpp)
+    value = rng.standard_normal(ndof)
+    env = {"AFB_DISABLE_TENSOR_PATH": "1"} if case == "p2_generic" else {}
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        nnz = ctx.pattern_build()
+        rowptr, colind = ctx.pattern_get()
+        ctx.dirichlet_set(flag, value)
+        val, rhs = np.full(nnz, np.nan), np.full(ndof, np.nan)
+        assert ctx.assemble(forms, rhsf, val, rhs) == 0
+        rp, ci, v, r, st = M.assemble(prob, co, te, dm, dirichlet=(flag, value))
+        assert np.array_equal(rowptr, rp) and np.array_equal(colind, ci)
+        rowmax = np.maximum.reduceat(np.abs(v), rp[:-1])
+        rowmax[rowmax == 0] = 1.0
+        # the rhs of a free row collects A_rc bc_c: scale with |A| |bc|
+        rscale = max(np.abs(r).max(), 1.0)
+        assert (np.abs(val - v) / np.repeat(rowmax, np.diff(rp))).max() <= RTOL
+        assert np.abs(rhs - r).max() <= RTOL * rscale * 10
+        # Dirichlet rows: deg on the diagonal, deg * bc in the rhs
+        rows = np.repeat(np.arange(ndof), np.diff(rp))
+        drow = flag[rows].astype(bool)
+        assert (val[drow & (rows != ci)] == 0).all() and (val[drow & (rows == ci)] >= 1).all()
+        # accumulate adds the constrained contribution once more; rhs-only needs no matrix output
+        v2, r2 = val.copy(), rhs.copy()
+        assert ctx.assemble(forms, rhsf, v2, r2, accumulate=True) == 0
+        assert np.abs(v2 - 2 * val).max() <= 1e-14 * np.abs(val).max() and np.abs(r2 - 2 * rhs).max() <= 1e-14 * rscale
+        r3 = np.full(ndof, np.nan)
+        assert ctx.assemble(forms, rhsf, None, r3) == 0
+        assert np.abs(r3 - rhs).max() <= 1e-14 * rscale
+        # cleared again: unconstrained system
+        ctx.dirichlet_set(None, None)
+        v4 = np.zeros(nnz)
+        assert ctx.assemble(forms, [], v4, None) == 0
+        rp, ci, v0, r0, st = M.assemble(prob, co, te, dm)
+        assert (np.abs(v4 - v0) / np.repeat(np.maximum(np.maximum.reduceat(np.abs(v0), rp[:-1]), 1e-300), np.diff(rp))).max() <= RTOL
+    finally:
+        ctx.dirichlet_set(None, None)
+        for k, vv in old.items():
+            if vv is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = vv
+
+
 def test_properties_at_scale(pkg, asm_oracle):
     """C2 at 48^3 x 6 = 663,552 tets (too large for the numpy oracle): properties that do not need one"""
     c = pkg.Context(0)
