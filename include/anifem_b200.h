@@ -83,6 +83,17 @@ int afb_tet_quadrature(int order, double* p, double* w, int capacity);
 int afb_quad_points(afb_ctx* ctx, int order, int64_t f, const double* XY0, const double* XY1,
                     const double* XY2, const double* XY3, double* XYG, int mem_space);
 
+/* FE-function evaluation, fem3DapplyL (fem/operations/eval.h:13-120, core.inl:369-404): Op(u_h) at q points given by barycentric
+ * coordinates XYL[4q] (the same on every tet): opU[k + dim*(n + q*r)] = sum_i Op(phi_i)(x_n)[k] * dofs[i + nfa*r]; dofs is nfa x f,
+ * opU is (dim*q) x f, both col-major. */
+int afb_fem3dapply_batched(afb_ctx* ctx, int op, int fem, int vec, int q, const double* XYL, int64_t f, const double* XY0,
+                           const double* XY1, const double* XY2, const double* XY3, const double* dofs, double* opU, int mem_space);
+/* The same on the context's mesh at the points of the rule `order`, the dofs of the variable occupying the local slots
+ * [col_off, col_off + Nfa) gathered from the global vector u[ncols_global] through the dof map (what InitValueSetFromTag +
+ * fem3DapplyL do inside a nonlinear local assembler, assembler.h:13-48).  out[dim*(n + q*e)] has the layout of a PER_POINT
+ * coefficient, so it can be passed to afb_assemble as form.D.  Returns q (>= 0) or an error code. */
+int afb_eval_quadrature(afb_ctx* ctx, int op, int fem, int vec, int col_off, int order, const double* u, double* out, int mem_space);
+
 /* ---- mesh: the per-cell inputs of AssemblerT::Assemble (assembler.inl:353-364) ---------------- */
 /* SoA coordinates + connectivity.  Copies into the context. */
 int afb_mesh_set(afb_ctx* ctx, int64_t nnode, const double* x, const double* y, const double* z,

@@ -41,7 +41,7 @@ EXPORTS = ["afb_ctx_create", "afb_ctx_destroy", "afb_last_error", "afb_sync", "a
            "afb_mesh_set", "afb_mesh_cube", "afb_mesh_orient", "afb_mesh_get",
            "afb_dofmap_set", "afb_dofmap_set_diag", "afb_dofmap_natural", "afb_dofmap_get",
            "afb_pattern_build", "afb_pattern_get", "afb_pattern_set", "afb_assemble", "afb_halo_add", "afb_last_times",
-           "afb_dirichlet_set"]
+           "afb_dirichlet_set", "afb_fem3dapply_batched", "afb_eval_quadrature"]
 
 
 def build(verbose=False):
@@ -90,6 +90,8 @@ def lib():
         L.afb_assemble.argtypes = [vp, ci, ctypes.POINTER(AfbForm), ci, ctypes.POINTER(AfbForm), vp, vp, ci, cd, ci]
         L.afb_last_times.argtypes = [vp, _dp]
         L.afb_dirichlet_set.argtypes = [vp, vp, vp, ci]
+        L.afb_fem3dapply_batched.argtypes = [vp, ci, ci, ci, ci, vp, c64, vp, vp, vp, vp, vp, vp, ci]
+        L.afb_eval_quadrature.argtypes = [vp, ci, ci, ci, ci, ci, vp, vp, ci]
         _lib = L
     return _lib
 
@@ -191,6 +193,36 @@ class Context:
         xs = [np.ascontiguousarray(XY[k]) for k in range(4)]
         self._ck(lib().afb_quad_points(self._h, order, f, xs[0].ctypes.data, xs[1].ctypes.data, xs[2].ctypes.data,
                                        xs[3].ctypes.data, out.ctypes.data, HOST))
+        return out
+
+    def fem3dapply(self, op, fem, vec, XYL, XY, dofs):
+        """Batched Ani::fem3DapplyL: XYL (q,4) barycentric points, XY (4,f,3), dofs (f,nfa) -> (f,q,dim)"""
+        XYL = np.ascontiguousarray(XYL, dtype=np.float64)
+        XY = np.ascontiguousarray(XY, dtype=np.float64)
+        dofs = np.ascontiguousarray(dofs, dtype=np.float64)
+        f, q = XY.shape[1], XYL.shape[0]
+        _, dim = op_dims(op, fem, vec)
+        out = np.zeros((f, q, dim))
+        xs = [np.ascontiguousarray(XY[k]) for k in range(4)]
+        self._ck(lib().afb_fem3dapply_batched(self._h, op, fem, vec, q, XYL.ctypes.data, f, xs[0].ctypes.data, xs[1].ctypes.data,
+                                              xs[2].ctypes.data, xs[3].ctypes.data, dofs.ctypes.data, out.ctypes.data, HOST))
+        return out
+
+    def eval_quadrature(self, op, fem, vec, col_off, order, u, out=None):
+        """Op(u_h) at the quadrature points of `order` on the context's mesh: (ntet, q, dim); u numpy or torch cuda"""
+        q = tet_quadrature(order)[1].size
+        _, dim = op_dims(op, fem, vec)
+        _, nt = self.mesh_sizes()
+        pu, su = _ptr(u)
+        if out is None:
+            if su == DEVICE:
+                import torch
+                out = torch.empty((nt, q, dim), dtype=torch.float64, device=u.device)
+            else:
+                out = np.zeros((nt, q, dim))
+        po, so = _ptr(out)
+        assert su == so
+        self._ck(lib().afb_eval_quadrature(self._h, op, fem, vec, col_off, order, pu, po, su))
         return out
 
     # ---- mesh ----------------------------------------------------------------------------------
