@@ -105,7 +105,8 @@ def cpu_reference_sample(n_sample, steps=1, warmup=0):
     info = {"kind": kind, "cores": cores, "ntet_sample": int(te.shape[0]), "ms_per_step": dt * 1e3,
             "sample": "cube %d^3 x6 = %d tets of the same P2 anisotropic problem (element matrices by the %s, restated "
                       "Assembler scatter into a pre-built CSR, %d std::threads over cell ranges); the true INMOST scatter is slower"
-                      % (n_sample, te.shape[0], "unmodified reference fem3Dtet" if kind == "reference" else "C port of fem3Dtet", cores)}
+                      % (n_sample, te.shape[0], "unmodified reference fem3Dtet" if kind == "reference" else "C port of fem3Dtet", cores)
+                      + "; mean of %d timed passes" % steps}
     return te.shape[0] / dt, info
 
 
@@ -140,8 +141,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--n", type=int, default=119, help="hexes per axis per GPU block (119 -> 10,110,954 tets)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--ref-n", type=int, default=32, help="hexes per axis of the CPU sample")
+    ap.add_argument("--ref-n", type=int, default=40, help="hexes per axis of the CPU sample (40 -> 384,000 tets)")
+    ap.add_argument("--ref-reps", type=int, default=12, help="timed passes of the CPU sample in the cpu_baseline leg (about 10-20 core-seconds)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the quick C1/C3/C4/C5 measurements")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -254,8 +257,20 @@ def main():
             "e2e": {"value": ntet / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "steps": e2e_steps,
                     "h2d_bytes_per_step": int(K_host.numel() * 8), "d2h_bytes_per_step": int((nnz + nrows) * 8)},
             "gpu_launches": int(launches), "roofline": roofline, "clocks": sampler.summary()}
+    if not args.no_secondary:
+        # the other BASELINE.json configs at sizes that keep the default run short (parity-test cases, not bench lines): evidence
+        # of which product path serves them and at what fraction of their own HBM roofline
+        import bench_configs
+        sec = {}
+        for name, nn in (("c1", 96), ("c3", 40), ("c4", 48), ("c5", 48)):
+            try:
+                r = bench_configs.run_config(pkg, name, nn, 3, stream, peak_gbs)
+                sec[name] = {k: r[k] for k in ("ntet", "nnz", "ms_per_assemble", "tets_per_s", "dof_per_s", "kernels", "path", "hbm_frac")}
+            except Exception as exc:  # noqa: BLE001 -- a secondary measurement must not void the headline line
+                sec[name] = {"error": str(exc)[:200]}
+        line["secondary_configs"] = sec
     if not args.no_cpu_baseline:
-        v, info = cpu_reference_sample(args.ref_n)
+        v, info = cpu_reference_sample(args.ref_n, steps=args.ref_reps, warmup=1)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]}
     print(json.dumps(line))
     ctx.close()

@@ -21,6 +21,69 @@ import golden_cases as gc  # noqa: E402
 import problems  # noqa: E402
 
 
+def run_config(pkg, name, n, steps, stream, peak):
+    """assemble config `name` on an n^3 x 6 cube on the current GPU; returns the measurement as a dict"""
+    import torch
+    variables = {"c1": [(gc.P1, 1)], "c2": [(gc.P2, 1)], "c3": [(gc.P3, 1)], "c4": [(gc.P2, 3)], "c5": [(gc.P2, 3), (gc.P1, 1)]}[name]
+    ctx = pkg.Context(torch.cuda.current_device(), stream.cuda_stream)
+    ctx.mesh_cube(n, n, n)
+    ctx.dofmap_natural(variables)
+    t0 = time.perf_counter()
+    nnz = ctx.pattern_build()
+    ctx.sync()
+    t_pat = (time.perf_counter() - t0) * 1e3
+    coords, tets = ctx.mesh_get()
+    nnode, ntet = coords.shape[0], tets.shape[0]
+    _, _, _, nrows, _ = ctx.dofmap_info()
+    if name == "c1":
+        _, forms, rhsf, _ = problems.c1_p1_diffusion(pkg, None, coords, tets)
+        coef_bytes = 0
+    elif name == "c2":
+        _, forms, rhsf, _ = problems.c2_p2_aniso(pkg, None, coords, tets)
+        coef_bytes = 72
+    elif name == "c3":
+        XY = coords[tets].transpose(1, 0, 2)
+        xyg4, xyg6 = ctx.quad_points(4, XY), ctx.quad_points(6, XY)
+        _, forms, rhsf, _ = problems.c3_p3_react_diff(pkg, None, coords, tets, xyg4, xyg6)
+        coef_bytes = 8 * (14 + 24)
+    elif name == "c4":
+        _, forms, rhsf, _ = problems.c4_p2_elasticity(pkg, None, coords, tets)
+        coef_bytes = 0
+    else:
+        _, forms, rhsf, _ = problems.c5_stokes(pkg, None, coords, tets)
+        coef_bytes = 0
+    # coefficients to the device once (device-resident arm)
+    dev = []
+    for f in forms + rhsf:
+        if f._keep is not None:
+            t = torch.from_numpy(np.ascontiguousarray(f._keep)).cuda()
+            dev.append(t)
+            f.D, f.coef_space, f._keep = t.data_ptr(), pkg.DEVICE, t
+    val = torch.zeros(nnz, dtype=torch.float64, device="cuda")
+    rhs = torch.zeros(nrows, dtype=torch.float64, device="cuda")
+    for _ in range(2):
+        assert ctx.assemble(forms, rhsf, val, rhs) == 0
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(steps):
+        assert ctx.assemble(forms, rhsf, val, rhs) == 0
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / steps
+    t = ctx.last_times()
+    nloc = sum(gc.NF[f] * v for f, v in variables)
+    alg = 4 * nloc * ntet + 24 * nnode + coef_bytes * ntet + 8 * nnz + 8 * nrows
+    out = {"config": name, "hexes_per_axis": n, "ntet": ntet, "nrows": nrows, "nnz": nnz, "ms_per_assemble": ms,
+           "tets_per_s": ntet / (ms * 1e-3), "dof_per_s": nrows / (ms * 1e-3), "element_ms": t["element_ms"],
+           "gather_ms": t["gather_ms"], "kernels": [t["element_kernel"], t["gather_kernel"]],
+           "path": "fused tensor-representation" if t["fused_path"] else "generic staged",
+           "algorithmic_bytes_per_tet": alg / ntet, "hbm_frac": alg / (ms * 1e-3) / 1e9 / peak, "pattern_build_ms": t_pat}
+    ctx.close()
+    del val, rhs, dev
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=48)
@@ -37,65 +100,8 @@ def main():
     peak = peaks.get("hbm_gbs", 6650.0)
     stream = torch.cuda.current_stream()
     for name in args.configs.split(","):
-        n = args.n
-        variables = {"c1": [(gc.P1, 1)], "c2": [(gc.P2, 1)], "c3": [(gc.P3, 1)], "c4": [(gc.P2, 3)], "c5": [(gc.P2, 3), (gc.P1, 1)]}[name]
-        if name in ("c3", "c4", "c5"):
-            n = max(8, args.n // 2)
-        ctx = pkg.Context(0, stream.cuda_stream)
-        ctx.mesh_cube(n, n, n)
-        ctx.dofmap_natural(variables)
-        t0 = time.perf_counter()
-        nnz = ctx.pattern_build()
-        ctx.sync()
-        t_pat = (time.perf_counter() - t0) * 1e3
-        coords, tets = ctx.mesh_get()
-        nnode, ntet = coords.shape[0], tets.shape[0]
-        _, _, _, nrows, _ = ctx.dofmap_info()
-        if name == "c1":
-            _, forms, rhsf, _ = problems.c1_p1_diffusion(pkg, None, coords, tets)
-            coef_bytes = 0
-        elif name == "c2":
-            _, forms, rhsf, _ = problems.c2_p2_aniso(pkg, None, coords, tets)
-            coef_bytes = 72
-        elif name == "c3":
-            XY = coords[tets].transpose(1, 0, 2)
-            xyg4, xyg6 = ctx.quad_points(4, XY), ctx.quad_points(6, XY)
-            _, forms, rhsf, _ = problems.c3_p3_react_diff(pkg, None, coords, tets, xyg4, xyg6)
-            coef_bytes = 8 * (14 + 24)
-        elif name == "c4":
-            _, forms, rhsf, _ = problems.c4_p2_elasticity(pkg, None, coords, tets)
-            coef_bytes = 0
-        else:
-            _, forms, rhsf, _ = problems.c5_stokes(pkg, None, coords, tets)
-            coef_bytes = 0
-        # coefficients to the device once (device-resident arm)
-        dev = []
-        for f in forms + rhsf:
-            if f._keep is not None:
-                t = torch.from_numpy(np.ascontiguousarray(f._keep)).cuda()
-                dev.append(t)
-                f.D, f.coef_space, f._keep = t.data_ptr(), pkg.DEVICE, t
-        val = torch.zeros(nnz, dtype=torch.float64, device="cuda")
-        rhs = torch.zeros(nrows, dtype=torch.float64, device="cuda")
-        for _ in range(2):
-            assert ctx.assemble(forms, rhsf, val, rhs) == 0
-        torch.cuda.synchronize()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record(stream)
-        for _ in range(args.steps):
-            assert ctx.assemble(forms, rhsf, val, rhs) == 0
-        ev1.record(stream)
-        torch.cuda.synchronize()
-        ms = ev0.elapsed_time(ev1) / args.steps
-        t = ctx.last_times()
-        nloc = sum(gc.NF[f] * v for f, v in variables)
-        alg = 4 * nloc * ntet + 24 * nnode + coef_bytes * ntet + 8 * nnz + 8 * nrows
-        print(json.dumps({"config": name, "hexes_per_axis": n, "ntet": ntet, "nrows": nrows, "nnz": nnz, "ms_per_assemble": ms,
-                          "tets_per_s": ntet / (ms * 1e-3), "dof_per_s": nrows / (ms * 1e-3), "element_ms": t["element_ms"],
-                          "gather_ms": t["gather_ms"], "path": "fused tensor-representation" if t["fused_path"] else "generic staged",
-                          "algorithmic_bytes_per_tet": alg / ntet, "hbm_frac": alg / (ms * 1e-3) / 1e9 / peak, "pattern_build_ms": t_pat}))
-        ctx.close()
-        del val, rhs, dev
+        n = args.n if name in ("c1", "c2") else max(8, args.n // 2)
+        print(json.dumps(run_config(pkg, name, n, args.steps, stream, peak)))
 
 
 if __name__ == "__main__":
