@@ -78,14 +78,21 @@ __global__ void __launch_bounds__(256) k_geom(long long ntet, GeomParams gp, con
                                               const double* __restrict__ z, const int32_t* __restrict__ v0, const int32_t* __restrict__ v1,
                                               const int32_t* __restrict__ v2, const int32_t* __restrict__ v3, double* __restrict__ gbuf,
                                               const unsigned* __restrict__ old2new /* NULL or the Morton id of every element */) {
-    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (e >= ntet) return;
+    // records are built in shared memory and leave the CTA as 16-byte pieces, `parts` consecutive lanes per record: full
+    // sectors per store instruction even though the records scatter (Morton order)
+    extern __shared__ double srec[];                       // [256][ngpad]
+    __shared__ long long sdst[256];
+    const long long e0 = blockIdx.x * (long long)blockDim.x;
+    const long long e = e0 + threadIdx.x;
+    const bool valid = e < ntet;
+    double* g = srec + (size_t)threadIdx.x * gp.ngpad;
+    if (valid) {
+    sdst[threadIdx.x] = old2new ? (long long)old2new[e] : e;
     const int nn[4] = {__ldg(v0 + e), __ldg(v1 + e), __ldg(v2 + e), __ldg(v3 + e)};
     double P[4][3], PSI[9];
 #pragma unroll
     for (int k = 0; k < 4; ++k) { P[k][0] = __ldg(x + nn[k]); P[k][1] = __ldg(y + nn[k]); P[k][2] = __ldg(z + nn[k]); }
     const double vol = fabs(jac_inv(P, PSI)) * (1.0 / 6.0);
-    double* g = gbuf + (old2new ? (long long)old2new[e] : e) * gp.ngpad;
     if (gp.ngpad > gp.ngtot) g[gp.ngtot] = 0.0;
     for (int f = 0; f < gp.nforms; ++f) {
         const TFormDev& F = gp.f[f];
@@ -134,6 +141,15 @@ __global__ void __launch_bounds__(256) k_geom(long long ntet, GeomParams gp, con
 #pragma unroll
             for (int a = 0; a < 3; ++a) o[a] = s * (PSI[a] * k0 + PSI[a + 3] * k1 + PSI[a + 6] * k2);
         }
+    }
+    }  // valid
+    __syncthreads();
+    const int parts = gp.ngpad >> 1;
+    const int nrec = (int)min((long long)blockDim.x, ntet - e0);
+    const double2* src = reinterpret_cast<const double2*>(srec);
+    for (int q = threadIdx.x; q < nrec * parts; q += blockDim.x) {
+        const int rec = q / parts, part = q - rec * parts;
+        reinterpret_cast<double2*>(gbuf + sdst[rec] * gp.ngpad)[part] = src[q];
     }
 }
 
@@ -489,7 +505,7 @@ int fused_group(afb_ctx* ctx, afb_ctx* plan, const std::vector<SForm>& mat, cons
 
     if (record_events) cudaEventRecord(ctx->ev[1], st);
     const unsigned gridg = (unsigned)((ctx->ntet + 255) / 256);
-    k_geom<<<gridg, 256, 0, st>>>(ctx->ntet, gp, ctx->x.as<double>(), ctx->y.as<double>(), ctx->z.as<double>(), ctx->v[0].as<int32_t>(),
+    k_geom<<<gridg, 256, (size_t)256 * ngpad * sizeof(double), st>>>(ctx->ntet, gp, ctx->x.as<double>(), ctx->y.as<double>(), ctx->z.as<double>(), ctx->v[0].as<int32_t>(),
                                  ctx->v[1].as<int32_t>(), ctx->v[2].as<int32_t>(), ctx->v[3].as<int32_t>(), gbuf,
                                  use_rows ? plan->rp_old2new.as<unsigned>() : nullptr);
     ctx->launches++;
