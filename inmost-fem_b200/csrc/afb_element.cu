@@ -387,9 +387,10 @@ int launch_form(afb_ctx* ctx, const afb_form& form, const OpInfo& A, const OpInf
 }
 
 // Launches k_element_sq for the forms sel[] (all square on one scalar space, same operator on both sides, full local
-// matrix): out[e*s_e + i*nf + j] = sum of the selected forms (store).  Returns 0 ok, < 0 error.
+// matrix) on the elements [e_lo, e_lo + ntet): out[(e - e_lo)*s_e + i*nf + j] = sum of the selected forms (store); Dd already points
+// at the data of element e_lo.  Returns 0 ok, < 0 error.
 int launch_forms_sq(afb_ctx* ctx, const std::vector<afb_form>& fm, const std::vector<OpInfo>& oa, const std::vector<const double*>& Dd,
-                    const std::vector<int>& sel, int64_t ntet, double* out, long long s_e) {
+                    const std::vector<int>& sel, int64_t e_lo, int64_t ntet, double* out, long long s_e) {
     if (sel.empty() || (int)sel.size() > SQ_MAXF) return -7;
     SqParams P;
     P.nforms = (int)sel.size();
@@ -409,7 +410,7 @@ int launch_forms_sq(afb_ctx* ctx, const std::vector<afb_form>& fm, const std::ve
     }
     GeomSrc g;
     g.x = ctx->x.as<double>(); g.y = ctx->y.as<double>(); g.z = ctx->z.as<double>();
-    g.v0 = ctx->v[0].as<int32_t>(); g.v1 = ctx->v[1].as<int32_t>(); g.v2 = ctx->v[2].as<int32_t>(); g.v3 = ctx->v[3].as<int32_t>();
+    g.v0 = ctx->v[0].as<int32_t>() + e_lo; g.v1 = ctx->v[1].as<int32_t>() + e_lo; g.v2 = ctx->v[2].as<int32_t>() + e_lo; g.v3 = ctx->v[3].as<int32_t>() + e_lo;
     for (int k = 0; k < 4; ++k) g.XY[k] = nullptr;
     const unsigned blocks = (unsigned)((ntet + 3) / 4);
     if (nf == 4) k_element_sq<4><<<blocks, 128, 0, ctx->stream>>>(P, ntet, g, out, s_e);

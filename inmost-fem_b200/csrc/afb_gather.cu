@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(256) k_gather(long long nrows, long long ntet,
                                                 const int32_t* __restrict__ e2r, const int32_t* __restrict__ e2c,
                                                 const double* __restrict__ stageA, const double* __restrict__ stageF,
                                                 double* __restrict__ val, double* __restrict__ rhs, int accumulate, double drop_val,
-                                                int* __restrict__ status) {
+                                                int* __restrict__ status, long long e_lo, long long e_hi) {
     extern __shared__ double sacc[];
     const int gl = threadIdx.x % G;                    // lane inside the group
     const int gib = threadIdx.x / G;                   // group inside the block
@@ -44,19 +44,20 @@ __global__ void __launch_bounds__(256) k_gather(long long nrows, long long ntet,
         for (long long a = a0; a < a1; ++a) {
             const unsigned t = __ldg(radj + a);
             double sr = 1.0;
-            long long e = 0;
+            const long long e = t / nrow_loc;
+            if (e < e_lo || e >= e_hi) continue;   // the staged element matrices cover the elements [e_lo, e_hi) (group-uniform branch)
+            const long long tl = (long long)t - e_lo * nrow_loc;  // index inside the staged chunk
             if (SIGNS) {
-                e = t / nrow_loc;
                 const int i = (int)(t - e * nrow_loc);
                 sr = e2r[(long long)i * ntet + e] < 0 ? -1.0 : 1.0;
             }
             if (stageF && gl == 0) {
-                const double fv = __ldg(stageF + t);
+                const double fv = __ldg(stageF + tl);
                 bad |= !isfinite(fv);
                 fsum += sr * fv;
             }
             if (stageA) {
-                const long long base = (long long)t * ncol_loc;
+                const long long base = tl * ncol_loc;
                 for (int j = gl; j < ncol_loc; j += G) {
                     double v = __ldg(stageA + base + j);
                     const int p = pos[a * ncol_loc + j];
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(256) k_gather(long long nrows, long long ntet,
 }
 
 template <int G, bool SIGNS, typename PosT>
-cudaError_t launch_g2(afb_ctx* c, const double* sA, const double* sF, double* val, double* rhs, int accumulate, double drop, int* status) {
+cudaError_t launch_g2(afb_ctx* c, const double* sA, const double* sF, double* val, double* rhs, int accumulate, double drop, int* status, long long e_lo, long long e_hi) {
     const long long nrows = c->row_end - c->row_begin;
     const int gpb = 256 / G;
     const size_t smem = (size_t)gpb * std::max(1, c->max_row_len) * sizeof(double);
@@ -89,18 +90,18 @@ cudaError_t launch_g2(afb_ctx* c, const double* sA, const double* sF, double* va
     if (e != cudaSuccess) return e;
     k_gather<G, SIGNS, PosT><<<grid, 256, smem, c->stream>>>(nrows, c->ntet, c->nrow_loc, c->ncol_loc, std::max(1, c->max_row_len), c->rowptr.as<long long>(),
                                                              c->radj_ptr.as<long long>(), c->radj.as<unsigned>(), c->pos.as<PosT>(), c->e2r.as<int32_t>(),
-                                                             c->e2c.as<int32_t>(), sA, sF, val, rhs, accumulate, drop, status);
+                                                             c->e2c.as<int32_t>(), sA, sF, val, rhs, accumulate, drop, status, e_lo, e_hi);
     return cudaGetLastError();
 }
 
 template <int G>
-cudaError_t launch_g(afb_ctx* c, const double* sA, const double* sF, double* val, double* rhs, int accumulate, double drop, int* status) {
+cudaError_t launch_g(afb_ctx* c, const double* sA, const double* sF, double* val, double* rhs, int accumulate, double drop, int* status, long long e_lo, long long e_hi) {
     if (c->has_signs) {
-        if (c->pos_bytes == 1) return launch_g2<G, true, unsigned char>(c, sA, sF, val, rhs, accumulate, drop, status);
-        return launch_g2<G, true, unsigned short>(c, sA, sF, val, rhs, accumulate, drop, status);
+        if (c->pos_bytes == 1) return launch_g2<G, true, unsigned char>(c, sA, sF, val, rhs, accumulate, drop, status, e_lo, e_hi);
+        return launch_g2<G, true, unsigned short>(c, sA, sF, val, rhs, accumulate, drop, status, e_lo, e_hi);
     }
-    if (c->pos_bytes == 1) return launch_g2<G, false, unsigned char>(c, sA, sF, val, rhs, accumulate, drop, status);
-    return launch_g2<G, false, unsigned short>(c, sA, sF, val, rhs, accumulate, drop, status);
+    if (c->pos_bytes == 1) return launch_g2<G, false, unsigned char>(c, sA, sF, val, rhs, accumulate, drop, status, e_lo, e_hi);
+    return launch_g2<G, false, unsigned short>(c, sA, sF, val, rhs, accumulate, drop, status, e_lo, e_hi);
 }
 
 }  // namespace
@@ -125,15 +126,15 @@ int assemble_tensor_path(afb_ctx* ctx, int nfA, int nfF, const std::vector<afb_f
                          int accumulate, double drop_val, int* status_flag);
 
 int launch_gather(afb_ctx* ctx, const double* stageA, const double* stageF, double* val, double* rhs, int accumulate, double drop_val,
-                  int* status_flag) {
+                  int* status_flag, long long e_lo, long long e_hi) {
     const size_t need = (size_t)(256 / 32) * std::max(1, ctx->max_row_len) * sizeof(double);
     if (need > 200 * 1024) { set_error(ctx, "afb_assemble: matrix rows too long for the shared-memory row image"); return -3; }
     cudaError_t e;
     const int nc = ctx->ncol_loc;
-    if (nc <= 4) e = launch_g<4>(ctx, stageA, stageF, val, rhs, accumulate, drop_val, status_flag);
-    else if (nc <= 8) e = launch_g<8>(ctx, stageA, stageF, val, rhs, accumulate, drop_val, status_flag);
-    else if (nc <= 16) e = launch_g<16>(ctx, stageA, stageF, val, rhs, accumulate, drop_val, status_flag);
-    else e = launch_g<32>(ctx, stageA, stageF, val, rhs, accumulate, drop_val, status_flag);
+    if (nc <= 4) e = launch_g<4>(ctx, stageA, stageF, val, rhs, accumulate, drop_val, status_flag, e_lo, e_hi);
+    else if (nc <= 8) e = launch_g<8>(ctx, stageA, stageF, val, rhs, accumulate, drop_val, status_flag, e_lo, e_hi);
+    else if (nc <= 16) e = launch_g<16>(ctx, stageA, stageF, val, rhs, accumulate, drop_val, status_flag, e_lo, e_hi);
+    else e = launch_g<32>(ctx, stageA, stageF, val, rhs, accumulate, drop_val, status_flag, e_lo, e_hi);
     ctx->launches++;
     if (e != cudaSuccess) return cuda_fail(ctx, e, "k_gather launch");
     return 0;
@@ -253,14 +254,19 @@ int afb_assemble(afb_ctx* ctx, int nforms, const afb_form* forms, int nrhs, cons
     }
     if (!handled) {
     // ---- generic path: stage full element matrices, then gather
+    // the staged matrices of all elements may not fit (P2^3 x P1 at 12.6 M tets = 116 GB): elements are processed in chunks
+    // of bounded staging size, every chunk gathered with accumulate (the row sums stay in ascending element order)
     double *sA = nullptr, *sF = nullptr;
+    size_t stage_cap = (size_t)8 << 30;
+    if (const char* sc = getenv("AFB_STAGE_BYTES")) stage_cap = (size_t)std::max(1LL, atoll(sc));
+    const size_t per_elem = ((doA ? (size_t)nrl * ncl : 0) + (doF ? (size_t)nrl : 0)) * sizeof(double);
+    const long long chunk = std::max<long long>(1, std::min<long long>(ntet, (long long)(stage_cap / std::max<size_t>(1, per_elem))));
     if (doA) {
-        const size_t bytes = (size_t)ntet * nrl * ncl * sizeof(double);
-        AFB_CUDA(ctx, ctx->stageA.reserve(bytes));
+        AFB_CUDA(ctx, ctx->stageA.reserve((size_t)chunk * nrl * ncl * sizeof(double)));
         sA = ctx->stageA.as<double>();
     }
     if (doF) {
-        AFB_CUDA(ctx, ctx->stageF.reserve((size_t)ntet * nrl * sizeof(double)));
+        AFB_CUDA(ctx, ctx->stageF.reserve((size_t)chunk * nrl * sizeof(double)));
         sF = ctx->stageF.as<double>();
     }
     // which launches may store and which must add: a block region already written -> add; uncovered area -> memset
@@ -305,27 +311,39 @@ int afb_assemble(afb_ctx* ctx, int nforms, const afb_form* forms, int nrhs, cons
         }
     }
     if (doF) plan(nfA, nfA + nfF, false, add, zeroF);
-    if (doA && zeroA) AFB_CUDA(ctx, cudaMemsetAsync(sA, 0, (size_t)ntet * nrl * ncl * sizeof(double), st));
-    if (doF && zeroF) AFB_CUDA(ctx, cudaMemsetAsync(sF, 0, (size_t)ntet * nrl * sizeof(double), st));
-
     cudaEventRecord(ctx->ev[1], st);
-    // ---- K1: element blocks
-    if (!sq.empty()) {
-        int rc = launch_forms_sq(ctx, fm, oa, Dd, sq, ntet, sA, (long long)nrl * ncl);
+    for (long long e_lo = 0; e_lo < ntet; e_lo += chunk) {
+        const long long e_hi = std::min<long long>(ntet, e_lo + chunk), nel = e_hi - e_lo;
+        if (doA && zeroA) AFB_CUDA(ctx, cudaMemsetAsync(sA, 0, (size_t)nel * nrl * ncl * sizeof(double), st));
+        if (doF && zeroF) AFB_CUDA(ctx, cudaMemsetAsync(sF, 0, (size_t)nel * nrl * sizeof(double), st));
+        // per-element coefficient data follow the element index
+        std::vector<const double*> Dc(Dd);
+        for (int k = 0; k < nfA + nfF; ++k) {
+            if (!Dc[k] || fm[k].coef_layout == AFB_COEF_CONST) continue;
+            const int dl = form_dlen(fm[k], oa[k], ob[k]);
+            const int qk = fm[k].coef_layout == AFB_COEF_PER_POINT ? afb_tet_quadrature(fm[k].quad_order, nullptr, nullptr, 0) : 1;
+            Dc[k] += (size_t)dl * qk * e_lo;
+        }
+        // ---- K1: element blocks
+        if (!sq.empty()) {
+            int rc = launch_forms_sq(ctx, fm, oa, Dc, sq, e_lo, nel, sA, (long long)nrl * ncl);
+            if (rc) return rc;
+        }
+        for (int k = 0; k < nfA + nfF; ++k) {
+            if (std::find(sq.begin(), sq.end(), k) != sq.end()) continue;
+            const bool matrix = k < nfA;
+            int rc = launch_form(ctx, fm[k], oa[k], ob[k], nel, ctx->x.as<double>(), ctx->y.as<double>(), ctx->z.as<double>(),
+                                 ctx->v[0].as<int32_t>() + e_lo, ctx->v[1].as<int32_t>() + e_lo, ctx->v[2].as<int32_t>() + e_lo,
+                                 ctx->v[3].as<int32_t>() + e_lo, nullptr, matrix ? sA : sF, matrix ? (long long)nrl * ncl : nrl, matrix ? ncl : 1,
+                                 matrix ? 1 : 0, add[k], Dc[k]);
+            if (rc) return rc;
+        }
+        if (e_hi == ntet) cudaEventRecord(ctx->ev[2], st);
+        // ---- K3: gather into CSR / rhs
+        int rc = launch_gather(ctx, doA ? sA : nullptr, doF ? sF : nullptr, dval, drhs, e_lo == 0 ? accumulate : 1, drop_val,
+                               ctx->flag.as<int>(), e_lo, e_hi);
         if (rc) return rc;
     }
-    for (int k = 0; k < nfA + nfF; ++k) {
-        if (std::find(sq.begin(), sq.end(), k) != sq.end()) continue;
-        const bool matrix = k < nfA;
-        int rc = launch_form(ctx, fm[k], oa[k], ob[k], ntet, ctx->x.as<double>(), ctx->y.as<double>(), ctx->z.as<double>(),
-                             ctx->v[0].as<int32_t>(), ctx->v[1].as<int32_t>(), ctx->v[2].as<int32_t>(), ctx->v[3].as<int32_t>(), nullptr,
-                             matrix ? sA : sF, matrix ? (long long)nrl * ncl : nrl, matrix ? ncl : 1, matrix ? 1 : 0, add[k], Dd[k]);
-        if (rc) return rc;
-    }
-    cudaEventRecord(ctx->ev[2], st);
-    // ---- K3: gather into CSR / rhs
-    int rc = launch_gather(ctx, doA ? sA : nullptr, doF ? sF : nullptr, dval, drhs, accumulate, drop_val, ctx->flag.as<int>());
-    if (rc) return rc;
     cudaEventRecord(ctx->ev[3], st);
     }
     if (dir) {

@@ -253,6 +253,26 @@ def test_dirichlet_conditions(pkg, ctx, asm_oracle, case):
                 os.environ[k] = vv
 
 
+@pytest.mark.parametrize("problem", ["c3", "c5"])
+def test_generic_path_in_element_chunks(pkg, ctx, asm_oracle, oracle, problem):
+    """the generic staged path bounds its staging memory (AFB_STAGE_BYTES): many element chunks give the same matrix up to the
+    re-association of the per-chunk partial sums"""
+    M = asm_oracle
+    variables = [(gc.P3, 1)] if problem == "c3" else [(gc.P2, 3), (gc.P1, 1)]
+    co, te, dm = _mesh(pkg, ctx, M, (3, 2, 2), variables)
+    if problem == "c3":
+        XY = co[te].transpose(1, 0, 2)
+        _, forms, rhsf, prob = problems.c3_p3_react_diff(pkg, M, co, te, oracle.quad_points(4, XY), oracle.quad_points(6, XY))
+    else:
+        _, forms, rhsf, prob = problems.c5_stokes(pkg, M, co, te)
+    a, fa, path = _oracle_compare(ctx, M, prob, forms, rhsf, co, te, dm, problem + " one chunk", {"AFB_DISABLE_TENSOR_PATH": "1"})
+    assert path["gather_kernel"] == "k_gather"
+    b, fb, _ = _oracle_compare(ctx, M, prob, forms, rhsf, co, te, dm, problem + " chunks of ~7 elements",
+                               {"AFB_DISABLE_TENSOR_PATH": "1", "AFB_STAGE_BYTES": str(7 * dm.nloc * (dm.nloc + 1) * 8)})
+    assert np.abs(a - b).max() <= 1e-14 * np.abs(a).max() and np.abs(fa - fb).max() <= 1e-14 * max(np.abs(fa).max(), 1.0)
+    assert not np.isnan(b).any()
+
+
 def test_properties_at_scale(pkg, asm_oracle):
     """C2 at 48^3 x 6 = 663,552 tets (too large for the numpy oracle): properties that do not need one"""
     c = pkg.Context(0)
