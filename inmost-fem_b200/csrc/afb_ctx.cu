@@ -686,6 +686,23 @@ int afb_fem3dtet_batched(afb_ctx* ctx, const afb_form* form, int64_t f, const do
     fm.row_off = 0; fm.col_off = 0;
     if (fm.alpha == 0.0) fm.alpha = 1.0;
     // reference layout A[ib + nfB*(ia + nfA*r)]
+    // square scalar forms with the same operator on both sides: the register-tiled kernel (afb_element.cu, k_element_sq)
+    {
+        const bool same = oa.vec == 1 && ob.vec == 1 && oa.fem == ob.fem && fm.opA == fm.opB && (fm.opA == AFB_GRAD || fm.opA == AFB_IDEN);
+        const bool dims_ok = fm.tensor_type < AFB_TENSOR_SYMMETRIC || dlen == (fm.opA == AFB_GRAD ? 9 : 1);
+        const bool valid = fm.tensor_type >= AFB_TENSOR_NULL && fm.tensor_type <= AFB_TENSOR_GENERAL && fm.coef_layout >= AFB_COEF_CONST &&
+                           fm.coef_layout <= AFB_COEF_PER_POINT;
+        if (same && dims_ok && valid && (oa.nfa == 4 || oa.nfa == 10 || oa.nfa == 20) && !getenv("AFB_DISABLE_SQ_ELEMENT")) {
+            std::vector<afb_form> fv(1, fm);
+            std::vector<afb::OpInfo> ov(1, oa);
+            std::vector<const double*> dv(1, Dd);
+            int rcs = afb::launch_forms_sq(ctx, fv, ov, dv, std::vector<int>(1, 0), 0, f, out, (long long)oa.nfa * ob.nfa, ctx->xy.as<double>(), 1);
+            if (rcs) return rcs;
+            if (mem_space == AFB_HOST) AFB_CUDA(ctx, cudaMemcpyAsync(A, out, asz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            AFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            return 0;
+        }
+    }
     int rc = afb::launch_form(ctx, fm, oa, ob, f, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ctx->xy.as<double>(),
                               out, (long long)oa.nfa * ob.nfa, 1, ob.nfa, 0, Dd);
     if (rc) return rc;

@@ -212,7 +212,7 @@ struct SqForm {
 struct SqParams { int nforms; SqForm f[SQ_MAXF]; };
 
 template <int NF>
-__global__ void __launch_bounds__(128) k_element_sq(SqParams P, long long ntet, GeomSrc g, double* __restrict__ out, long long s_e) {
+__global__ void __launch_bounds__(128) k_element_sq(SqParams P, long long ntet, GeomSrc g, double* __restrict__ out, long long s_e, int s_i, int s_j) {
     constexpr int TR = (NF + 7) / 8, TC = (NF + 3) / 4;
     __shared__ double sU[4][3 * SQ_QC * NF];
     __shared__ double sDU[4][3 * SQ_QC * NF];
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(128) k_element_sq(SqParams P, long long ntet, 
 #pragma unroll
         for (int u = 0; u < TC; ++u) {
             const int i = li + 8 * t, j = lj + 4 * u;
-            if (i < NF && j < NF) o[i * NF + j] = acc[t][u];
+            if (i < NF && j < NF) o[i * s_i + j * s_j] = acc[t][u];   // (NF, 1): staged row-major; (1, NF): fem3Dtet's column-major block
         }
 }
 
@@ -390,7 +390,7 @@ int launch_form(afb_ctx* ctx, const afb_form& form, const OpInfo& A, const OpInf
 // matrix) on the elements [e_lo, e_lo + ntet): out[(e - e_lo)*s_e + i*nf + j] = sum of the selected forms (store); Dd already points
 // at the data of element e_lo.  Returns 0 ok, < 0 error.
 int launch_forms_sq(afb_ctx* ctx, const std::vector<afb_form>& fm, const std::vector<OpInfo>& oa, const std::vector<const double*>& Dd,
-                    const std::vector<int>& sel, int64_t e_lo, int64_t ntet, double* out, long long s_e) {
+                    const std::vector<int>& sel, int64_t e_lo, int64_t ntet, double* out, long long s_e, const double* XY, int colmajor) {
     if (sel.empty() || (int)sel.size() > SQ_MAXF) return -7;
     SqParams P;
     P.nforms = (int)sel.size();
@@ -412,10 +412,15 @@ int launch_forms_sq(afb_ctx* ctx, const std::vector<afb_form>& fm, const std::ve
     g.x = ctx->x.as<double>(); g.y = ctx->y.as<double>(); g.z = ctx->z.as<double>();
     g.v0 = ctx->v[0].as<int32_t>() + e_lo; g.v1 = ctx->v[1].as<int32_t>() + e_lo; g.v2 = ctx->v[2].as<int32_t>() + e_lo; g.v3 = ctx->v[3].as<int32_t>() + e_lo;
     for (int k = 0; k < 4; ++k) g.XY[k] = nullptr;
+    if (XY) {  // batched fem3Dtet call: 4 blocks 3 x f instead of the context's mesh
+        g.x = g.y = g.z = nullptr;
+        for (int k = 0; k < 4; ++k) g.XY[k] = XY + (size_t)3 * ntet * k;
+    }
+    const int s_i = colmajor ? 1 : nf, s_j = colmajor ? nf : 1;
     const unsigned blocks = (unsigned)((ntet + 3) / 4);
-    if (nf == 4) k_element_sq<4><<<blocks, 128, 0, ctx->stream>>>(P, ntet, g, out, s_e);
-    else if (nf == 10) k_element_sq<10><<<blocks, 128, 0, ctx->stream>>>(P, ntet, g, out, s_e);
-    else if (nf == 20) k_element_sq<20><<<blocks, 128, 0, ctx->stream>>>(P, ntet, g, out, s_e);
+    if (nf == 4) k_element_sq<4><<<blocks, 128, 0, ctx->stream>>>(P, ntet, g, out, s_e, s_i, s_j);
+    else if (nf == 10) k_element_sq<10><<<blocks, 128, 0, ctx->stream>>>(P, ntet, g, out, s_e, s_i, s_j);
+    else if (nf == 20) k_element_sq<20><<<blocks, 128, 0, ctx->stream>>>(P, ntet, g, out, s_e, s_i, s_j);
     else return -7;
     ctx->launches++;
     cudaError_t e = cudaGetLastError();

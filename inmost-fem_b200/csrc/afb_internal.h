@@ -171,7 +171,8 @@ int launch_form(afb_ctx* ctx, const afb_form& form, const OpInfo& A, const OpInf
                 double* out, long long s_e, long long s_ib, long long s_ia, int add, const double* Ddev);
 int form_dlen(const afb_form& form, const OpInfo& A, const OpInfo& B);
 int launch_forms_sq(afb_ctx* ctx, const std::vector<afb_form>& fm, const std::vector<OpInfo>& oa, const std::vector<const double*>& Dd,
-                    const std::vector<int>& sel, int64_t e_lo, int64_t nel, double* out, long long s_e);
+                    const std::vector<int>& sel, int64_t e_lo, int64_t nel, double* out, long long s_e, const double* XY = nullptr,
+                    int colmajor = 0);
 // device tables W[q], phi[q*nf], G^[q*nf*3] of (space, rule); uploaded on first use (afb_ctx.cu)
 int get_tables(afb_ctx* ctx, int fem, int order, const double** W, const double** phi, const double** grd);
 // block-decomposed fused path of vector / mixed spaces (afb_blocks.cu)
