@@ -139,7 +139,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--n", type=int, default=119, help="hexes per axis per GPU block (119 -> 10,110,954 tets)")
+    ap.add_argument("--n", "--hexes-per-axis", dest="n", type=int, default=119,
+                    help="hexes per axis per GPU block (119 -> 10,110,954 tets); under torchrun use the long spelling (--n is ambiguous for its parser)")
+    ap.add_argument("--global-n", type=int, default=0, help="strong scaling: fix the GLOBAL mesh to this many hexes per axis (default: weak scaling, --n per GPU)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-n", type=int, default=40, help="hexes per axis of the CPU sample (40 -> 384,000 tets)")
     ap.add_argument("--ref-reps", type=int, default=12, help="timed passes of the CPU sample in the cpu_baseline leg (about 10-20 core-seconds)")
@@ -168,7 +170,7 @@ def main():
 
     stream = torch.cuda.current_stream()
     ctx = pkg.Context(local_rank, stream.cuda_stream)
-    n = args.n
+    n = args.global_n or args.n
     t0 = time.perf_counter()
     ctx.mesh_cube(n, n, n)
     ctx.dofmap_natural([(pkg.P2, 1)])
@@ -251,7 +253,7 @@ def main():
                          "note": "whole step = element kernels + gather; frac of the step is the honest end figure"}}
 
     line = {"metric": METRIC, "value": ntet / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong" if args.global_n else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(n, {"nnode": nnode, "nrows": nrows, "nnz": nnz, "mesh_dofmap_ms": (t1 - t0) * 1e3, "pattern_build_ms": (t2 - t1) * 1e3}),
             "dof_per_s": nrows / (ms_dev * 1e-3),
             "e2e": {"value": ntet / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "steps": e2e_steps,

@@ -16,9 +16,14 @@ import bench
 def run(args, pkg, rank, world, local_rank):
     par = importlib.import_module("inmost_fem_b200.parallel")
     n = args.n
-    ppa = par.proc_grid(world, (n, n, n))
-    dims = (n * ppa[0], n * ppa[1], n * ppa[2])
-    assert par.proc_grid(world, dims) == ppa
+    if args.global_n:
+        # strong scaling: the global mesh is fixed, the blocks shrink with the number of GPUs
+        dims = (args.global_n,) * 3
+        ppa = par.proc_grid(world, dims)
+    else:
+        ppa = par.proc_grid(world, (n, n, n))
+        dims = (n * ppa[0], n * ppa[1], n * ppa[2])
+        assert par.proc_grid(world, dims) == ppa
     stream = torch.cuda.current_stream()
     ctx = pkg.Context(local_rank, stream.cuda_stream)
     t0 = time.perf_counter()
@@ -91,7 +96,7 @@ def run(args, pkg, rank, world, local_rank):
         alg_bytes = 4 * 10 * ntet_all + 24 * nn_all + 72 * ntet_all + 8 * nnz_all + 8 * nrows_all
         gbs = alg_bytes / (ms.item() * 1e-3) / 1e9
         line = {"metric": bench.METRIC, "value": ntet_all / (ms.item() * 1e-3), "unit": bench.UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms.item(), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "warmup": args.warmup, "ms_per_step": ms.item(), "higher_is_better": True, "scaling": "strong" if args.global_n else "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": bench.config_dict(n, {"global_hexes": list(dims), "proc_grid": ppa, "ntet": ntet_all, "nrows": nrows_all, "nnz": nnz_all,
                                                 "interface_rows_sent": nfor_all, "interface_values_sent_per_step": nsend_all,
