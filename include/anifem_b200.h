@@ -153,6 +153,16 @@ int afb_assemble(afb_ctx* ctx, int nforms, const afb_form* forms, int nrhs_forms
  * Dirichlet columns to the rhs (b_r -= A_rc bc_c).  The setting is dropped when the dof map changes. */
 int afb_dirichlet_set(afb_ctx* ctx, const unsigned char* is_dirichlet, const double* value, int mem_space);
 
+/* Phased assembly for overlapping the interface exchange with the bulk of the work (multi-GPU, device buffers, values are
+ * overwritten like accumulate = 0).  afb_priority_rows_set marks the rows >= first_priority_row (the interface rows of other
+ * ranks, which come last in the local row space) as priority; -1 clears.  afb_assemble_phase(.., phase = 1) enqueues the
+ * coefficient kernel and the part of the gather that produces the priority rows and returns WITHOUT synchronising: the caller
+ * starts its exchange on those rows; phase = 2 (same forms, same buffers) enqueues the rest, synchronises and returns the
+ * status.  When the phased cluster gather does not apply, phase 1 does the whole assembly and phase 2 only returns its status. */
+int afb_priority_rows_set(afb_ctx* ctx, int64_t first_priority_row);
+int afb_assemble_phase(afb_ctx* ctx, int nforms, const afb_form* forms, int nrhs_forms, const afb_form* rhs_forms, double* csr_val,
+                       double* rhs, double drop_val, int phase);
+
 /* Multi-GPU interface rows: dst[slot[k]] += contrib[k] for the n contributions received from ONE peer (device
  * pointers; the slots of one call are distinct, peers are applied in rank order => deterministic, no atomics).
  * Replaces the value exchange the reference avoids by recomputing ghost cells (assembler.inl:162-183). */

@@ -41,7 +41,7 @@ EXPORTS = ["afb_ctx_create", "afb_ctx_destroy", "afb_last_error", "afb_sync", "a
            "afb_mesh_set", "afb_mesh_cube", "afb_mesh_orient", "afb_mesh_get",
            "afb_dofmap_set", "afb_dofmap_set_diag", "afb_dofmap_natural", "afb_dofmap_get",
            "afb_pattern_build", "afb_pattern_get", "afb_pattern_set", "afb_assemble", "afb_halo_add", "afb_last_times",
-           "afb_dirichlet_set", "afb_fem3dapply_batched", "afb_eval_quadrature"]
+           "afb_dirichlet_set", "afb_fem3dapply_batched", "afb_eval_quadrature", "afb_priority_rows_set", "afb_assemble_phase"]
 
 
 def build(verbose=False):
@@ -90,6 +90,8 @@ def lib():
         L.afb_assemble.argtypes = [vp, ci, ctypes.POINTER(AfbForm), ci, ctypes.POINTER(AfbForm), vp, vp, ci, cd, ci]
         L.afb_last_times.argtypes = [vp, _dp]
         L.afb_dirichlet_set.argtypes = [vp, vp, vp, ci]
+        L.afb_priority_rows_set.argtypes = [vp, c64]
+        L.afb_assemble_phase.argtypes = [vp, ci, ctypes.POINTER(AfbForm), ci, ctypes.POINTER(AfbForm), vp, vp, cd, ci]
         L.afb_fem3dapply_batched.argtypes = [vp, ci, ci, ci, ci, vp, c64, vp, vp, vp, vp, vp, vp, ci]
         L.afb_eval_quadrature.argtypes = [vp, ci, ci, ci, ci, ci, vp, vp, ci]
         _lib = L
@@ -360,6 +362,18 @@ class Context:
             assert sv == sr
         return self._ck(lib().afb_assemble(self._h, len(forms), fa, len(rhs_forms), fr, pv, pr, 1 if accumulate else 0,
                                            drop_val, space), allow=(-1,))
+
+    def priority_rows_set(self, first_priority_row):
+        self._ck(lib().afb_priority_rows_set(self._h, int(first_priority_row)))
+
+    def assemble_phase(self, forms, rhs_forms, val, rhs, phase, drop_val=1e-100):
+        """afb_assemble_phase on torch cuda tensors: phase 1 returns without synchronising, phase 2 returns the status"""
+        fa = (AfbForm * max(1, len(forms)))(*forms)
+        fr = (AfbForm * max(1, len(rhs_forms)))(*rhs_forms)
+        pv, sv = _ptr(val)
+        pr, sr = _ptr(rhs)
+        assert (val is None or sv == DEVICE) and (rhs is None or sr == DEVICE)
+        return self._ck(lib().afb_assemble_phase(self._h, len(forms), fa, len(rhs_forms), fr, pv, pr, drop_val, phase), allow=(-1,))
 
     def last_times(self):
         t = (ctypes.c_double * 4)()

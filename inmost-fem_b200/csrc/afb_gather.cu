@@ -123,7 +123,7 @@ namespace afb {
 
 int assemble_tensor_path(afb_ctx* ctx, int nfA, int nfF, const std::vector<afb_form>& fm, const std::vector<OpInfo>& oa,
                          const std::vector<OpInfo>& ob, const std::vector<const double*>& Dd, double* dval, double* drhs,
-                         int accumulate, double drop_val, int* status_flag);
+                         int accumulate, double drop_val, int* status_flag, int phase);
 
 int launch_gather(afb_ctx* ctx, const double* stageA, const double* stageF, double* val, double* rhs, int accumulate, double drop_val,
                   int* status_flag, long long e_lo, long long e_hi) {
@@ -144,9 +144,33 @@ int launch_gather(afb_ctx* ctx, const double* stageA, const double* stageF, doub
 
 extern "C" {
 
+static int assemble_impl(afb_ctx* ctx, int nforms, const afb_form* forms, int nrhs, const afb_form* rhs_forms, double* csr_val, double* rhs,
+                         int accumulate, double drop_val, int mem_space, int phase_req);
+
 int afb_assemble(afb_ctx* ctx, int nforms, const afb_form* forms, int nrhs, const afb_form* rhs_forms,
                  double* csr_val, double* rhs, int accumulate, double drop_val, int mem_space) {
+    return assemble_impl(ctx, nforms, forms, nrhs, rhs_forms, csr_val, rhs, accumulate, drop_val, mem_space, 0);
+}
+
+int afb_priority_rows_set(afb_ctx* ctx, int64_t first_priority_row) {
     if (!ctx) return -7;
+    if (!ctx->has_pattern) { set_error(ctx, "pattern was not built"); return -6; }
+    cudaSetDevice(ctx->device);
+    ctx->priority_row = first_priority_row;
+    if (first_priority_row < 0) { ctx->rp_prio_valid = false; return 0; }
+    return rows_priority_build(ctx, first_priority_row);
+}
+
+int afb_assemble_phase(afb_ctx* ctx, int nforms, const afb_form* forms, int nrhs, const afb_form* rhs_forms, double* csr_val, double* rhs,
+                       double drop_val, int phase) {
+    if (phase != 1 && phase != 2) { if (ctx) set_error(ctx, "afb_assemble_phase: phase must be 1 or 2"); return -7; }
+    return assemble_impl(ctx, nforms, forms, nrhs, rhs_forms, csr_val, rhs, 0, drop_val, AFB_DEVICE, phase);
+}
+
+static int assemble_impl(afb_ctx* ctx, int nforms, const afb_form* forms, int nrhs, const afb_form* rhs_forms, double* csr_val, double* rhs,
+                         int accumulate, double drop_val, int mem_space, int phase_req) {
+    if (!ctx) return -7;
+    if (phase_req == 2 && ctx->phase_done) { ctx->phase_done = false; return ctx->phase_status; }
     if (ctx->ntet <= 0) { set_error(ctx, "Mesh was not specified"); return -6; }
     if (!ctx->has_pattern) { set_error(ctx, "pattern was not built: call afb_pattern_build first"); return -6; }
     if ((nforms > 0 && !forms) || (nrhs > 0 && !rhs_forms) || nforms < 0 || nrhs < 0) { set_error(ctx, "afb_assemble: bad form arrays"); return -7; }
@@ -159,6 +183,11 @@ int afb_assemble(afb_ctx* ctx, int nforms, const afb_form* forms, int nrhs, cons
     const bool doA = userA || (dir && doF && nforms > 0);
     const int user_accumulate = accumulate;
     if (dir) accumulate = 0;
+    // phased assembly (afb_assemble_phase): phase 1 runs k_geom + the clusters holding priority rows and returns without
+    // synchronising, phase 2 runs the other clusters and reports the status.  Anything the phased cluster gather cannot do is
+    // completed in phase 1 (phase 2 then only returns the status).
+    const int ph = (phase_req != 0 && !dir && ctx->rp_prio_valid && !ctx->blocks_ready) ? phase_req : 0;
+    if (phase_req == 2 && ph == 0) return 0;
     if (doA && nforms == 0 && doF && nrhs == 0) { set_error(ctx, "System local evaluator is not specified"); return -6; }
     cudaSetDevice(ctx->device);
     cudaStream_t st = ctx->stream;
@@ -237,17 +266,19 @@ int afb_assemble(afb_ctx* ctx, int nforms, const afb_form* forms, int nrhs, cons
         }
     }
     AFB_CUDA(ctx, ctx->flag.reserve(64));
-    AFB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p, 0, 64, st));
+    if (ph != 2) AFB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p, 0, 64, st));
 
     // ---- fused fast path (afb_tensor.cu): element-wise constant coefficients on scalar P0..P3 spaces
     //      and, for vector / mixed spaces numbered by afb_dofmap_natural, the same path block by block (afb_blocks.cu)
     // an output without forms (e.g. Assemble(A, b) of a problem without load) is not touched by the fused kernels
     double* fval = (doA && nfA > 0) ? dval : nullptr;
     double* frhs = (doF && nfF > 0) ? drhs : nullptr;
-    int handled = assemble_block_path(ctx, nfA, nfF, fm, oa, ob, Dd, fval, frhs, accumulate, drop_val, ctx->flag.as<int>());
+    int handled = ph ? 0 : assemble_block_path(ctx, nfA, nfF, fm, oa, ob, Dd, fval, frhs, accumulate, drop_val, ctx->flag.as<int>());
     if (handled < 0) return handled;
-    if (!handled) handled = assemble_tensor_path(ctx, nfA, nfF, fm, oa, ob, Dd, fval, frhs, accumulate, drop_val, ctx->flag.as<int>());
+    if (!handled) handled = assemble_tensor_path(ctx, nfA, nfF, fm, oa, ob, Dd, fval, frhs, accumulate, drop_val, ctx->flag.as<int>(), ph);
     if (handled < 0) return handled;
+    if (ph == 1 && handled == 2) { ctx->phase_done = false; return 0; }   // phase 2 follows
+    if (ph == 2 && handled != 2) { set_error(ctx, "afb_assemble_phase: phase 2 does not match phase 1"); return -6; }
     if (handled && !accumulate) {
         if (doA && !fval && ctx->nnz) AFB_CUDA(ctx, cudaMemsetAsync(dval, 0, ctx->nnz * sizeof(double), st));
         if (doF && !frhs && nrows) AFB_CUDA(ctx, cudaMemsetAsync(drhs, 0, nrows * sizeof(double), st));
@@ -364,8 +395,10 @@ int afb_assemble(afb_ctx* ctx, int nforms, const afb_form* forms, int nrhs, cons
     cudaEventElapsedTime(&t12, ctx->ev[1], ctx->ev[2]);
     cudaEventElapsedTime(&t23, ctx->ev[2], ctx->ev[3]);
     ctx->times[0] = t12; ctx->times[1] = t23; ctx->times[2] = t01; ctx->times[3] = (double)handled;
-    if (bad) { set_error(ctx, "not a number in local matrix or rhs"); return -1; }
-    return 0;
+    const int status = bad ? -1 : 0;
+    if (bad) set_error(ctx, "not a number in local matrix or rhs");
+    if (phase_req == 1) { ctx->phase_done = true; ctx->phase_status = status; }   // everything was done in phase 1
+    return status;
 }
 
 int afb_last_times(afb_ctx* ctx, double* ms4) {

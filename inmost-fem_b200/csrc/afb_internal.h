@@ -133,6 +133,10 @@ struct afb_ctx {
     afb::DevBuf rp_cnt;           // uint16[nslices*nloc]: visit-steps of class i in slice s
     afb::DevBuf rp_sptr;          // int64[nslices+1]: first visit-step of a slice
     afb::DevBuf rp_ell;           // uint32[steps*NW*32]: slot bytes + local element per (step, lane)
+    afb::DevBuf rp_clist;         // int32[ncl]: clusters holding priority rows first, then the others (phased assembly)
+    bool rp_prio_valid = false, phase_done = false;
+    int phase_status = 0;
+    long long rp_nprio = 0, priority_row = -1;
 
     // essential boundary conditions (afb_dirichlet.cu): per global dof flag + value, list of affected rows
     bool has_dirichlet = false, dir_rows_valid = false;
@@ -162,7 +166,7 @@ struct SForm {
 namespace afb {
 bool make_sform(const afb_form& f, const OpInfo& oa, const OpInfo& ob, const double* Ddev, SForm* out);
 int fused_group(afb_ctx* ctx, afb_ctx* plan, const std::vector<SForm>& mat, const std::vector<SForm>& rhsf, double* dval, double* drhs,
-                const long long* p0_override, int accumulate, double drop_val, int* status_flag, bool record_events);
+                const long long* p0_override, int accumulate, double drop_val, int* status_flag, bool record_events, int phase = 0);
 // element kernels (afb_element.cu)
 int launch_form(afb_ctx* ctx, const afb_form& form, const OpInfo& A, const OpInfo& B, int64_t f,
                 const double* x, const double* y, const double* z,                 // SoA nodes (or NULL)
@@ -187,7 +191,8 @@ int dirichlet_apply(afb_ctx* ctx, double* val, double* rhs);
 int build_rows_plan(afb_ctx* ctx);
 bool rows_supports(const afb_ctx* ctx, int nga, int ngf);
 int launch_rows(afb_ctx* ctx, int nga, int ngf, const double* TA, const double* TF, const double* gbuf, double* val, double* rhs,
-                int accumulate, double drop_val, int* status, const long long* p0_override = nullptr);
+                int accumulate, double drop_val, int* status, const long long* p0_override = nullptr, int phase = 0);
+int rows_priority_build(afb_ctx* ctx, long long first_priority_row);
 // gather (afb_gather.cu)
 int launch_gather(afb_ctx* ctx, const double* stageA, const double* stageF, double* val, double* rhs,
                   int accumulate, double drop_val, int* status_flag, long long e_lo, long long e_hi);

@@ -258,6 +258,8 @@ static int pattern_impl(afb_ctx* ctx, int64_t* nnz_out, const int64_t* user_rowp
     if (nnz_out) *nnz_out = nnz;
     const int rcp = build_rows_plan(ctx);
     if (rcp) return rcp;
+    ctx->rp_prio_valid = false;
+    if (ctx->priority_row >= 0 && !ctx->is_sub) { const int rcq = rows_priority_build(ctx, ctx->priority_row); if (rcq) return rcq; }
     return user_rowptr ? 0 : blocks_build(ctx);  // pair plans of vector / mixed spaces (structural pattern only)
 }
 

@@ -277,6 +277,7 @@ struct RowsArgs {
     int nbig;           // warps 0..nbig-1 own big regions and serve the long slices first
     int gcap;           // elements of coefficient staging per CTA
     int zero;           // always 0; k & zero keeps the table loads inside the visit loop (see k_rows_cl)
+    const int* clist;   // NULL: CTA b works on cluster b; else on cluster clist[b] (priority / remaining clusters of a phased assembly)
     const int* cs;      // [ncl+1] slice range of a cluster
     const int* eptr;    // [ncl+1] element-list range of a cluster
     const unsigned* elist;   // Morton ids of the elements a cluster touches
@@ -343,7 +344,7 @@ __global__ void __launch_bounds__(384, 1) k_rows_cl(const __grid_constant__ RowT
     __shared__ int s_q[2];  // slices handed out: [0] long ones, [1] short ones
     __shared__ int s_sb;    // first long slice of the cluster
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c = blockIdx.x;
+    const int c = p.clist ? p.clist[blockIdx.x] : (int)blockIdx.x;
     const int e0 = p.eptr[c], ne = p.eptr[c + 1] - e0;
     const int sl0 = p.cs[c], sl1 = p.cs[c + 1];
     const unsigned g_a = (unsigned)__cvta_generic_to_shared(smraw);
@@ -642,7 +643,7 @@ RowsShape rows_shape(const afb_ctx* ctx, int ngp) {
 
 template <int NLOC, int NC, int NGA, int NGF>
 int launch_rows_t(afb_ctx* ctx, const double* TA, const double* TF, const double* gbuf, double* val, double* rhs, int accumulate,
-                  double drop_val, int* status, const long long* p0_override) {
+                  double drop_val, int* status, const long long* p0_override, int phase) {
     constexpr int NGP = (NGA + NGF + 1) & ~1;
     static RowTab<NLOC, NC, NGA, NGF> T;  // host staging of the parameter (copied by value at launch)
     // TA is [c][i][j], TF is [c][i]
@@ -667,7 +668,15 @@ int launch_rows_t(afb_ctx* ctx, const double* TA, const double* TF, const double
     auto kern = k_rows_cl<NLOC, NC, NGA, NGF>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaFuncSetAttribute(k_rows_cl)");
-    kern<<<(unsigned)ctx->rp_ncl, sh.nwarps * 32, sh.smem, ctx->stream>>>(T, p);
+    // phased assembly (afb_assemble_phase): 1 = the clusters holding priority rows, 2 = the others, 0 = all
+    long long nblocks = ctx->rp_ncl;
+    p.clist = nullptr;
+    if (phase != 0 && ctx->rp_prio_valid) {
+        nblocks = phase == 1 ? ctx->rp_nprio : ctx->rp_ncl - ctx->rp_nprio;
+        p.clist = ctx->rp_clist.as<int>() + (phase == 1 ? 0 : ctx->rp_nprio);
+    } else if (phase == 2) nblocks = 0;   // everything ran in phase 1
+    if (nblocks <= 0) return 1;
+    kern<<<(unsigned)nblocks, sh.nwarps * 32, sh.smem, ctx->stream>>>(T, p);
     ctx->launches++;
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(ctx, e, "k_rows_cl launch");
@@ -676,8 +685,8 @@ int launch_rows_t(afb_ctx* ctx, const double* TA, const double* TF, const double
 
 template <int NLOC, int NC>
 int launch_rows_n(afb_ctx* ctx, int nga, int ngf, const double* TA, const double* TF, const double* gbuf, double* val, double* rhs,
-                  int accumulate, double drop_val, int* status, const long long* p0_override) {
-#define RW(A, F) if (nga == A && ngf == F) return launch_rows_t<NLOC, NC, A, F>(ctx, TA, TF, gbuf, val, rhs, accumulate, drop_val, status, p0_override);
+                  int accumulate, double drop_val, int* status, const long long* p0_override, int phase) {
+#define RW(A, F) if (nga == A && ngf == F) return launch_rows_t<NLOC, NC, A, F>(ctx, TA, TF, gbuf, val, rhs, accumulate, drop_val, status, p0_override, phase);
     RW(6, 1) RW(6, 0) RW(7, 1) RW(7, 0) RW(1, 1) RW(1, 0) RW(0, 1) RW(3, 0) RW(3, 1)
     if constexpr (NLOC <= 10) { RW(9, 1) RW(9, 0) RW(10, 1) RW(10, 0) }
 #undef RW
@@ -905,13 +914,40 @@ int build_rows_plan(afb_ctx* ctx) {
     return 0;
 }
 
+// Splits the clusters into those that hold a row >= first_priority_row (they are listed first) and the others: a phased
+// assembly runs the first group, lets the caller start the exchange of those rows, and runs the rest meanwhile.
+int rows_priority_build(afb_ctx* ctx, long long first_priority_row) {
+    ctx->rp_prio_valid = false;
+    if (!ctx->has_rows_plan) return 0;
+    const long long ncl = ctx->rp_ncl, nsl = ctx->rp_nslices;
+    std::vector<int> cs(ncl + 1);
+    std::vector<unsigned> srow((size_t)nsl * 32);
+    if (cudaMemcpy(cs.data(), ctx->rp_cs.p, (ncl + 1) * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(srow.data(), ctx->rp_order.p, (size_t)nsl * 32 * sizeof(unsigned), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return cuda_fail(ctx, cudaGetLastError(), "rows_priority_build");
+    std::vector<int> first, rest;
+    for (long long c = 0; c < ncl; ++c) {
+        bool prio = false;
+        for (long long t = (long long)cs[c] * 32; t < (long long)cs[c + 1] * 32 && !prio; ++t)
+            prio = srow[t] != 0xffffffffu && (long long)srow[t] >= first_priority_row;
+        (prio ? first : rest).push_back((int)c);
+    }
+    ctx->rp_nprio = (long long)first.size();
+    first.insert(first.end(), rest.begin(), rest.end());
+    if (ctx->rp_clist.reserve(std::max<long long>(1, ncl) * sizeof(int)) != cudaSuccess ||
+        cudaMemcpy(ctx->rp_clist.p, first.data(), ncl * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess)
+        return cuda_fail(ctx, cudaGetLastError(), "rows_priority_build");
+    ctx->rp_prio_valid = true;
+    return 0;
+}
+
 // 1 = launched, 0 = combination not covered (caller uses the lane-group gather), < 0 error.  gbuf must be in Morton order.
 // p0_override: first CSR entry of every (slice, lane) row when the rows of this plan are sub-blocks of longer rows (afb_blocks.cu).
 int launch_rows(afb_ctx* ctx, int nga, int ngf, const double* TA, const double* TF, const double* gbuf, double* val, double* rhs,
-                int accumulate, double drop_val, int* status, const long long* p0_override) {
+                int accumulate, double drop_val, int* status, const long long* p0_override, int phase) {
     if (!rows_supports(ctx, nga, ngf)) return 0;
     const int nl = ctx->rp_nloc, nc = ctx->rp_ncol;
-#define RWD(NRr, NCc) if (nl == NRr && nc == NCc) return launch_rows_n<NRr, NCc>(ctx, nga, ngf, TA, TF, gbuf, val, rhs, accumulate, drop_val, status, p0_override);
+#define RWD(NRr, NCc) if (nl == NRr && nc == NCc) return launch_rows_n<NRr, NCc>(ctx, nga, ngf, TA, TF, gbuf, val, rhs, accumulate, drop_val, status, p0_override, phase);
     RWD(4, 4) RWD(10, 10) RWD(20, 20) RWD(10, 4) RWD(4, 10)
 #undef RWD
     return 0;

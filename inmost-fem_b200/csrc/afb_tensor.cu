@@ -458,7 +458,7 @@ namespace afb {
 // plan row inside the caller's matrix).  Returns 1 (lane-group gather) or 2 (cluster gather k_rows_cl), 0 if the group
 // cannot be handled (nothing was launched), < 0 on error.
 int fused_group(afb_ctx* ctx, afb_ctx* plan, const std::vector<SForm>& mat, const std::vector<SForm>& rhsf, double* dval, double* drhs,
-                const long long* p0_override, int accumulate, double drop_val, int* status_flag, bool record_events) {
+                const long long* p0_override, int accumulate, double drop_val, int* status_flag, bool record_events, int phase) {
     const int nfA = (int)mat.size(), nfF = (int)rhsf.size(), nforms = nfA + nfF;
     if (nforms == 0 || nforms > MAX_TFORMS) return 0;
     const int nrl = plan->nrow_loc, ncl = plan->ncol_loc;
@@ -505,6 +505,7 @@ int fused_group(afb_ctx* ctx, afb_ctx* plan, const std::vector<SForm>& mat, cons
 
     if (record_events) cudaEventRecord(ctx->ev[1], st);
     const unsigned gridg = (unsigned)((ctx->ntet + 255) / 256);
+    if (phase != 2)   // phase 2 of a phased assembly reuses the coefficients phase 1 left in the context
     k_geom<<<gridg, 256, (size_t)256 * ngpad * sizeof(double), st>>>(ctx->ntet, gp, ctx->x.as<double>(), ctx->y.as<double>(), ctx->z.as<double>(), ctx->v[0].as<int32_t>(),
                                  ctx->v[1].as<int32_t>(), ctx->v[2].as<int32_t>(), ctx->v[3].as<int32_t>(), gbuf,
                                  use_rows ? plan->rp_old2new.as<unsigned>() : nullptr);
@@ -515,7 +516,7 @@ int fused_group(afb_ctx* ctx, afb_ctx* plan, const std::vector<SForm>& mat, cons
     if (use_rows) {
         // cluster-tiled thread-per-row gather (afb_rows.cu)
         plan->stream = ctx->stream;
-        const int rc = launch_rows(plan, nga, ngf, TA.data(), TF.data(), gbuf, dval, drhs, accumulate, drop_val, status_flag, p0_override);
+        const int rc = launch_rows(plan, nga, ngf, TA.data(), TF.data(), gbuf, dval, drhs, accumulate, drop_val, status_flag, p0_override, phase);
         if (plan != ctx) { ctx->launches += plan->launches; plan->launches = 0; if (rc < 0) set_error(ctx, plan->err); }
         if (rc < 0) return rc;
         if (rc != 1) { set_error(ctx, "internal: cluster gather refused a case it advertised"); return -4; }
@@ -622,7 +623,7 @@ bool make_sform(const afb_form& f, const OpInfo& oa, const OpInfo& ob, const dou
 // Single-field entry: every form is a scalar form on the context's own plan.
 int assemble_tensor_path(afb_ctx* ctx, int nfA, int nfF, const std::vector<afb_form>& fm, const std::vector<OpInfo>& oa,
                          const std::vector<OpInfo>& ob, const std::vector<const double*>& Dd, double* dval, double* drhs,
-                         int accumulate, double drop_val, int* status_flag) {
+                         int accumulate, double drop_val, int* status_flag, int phase) {
     if (getenv("AFB_DISABLE_TENSOR_PATH")) return 0;
     if (ctx->has_signs) return 0;
     std::vector<SForm> mat, rhsf;
@@ -631,7 +632,7 @@ int assemble_tensor_path(afb_ctx* ctx, int nfA, int nfF, const std::vector<afb_f
         if (!make_sform(fm[k], oa[k], ob[k], Dd[k], &s)) return 0;
         (k < nfA ? mat : rhsf).push_back(s);
     }
-    return fused_group(ctx, ctx, mat, rhsf, dval, drhs, nullptr, accumulate, drop_val, status_flag, true);
+    return fused_group(ctx, ctx, mat, rhsf, dval, drhs, nullptr, accumulate, drop_val, status_flag, true, phase);
 }
 
 }  // namespace afb

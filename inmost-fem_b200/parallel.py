@@ -256,34 +256,50 @@ class InterfacePlan:
         self.nnz_ext = int(colind_ext.numel())
         return rowptr_ext.contiguous(), colind_ext.contiguous()
 
+    def exchange_start(self, val_ext, rhs_ext):
+        """launch the interface exchange (NCCL all_to_all_single, asynchronous): the foreign rows are sorted by global id =
+        grouped by owner, so the tail of val_ext / rhs_ext IS the send buffer; all sizes are known from the plan, no size
+        exchange, no host synchronisation.  Returns the handles for exchange_finish."""
+        nb = self.nb
+        works = []
+        if val_ext is not None:
+            if getattr(self, "_vrecv", None) is None:
+                self._vrecv = torch.empty(sum(self.recv_nnz), dtype=val_ext.dtype, device=val_ext.device)
+            works.append(dist.all_to_all_single(self._vrecv, val_ext[self.nnz_own:], self.recv_nnz, self.send_nnz, group=nb.group, async_op=True))
+        if rhs_ext is not None:
+            sizes = [int(r.numel()) for r in self.rhs_slots]
+            if getattr(self, "_rrecv", None) is None:
+                self._rrecv = torch.empty(sum(sizes), dtype=rhs_ext.dtype, device=rhs_ext.device)
+            works.append(dist.all_to_all_single(self._rrecv, rhs_ext[self.n_own:], sizes, self.for_per_peer, group=nb.group, async_op=True))
+        return works
+
+    def exchange_finish(self, works, val_ext, rhs_ext, add):
+        """wait for the exchange and add what arrived, peers in rank order (add = afb_halo_add: dst[slots] += contrib)"""
+        for w in works:
+            w.wait()
+        if val_ext is not None:
+            for p, r in enumerate(torch.split(self._vrecv, self.recv_nnz)):
+                if r.numel():
+                    add(self.val_slots[p], r, val_ext)
+        if rhs_ext is not None:
+            for p, r in enumerate(torch.split(self._rrecv, [int(r.numel()) for r in self.rhs_slots])):
+                if r.numel():
+                    add(self.rhs_slots[p], r, rhs_ext)
+
     def exchange(self, val_ext, rhs_ext, add):
         """send the foreign-row values / rhs entries to their owners and add what arrives, peers in rank order.
-        add(slots, contrib, dst) performs dst[slots] += contrib (afb_halo_add on the GPU).
-        The foreign rows are sorted by global id = grouped by owner, so the tail of val_ext / rhs_ext IS the send buffer;
-        all sizes are known from the plan: one all_to_all_single per array, no size exchange, no host synchronisation."""
+        add(slots, contrib, dst) performs dst[slots] += contrib (afb_halo_add on the GPU)."""
         nb = self.nb
         fixed = val_ext.is_cuda if val_ext is not None else (rhs_ext is not None and rhs_ext.is_cuda)
+        if fixed:
+            self.exchange_finish(self.exchange_start(val_ext, rhs_ext), val_ext, rhs_ext, add)
+            return
         if val_ext is not None:
-            if fixed:
-                if getattr(self, "_vrecv", None) is None:
-                    self._vrecv = torch.empty(sum(self.recv_nnz), dtype=val_ext.dtype, device=val_ext.device)
-                dist.all_to_all_single(self._vrecv, val_ext[self.nnz_own:], self.recv_nnz, self.send_nnz, group=nb.group)
-                got = torch.split(self._vrecv, self.recv_nnz)
-            else:
-                got = _all_to_all_var(list(torch.split(val_ext[self.nnz_own:], self.send_nnz)), nb.group)
-            for p, r in enumerate(got):
+            for p, r in enumerate(_all_to_all_var(list(torch.split(val_ext[self.nnz_own:], self.send_nnz)), nb.group)):
                 if r.numel():
                     add(self.val_slots[p], r.contiguous(), val_ext)
         if rhs_ext is not None:
-            if fixed:
-                sizes = [int(r.numel()) for r in self.rhs_slots]
-                if getattr(self, "_rrecv", None) is None:
-                    self._rrecv = torch.empty(sum(sizes), dtype=rhs_ext.dtype, device=rhs_ext.device)
-                dist.all_to_all_single(self._rrecv, rhs_ext[self.n_own:], sizes, self.for_per_peer, group=nb.group)
-                got = torch.split(self._rrecv, sizes)
-            else:
-                got = _all_to_all_var(list(torch.split(rhs_ext[self.n_own:], self.for_per_peer)), nb.group)
-            for p, r in enumerate(got):
+            for p, r in enumerate(_all_to_all_var(list(torch.split(rhs_ext[self.n_own:], self.for_per_peer)), nb.group)):
                 if r.numel():
                     add(self.rhs_slots[p], r.contiguous(), rhs_ext)
 
@@ -317,9 +333,17 @@ class DistributedAssembler:
         rp, ci = ctx.pattern_get_torch()
         self.rowptr_ext, self.colind_ext = plan.finalize_pattern(rp, ci)
         ctx.pattern_set(self.rowptr_ext, self.colind_ext)
+        # phased assembly: the interface rows of other ranks (local rows >= n_own) are produced first, their exchange
+        # overlaps the rest of the assembly (afb_assemble_phase)
+        self.phased = bool(self.val_is_cuda()) and self.world > 1
+        if self.phased:
+            ctx.priority_rows_set(plan.n_own)
         self.val = torch.zeros(plan.nnz_ext, dtype=torch.float64, device=dev)
         self.rhs = torch.zeros(n_ext, dtype=torch.float64, device=dev)
         self.ntet = int(self.tets.shape[0])
+
+    def val_is_cuda(self):
+        return self.tets.is_cuda
 
     @property
     def rowptr(self):
@@ -332,6 +356,12 @@ class DistributedAssembler:
     def assemble(self, forms, rhs_forms, drop_val=1e-100):
         """Assemble the owned rows [row_begin,row_end): local element contributions + interface contributions of peers.
         Results: self.val[:nnz_own] (CSR values of the owned rows), self.rhs[:n_own]."""
+        if self.phased:
+            self.ctx.assemble_phase(forms, rhs_forms, self.val, self.rhs, 1, drop_val=drop_val)
+            works = self.plan.exchange_start(self.val, self.rhs)
+            st = self.ctx.assemble_phase(forms, rhs_forms, self.val, self.rhs, 2, drop_val=drop_val)
+            self.plan.exchange_finish(works, self.val, self.rhs, self.ctx.halo_add)
+            return st
         st = self.ctx.assemble(forms, rhs_forms, self.val, self.rhs, accumulate=False, drop_val=drop_val)
         self.plan.exchange(self.val, self.rhs, self.ctx.halo_add)
         return st
