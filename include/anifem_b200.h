@@ -122,6 +122,17 @@ int afb_dofmap_natural(afb_ctx* ctx, int nvars, const int* fem, const int* vec);
  * assembler.inl:114-136) when rows are not numbered like columns (multi-GPU: owned rows followed by the
  * interface rows of other ranks); -1 = no forced entry.  Default: row_begin + r. */
 int afb_dofmap_set_diag(afb_ctx* ctx, const int64_t* diag_col /*nrows*/, int mem_space);
+/* Optional, for vector-valued / mixed problems with an explicit dof map (afb_dofmap_set): the scalar fields (variable,
+ * component) behind the local dofs, so that the assembly can run block by block on scalar gather plans like it does after
+ * afb_dofmap_natural (BandDenseMatrix structure of FemVec / FemCom operators, fem/operators.h:127-155,189-259).  Field f
+ * lives on base space fem[f] and owns the local dofs loff[f] .. loff[f]+nf(fem[f])-1.  Under the per-rank NATURAL
+ * enumeration (global_enumerator.cpp:594-604,702-777) a field is contiguous inside every rank's interval only: its rows
+ * (ids relative to row_begin) are nseg_row intervals row_seg[(f*nseg_row + k)*2 + {0,1}] = {first, count} and its global
+ * columns nseg_col intervals (count 0 = unused entry); the scalar numbering of a field is the concatenation of its
+ * intervals and must enumerate the entities of all fields of one space in the same order.  Call after afb_dofmap_set
+ * [+ afb_dofmap_set_diag] and before afb_pattern_build / afb_pattern_set.  nfields = 0 clears. */
+int afb_fields_set(afb_ctx* ctx, int nfields, const int* fem, const int* loff, int nseg_row, const int64_t* row_seg,
+                   int nseg_col, const int64_t* col_seg);
 int afb_dofmap_get(afb_ctx* ctx, int* nrow_loc, int* ncol_loc, int64_t* row_begin, int64_t* row_end,
                    int64_t* ncols_global, int64_t* elem2row, int64_t* elem2col, int mem_space);
 

@@ -41,7 +41,8 @@ EXPORTS = ["afb_ctx_create", "afb_ctx_destroy", "afb_last_error", "afb_sync", "a
            "afb_mesh_set", "afb_mesh_cube", "afb_mesh_orient", "afb_mesh_get",
            "afb_dofmap_set", "afb_dofmap_set_diag", "afb_dofmap_natural", "afb_dofmap_get",
            "afb_pattern_build", "afb_pattern_get", "afb_pattern_set", "afb_assemble", "afb_halo_add", "afb_last_times",
-           "afb_dirichlet_set", "afb_fem3dapply_batched", "afb_eval_quadrature", "afb_priority_rows_set", "afb_assemble_phase"]
+           "afb_dirichlet_set", "afb_fem3dapply_batched", "afb_eval_quadrature", "afb_priority_rows_set", "afb_assemble_phase",
+           "afb_fields_set"]
 
 
 def build(verbose=False):
@@ -83,6 +84,7 @@ def lib():
         L.afb_dofmap_natural.argtypes = [vp, ci, ctypes.POINTER(ci), ctypes.POINTER(ci)]
         L.afb_dofmap_get.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(ci), _i64p, _i64p, _i64p, vp, vp, ci]
         L.afb_dofmap_set_diag.argtypes = [vp, vp, ci]
+        L.afb_fields_set.argtypes = [vp, ci, ctypes.POINTER(ci), ctypes.POINTER(ci), ci, _i64p, ci, _i64p]
         L.afb_pattern_set.argtypes = [vp, vp, vp, c64, ci]
         L.afb_halo_add.argtypes = [vp, c64, vp, vp, vp]
         L.afb_pattern_build.argtypes = [vp, _i64p]
@@ -288,6 +290,26 @@ class Context:
         if diag_col is not None:
             pd, sd = _ptr(diag_col)
             self._ck(lib().afb_dofmap_set_diag(self._h, pd, sd))
+
+    def fields_set(self, fields):
+        """scalar fields of an explicit dof map: [(fem, loff, [(row_first, row_count), ...], [(col_first, col_count), ...]), ...]
+        (afb_fields_set: row intervals relative to row_begin, column intervals global); [] clears"""
+        n = len(fields)
+        if n == 0:
+            self._ck(lib().afb_fields_set(self._h, 0, None, None, 1, None, 1, None))
+            return
+        nsr = max(1, max(len(f[2]) for f in fields))
+        nsc = max(1, max(len(f[3]) for f in fields))
+        rs = np.zeros((n, nsr, 2), dtype=np.int64)
+        cs = np.zeros((n, nsc, 2), dtype=np.int64)
+        for k, f in enumerate(fields):
+            for j, (a, b) in enumerate(f[2]):
+                rs[k, j] = (a, b)
+            for j, (a, b) in enumerate(f[3]):
+                cs[k, j] = (a, b)
+        fem = (ctypes.c_int * n)(*[int(f[0]) for f in fields])
+        loff = (ctypes.c_int * n)(*[int(f[1]) for f in fields])
+        self._ck(lib().afb_fields_set(self._h, n, fem, loff, nsr, rs.ctypes.data_as(_i64p), nsc, cs.ctypes.data_as(_i64p)))
 
     def pattern_set(self, rowptr, colind):
         pr, sr = _ptr(rowptr)

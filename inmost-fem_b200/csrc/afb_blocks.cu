@@ -10,7 +10,10 @@
 // So the vector / mixed assembly runs as one fused scalar assembly (k_geom + k_rows_cl) per field pair, on the gather plan of
 // the pair of base spaces, writing straight into its sub-block of the caller's CSR rows.  The pair plans live in
 // sub-contexts that borrow the mesh of the owning context.
+#include <cub/cub.cuh>
+
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 
 #include "afb_internal.h"
@@ -25,38 +28,86 @@ inline unsigned grid_for(long long n, int block = 256) {
 }
 #define GRID_STRIDE(i, n) for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (n); i += (long long)gridDim.x * blockDim.x)
 
-// scalar codes of one field: dst[i*ntet + e] = src[(loff+i)*ntet + e] - goff   (codes stay id+1)
-__global__ void k_extract_codes(long long ntet, int nloc, int loff, int goff, const int32_t* __restrict__ src, int32_t* dst) {
+// scalar codes of one field: code c of local dof loff+i -> 1 + scalar id of (c - 1) inside the field's intervals (0 stays 0)
+__global__ void k_extract_codes(long long ntet, int nloc, int loff, SegMap map, const int32_t* __restrict__ src, int32_t* dst, int* bad) {
     GRID_STRIDE(t, ntet * nloc) {
         const long long i = t / ntet, e = t - i * ntet;
-        dst[t] = src[(long long)(loff + i) * ntet + e] - goff;
+        const int c = src[(long long)(loff + i) * ntet + e];
+        int o = 0;
+        if (c > 0) {
+            const long long sid = map.to_scalar(c - 1);
+            if (sid < 0) *bad = 1; else o = (int)sid + 1;
+        } else if (c < 0) *bad = 1;
+        dst[t] = o;
     }
 }
 
-struct LenSrc { const long long* rowptr[3]; int mult[3]; };
+__device__ __forceinline__ long long find_col(const int32_t* __restrict__ gcol, long long b0, long long b1, long long g) {
+    long long lo = b0, hi = b1;
+    while (lo < hi) { const long long mid = (lo + hi) >> 1; if (gcol[mid] < g) lo = mid + 1; else hi = mid; }
+    return (lo < b1 && gcol[lo] == g) ? lo : -1;
+}
 
-// every row of field R must be the concatenation of its pair-pattern rows (mult = number of fields per base space)
-__global__ void k_check_rows(long long nrows, long long goff, const long long* __restrict__ grow, LenSrc ls, int* bad) {
-    GRID_STRIDE(r, nrows) {
-        long long len = 0;
-        for (int k = 0; k < 3; ++k)
-            if (ls.rowptr[k]) len += ls.mult[k] * (ls.rowptr[k][r + 1] - ls.rowptr[k][r]);
-        if (len != grow[goff + r + 1] - grow[goff + r]) *bad = 1;
+// Where the block (R, C) of every scalar row sits inside the caller's CSR row: p0 = first entry when the block is a
+// contiguous run of the row (NATURAL numbering on one rank: the row is the concatenation of its field blocks), else
+// p0 = row start and tcount = block length: the entries then go through an offset table (per-rank numbering of a partitioned
+// mesh: the columns of a field are split by owner rank; columns contributed by other ranks only sit in between).
+__global__ void k_block_scan(long long nrows_s, SegMap rowsR, SegMap colsC, const long long* __restrict__ srowptr, const int32_t* __restrict__ scol,
+                             const long long* __restrict__ grow, const int32_t* __restrict__ gcol, long long* p0, int* tcount, int* bad,
+                             unsigned long long* covered) {
+    unsigned long long mine = 0;
+    GRID_STRIDE(r, nrows_s) {
+        const long long R = rowsR.to_full(r);
+        const long long a0 = srowptr[r], a1 = srowptr[r + 1];
+        long long first = 0;
+        int tc = 0;
+        if (R < 0) { if (a1 > a0) *bad = 1; }
+        else {
+            const long long b0 = grow[R], b1 = grow[R + 1];
+            first = b0;
+            bool contig = true;
+            long long prev = -1;
+            for (long long a = a0; a < a1; ++a) {
+                const long long pos = find_col(gcol, b0, b1, colsC.to_full(scol[a]));
+                if (pos < 0) { *bad = 1; break; }
+                if (a == a0) first = pos; else if (pos != prev + 1) contig = false;
+                prev = pos;
+            }
+            if (!contig) { first = b0; tc = (int)(a1 - a0); if (b1 - b0 > 65535) *bad = 1; }
+            mine += (unsigned long long)(a1 - a0);
+        }
+        p0[r] = first;
+        tcount[r] = tc;
+    }
+    if (mine) atomicAdd(covered, mine);   // setup-time integer count
+}
+
+__global__ void k_block_tab(long long nrows_s, SegMap rowsR, SegMap colsC, const long long* __restrict__ srowptr, const int32_t* __restrict__ scol,
+                            const long long* __restrict__ grow, const int32_t* __restrict__ gcol, const int* __restrict__ tcount,
+                            const int* __restrict__ toff, unsigned short* tab) {
+    GRID_STRIDE(r, nrows_s) {
+        if (!tcount[r]) continue;
+        const long long R = rowsR.to_full(r);
+        const long long a0 = srowptr[r], a1 = srowptr[r + 1], b0 = grow[R], b1 = grow[R + 1];
+        for (long long a = a0; a < a1; ++a) tab[toff[r] + (a - a0)] = (unsigned short)(find_col(gcol, b0, b1, colsC.to_full(scol[a])) - b0);
     }
 }
 
-// first CSR entry of the block (R, C) of every (slice, lane) row of the pair plan: row start + the blocks of the fields before C
-__global__ void k_block_dst(long long n, const unsigned* __restrict__ srow, long long goff, const long long* __restrict__ grow, LenSrc before,
-                            long long* dst) {
+// per (slice, lane) of the pair plan: first entry of the block, table index (0 = contiguous)
+__global__ void k_block_dst(long long n, const unsigned* __restrict__ srow, const long long* __restrict__ p0, const int* __restrict__ tcount,
+                            const int* __restrict__ toff, long long* dst, int* tix) {
     GRID_STRIDE(t, n) {
         const unsigned r = srow[t];
-        long long p0 = 0;
-        if (r != 0xffffffffu) {
-            p0 = grow[goff + r];
-            for (int k = 0; k < 3; ++k)
-                if (before.rowptr[k]) p0 += before.mult[k] * (before.rowptr[k][r + 1] - before.rowptr[k][r]);
-        }
-        dst[t] = p0;
+        dst[t] = r != 0xffffffffu ? p0[r] : 0;
+        tix[t] = (r != 0xffffffffu && tcount[r]) ? 1 + toff[r] : 0;
+    }
+}
+
+// per (slice, lane): local row of the caller that receives the rhs entry of the scalar row
+__global__ void k_block_rdst(long long n, const unsigned* __restrict__ srow, SegMap rowsR, int* rdst) {
+    GRID_STRIDE(t, n) {
+        const unsigned r = srow[t];
+        rdst[t] = r != 0xffffffffu ? (int)rowsR.to_full(r) : -1;
     }
 }
 
@@ -82,38 +133,65 @@ SForm blank_sform(int kind, int ng, int femA, int femB, int order, double alpha,
 
 namespace afb {
 
+// drops the block destinations (they depend on the installed pattern); the pair plans depend on the dof map only and stay
+void blocks_clear_dst(afb_ctx* ctx) {
+    for (auto* v : {&ctx->block_dst, &ctx->block_tix, &ctx->block_tab, &ctx->block_rdst}) {
+        for (auto& d : *v) d.release();
+        v->clear();
+    }
+    ctx->blocks_ready = false;
+    ctx->blocks_cover = true;
+}
+
 void blocks_clear(afb_ctx* ctx) {
     for (auto& p : ctx->pairs) {
         if (p.sub) afb_ctx_destroy(p.sub);
     }
     ctx->pairs.clear();
-    for (auto& d : ctx->block_dst) d.release();
-    ctx->block_dst.clear();
+    for (auto* v : {&ctx->block_dst, &ctx->block_tix, &ctx->block_tab, &ctx->block_rdst}) {
+        for (auto& d : *v) d.release();
+        v->clear();
+    }
     ctx->blocks_ready = false;
+    ctx->blocks_cover = true;
 }
 
 // Builds the pair plans and block destinations after the main pattern exists.  Never fails the caller: when something
 // does not fit the scheme the block path is simply not offered (the generic staged path assembles the problem).
 int blocks_build(afb_ctx* ctx) {
-    blocks_clear(ctx);
+    blocks_clear_dst(ctx);
+    const bool reuse_pairs = !ctx->pairs.empty();   // same dof map and fields, new pattern (afb_pattern_set after afb_pattern_build)
     if (ctx->is_sub || getenv("AFB_DISABLE_BLOCKS")) return 0;
     const int nf = (int)ctx->fields.size();
-    if (nf < 2 || nf > 8 || ctx->has_signs || ctx->has_diag || ctx->nrow_loc != ctx->ncol_loc) return 0;
+    if (nf < 2 || nf > 8 || ctx->has_signs || ctx->nrow_loc != ctx->ncol_loc || (ctx->has_diag && !ctx->fields_custom)) { blocks_clear(ctx); return 0; }
     std::vector<int> fems;
     for (const Field& f : ctx->fields) {
-        if (f.fem != AFB_FEM_P1 && f.fem != AFB_FEM_P2) return 0;
+        if (f.fem != AFB_FEM_P1 && f.fem != AFB_FEM_P2) { blocks_clear(ctx); return 0; }
         if (std::find(fems.begin(), fems.end(), f.fem) == fems.end()) fems.push_back(f.fem);
     }
+    if (fems.size() > 3) { blocks_clear(ctx); return 0; }
     cudaStream_t st = ctx->stream;
     const long long ntet = ctx->ntet;
+    if (ctx->flag.reserve(64) != cudaSuccess) { blocks_clear(ctx); return 0; }
+    cudaMemsetAsync(ctx->flag.p, 0, 64, st);
+    int* bad = ctx->flag.as<int>();
+    unsigned long long* covered = reinterpret_cast<unsigned long long*>(ctx->flag.as<char>() + 16);
     // first field of every base space (all fields of a space share the scalar numbering)
     auto first_field = [&](int fem) -> const Field& {
         for (const Field& f : ctx->fields)
             if (f.fem == fem) return f;
         return ctx->fields[0];
     };
+    for (const Field& f : ctx->fields) {   // same interval structure for all fields of a space
+        const Field& g = first_field(f.fem);
+        bool same = f.rows.n == g.rows.n && f.cols.n == g.cols.n;
+        for (int k = 0; same && k < f.rows.n; ++k) same = f.rows.count[k] == g.rows.count[k];
+        for (int k = 0; same && k < f.cols.n; ++k) same = f.cols.count[k] == g.cols.count[k];
+        if (!same) { blocks_clear(ctx); return 0; }
+    }
     for (int femR : fems)
         for (int femC : fems) {
+            if (reuse_pairs) break;
             const Field& fr = first_field(femR);
             const Field& fc = first_field(femC);
             afb_ctx* sub = new afb_ctx();
@@ -125,15 +203,17 @@ int blocks_build(afb_ctx* ctx) {
             ctx->pairs.push_back({femR, femC, sub});
             sub->nrow_loc = fr.nloc; sub->ncol_loc = fc.nloc;
             if (sub->e2r.reserve((size_t)ntet * fr.nloc * 4) != cudaSuccess || sub->e2c.reserve((size_t)ntet * fc.nloc * 4) != cudaSuccess) { blocks_clear(ctx); return 0; }
-            k_extract_codes<<<grid_for(ntet * fr.nloc), 256, 0, st>>>(ntet, fr.nloc, fr.loff, (int)fr.goff, ctx->e2r.as<int32_t>(), sub->e2r.as<int32_t>());
-            k_extract_codes<<<grid_for(ntet * fc.nloc), 256, 0, st>>>(ntet, fc.nloc, fc.loff, (int)fc.goff, ctx->e2c.as<int32_t>(), sub->e2c.as<int32_t>());
+            k_extract_codes<<<grid_for(ntet * fr.nloc), 256, 0, st>>>(ntet, fr.nloc, fr.loff, fr.rows, ctx->e2r.as<int32_t>(), sub->e2r.as<int32_t>(), bad);
+            k_extract_codes<<<grid_for(ntet * fc.nloc), 256, 0, st>>>(ntet, fc.nloc, fc.loff, fc.cols, ctx->e2c.as<int32_t>(), sub->e2c.as<int32_t>(), bad);
             ctx->launches += 2;
-            sub->row_begin = 0; sub->row_end = fr.count; sub->ncols_global = fc.count;
+            const long long nr = fr.rows.total();
+            sub->row_begin = 0; sub->row_end = nr; sub->ncols_global = fc.cols.total();
             sub->has_dofmap = true; sub->has_signs = false;
-            if (femR != femC) {
-                // no forced diagonal in a rectangular block
-                if (sub->diag_col.reserve(std::max<long long>(1, fr.count) * 4) != cudaSuccess) { blocks_clear(ctx); return 0; }
-                cudaMemsetAsync(sub->diag_col.p, 0xFF, fr.count * 4, st);
+            if (femR != femC || ctx->fields_custom) {
+                // no forced diagonal in a rectangular block; under a segmented numbering the scalar row and column numberings
+                // differ, and the diagonal entry is structural in the caller's pattern anyway
+                if (sub->diag_col.reserve(std::max<long long>(1, nr) * 4) != cudaSuccess) { blocks_clear(ctx); return 0; }
+                cudaMemsetAsync(sub->diag_col.p, 0xFF, nr * 4, st);
                 sub->has_diag = true;
             }
             int64_t nnz = 0;
@@ -141,43 +221,62 @@ int blocks_build(afb_ctx* ctx) {
             ctx->launches += sub->launches; sub->launches = 0;
             if (rc != 0 || !sub->has_rows_plan) { blocks_clear(ctx); return 0; }
         }
-    // ---- consistency of the row structure + destinations of every field pair
-    if (ctx->flag.reserve(64) != cudaSuccess) { blocks_clear(ctx); return 0; }
-    cudaMemsetAsync(ctx->flag.p, 0, 64, st);
+    // ---- destinations of every field pair inside the caller's rows
     const long long* grow = ctx->rowptr.as<long long>();
-    auto len_src = [&](int femR, int upto_field) {
-        LenSrc ls;
-        for (int k = 0; k < 3; ++k) { ls.rowptr[k] = nullptr; ls.mult[k] = 0; }
-        for (size_t k = 0; k < fems.size() && k < 3; ++k) {
-            int m = 0;
-            for (int g = 0; g < upto_field; ++g) m += ctx->fields[g].fem == fems[k];
-            if (m) { ls.rowptr[k] = find_pair(ctx, femR, fems[k])->rowptr.as<long long>(); ls.mult[k] = m; }
-        }
-        return ls;
+    const int32_t* gcol = ctx->colind.as<int32_t>();
+    ctx->block_dst.resize((size_t)nf * nf); ctx->block_tix.resize((size_t)nf * nf); ctx->block_tab.resize((size_t)nf * nf);
+    ctx->block_rdst.resize((size_t)nf);
+    afb::DevBuf p0, tcount, toff, cubtmp;
+    auto fail = [&]() {
+        if (getenv("AFB_VERBOSE")) fprintf(stderr, "[afb] block path not offered: block destinations could not be resolved (%s)\n", cudaGetErrorString(cudaGetLastError()));
+        p0.release(); tcount.release(); toff.release(); cubtmp.release(); cudaGetLastError(); blocks_clear(ctx); return 0;
     };
-    if (fems.size() > 3) { blocks_clear(ctx); return 0; }
-    for (int fR = 0; fR < nf; ++fR) {
-        const Field& f = ctx->fields[fR];
-        k_check_rows<<<grid_for(f.count), 256, 0, st>>>(f.count, f.goff, grow, len_src(f.fem, nf), ctx->flag.as<int>());
-    }
-    ctx->block_dst.resize((size_t)nf * nf);
     for (int fR = 0; fR < nf; ++fR)
         for (int fC = 0; fC < nf; ++fC) {
             const Field& f = ctx->fields[fR];
-            afb_ctx* sub = find_pair(ctx, f.fem, ctx->fields[fC].fem);
-            const long long n = sub->rp_nslices * 32;
-            afb::DevBuf& d = ctx->block_dst[(size_t)fR * nf + fC];
-            if (d.reserve(std::max<long long>(1, n) * 8) != cudaSuccess) { blocks_clear(ctx); return 0; }
-            k_block_dst<<<grid_for(n), 256, 0, st>>>(n, sub->rp_order.as<unsigned>(), f.goff, grow, len_src(f.fem, fC), d.as<long long>());
+            const Field& g = ctx->fields[fC];
+            afb_ctx* sub = find_pair(ctx, f.fem, g.fem);
+            const long long nrs = sub->row_end, n = sub->rp_nslices * 32;
+            const size_t b = (size_t)fR * nf + fC;
+            if (p0.reserve(std::max<long long>(1, nrs) * 8) != cudaSuccess || tcount.reserve((nrs + 1) * 4) != cudaSuccess || toff.reserve((nrs + 1) * 4) != cudaSuccess ||
+                ctx->block_dst[b].reserve(std::max<long long>(1, n) * 8) != cudaSuccess || ctx->block_tix[b].reserve(std::max<long long>(1, n) * 4) != cudaSuccess)
+                return fail();
+            cudaMemsetAsync(tcount.p, 0, (nrs + 1) * 4, st);
+            k_block_scan<<<grid_for(nrs), 256, 0, st>>>(nrs, f.rows, g.cols, sub->rowptr.as<long long>(), sub->colind.as<int32_t>(), grow, gcol, p0.as<long long>(),
+                                                       tcount.as<int>(), bad, covered);
+            size_t tb = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, tb, tcount.as<int>(), toff.as<int>(), nrs + 1, st);
+            if (cubtmp.reserve(tb) != cudaSuccess) return fail();
+            if (cub::DeviceScan::ExclusiveSum(cubtmp.p, tb, tcount.as<int>(), toff.as<int>(), nrs + 1, st) != cudaSuccess) return fail();
+            int ntab = 0, hb = 0;
+            if (cudaMemcpyAsync(&ntab, toff.as<int>() + nrs, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                cudaMemcpyAsync(&hb, bad, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess || hb || ntab < 0)
+                return fail();
+            if (ntab > 0) {
+                if (ctx->block_tab[b].reserve((size_t)ntab * 2) != cudaSuccess) return fail();
+                k_block_tab<<<grid_for(nrs), 256, 0, st>>>(nrs, f.rows, g.cols, sub->rowptr.as<long long>(), sub->colind.as<int32_t>(), grow, gcol, tcount.as<int>(),
+                                                          toff.as<int>(), ctx->block_tab[b].as<unsigned short>());
+            }
+            k_block_dst<<<grid_for(n), 256, 0, st>>>(n, sub->rp_order.as<unsigned>(), p0.as<long long>(), tcount.as<int>(), toff.as<int>(),
+                                                    ctx->block_dst[b].as<long long>(), ctx->block_tix[b].as<int>());
+            if (ntab == 0) ctx->block_tix[b].release();   // all blocks contiguous: the gather skips the table lookups
+            if (fC == fR) {
+                if (ctx->block_rdst[fR].reserve(std::max<long long>(1, n) * 4) != cudaSuccess) return fail();
+                k_block_rdst<<<grid_for(n), 256, 0, st>>>(n, sub->rp_order.as<unsigned>(), f.rows, ctx->block_rdst[fR].as<int>());
+            }
+            ctx->launches += 4;
         }
-    ctx->launches += nf + nf * nf;
-    int bad = 0;
-    if (cudaMemcpyAsync(&bad, ctx->flag.p, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess || bad) {
-        cudaGetLastError();
-        blocks_clear(ctx);
-        return 0;
-    }
+    int hb = 0;
+    unsigned long long hcov = 0;
+    if (cudaMemcpyAsync(&hb, bad, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaMemcpyAsync(&hcov, covered, sizeof(hcov), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess || hb)
+        return fail();
+    p0.release(); tcount.release(); toff.release(); cubtmp.release();
+    ctx->blocks_cover = hcov == (unsigned long long)ctx->nnz;
     ctx->blocks_ready = true;
+    if (getenv("AFB_VERBOSE"))
+        fprintf(stderr, "[afb] block path: %d fields, %zu pair plans, blocks cover %llu of %lld entries%s\n", nf, ctx->pairs.size(), hcov, (long long)ctx->nnz,
+                ctx->fields_custom ? " (segmented numbering)" : "");
     return 0;
 }
 
@@ -292,7 +391,7 @@ int assemble_block_path(afb_ctx* ctx, int nfA, int nfF, const std::vector<afb_fo
     cudaEventRecord(ctx->ev[2], st);
     if (!accumulate) {
         // blocks no form touches are structural zeros of the template (assembler.inl:642-684)
-        if (dval && empty_mat && ctx->nnz) AFB_CUDA(ctx, cudaMemsetAsync(dval, 0, ctx->nnz * sizeof(double), st));
+        if (dval && (empty_mat || !ctx->blocks_cover) && ctx->nnz) AFB_CUDA(ctx, cudaMemsetAsync(dval, 0, ctx->nnz * sizeof(double), st));
         if (drhs && std::find(row_has_rhs.begin(), row_has_rhs.end(), 0) != row_has_rhs.end() && nrows)
             AFB_CUDA(ctx, cudaMemsetAsync(drhs, 0, nrows * sizeof(double), st));
     }
@@ -301,9 +400,11 @@ int assemble_block_path(afb_ctx* ctx, int nfA, int nfF, const std::vector<afb_fo
             Group& g = groups[(size_t)fR * nf + fC];
             if (g.mat.empty() && g.rhs.empty()) continue;
             afb_ctx* sub = find_pair(ctx, ctx->fields[fR].fem, ctx->fields[fC].fem);
-            const int rc = fused_group(ctx, sub, g.mat, g.rhs, g.mat.empty() ? nullptr : dval,
-                                       g.rhs.empty() ? nullptr : drhs + ctx->fields[fR].goff,
-                                       ctx->block_dst[(size_t)fR * nf + fC].as<long long>(), accumulate, drop_val, status_flag, false);
+            const size_t b = (size_t)fR * nf + fC;
+            const int rc = fused_group(ctx, sub, g.mat, g.rhs, g.mat.empty() ? nullptr : dval, g.rhs.empty() ? nullptr : drhs,
+                                       ctx->block_dst[b].as<long long>(), accumulate, drop_val, status_flag, false, 0,
+                                       ctx->block_tix[b].as<int>(), ctx->block_tab[b].as<unsigned short>(),
+                                       g.rhs.empty() ? nullptr : ctx->block_rdst[fR].as<int>());
             if (rc < 0) return rc;
             if (rc != 2) { set_error(ctx, "internal: block path lost a group after the support check"); return -4; }
         }

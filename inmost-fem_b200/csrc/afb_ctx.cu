@@ -351,7 +351,7 @@ int afb_mesh_set(afb_ctx* ctx, int64_t nnode, const double* x, const double* y, 
     AFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->nnode = nnode; ctx->ntet = ntet;
     ctx->has_dofmap = false; ctx->has_pattern = false;
-    ctx->fields.clear(); afb::blocks_clear(ctx);
+    ctx->fields.clear(); ctx->fields_custom = false; afb::blocks_clear(ctx);
     return 0;
 }
 
@@ -372,7 +372,7 @@ int afb_mesh_cube(afb_ctx* ctx, int nx, int ny, int nz, double size, int bx, int
     AFB_CUDA(ctx, cudaGetLastError());
     ctx->nnode = nnode; ctx->ntet = ntet;
     ctx->has_dofmap = false; ctx->has_pattern = false;
-    ctx->fields.clear(); afb::blocks_clear(ctx);
+    ctx->fields.clear(); ctx->fields_custom = false; afb::blocks_clear(ctx);
     return afb_mesh_orient(ctx);
 }
 
@@ -437,7 +437,7 @@ int afb_dofmap_set(afb_ctx* ctx, int nrow_loc, int ncol_loc, const int64_t* elem
     ctx->nrow_loc = nrow_loc; ctx->ncol_loc = ncol_loc;
     ctx->row_begin = row_begin; ctx->row_end = row_end; ctx->ncols_global = ncols_global;
     ctx->has_dofmap = true; ctx->has_pattern = false; ctx->has_diag = false;
-    ctx->fields.clear(); afb::blocks_clear(ctx);
+    ctx->fields.clear(); ctx->fields_custom = false; afb::blocks_clear(ctx);
     ctx->has_dirichlet = false; ctx->dir_rows_valid = false;
     return 0;
 }
@@ -580,6 +580,9 @@ int afb_dofmap_natural(afb_ctx* ctx, int nvars, const int* fem, const int* vec) 
                 off += nent[d] * ndof[d];
             }
             f.count = off - f.goff;
+            f.rows.n = f.cols.n = 1;
+            f.rows.start[0] = f.cols.start[0] = f.goff;
+            f.rows.count[0] = f.cols.count[0] = f.count;
             fields.push_back(f);
         }
         nloc += vec[v] * nl1;
@@ -602,7 +605,52 @@ int afb_dofmap_natural(afb_ctx* ctx, int nvars, const int* fem, const int* vec) 
     ctx->has_dofmap = true; ctx->has_pattern = false;
     afb::blocks_clear(ctx);
     ctx->fields = fields;
+    ctx->fields_custom = false;
     ctx->has_dirichlet = false; ctx->dir_rows_valid = false;
+    return 0;
+}
+
+// Scalar fields of a caller-supplied dof map.  Under the per-rank NATURAL numbering of a partitioned mesh
+// (inmost_interface/global_enumerator.cpp:594-604,702-777) a field (variable, component) is contiguous inside every rank's
+// interval only, so its rows (local ids) and columns (global ids) are lists of intervals.
+int afb_fields_set(afb_ctx* ctx, int nfields, const int* fem, const int* loff, int nseg_row, const int64_t* row_seg, int nseg_col,
+                   const int64_t* col_seg) {
+    if (!ctx) return -7;
+    if (!ctx->has_dofmap) { set_error(ctx, "dof map was not specified"); return -6; }
+    afb::blocks_clear(ctx);
+    ctx->fields.clear();
+    ctx->fields_custom = false;
+    ctx->has_pattern = false;
+    if (nfields == 0) return 0;
+    if (nfields < 0 || nfields > 8 || !fem || !loff || !row_seg || !col_seg || nseg_row < 1 || nseg_col < 1 || nseg_row > AFB_MAX_SEG ||
+        nseg_col > AFB_MAX_SEG) { set_error(ctx, "afb_fields_set: 1..8 fields with 1..8 row / column intervals each"); return -7; }
+    std::vector<Field> fields;
+    for (int f = 0; f < nfields; ++f) {
+        if (fem[f] != AFB_FEM_P1 && fem[f] != AFB_FEM_P2 && fem[f] != AFB_FEM_P3) { set_error(ctx, "afb_fields_set: fields live on P1, P2 or P3"); return -3; }
+        Field fl;
+        std::memset(&fl, 0, sizeof(fl));
+        fl.fem = fem[f];
+        fl.nloc = fem[f] == AFB_FEM_P1 ? 4 : (fem[f] == AFB_FEM_P2 ? 10 : 20);
+        fl.loff = loff[f];
+        if (fl.loff < 0 || fl.loff + fl.nloc > ctx->nrow_loc || fl.loff + fl.nloc > ctx->ncol_loc) { set_error(ctx, "afb_fields_set: local offsets outside the dof map"); return -7; }
+        for (int side = 0; side < 2; ++side) {
+            SegMap& m = side ? fl.cols : fl.rows;
+            const int ns = side ? nseg_col : nseg_row;
+            const int64_t* src = (side ? col_seg : row_seg) + (size_t)f * ns * 2;
+            const long long limit = side ? ctx->ncols_global : ctx->row_end - ctx->row_begin;
+            for (int k = 0; k < ns; ++k) {
+                if (src[2 * k] < 0 || src[2 * k + 1] < 0 || src[2 * k] + src[2 * k + 1] > limit) { set_error(ctx, "afb_fields_set: interval outside the row / column space"); return -7; }
+                if (src[2 * k + 1] == 0) continue;
+                m.start[m.n] = src[2 * k]; m.count[m.n] = src[2 * k + 1]; ++m.n;
+            }
+        }
+        if (fl.rows.total() > 2147483000LL || fl.cols.total() > 2147483000LL) { set_error(ctx, "afb_fields_set: field too large"); return -7; }
+        fl.goff = fl.rows.n ? fl.rows.start[0] : 0;
+        fl.count = fl.rows.total();
+        fields.push_back(fl);
+    }
+    ctx->fields = fields;
+    ctx->fields_custom = true;
     return 0;
 }
 

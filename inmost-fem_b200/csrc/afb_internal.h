@@ -75,8 +75,32 @@ struct TableEntry {
     double *W, *phi, *grd;  // device
 };
 
-// scalar field (variable, component) of a NATURAL dof map: base space, local and global offsets
-struct Field { int fem, nloc, loff; long long goff, count; };
+// intervals of a scalar field inside the row (local ids) or column (global ids) space; the scalar numbering of the field is
+// the concatenation of the intervals.  One interval under a single-rank NATURAL numbering, one per owner rank under the
+// per-rank numbering of a partitioned mesh (afb_fields_set).
+#define AFB_MAX_SEG 8
+struct SegMap {
+    int n;
+    long long start[AFB_MAX_SEG], count[AFB_MAX_SEG];
+    __host__ __device__ long long total() const { long long t = 0; for (int k = 0; k < n; ++k) t += count[k]; return t; }
+    __host__ __device__ long long to_scalar(long long id) const {   // -1: not in the field
+        long long pre = 0;
+        for (int k = 0; k < n; ++k) {
+            if (id >= start[k] && id < start[k] + count[k]) return pre + (id - start[k]);
+            pre += count[k];
+        }
+        return -1;
+    }
+    __host__ __device__ long long to_full(long long s) const {
+        for (int k = 0; k < n; ++k) {
+            if (s < count[k]) return start[k] + s;
+            s -= count[k];
+        }
+        return -1;
+    }
+};
+// scalar field (variable, component) of a dof map: base space, local offset, row / column intervals
+struct Field { int fem, nloc, loff; long long goff, count; SegMap rows, cols; };
 struct PairPlan { int femR, femC; afb_ctx* sub; };
 
 struct afb_ctx {
@@ -85,7 +109,12 @@ struct afb_ctx {
     std::vector<Field> fields;    // set by afb_dofmap_natural
     std::vector<PairPlan> pairs;  // gather plans of (row space, column space) pairs
     std::vector<afb::DevBuf> block_dst;   // [fR*nf + fC]: first CSR entry of block (fR,fC) per (slice, lane) of its pair plan
+    std::vector<afb::DevBuf> block_tix;   // [fR*nf + fC]: int32 per (slice, lane): 0 = the block is contiguous in the row, else 1 + first entry of its offset table
+    std::vector<afb::DevBuf> block_tab;   // [fR*nf + fC]: uint16 offsets (relative to block_dst) of the entries of non-contiguous blocks
+    std::vector<afb::DevBuf> block_rdst;  // [fR]: int32 per (slice, lane) of the pair plan (space of fR, space of fR): local row that receives the rhs
     bool blocks_ready = false;
+    bool blocks_cover = true;     // every entry of the pattern belongs to some block (else the values are cleared before a non-accumulating assembly)
+    bool fields_custom = false;   // fields came from afb_fields_set (segmented numbering)
     std::vector<TableEntry> table_cache;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
@@ -166,7 +195,8 @@ struct SForm {
 namespace afb {
 bool make_sform(const afb_form& f, const OpInfo& oa, const OpInfo& ob, const double* Ddev, SForm* out);
 int fused_group(afb_ctx* ctx, afb_ctx* plan, const std::vector<SForm>& mat, const std::vector<SForm>& rhsf, double* dval, double* drhs,
-                const long long* p0_override, int accumulate, double drop_val, int* status_flag, bool record_events, int phase = 0);
+                const long long* p0_override, int accumulate, double drop_val, int* status_flag, bool record_events, int phase = 0,
+                const int* tix = nullptr, const unsigned short* rtab = nullptr, const int* rdst = nullptr);
 // element kernels (afb_element.cu)
 int launch_form(afb_ctx* ctx, const afb_form& form, const OpInfo& A, const OpInfo& B, int64_t f,
                 const double* x, const double* y, const double* z,                 // SoA nodes (or NULL)
@@ -181,6 +211,7 @@ int launch_forms_sq(afb_ctx* ctx, const std::vector<afb_form>& fm, const std::ve
 int get_tables(afb_ctx* ctx, int fem, int order, const double** W, const double** phi, const double** grd);
 // block-decomposed fused path of vector / mixed spaces (afb_blocks.cu)
 void blocks_clear(afb_ctx* ctx);
+void blocks_clear_dst(afb_ctx* ctx);
 int blocks_build(afb_ctx* ctx);
 int assemble_block_path(afb_ctx* ctx, int nfA, int nfF, const std::vector<afb_form>& fm, const std::vector<OpInfo>& oa,
                         const std::vector<OpInfo>& ob, const std::vector<const double*>& Dd, double* dval, double* drhs, int accumulate,
@@ -191,7 +222,8 @@ int dirichlet_apply(afb_ctx* ctx, double* val, double* rhs);
 int build_rows_plan(afb_ctx* ctx);
 bool rows_supports(const afb_ctx* ctx, int nga, int ngf);
 int launch_rows(afb_ctx* ctx, int nga, int ngf, const double* TA, const double* TF, const double* gbuf, double* val, double* rhs,
-                int accumulate, double drop_val, int* status, const long long* p0_override = nullptr, int phase = 0);
+                int accumulate, double drop_val, int* status, const long long* p0_override = nullptr, int phase = 0,
+                const int* tix = nullptr, const unsigned short* rtab = nullptr, const int* rdst = nullptr);
 int rows_priority_build(afb_ctx* ctx, long long first_priority_row);
 // gather (afb_gather.cu)
 int launch_gather(afb_ctx* ctx, const double* stageA, const double* stageF, double* val, double* rhs,

@@ -162,7 +162,7 @@ static int pattern_impl(afb_ctx* ctx, int64_t* nnz_out, const int64_t* user_rowp
     if (ctx->ntet <= 0) { set_error(ctx, "Mesh was not specified"); return -6; }
     if (!ctx->has_dofmap) { set_error(ctx, "dof map was not specified (afb_dofmap_set / afb_dofmap_natural)"); return -6; }
     cudaSetDevice(ctx->device);
-    blocks_clear(ctx);
+    blocks_clear_dst(ctx);
     ctx->dir_rows_valid = false;
     const long long ntet = ctx->ntet, nrows = ctx->row_end - ctx->row_begin;
     const int nrl = ctx->nrow_loc, ncl = ctx->ncol_loc;
@@ -260,7 +260,7 @@ static int pattern_impl(afb_ctx* ctx, int64_t* nnz_out, const int64_t* user_rowp
     if (rcp) return rcp;
     ctx->rp_prio_valid = false;
     if (ctx->priority_row >= 0 && !ctx->is_sub) { const int rcq = rows_priority_build(ctx, ctx->priority_row); if (rcq) return rcq; }
-    return user_rowptr ? 0 : blocks_build(ctx);  // pair plans of vector / mixed spaces (structural pattern only)
+    return blocks_build(ctx);  // pair plans of vector / mixed spaces; block destinations are searched in whatever pattern is installed
 }
 
 int afb_pattern_get(afb_ctx* ctx, int64_t* rowptr, int32_t* colind, int mem_space) {

@@ -283,6 +283,9 @@ struct RowsArgs {
     const unsigned* elist;   // Morton ids of the elements a cluster touches
     const unsigned* srow;    // [nslices*32] rows of a slice (0xFFFFFFFF = empty lane)
     const long long* sp0;    // [nslices*32] first CSR entry of the row
+    const int* tix;          // NULL, or [nslices*32]: 0 = the row's entries are contiguous from sp0, else 1 + first entry of its offset table
+    const unsigned short* rtab;   // offsets (relative to sp0) of the entries of non-contiguous rows (blocks of segmented numberings, afb_blocks.cu)
+    const int* rdst;         // NULL (rhs[row]), or [nslices*32]: index into rhs that receives the row's load entry
     const unsigned short* slen;   // [nslices*32] row length
     const unsigned short* smax;   // [nslices] longest row of the slice
     const unsigned short* cnt;    // [nslices*NLOC]
@@ -331,6 +334,7 @@ struct SliceMeta {
     unsigned r;
     long long p0;
     int len;
+    int tix, rdst;
     long long st, en;
     int cn[NLOC];
 };
@@ -425,6 +429,8 @@ __global__ void __launch_bounds__(384, 1) k_rows_cl(const __grid_constant__ RowT
         m.r = __ldg(p.srow + (size_t)s * 32 + lane);
         m.p0 = __ldg(p.sp0 + (size_t)s * 32 + lane);
         m.len = (int)__ldg(p.slen + (size_t)s * 32 + lane);
+        m.tix = p.tix ? __ldg(p.tix + (size_t)s * 32 + lane) : 0;
+        m.rdst = p.rdst ? __ldg(p.rdst + (size_t)s * 32 + lane) : (int)m.r;
         m.st = __ldg(p.sptr + s);
         m.en = __ldg(p.sptr + s + 1);
 #pragma unroll
@@ -547,7 +553,7 @@ __global__ void __launch_bounds__(384, 1) k_rows_cl(const __grid_constant__ RowT
             RowDst rd;
             rd.ptr = p.val + cur.p0;
             rd.len = cur.len;
-            rd.pad = 0;
+            rd.pad = cur.tix;
             sdst[lane] = rd;
             double chk = 0.0;  // becomes NaN iff some finished entry is NaN or +-Inf (x*0 is NaN for those)
             for (int s0 = 0; s0 < Lw; s0 += 16) {
@@ -582,7 +588,9 @@ __global__ void __launch_bounds__(384, 1) k_rows_cl(const __grid_constant__ RowT
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         if (sl < d[u].len) {
-                            if (p.accumulate) d[u].ptr[sl] += y[u]; else d[u].ptr[sl] = y[u];
+                            // d[u] is warp-uniform (one row per step): the table branch does not diverge
+                            const int off = d[u].pad ? (int)__ldg(p.rtab + (d[u].pad - 1 + sl)) : sl;
+                            if (p.accumulate) d[u].ptr[off] += y[u]; else d[u].ptr[off] = y[u];
                         }
                     }
                 }
@@ -592,7 +600,7 @@ __global__ void __launch_bounds__(384, 1) k_rows_cl(const __grid_constant__ RowT
         if (NGF > 0) {
             bad |= ((unsigned)__double2hiint(fsum) & 0x7ff00000u) == 0x7ff00000u;
             if (cur.r != 0xffffffffu) {
-                if (p.accumulate) p.rhs[cur.r] += fsum; else p.rhs[cur.r] = fsum;
+                if (p.accumulate) p.rhs[cur.rdst] += fsum; else p.rhs[cur.rdst] = fsum;
             }
         }
         s = sn;
@@ -643,7 +651,7 @@ RowsShape rows_shape(const afb_ctx* ctx, int ngp) {
 
 template <int NLOC, int NC, int NGA, int NGF>
 int launch_rows_t(afb_ctx* ctx, const double* TA, const double* TF, const double* gbuf, double* val, double* rhs, int accumulate,
-                  double drop_val, int* status, const long long* p0_override, int phase) {
+                  double drop_val, int* status, const long long* p0_override, int phase, const int* tix, const unsigned short* rtab, const int* rdst) {
     constexpr int NGP = (NGA + NGF + 1) & ~1;
     static RowTab<NLOC, NC, NGA, NGF> T;  // host staging of the parameter (copied by value at launch)
     // TA is [c][i][j], TF is [c][i]
@@ -661,6 +669,7 @@ int launch_rows_t(afb_ctx* ctx, const double* TA, const double* TF, const double
     p.cs = ctx->rp_cs.as<int>(); p.eptr = ctx->rp_eptr.as<int>(); p.elist = ctx->rp_elist.as<unsigned>();
     p.srow = ctx->rp_order.as<unsigned>(); p.sp0 = p0_override ? p0_override : ctx->rp_p0.as<long long>(); p.slen = ctx->rp_len.as<unsigned short>();
     p.smax = ctx->rp_smax.as<unsigned short>();
+    p.tix = rtab ? tix : nullptr; p.rtab = rtab; p.rdst = rdst;
     p.cnt = ctx->rp_cnt.as<unsigned short>(); p.sptr = ctx->rp_sptr.as<long long>();
     p.ell = ctx->rp_ell.as<unsigned>(); p.gbuf = gbuf;
     p.val = val; p.rhs = rhs; p.accumulate = accumulate; p.status = status;
@@ -685,8 +694,9 @@ int launch_rows_t(afb_ctx* ctx, const double* TA, const double* TF, const double
 
 template <int NLOC, int NC>
 int launch_rows_n(afb_ctx* ctx, int nga, int ngf, const double* TA, const double* TF, const double* gbuf, double* val, double* rhs,
-                  int accumulate, double drop_val, int* status, const long long* p0_override, int phase) {
-#define RW(A, F) if (nga == A && ngf == F) return launch_rows_t<NLOC, NC, A, F>(ctx, TA, TF, gbuf, val, rhs, accumulate, drop_val, status, p0_override, phase);
+                  int accumulate, double drop_val, int* status, const long long* p0_override, int phase, const int* tix, const unsigned short* rtab,
+                  const int* rdst) {
+#define RW(A, F) if (nga == A && ngf == F) return launch_rows_t<NLOC, NC, A, F>(ctx, TA, TF, gbuf, val, rhs, accumulate, drop_val, status, p0_override, phase, tix, rtab, rdst);
     RW(6, 1) RW(6, 0) RW(7, 1) RW(7, 0) RW(1, 1) RW(1, 0) RW(0, 1) RW(3, 0) RW(3, 1)
     if constexpr (NLOC <= 10) { RW(9, 1) RW(9, 0) RW(10, 1) RW(10, 0) }
 #undef RW
@@ -944,10 +954,11 @@ int rows_priority_build(afb_ctx* ctx, long long first_priority_row) {
 // 1 = launched, 0 = combination not covered (caller uses the lane-group gather), < 0 error.  gbuf must be in Morton order.
 // p0_override: first CSR entry of every (slice, lane) row when the rows of this plan are sub-blocks of longer rows (afb_blocks.cu).
 int launch_rows(afb_ctx* ctx, int nga, int ngf, const double* TA, const double* TF, const double* gbuf, double* val, double* rhs,
-                int accumulate, double drop_val, int* status, const long long* p0_override, int phase) {
+                int accumulate, double drop_val, int* status, const long long* p0_override, int phase, const int* tix, const unsigned short* rtab,
+                const int* rdst) {
     if (!rows_supports(ctx, nga, ngf)) return 0;
     const int nl = ctx->rp_nloc, nc = ctx->rp_ncol;
-#define RWD(NRr, NCc) if (nl == NRr && nc == NCc) return launch_rows_n<NRr, NCc>(ctx, nga, ngf, TA, TF, gbuf, val, rhs, accumulate, drop_val, status, p0_override, phase);
+#define RWD(NRr, NCc) if (nl == NRr && nc == NCc) return launch_rows_n<NRr, NCc>(ctx, nga, ngf, TA, TF, gbuf, val, rhs, accumulate, drop_val, status, p0_override, phase, tix, rtab, rdst);
     RWD(4, 4) RWD(10, 10) RWD(20, 20) RWD(10, 4) RWD(4, 10)
 #undef RWD
     return 0;

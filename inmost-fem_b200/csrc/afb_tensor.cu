@@ -458,7 +458,8 @@ namespace afb {
 // plan row inside the caller's matrix).  Returns 1 (lane-group gather) or 2 (cluster gather k_rows_cl), 0 if the group
 // cannot be handled (nothing was launched), < 0 on error.
 int fused_group(afb_ctx* ctx, afb_ctx* plan, const std::vector<SForm>& mat, const std::vector<SForm>& rhsf, double* dval, double* drhs,
-                const long long* p0_override, int accumulate, double drop_val, int* status_flag, bool record_events, int phase) {
+                const long long* p0_override, int accumulate, double drop_val, int* status_flag, bool record_events, int phase,
+                const int* tix, const unsigned short* rtab, const int* rdst) {
     const int nfA = (int)mat.size(), nfF = (int)rhsf.size(), nforms = nfA + nfF;
     if (nforms == 0 || nforms > MAX_TFORMS) return 0;
     const int nrl = plan->nrow_loc, ncl = plan->ncol_loc;
@@ -516,7 +517,7 @@ int fused_group(afb_ctx* ctx, afb_ctx* plan, const std::vector<SForm>& mat, cons
     if (use_rows) {
         // cluster-tiled thread-per-row gather (afb_rows.cu)
         plan->stream = ctx->stream;
-        const int rc = launch_rows(plan, nga, ngf, TA.data(), TF.data(), gbuf, dval, drhs, accumulate, drop_val, status_flag, p0_override, phase);
+        const int rc = launch_rows(plan, nga, ngf, TA.data(), TF.data(), gbuf, dval, drhs, accumulate, drop_val, status_flag, p0_override, phase, tix, rtab, rdst);
         if (plan != ctx) { ctx->launches += plan->launches; plan->launches = 0; if (rc < 0) set_error(ctx, plan->err); }
         if (rc < 0) return rc;
         if (rc != 1) { set_error(ctx, "internal: cluster gather refused a case it advertised"); return -4; }

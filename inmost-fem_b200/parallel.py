@@ -196,6 +196,34 @@ class Numbering:
         self.elem2dof = torch.stack(cols, 1).contiguous()
         self.nloc = self.elem2dof.shape[1]
         self.row_begin, self.row_end = int(self.beg_ind[self.rank]), int(self.end_ind[self.rank])
+        self.num, self.grp_off, self.nd_types = num, grp_off, nd_types
+
+    def fields(self, plan):
+        """Scalar fields (variable, component) for afb_fields_set: (fem, first local dof, row intervals, column intervals).
+        A field is contiguous inside every rank's interval (NATURAL: VAR, component, DIM, ... global_enumerator.cpp:702-777):
+        its global columns are one interval per rank; its local rows are the own interval followed by the runs of its
+        dofs inside the sorted list of foreign rows (one run per peer)."""
+        out, loff = [], 0
+        foreign = plan.foreign.cpu()
+        for v, (fem, vec) in enumerate(self.vars):
+            ds = [d for d in range(self.nd_types) if NDOF[fem][d]]
+            nl = 4 * NDOF[fem][0] + 6 * NDOF[fem][1]
+            for c in range(vec):
+                cols = []
+                for p in range(self.world):
+                    start = int(self.beg_ind[p] + self.grp_off[(v, c, ds[0])][p])
+                    count = int(sum(int(self.num[d][p]) * NDOF[fem][d] for d in ds))
+                    cols.append((start, count))
+                rows = [(cols[self.rank][0] - self.row_begin, cols[self.rank][1])]
+                for p in range(self.world):
+                    if p == self.rank or foreign.numel() == 0:
+                        continue
+                    lo = int(torch.searchsorted(foreign, torch.tensor([cols[p][0]])).item())
+                    hi = int(torch.searchsorted(foreign, torch.tensor([cols[p][0] + cols[p][1]])).item())
+                    rows.append((plan.n_own + lo, hi - lo))
+                out.append((fem, loff, rows, cols))
+                loff += nl
+        return out
 
 
 class InterfacePlan:
@@ -329,6 +357,10 @@ class DistributedAssembler:
         self.plan = plan = InterfacePlan(nb)
         n_ext = plan.n_own + plan.n_for
         ctx.dofmap_set_any(plan.rowcode, plan.colcode, 0, n_ext, nb.nrows_global, plan.diag_col)
+        self.fields = nb.fields(plan)
+        if len(self.fields) > 1 and hasattr(ctx, "fields_set"):
+            # vector-valued / mixed spaces: the assembly runs block by block on scalar gather plans (afb_blocks.cu)
+            ctx.fields_set(self.fields)
         ctx.pattern_build()
         rp, ci = ctx.pattern_get_torch()
         self.rowptr_ext, self.colind_ext = plan.finalize_pattern(rp, ci)

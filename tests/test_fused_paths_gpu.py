@@ -168,6 +168,60 @@ def test_block_path_mixed_p2_p1_scalars(pkg, ctx, asm_oracle):
     assert path["gather_kernel"] == "k_rows_cl"
 
 
+def _segmented_fields(M, dm, variables, world):
+    """fields of a per-rank NATURAL numbering held by ONE context (rows = global ids): one interval per owner rank"""
+    fields, loff = [], 0
+    num = [np.bincount(dm.owner[d], minlength=world) for d in range(4)]
+    for v, (fem, vec) in enumerate(variables):
+        ds = [d for d in range(4) if M.NDOF[fem][d]]
+        for c in range(vec):
+            segs = [(int(dm.beg_ind[p] + dm.grp_off[(v, c, ds[0])][p]), int(sum(num[d][p] * M.NDOF[fem][d] for d in ds))) for p in range(world)]
+            fields.append((fem, loff, segs, segs))
+            loff += gc.NF[fem]
+    return fields
+
+
+@pytest.mark.parametrize("problem,world", [("c5", 2), ("c4", 3), ("c5", 8)])
+def test_block_path_segmented_numbering(pkg, ctx, asm_oracle, problem, world):
+    """the per-rank NATURAL numbering of a partitioned mesh (fields contiguous inside every rank's interval only,
+    global_enumerator.cpp:594-604) on one context: afb_fields_set keeps the problem on the block path; blocks of a row
+    are then non-contiguous runs found by search.  Also with a superset pattern (columns no local cell touches, as the
+    interface rows of a multi-GPU run have): the extra entries stay zero."""
+    M = asm_oracle
+    variables = [(gc.P2, 3)] if problem == "c4" else [(gc.P2, 3), (gc.P1, 1)]
+    n = (4, 3, 2) if world < 8 else (4, 4, 2)
+    co, te, cr = M.cube_mesh(*n, nranks=world)
+    ctx.mesh_set(co, te)
+    dm = M.DofMap(te, variables, cr, world, nnode=co.shape[0])
+    rowcode, colcode = dm.codes(None)
+    ctx.dofmap_set(rowcode, colcode, 0, dm.nrows, dm.nrows)
+    ctx.fields_set(_segmented_fields(M, dm, variables, world))
+    _, forms, rhsf, prob = (problems.c4_p2_elasticity if problem == "c4" else problems.c5_stokes)(pkg, M, co, te)
+    a, fa, path = _oracle_compare(ctx, M, prob, forms, rhsf, co, te, dm, "%s segmented x%d" % (problem, world))
+    assert path["gather_kernel"] == "k_rows_cl", "the block path did not run"
+    b, fb = a.copy(), fa.copy()
+    assert ctx.assemble(forms, rhsf, b, fb, accumulate=True) == 0
+    assert np.array_equal(b, 2 * a) and np.array_equal(fb, 2 * fa)
+    # superset pattern: one extra column in every third row
+    rowptr, colind = ctx.pattern_get()
+    nrows = rowptr.size - 1
+    rows = np.repeat(np.arange(nrows), np.diff(rowptr))
+    key = rows.astype(np.int64) * dm.nrows + colind
+    extra_r = np.arange(0, nrows, 3)
+    extra = extra_r.astype(np.int64) * dm.nrows + (extra_r * 7 + 3) % dm.nrows
+    key2 = np.union1d(key, extra)
+    rp2 = np.zeros(nrows + 1, dtype=np.int64)
+    np.add.at(rp2, key2 // dm.nrows + 1, 1)
+    rp2 = np.cumsum(rp2)
+    ci2 = (key2 % dm.nrows).astype(np.int32)
+    ctx.pattern_set(rp2, ci2)
+    v2, f2 = np.full(ci2.size, np.nan), np.full(nrows, np.nan)
+    assert ctx.assemble(forms, rhsf, v2, f2) == 0
+    assert ctx.last_times()["gather_kernel"] == "k_rows_cl"
+    old = np.isin(key2, key)
+    assert np.array_equal(v2[old], a) and np.all(v2[~old] == 0.0) and np.array_equal(f2, fa)
+
+
 @pytest.mark.parametrize("ttype", [gc.T_NULL, gc.T_SCALAR, gc.T_SYMMETRIC, gc.T_GENERAL])
 @pytest.mark.parametrize("layout", [gc.L_CONST, gc.L_PER_TET, gc.L_PER_POINT])
 def test_tiled_element_kernel_all_tensor_kinds(pkg, ctx, asm_oracle, ttype, layout):
