@@ -145,6 +145,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-n", type=int, default=40, help="hexes per axis of the CPU sample (40 -> 384,000 tets)")
     ap.add_argument("--ref-reps", type=int, default=12, help="timed passes of the CPU sample in the cpu_baseline leg (about 10-20 core-seconds)")
+    ap.add_argument("--config", default="c2", choices=["c2", "c4", "c5"],
+                    help="multi-GPU runs only: c4 = FemVec<3,P2> elasticity, c5 = Taylor-Hood Stokes (single GPU: bench_configs.py); the contract line is c2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the quick C1/C3/C4/C5 measurements")
     args = ap.parse_args()
@@ -167,6 +169,8 @@ def main():
     if world > 1:
         import bench_multi
         return bench_multi.run(args, pkg, rank, world, local_rank)
+    if args.config != "c2":
+        raise SystemExit("--config c4/c5 is the multi-GPU leg; on one GPU run bench_configs.py --configs c4,c5")
 
     stream = torch.cuda.current_stream()
     ctx = pkg.Context(local_rank, stream.cuda_stream)

@@ -27,20 +27,30 @@ def run(args, pkg, rank, world, local_rank):
     stream = torch.cuda.current_stream()
     ctx = pkg.Context(local_rank, stream.cuda_stream)
     t0 = time.perf_counter()
-    da = par.DistributedAssembler(ctx, dims, [(pkg.P2, 1)])
+    config = getattr(args, "config", "c2")
+    variables = {"c2": [(pkg.P2, 1)], "c4": [(pkg.P2, 3)], "c5": [(pkg.P2, 3), (pkg.P1, 1)]}[config]
+    da = par.DistributedAssembler(ctx, dims, variables)
     torch.cuda.synchronize()
     setup_ms = (time.perf_counter() - t0) * 1e3
     ntet = da.ntet
-    xc = da.coords[da.tets.long()].mean(dim=1)
-    K_dev = torch.zeros((ntet, 9), dtype=torch.float64, device="cuda")
-    K_dev[:, 0] = 2 + xc[:, 0]; K_dev[:, 4] = 1; K_dev[:, 8] = 3
-    K_dev[:, 1] = K_dev[:, 3] = 0.5
-    K_dev[:, 5] = K_dev[:, 7] = -0.25
-    K_host = K_dev.cpu().pin_memory()
-    mk = lambda K: ([pkg.make_form(pkg.GRAD, pkg.P2, 1, pkg.GRAD, pkg.P2, 1, 2, pkg.TENSOR_SYMMETRIC, pkg.COEF_PER_TET, K)],
-                    [pkg.make_form(pkg.IDEN, pkg.P0, 1, pkg.IDEN, pkg.P2, 1, 2, pkg.TENSOR_NULL, pkg.COEF_CONST)])
-    forms_d, rhsf_d = mk(K_dev)
-    forms_h, rhsf_h = mk(K_host)
+    if config == "c2":
+        xc = da.coords[da.tets.long()].mean(dim=1)
+        K_dev = torch.zeros((ntet, 9), dtype=torch.float64, device="cuda")
+        K_dev[:, 0] = 2 + xc[:, 0]; K_dev[:, 4] = 1; K_dev[:, 8] = 3
+        K_dev[:, 1] = K_dev[:, 3] = 0.5
+        K_dev[:, 5] = K_dev[:, 7] = -0.25
+        K_host = K_dev.cpu().pin_memory()
+        mk = lambda K: ([pkg.make_form(pkg.GRAD, pkg.P2, 1, pkg.GRAD, pkg.P2, 1, 2, pkg.TENSOR_SYMMETRIC, pkg.COEF_PER_TET, K)],
+                        [pkg.make_form(pkg.IDEN, pkg.P0, 1, pkg.IDEN, pkg.P2, 1, 2, pkg.TENSOR_NULL, pkg.COEF_CONST)])
+        forms_d, rhsf_d = mk(K_dev)
+        forms_h, rhsf_h = mk(K_host)
+        h2d_bytes = int(K_host.numel() * 8)
+    else:
+        # C4 (FemVec<3,P2> elasticity, constant 9x9 tensor) / C5 (Taylor-Hood Stokes): constant coefficients, nothing per tet to ship
+        import problems
+        _, forms_d, rhsf_d, _ = (problems.c4_p2_elasticity if config == "c4" else problems.c5_stokes)(pkg, None, None, None)
+        forms_h, rhsf_h = forms_d, rhsf_d
+        h2d_bytes = 0
     for _ in range(args.warmup):
         assert da.assemble(forms_d, rhsf_d) == 0
     sampler = bench.ClockSampler(local_rank)
@@ -93,9 +103,13 @@ def run(args, pkg, rank, world, local_rank):
             pass
         peak_gbs = peaks.get("hbm_gbs", 6650.0)
         nn_all = (dims[0] + 1) * (dims[1] + 1) * (dims[2] + 1)
-        alg_bytes = 4 * 10 * ntet_all + 24 * nn_all + 72 * ntet_all + 8 * nnz_all + 8 * nrows_all
+        nloc = sum({pkg.P1: 4, pkg.P2: 10}[f] * v for f, v in variables)
+        alg_bytes = 4 * nloc * ntet_all + 24 * nn_all + (72 * ntet_all if config == "c2" else 0) + 8 * nnz_all + 8 * nrows_all
+        times = ctx.last_times()
         gbs = alg_bytes / (ms.item() * 1e-3) / 1e9
-        line = {"metric": bench.METRIC, "value": ntet_all / (ms.item() * 1e-3), "unit": bench.UNIT, "n_gpus": world, "steps": args.steps,
+        metric = bench.METRIC if config == "c2" else "assembled tets/sec (%s, FP64, CSR values + rhs)" % (
+            "C4: FemVec<3,P2> linear elasticity, constant 9x9 tensor" if config == "c4" else "C5: Taylor-Hood P2^3 x P1 Stokes")
+        line = {"metric": metric, "value": ntet_all / (ms.item() * 1e-3), "unit": bench.UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms.item(), "higher_is_better": True, "scaling": "strong" if args.global_n else "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": bench.config_dict(n, {"global_hexes": list(dims), "proc_grid": ppa, "ntet": ntet_all, "nrows": nrows_all, "nnz": nnz_all,
@@ -104,11 +118,14 @@ def run(args, pkg, rank, world, local_rank):
                                                 "setup_ms_rank0": setup_ms}),
                 "dof_per_s": nrows_all / (ms.item() * 1e-3),
                 "e2e": {"value": ntet_all / (ms_e2e.item() * 1e-3), "unit": bench.UNIT, "ms_per_step": ms_e2e.item(), "steps": e2e_steps,
-                        "h2d_bytes_per_step": int(K_host.numel() * 8) * world, "d2h_bytes_per_step": int((nnz_all + nrows_all) * 8)},
+                        "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": int((nnz_all + nrows_all) * 8)},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": gbs / world, "peak": peak_gbs, "unit": "GB/s", "frac": gbs / world / peak_gbs, "traffic": None,
-                             "kernel": "whole step per GPU (k_geom + k_rows_cl + exchange)", "algorithmic_bytes_per_launch": alg_bytes // world},
+                             "kernel": "whole step per GPU (%s + %s + exchange)" % (times["element_kernel"], times["gather_kernel"]),
+                             "algorithmic_bytes_per_launch": alg_bytes // world},
                 "clocks": sampler.summary()}
+        if config != "c2":
+            line["config"]["workload"] = metric + ", per-GPU block %d^3 hexes x 6 tets, structural pattern pre-built" % n
         print(json.dumps(line))
     ctx.close()
     dist.barrier()

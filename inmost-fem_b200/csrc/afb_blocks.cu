@@ -54,7 +54,7 @@ __device__ __forceinline__ long long find_col(const int32_t* __restrict__ gcol, 
 // mesh: the columns of a field are split by owner rank; columns contributed by other ranks only sit in between).
 __global__ void k_block_scan(long long nrows_s, SegMap rowsR, SegMap colsC, const long long* __restrict__ srowptr, const int32_t* __restrict__ scol,
                              const long long* __restrict__ grow, const int32_t* __restrict__ gcol, long long* p0, int* tcount, int* bad,
-                             unsigned long long* covered) {
+                             unsigned long long* covered, int* rowcov) {
     unsigned long long mine = 0;
     GRID_STRIDE(r, nrows_s) {
         const long long R = rowsR.to_full(r);
@@ -75,6 +75,7 @@ __global__ void k_block_scan(long long nrows_s, SegMap rowsR, SegMap colsC, cons
             }
             if (!contig) { first = b0; tc = (int)(a1 - a0); if (b1 - b0 > 65535) *bad = 1; }
             mine += (unsigned long long)(a1 - a0);
+            if (a1 > a0) atomicAdd(rowcov + R, (int)(a1 - a0));   // setup-time integer count
         }
         p0[r] = first;
         tcount[r] = tc;
@@ -90,6 +91,23 @@ __global__ void k_block_tab(long long nrows_s, SegMap rowsR, SegMap colsC, const
         const long long R = rowsR.to_full(r);
         const long long a0 = srowptr[r], a1 = srowptr[r + 1], b0 = grow[R], b1 = grow[R + 1];
         for (long long a = a0; a < a1; ++a) tab[toff[r] + (a - a0)] = (unsigned short)(find_col(gcol, b0, b1, colsC.to_full(scol[a])) - b0);
+    }
+}
+
+// rows with entries that belong to no block (columns only other ranks contribute to): flag for the compaction
+__global__ void k_gap_flag(long long nrows, const long long* __restrict__ grow, const int* __restrict__ rowcov, int* flag) {
+    GRID_STRIDE(r, nrows) flag[r] = rowcov[r] < (int)(grow[r + 1] - grow[r]) ? 1 : 0;
+}
+__global__ void k_gap_list(long long nrows, const int* __restrict__ flag, const int* __restrict__ off, int* list) {
+    GRID_STRIDE(r, nrows) if (flag[r]) list[off[r]] = (int)r;
+}
+// one warp per listed row: clear its values
+__global__ void k_zero_rows(int n, const int* __restrict__ list, const long long* __restrict__ grow, double* val) {
+    const int lane = threadIdx.x & 31;
+    const long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long k = w; k < n; k += nw) {
+        const long long r = list[k];
+        for (long long a = grow[r] + lane; a < grow[r + 1]; a += 32) val[a] = 0.0;
     }
 }
 
@@ -139,6 +157,8 @@ void blocks_clear_dst(afb_ctx* ctx) {
         for (auto& d : *v) d.release();
         v->clear();
     }
+    ctx->block_gap.release();
+    ctx->n_gap_rows = 0;
     ctx->blocks_ready = false;
     ctx->blocks_cover = true;
 }
@@ -148,12 +168,7 @@ void blocks_clear(afb_ctx* ctx) {
         if (p.sub) afb_ctx_destroy(p.sub);
     }
     ctx->pairs.clear();
-    for (auto* v : {&ctx->block_dst, &ctx->block_tix, &ctx->block_tab, &ctx->block_rdst}) {
-        for (auto& d : *v) d.release();
-        v->clear();
-    }
-    ctx->blocks_ready = false;
-    ctx->blocks_cover = true;
+    blocks_clear_dst(ctx);
 }
 
 // Builds the pair plans and block destinations after the main pattern exists.  Never fails the caller: when something
@@ -226,10 +241,13 @@ int blocks_build(afb_ctx* ctx) {
     const int32_t* gcol = ctx->colind.as<int32_t>();
     ctx->block_dst.resize((size_t)nf * nf); ctx->block_tix.resize((size_t)nf * nf); ctx->block_tab.resize((size_t)nf * nf);
     ctx->block_rdst.resize((size_t)nf);
-    afb::DevBuf p0, tcount, toff, cubtmp;
+    afb::DevBuf p0, tcount, toff, cubtmp, rowcov, gflag, goff;
+    const long long nrows_main = ctx->row_end - ctx->row_begin;
+    if (rowcov.reserve(std::max<long long>(1, nrows_main) * 4) != cudaSuccess) { blocks_clear(ctx); return 0; }
+    cudaMemsetAsync(rowcov.p, 0, std::max<long long>(1, nrows_main) * 4, st);
     auto fail = [&]() {
         if (getenv("AFB_VERBOSE")) fprintf(stderr, "[afb] block path not offered: block destinations could not be resolved (%s)\n", cudaGetErrorString(cudaGetLastError()));
-        p0.release(); tcount.release(); toff.release(); cubtmp.release(); cudaGetLastError(); blocks_clear(ctx); return 0;
+        p0.release(); tcount.release(); toff.release(); cubtmp.release(); rowcov.release(); gflag.release(); goff.release(); cudaGetLastError(); blocks_clear(ctx); return 0;
     };
     for (int fR = 0; fR < nf; ++fR)
         for (int fC = 0; fC < nf; ++fC) {
@@ -243,7 +261,7 @@ int blocks_build(afb_ctx* ctx) {
                 return fail();
             cudaMemsetAsync(tcount.p, 0, (nrs + 1) * 4, st);
             k_block_scan<<<grid_for(nrs), 256, 0, st>>>(nrs, f.rows, g.cols, sub->rowptr.as<long long>(), sub->colind.as<int32_t>(), grow, gcol, p0.as<long long>(),
-                                                       tcount.as<int>(), bad, covered);
+                                                       tcount.as<int>(), bad, covered, rowcov.as<int>());
             size_t tb = 0;
             cub::DeviceScan::ExclusiveSum(nullptr, tb, tcount.as<int>(), toff.as<int>(), nrs + 1, st);
             if (cubtmp.reserve(tb) != cudaSuccess) return fail();
@@ -271,12 +289,30 @@ int blocks_build(afb_ctx* ctx) {
     if (cudaMemcpyAsync(&hb, bad, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
         cudaMemcpyAsync(&hcov, covered, sizeof(hcov), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess || hb)
         return fail();
-    p0.release(); tcount.release(); toff.release(); cubtmp.release();
     ctx->blocks_cover = hcov == (unsigned long long)ctx->nnz;
+    ctx->n_gap_rows = 0;
+    if (!ctx->blocks_cover && nrows_main > 0) {
+        // rows holding entries outside every block are cleared before a non-accumulating assembly (k_zero_rows)
+        size_t tb = 0;
+        if (gflag.reserve((nrows_main + 1) * 4) != cudaSuccess || goff.reserve((nrows_main + 1) * 4) != cudaSuccess) return fail();
+        cudaMemsetAsync(gflag.p, 0, (nrows_main + 1) * 4, st);
+        k_gap_flag<<<grid_for(nrows_main), 256, 0, st>>>(nrows_main, grow, rowcov.as<int>(), gflag.as<int>());
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, gflag.as<int>(), goff.as<int>(), nrows_main + 1, st);
+        if (cubtmp.reserve(tb) != cudaSuccess) return fail();
+        if (cub::DeviceScan::ExclusiveSum(cubtmp.p, tb, gflag.as<int>(), goff.as<int>(), nrows_main + 1, st) != cudaSuccess) return fail();
+        int ngap = 0;
+        if (cudaMemcpyAsync(&ngap, goff.as<int>() + nrows_main, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return fail();
+        if (ctx->block_gap.reserve(std::max(1, ngap) * 4) != cudaSuccess) return fail();
+        k_gap_list<<<grid_for(nrows_main), 256, 0, st>>>(nrows_main, gflag.as<int>(), goff.as<int>(), ctx->block_gap.as<int>());
+        if (cudaStreamSynchronize(st) != cudaSuccess) return fail();
+        ctx->n_gap_rows = ngap;
+        ctx->launches += 2;
+    }
+    p0.release(); tcount.release(); toff.release(); cubtmp.release(); rowcov.release(); gflag.release(); goff.release();
     ctx->blocks_ready = true;
     if (getenv("AFB_VERBOSE"))
-        fprintf(stderr, "[afb] block path: %d fields, %zu pair plans, blocks cover %llu of %lld entries%s\n", nf, ctx->pairs.size(), hcov, (long long)ctx->nnz,
-                ctx->fields_custom ? " (segmented numbering)" : "");
+        fprintf(stderr, "[afb] block path: %d fields, %zu pair plans, blocks cover %llu of %lld entries (%d rows with uncovered entries)%s\n", nf,
+                ctx->pairs.size(), hcov, (long long)ctx->nnz, ctx->n_gap_rows, ctx->fields_custom ? " (segmented numbering)" : "");
     return 0;
 }
 
@@ -391,7 +427,11 @@ int assemble_block_path(afb_ctx* ctx, int nfA, int nfF, const std::vector<afb_fo
     cudaEventRecord(ctx->ev[2], st);
     if (!accumulate) {
         // blocks no form touches are structural zeros of the template (assembler.inl:642-684)
-        if (dval && (empty_mat || !ctx->blocks_cover) && ctx->nnz) AFB_CUDA(ctx, cudaMemsetAsync(dval, 0, ctx->nnz * sizeof(double), st));
+        if (dval && empty_mat && ctx->nnz) AFB_CUDA(ctx, cudaMemsetAsync(dval, 0, ctx->nnz * sizeof(double), st));
+        else if (dval && ctx->n_gap_rows > 0) {
+            k_zero_rows<<<grid_for((long long)ctx->n_gap_rows * 32), 256, 0, st>>>(ctx->n_gap_rows, ctx->block_gap.as<int>(), ctx->rowptr.as<long long>(), dval);
+            ctx->launches++;
+        }
         if (drhs && std::find(row_has_rhs.begin(), row_has_rhs.end(), 0) != row_has_rhs.end() && nrows)
             AFB_CUDA(ctx, cudaMemsetAsync(drhs, 0, nrows * sizeof(double), st));
     }

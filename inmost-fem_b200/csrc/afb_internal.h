@@ -112,6 +112,8 @@ struct afb_ctx {
     std::vector<afb::DevBuf> block_tix;   // [fR*nf + fC]: int32 per (slice, lane): 0 = the block is contiguous in the row, else 1 + first entry of its offset table
     std::vector<afb::DevBuf> block_tab;   // [fR*nf + fC]: uint16 offsets (relative to block_dst) of the entries of non-contiguous blocks
     std::vector<afb::DevBuf> block_rdst;  // [fR]: int32 per (slice, lane) of the pair plan (space of fR, space of fR): local row that receives the rhs
+    afb::DevBuf block_gap;        // int32[n_gap_rows]: rows holding entries that belong to no block
+    int n_gap_rows = 0;
     bool blocks_ready = false;
     bool blocks_cover = true;     // every entry of the pattern belongs to some block (else the values are cleared before a non-accumulating assembly)
     bool fields_custom = false;   // fields came from afb_fields_set (segmented numbering)

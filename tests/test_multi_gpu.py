@@ -52,6 +52,8 @@ def _worker(rank, world, port, dims, variables, errq):
         for rep in range(2):
             assert da.assemble(forms, rhsf) == 0
             torch.cuda.synchronize()
+            if len(da.fields) > 1:   # vector / mixed spaces must stay on the block path under the per-rank numbering
+                assert ctx.last_times()["gather_kernel"] == "k_rows_cl", "the block path did not run"
             val = da.val[:da.plan.nnz_own].cpu().numpy()
             rhs = da.rhs[:da.plan.n_own].cpu().numpy()
             rowmax = np.maximum.reduceat(np.abs(v_o), rp_o[:-1])
