@@ -441,10 +441,14 @@ int assemble_block_path(afb_ctx* ctx, int nfA, int nfF, const std::vector<afb_fo
             if (g.mat.empty() && g.rhs.empty()) continue;
             afb_ctx* sub = find_pair(ctx, ctx->fields[fR].fem, ctx->fields[fC].fem);
             const size_t b = (size_t)fR * nf + fC;
-            const int rc = fused_group(ctx, sub, g.mat, g.rhs, g.mat.empty() ? nullptr : dval, g.rhs.empty() ? nullptr : drhs,
+            // one interval per field (NATURAL numbering on one rank): the load entries of field fR are a contiguous piece of the
+            // rhs and the plain kernel serves the block unless it needs offset tables; else the rows go through the row map
+            const bool mapped = ctx->fields[fR].rows.n != 1;
+            double* rdst_base = g.rhs.empty() ? nullptr : (mapped ? drhs : drhs + ctx->fields[fR].rows.start[0]);
+            const int rc = fused_group(ctx, sub, g.mat, g.rhs, g.mat.empty() ? nullptr : dval, rdst_base,
                                        ctx->block_dst[b].as<long long>(), accumulate, drop_val, status_flag, false, 0,
                                        ctx->block_tix[b].as<int>(), ctx->block_tab[b].as<unsigned short>(),
-                                       g.rhs.empty() ? nullptr : ctx->block_rdst[fR].as<int>());
+                                       (g.rhs.empty() || !mapped) ? nullptr : ctx->block_rdst[fR].as<int>());
             if (rc < 0) return rc;
             if (rc != 2) { set_error(ctx, "internal: block path lost a group after the support check"); return -4; }
         }

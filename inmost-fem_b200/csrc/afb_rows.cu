@@ -297,6 +297,7 @@ struct RowsArgs {
     int accumulate;
     double drop;         // drop_val: contributions with |v| <= drop are not added (assembler.inl:416)
     int* status;
+    unsigned long long* diag;   // AFB_DIAG_TIMELINE builds only
 };
 
 constexpr int RW_RING = 4;  // visit-steps of plan words in flight per warp (cp.async ring)
@@ -339,7 +340,10 @@ struct SliceMeta {
     int cn[NLOC];
 };
 
-template <int NLOC, int NC, int NGA, int NGF>
+// TAB: rows may be non-contiguous blocks written through offset tables, and the load entry may go to a mapped row (blocks of
+// segmented numberings, afb_blocks.cu).  A template switch: the extra row metadata and the table branch in the write-out cost
+// the plain kernel 30 % when they are merely present (138 instead of 131 registers, the 8 row stores of a batch serialised).
+template <int NLOC, int NC, int NGA, int NGF, bool TAB>
 __global__ void __launch_bounds__(384, 1) k_rows_cl(const __grid_constant__ RowTab<NLOC, NC, NGA, NGF> T, const RowsArgs p) {
     constexpr int NW = (NC + 2 + 3) / 4;
     constexpr int NG = NGA + NGF, NGP = (NG + 1) & ~1, PARTS = NGP / 2;
@@ -348,6 +352,10 @@ __global__ void __launch_bounds__(384, 1) k_rows_cl(const __grid_constant__ RowT
     __shared__ int s_q[2];  // slices handed out: [0] long ones, [1] short ones
     __shared__ int s_sb;    // first long slice of the cluster
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#ifdef AFB_DIAG_TIMELINE   // diagnostic: [0] sum over warps of (end of the warp's last slice - CTA start), [1] sum of (CTA end - CTA start),
+                           // [2] sum of (staging barrier - CTA start), all per warp; p.diag = 3 counters
+    const long long tl0 = clock64();
+#endif
     const int c = p.clist ? p.clist[blockIdx.x] : (int)blockIdx.x;
     const int e0 = p.eptr[c], ne = p.eptr[c + 1] - e0;
     const int sl0 = p.cs[c], sl1 = p.cs[c + 1];
@@ -365,7 +373,11 @@ __global__ void __launch_bounds__(384, 1) k_rows_cl(const __grid_constant__ RowT
         // first so that their latencies overlap).  Measured alternatives: lane-per-piece cp.async and LDG.128+STS.128 are
         // 5-8 % slower end to end -- the phase is latency-bound (one CTA per SM), not LSU-bound.
         constexpr int U = 4;
+#ifdef AFB_DIAG_SKIP_STAGING   // timing diagnostic only (wrong results)
+        for (int base = 0; base < (p.zero ? ne : 0); base += U * (int)blockDim.x) {
+#else
         for (int base = 0; base < ne; base += U * (int)blockDim.x) {
+#endif
             unsigned id[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -395,6 +407,9 @@ __global__ void __launch_bounds__(384, 1) k_rows_cl(const __grid_constant__ RowT
     }
     cp_async_wait<0>();
     __syncthreads();
+#ifdef AFB_DIAG_TIMELINE
+    const long long tl1 = clock64();
+#endif
     const int sb = s_sb;
     const bool isbig = warp < p.nbig;
     const int L16 = isbig ? p.L16b : p.L16s;
@@ -429,17 +444,34 @@ __global__ void __launch_bounds__(384, 1) k_rows_cl(const __grid_constant__ RowT
         m.r = __ldg(p.srow + (size_t)s * 32 + lane);
         m.p0 = __ldg(p.sp0 + (size_t)s * 32 + lane);
         m.len = (int)__ldg(p.slen + (size_t)s * 32 + lane);
-        m.tix = p.tix ? __ldg(p.tix + (size_t)s * 32 + lane) : 0;
-        m.rdst = p.rdst ? __ldg(p.rdst + (size_t)s * 32 + lane) : (int)m.r;
+        if (TAB) {
+            m.tix = p.tix ? __ldg(p.tix + (size_t)s * 32 + lane) : 0;
+            m.rdst = p.rdst ? __ldg(p.rdst + (size_t)s * 32 + lane) : (int)m.r;
+        }
         m.st = __ldg(p.sptr + s);
         m.en = __ldg(p.sptr + s + 1);
 #pragma unroll
         for (int i = 0; i < NLOC; ++i) m.cn[i] = (int)__ldg(p.cnt + (size_t)s * NLOC + i);
     };
 
+    // plan words: cp.async ring, RW_RING-1 visit-steps ahead (one group per step, possibly empty)
+    auto ring_prologue = [&](long long st0, long long en0) {
+        const int nst0 = (int)(en0 - st0);
+        const unsigned* pf0 = p.ell + (size_t)st0 * NW * 32 + lane;
+#pragma unroll
+        for (int d = 0; d < RW_RING - 1; ++d) {
+            if (d < nst0) {
+#pragma unroll
+                for (int q = 0; q < NW; ++q) cp_async4(ring_a + (d * NW + q) * 128, pf0 + q * 32);
+            }
+            cp_async_commit();
+            pf0 += NW * 32;
+        }
+    };
+
     SliceMeta<NLOC> cur, nxt;
     int s = next_slice();
-    if (s >= 0) load_meta(s, cur);
+    if (s >= 0) { load_meta(s, cur); ring_prologue(cur.st, cur.en); }
     while (s >= 0) {
         const int sn = next_slice();
         if (sn >= 0) load_meta(sn, nxt);  // in flight while this slice is processed
@@ -452,22 +484,18 @@ __global__ void __launch_bounds__(384, 1) k_rows_cl(const __grid_constant__ RowT
         }
 
         const int nst = (int)(cur.en - cur.st);
-        const unsigned* pf = p.ell + (size_t)cur.st * NW * 32 + lane;  // next visit-step to prefetch
-        // plan words: cp.async ring, RW_RING-1 visit-steps ahead (one group per step, possibly empty)
-#pragma unroll
-        for (int d = 0; d < RW_RING - 1; ++d) {
-            if (d < nst) {
-#pragma unroll
-                for (int q = 0; q < NW; ++q) cp_async4(ring_a + (d * NW + q) * 128, pf + q * 32);
-            }
-            cp_async_commit();
-            pf += NW * 32;
-        }
+        // the first RW_RING-1 visit-steps are already in flight (ring_prologue: issued before the write-out of the previous
+        // slice; measured gain 0.6 %)
+        const unsigned* pf = p.ell + ((size_t)cur.st + (RW_RING - 1)) * NW * 32 + lane;  // next visit-step to prefetch
         int t = 0;
         double fsum = 0.0;
 #pragma unroll
         for (int i = 0; i < NLOC; ++i) {
+#ifdef AFB_DIAG_SKIP_VISITS   // timing diagnostic only (wrong results)
+            const int n = p.zero ? __reduce_max_sync(0xffffffffu, cur.cn[i]) : 0;
+#else
             const int n = __reduce_max_sync(0xffffffffu, cur.cn[i]);  // warp-uniform trip count in a uniform register
+#endif
             for (int k = 0; k < n; ++k) {
                 // z2 is 0 at run time but loop-variant for the compiler: the table entries are then fetched by uniform
                 // constant loads (LDCU) next to their DFMA instead of being hoisted out of the loop, where 600 values
@@ -547,13 +575,18 @@ __global__ void __launch_bounds__(384, 1) k_rows_cl(const __grid_constant__ RowT
             }
         }
         cp_async_wait<0>();
+        if (sn >= 0) ring_prologue(nxt.st, nxt.en);   // every lane has read its ring words of this slice: the ring is free
 
         // ---- write-out: 16-slot tiles transposed in place (XOR swizzle), then one row per step, lanes <-> slots
+#ifdef AFB_DIAG_SKIP_WRITEOUT   // timing diagnostic only (wrong results): what the write-out costs (profiles/r01e_*.md)
+        if (NGA > 0 && p.zero) {
+#else
         if (NGA > 0) {
+#endif
             RowDst rd;
             rd.ptr = p.val + cur.p0;
             rd.len = cur.len;
-            rd.pad = cur.tix;
+            rd.pad = TAB ? cur.tix : 0;
             sdst[lane] = rd;
             double chk = 0.0;  // becomes NaN iff some finished entry is NaN or +-Inf (x*0 is NaN for those)
             for (int s0 = 0; s0 < Lw; s0 += 16) {
@@ -589,7 +622,7 @@ __global__ void __launch_bounds__(384, 1) k_rows_cl(const __grid_constant__ RowT
                     for (int u = 0; u < 8; ++u) {
                         if (sl < d[u].len) {
                             // d[u] is warp-uniform (one row per step): the table branch does not diverge
-                            const int off = d[u].pad ? (int)__ldg(p.rtab + (d[u].pad - 1 + sl)) : sl;
+                            const int off = (TAB && d[u].pad) ? (int)__ldg(p.rtab + (d[u].pad - 1 + sl)) : sl;
                             if (p.accumulate) d[u].ptr[off] += y[u]; else d[u].ptr[off] = y[u];
                         }
                     }
@@ -600,12 +633,25 @@ __global__ void __launch_bounds__(384, 1) k_rows_cl(const __grid_constant__ RowT
         if (NGF > 0) {
             bad |= ((unsigned)__double2hiint(fsum) & 0x7ff00000u) == 0x7ff00000u;
             if (cur.r != 0xffffffffu) {
-                if (p.accumulate) p.rhs[cur.rdst] += fsum; else p.rhs[cur.rdst] = fsum;
+                const long long rr = TAB ? (long long)cur.rdst : (long long)cur.r;
+                if (p.accumulate) p.rhs[rr] += fsum; else p.rhs[rr] = fsum;
             }
         }
         s = sn;
         cur = nxt;
     }
+#ifdef AFB_DIAG_TIMELINE
+    {
+        const long long tl2 = clock64();
+        __syncthreads();
+        const long long tl3 = clock64();
+        if (lane == 0) {
+            atomicAdd(p.diag + 0, (unsigned long long)(tl2 - tl0));
+            atomicAdd(p.diag + 1, (unsigned long long)(tl3 - tl0));
+            atomicAdd(p.diag + 2, (unsigned long long)(tl1 - tl0));
+        }
+    }
+#endif
     if (bad) *p.status = 1;  // benign race: every writer stores the same value
 }
 
@@ -674,7 +720,7 @@ int launch_rows_t(afb_ctx* ctx, const double* TA, const double* TF, const double
     p.ell = ctx->rp_ell.as<unsigned>(); p.gbuf = gbuf;
     p.val = val; p.rhs = rhs; p.accumulate = accumulate; p.status = status;
     p.drop = drop_val;
-    auto kern = k_rows_cl<NLOC, NC, NGA, NGF>;
+    auto kern = (p.rtab || p.rdst) ? k_rows_cl<NLOC, NC, NGA, NGF, true> : k_rows_cl<NLOC, NC, NGA, NGF, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaFuncSetAttribute(k_rows_cl)");
     // phased assembly (afb_assemble_phase): 1 = the clusters holding priority rows, 2 = the others, 0 = all
@@ -685,7 +731,24 @@ int launch_rows_t(afb_ctx* ctx, const double* TA, const double* TF, const double
         p.clist = ctx->rp_clist.as<int>() + (phase == 1 ? 0 : ctx->rp_nprio);
     } else if (phase == 2) nblocks = 0;   // everything ran in phase 1
     if (nblocks <= 0) return 1;
+#ifdef AFB_DIAG_TIMELINE
+    static unsigned long long* ddiag = nullptr;
+    if (!ddiag) cudaMalloc(&ddiag, 24);
+    cudaMemsetAsync(ddiag, 0, 24, ctx->stream);
+    p.diag = ddiag;
+#else
+    p.diag = nullptr;
+#endif
     kern<<<(unsigned)nblocks, sh.nwarps * 32, sh.smem, ctx->stream>>>(T, p);
+#ifdef AFB_DIAG_TIMELINE
+    {
+        unsigned long long h[3];
+        cudaMemcpyAsync(h, ddiag, 24, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        fprintf(stderr, "[afb diag] warps busy until %.1f%% of their CTA's lifetime on average; staging barrier at %.1f%%; mean CTA lifetime %.0f cycles\n",
+                100.0 * h[0] / h[1], 100.0 * h[2] / h[1], (double)h[1] / ((double)nblocks * sh.nwarps));
+    }
+#endif
     ctx->launches++;
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(ctx, e, "k_rows_cl launch");
