@@ -75,6 +75,15 @@ int64_t afb_launch_count(afb_ctx* ctx, int reset);
 int afb_fem3dtet_batched(afb_ctx* ctx, const afb_form* form, int64_t f,
                          const double* XY0, const double* XY1, const double* XY2, const double* XY3,
                          double* A, int mem_space);
+/* Ani::fem3Dface<OpA,OpB,FuncTraits> (fem/operations/int_face.h:15-159, int_face.inl:160-199): element matrices of the
+ * surface integral int_f (D OpA(u)) . OpB(v) over face face_num[r] of tet r; face k = vertices {k, k+1, k+2 mod 4}
+ * (int_face.h:49-55).  Operators, tensor kinds, layouts and the layout of A as afb_fem3dtet_batched; the rule is the
+ * reference's triangle rule of form->quad_order (PER_POINT coefficients follow its points), the measure the face area.
+ * Errors: -7 "Wrong face index" (int_face.inl:28), the others as afb_fem3dtet_batched. */
+int afb_fem3dface_batched(afb_ctx* ctx, const afb_form* form, int64_t f, const int32_t* face_num /*[f]*/,
+                          const double* XY0, const double* XY1, const double* XY2, const double* XY3, double* A, int mem_space);
+/* triangle_quadrature_formulas(order) (fem/quadrature_formulas.cpp:109-516): p[3*q] barycentric, w[q], sum w = 1; returns q */
+int afb_tri_quadrature(int order, double* p, double* w, int capacity);
 /* Nfa / Dim of an operator (Operator<>::Nfa, ::Dim) */
 int afb_op_dims(int op, int fem, int vec, int* nfa, int* dim);
 /* quadrature rule (fem/quadrature_formulas.cpp:526,1493-1502): returns q, fills p[4q], w[q] if non-NULL */

@@ -42,7 +42,7 @@ EXPORTS = ["afb_ctx_create", "afb_ctx_destroy", "afb_last_error", "afb_sync", "a
            "afb_dofmap_set", "afb_dofmap_set_diag", "afb_dofmap_natural", "afb_dofmap_get",
            "afb_pattern_build", "afb_pattern_get", "afb_pattern_set", "afb_assemble", "afb_halo_add", "afb_last_times",
            "afb_dirichlet_set", "afb_fem3dapply_batched", "afb_eval_quadrature", "afb_priority_rows_set", "afb_assemble_phase",
-           "afb_fields_set"]
+           "afb_fields_set", "afb_fem3dface_batched", "afb_tri_quadrature"]
 
 
 def build(verbose=False):
@@ -73,6 +73,8 @@ def lib():
         L.afb_launch_count.argtypes = [vp, ci]
         L.afb_launch_count.restype = c64
         L.afb_fem3dtet_batched.argtypes = [vp, ctypes.POINTER(AfbForm), c64, vp, vp, vp, vp, vp, ci]
+        L.afb_fem3dface_batched.argtypes = [vp, ctypes.POINTER(AfbForm), c64, vp, vp, vp, vp, vp, vp, ci]
+        L.afb_tri_quadrature.argtypes = [ci, vp, vp, ci]
         L.afb_op_dims.argtypes = [ci, ci, ci, ctypes.POINTER(ci), ctypes.POINTER(ci)]
         L.afb_tet_quadrature.argtypes = [ci, vp, vp, ci]
         L.afb_quad_points.argtypes = [vp, ci, c64, vp, vp, vp, vp, vp, ci]
@@ -135,6 +137,15 @@ def tet_quadrature(order):
     return p.reshape(q, 4), w
 
 
+def tri_quadrature(order):
+    q = lib().afb_tri_quadrature(order, None, None, 0)
+    if q < 0:
+        raise AfbError(q, "quadrature order must be in 0..20")
+    p, w = np.zeros(3 * q), np.zeros(q)
+    lib().afb_tri_quadrature(order, p.ctypes.data, w.ctypes.data, q)
+    return p.reshape(q, 3), w
+
+
 def make_form(opA, femA, vecA, opB, femB, vecB, order, ttype, layout, D=None, alpha=1.0, row_off=0, col_off=0):
     """afb_form + a reference to D so that it outlives the call (the reference takes the tensor
     functor by const-ref with the same lifetime rule, fem/diff_tensor.h:67-70)"""
@@ -187,6 +198,19 @@ class Context:
         xs = [np.ascontiguousarray(XY[k]) for k in range(4)]
         self._ck(lib().afb_fem3dtet_batched(self._h, ctypes.byref(form), f, xs[0].ctypes.data, xs[1].ctypes.data,
                                             xs[2].ctypes.data, xs[3].ctypes.data, A.ctypes.data, HOST))
+        return A
+
+    def fem3dface(self, form, XY, face, out=None):
+        """Batched Ani::fem3Dface: XY (4, f, 3), face (f,) in 0..3 -> A (f, nfA, nfB) like fem3dtet"""
+        XY = np.ascontiguousarray(XY, dtype=np.float64)
+        f = XY.shape[1]
+        nfa, _ = op_dims(form.opA, form.femA, form.vecA)
+        nfb, _ = op_dims(form.opB, form.femB, form.vecB)
+        A = np.zeros((f, nfa, nfb)) if out is None else out
+        fc = np.ascontiguousarray(np.broadcast_to(np.asarray(face, dtype=np.int32), (f,)))
+        xs = [np.ascontiguousarray(XY[k]) for k in range(4)]
+        self._ck(lib().afb_fem3dface_batched(self._h, ctypes.byref(form), f, fc.ctypes.data, xs[0].ctypes.data, xs[1].ctypes.data,
+                                             xs[2].ctypes.data, xs[3].ctypes.data, A.ctypes.data, HOST))
         return A
 
     def quad_points(self, order, XY):

@@ -38,24 +38,39 @@ void DevBuf::release() {
     p = nullptr; cap = 0; borrowed = false;
 }
 
-int get_tables(afb_ctx* ctx, int fem, int order, const double** W, const double** phi, const double** grd) {
+int get_tables(afb_ctx* ctx, int fem, int order, const double** W, const double** phi, const double** grd, bool faces) {
+    const int key = faces ? order + 1000 : order;
     for (auto& t : ctx->table_cache)
-        if (t.fem == fem && t.order == order) { *W = t.W; *phi = t.phi; *grd = t.grd; return 0; }
+        if (t.fem == fem && t.order == key) { *W = t.W; *phi = t.phi; *grd = t.grd; return 0; }
     const double *p, *w;
-    const int q = tet_rule(order, &p, &w);
+    const int q = faces ? tri_rule(order, &p, &w) : tet_rule(order, &p, &w);
     if (q < 0) { set_error(ctx, "quadrature order must be in 0..20"); return -7; }
     OpInfo o;
     if (resolve_op(AFB_IDEN, fem, 1, &o)) { set_error(ctx, "unsupported finite element space"); return -3; }
     const int nf = o.nf_base;
-    std::vector<double> h((size_t)q + (size_t)q * nf * 4);
+    const int nvar = faces ? 4 : 1;   // faces: the triangle rule lifted to each of the four faces (int_face.inl:175-180)
+    std::vector<double> h((size_t)q + (size_t)nvar * q * nf * 4);
     std::copy(w, w + q, h.begin());
-    basis_values(fem, q, p, h.data() + q);
-    basis_ref_grads(fem, q, p, h.data() + q + (size_t)q * nf);
+    std::vector<double> xyl((size_t)4 * q);
+    for (int fc = 0; fc < nvar; ++fc) {
+        const double* pts = p;
+        if (faces) {
+            for (int n = 0; n < q; ++n) {
+                xyl[4 * n + fc] = p[3 * n + 0];
+                xyl[4 * n + (fc + 1) % 4] = p[3 * n + 1];
+                xyl[4 * n + (fc + 2) % 4] = p[3 * n + 2];
+                xyl[4 * n + (fc + 3) % 4] = 0.0;
+            }
+            pts = xyl.data();
+        }
+        basis_values(fem, q, pts, h.data() + q + (size_t)fc * q * nf);
+        basis_ref_grads(fem, q, pts, h.data() + q + (size_t)nvar * q * nf + (size_t)fc * q * nf * 3);
+    }
     double* d = nullptr;
     AFB_CUDA(ctx, cudaMalloc(&d, h.size() * sizeof(double)));
     AFB_CUDA(ctx, cudaMemcpyAsync(d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     AFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    TableEntry t{fem, order, d, d + q, d + q + (size_t)q * nf};
+    TableEntry t{fem, key, d, d + q, d + q + (size_t)nvar * q * nf};
     ctx->table_cache.push_back(t);
     *W = t.W; *phi = t.phi; *grd = t.grd;
     return 0;
@@ -753,6 +768,62 @@ int afb_fem3dtet_batched(afb_ctx* ctx, const afb_form* form, int64_t f, const do
     }
     int rc = afb::launch_form(ctx, fm, oa, ob, f, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ctx->xy.as<double>(),
                               out, (long long)oa.nfa * ob.nfa, 1, ob.nfa, 0, Dd);
+    if (rc) return rc;
+    if (mem_space == AFB_HOST) AFB_CUDA(ctx, cudaMemcpyAsync(A, out, asz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    AFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// Ani::fem3Dface (fem/operations/int_face.h:15-159, int_face.inl:160-199): element matrices of the surface integral over face
+// face_num[r] of tet r.  Same operators, tensor kinds and layouts as afb_fem3dtet_batched; the rule is the reference's triangle
+// rule of that order (PER_POINT coefficients follow its points), the measure the face area.
+int afb_fem3dface_batched(afb_ctx* ctx, const afb_form* form, int64_t f, const int32_t* face_num, const double* XY0, const double* XY1,
+                          const double* XY2, const double* XY3, double* A, int mem_space) {
+    if (!ctx || !form) return -7;
+    if (f <= 0) return 0;
+    if (!XY0 || !XY1 || !XY2 || !XY3 || !A || !face_num) { set_error(ctx, "afb_fem3dface_batched: null buffer"); return -7; }
+    cudaSetDevice(ctx->device);
+    afb::OpInfo oa, ob;
+    if (afb::resolve_op(form->opA, form->femA, form->vecA, &oa) || afb::resolve_op(form->opB, form->femB, form->vecB, &ob)) {
+        set_error(ctx, "unsupported operator/space");
+        return -3;
+    }
+    const int dlen = afb::form_dlen(*form, oa, ob);
+    const double* X[4] = {XY0, XY1, XY2, XY3};
+    AFB_CUDA(ctx, ctx->xy.reserve((size_t)12 * f * sizeof(double)));
+    for (int k = 0; k < 4; ++k)
+        AFB_CUDA(ctx, cudaMemcpyAsync(ctx->xy.as<double>() + (size_t)3 * f * k, X[k], (size_t)3 * f * sizeof(double), kind_in(mem_space), ctx->stream));
+    const int32_t* dface = face_num;
+    if (mem_space == AFB_HOST) {
+        for (int64_t r = 0; r < f; ++r)
+            if (face_num[r] < 0 || face_num[r] > 3) { set_error(ctx, "Wrong face index"); return -7; }   // int_face.inl:28
+        AFB_CUDA(ctx, ctx->tmp1.reserve((size_t)f * sizeof(int32_t)));
+        AFB_CUDA(ctx, cudaMemcpyAsync(ctx->tmp1.p, face_num, (size_t)f * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        dface = ctx->tmp1.as<int32_t>();
+    }
+    const double* Dd = form->D;
+    if (dlen > 0) {
+        if (!form->D) { set_error(ctx, "tensor data missing"); return -7; }
+        const int q = afb_tri_quadrature(form->quad_order, nullptr, nullptr, 0);
+        if (q < 0) { set_error(ctx, "quadrature order must be in 0..20"); return -7; }
+        const size_t n = form->coef_layout == AFB_COEF_CONST ? 1 : (form->coef_layout == AFB_COEF_PER_TET ? (size_t)f : (size_t)f * q);
+        if (form->coef_space == AFB_HOST) {
+            AFB_CUDA(ctx, ctx->coef.reserve(n * dlen * sizeof(double)));
+            AFB_CUDA(ctx, cudaMemcpyAsync(ctx->coef.p, form->D, n * dlen * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            Dd = ctx->coef.as<double>();
+        }
+    }
+    double* out = A;
+    const size_t asz = (size_t)oa.nfa * ob.nfa * f;
+    if (mem_space == AFB_HOST) {
+        AFB_CUDA(ctx, ctx->stageA.reserve(asz * sizeof(double)));
+        out = ctx->stageA.as<double>();
+    }
+    afb_form fm = *form;
+    fm.row_off = 0; fm.col_off = 0;
+    if (fm.alpha == 0.0) fm.alpha = 1.0;
+    int rc = afb::launch_form(ctx, fm, oa, ob, f, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ctx->xy.as<double>(),
+                              out, (long long)oa.nfa * ob.nfa, 1, ob.nfa, 0, Dd, dface, nullptr);
     if (rc) return rc;
     if (mem_space == AFB_HOST) AFB_CUDA(ctx, cudaMemcpyAsync(A, out, asz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     AFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

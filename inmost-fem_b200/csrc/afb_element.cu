@@ -84,9 +84,28 @@ __global__ void __launch_bounds__(128) k_element_generic(FormDev F, long long f,
     if (F.same) UbB = UbA;
 
     double P[4][3], PSI[9];
-    load_tet(g, e, P);
+    load_tet(g, F.item_tet ? (long long)__ldg(F.item_tet + e) : e, P);
     const double det = jacobian_inverse(P, PSI);
-    const double vol = fabs(det) * (1.0 / 6.0);
+    double vol = fabs(det) * (1.0 / 6.0);
+    const double *phiA = F.phiA, *grdA = F.grdA, *phiB = F.phiB, *grdB = F.grdB;
+    if (F.face) {
+        // fem3Dface (int_face.inl:160-199): tables of the triangle rule lifted to face fc, measure = area of the face, computed
+        // from the vertices relative to P0 like the reference's XYP (core.inl:231-240, geometry.h:67-72)
+        const int fc = __ldg(F.face + e) & 3;
+        phiA += (size_t)fc * F.q * F.nfbA; grdA += (size_t)3 * fc * F.q * F.nfbA;
+        phiB += (size_t)fc * F.q * F.nfbB; grdB += (size_t)3 * fc * F.q * F.nfbB;
+        const int i0 = fc, i1 = (fc + 1) & 3, i2 = (fc + 2) & 3;
+        double a[3], b[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            // selects instead of P[i][d] with a run-time i: the coordinates stay in registers
+            auto pick = [&](int i) { return i == 0 ? P[0][d] : (i == 1 ? P[1][d] : (i == 2 ? P[2][d] : P[3][d])); };
+            const double x0 = pick(i0) - P[0][d], x1 = pick(i1) - P[0][d], x2 = pick(i2) - P[0][d];
+            a[d] = x0 - x2; b[d] = x1 - x2;
+        }
+        const double c0 = a[1] * b[2] - a[2] * b[1], c1 = -a[0] * b[2] + a[2] * b[0], c2 = a[0] * b[1] - a[1] * b[0];
+        vol = sqrt(c0 * c0 + c1 * c1 + c2 * c2) * 0.5;
+    }
 
     double acc[ACC];
 #pragma unroll
@@ -99,7 +118,7 @@ __global__ void __launch_bounds__(128) k_element_generic(FormDev F, long long f,
         if (gradA) {
             for (int it = lane; it < qn * F.nfbA; it += 32) {
                 const int nl = it / F.nfbA, a = it - nl * F.nfbA;
-                const double* G = F.grdA + ((size_t)(n0 + nl) * F.nfbA + a) * 3;
+                const double* G = grdA + ((size_t)(n0 + nl) * F.nfbA + a) * 3;
                 const double g0 = __ldg(G), g1 = __ldg(G + 1), g2 = __ldg(G + 2);
 #pragma unroll
                 for (int d = 0; d < 3; ++d)
@@ -109,7 +128,7 @@ __global__ void __launch_bounds__(128) k_element_generic(FormDev F, long long f,
         if (gradB && !F.same) {
             for (int it = lane; it < qn * F.nfbB; it += 32) {
                 const int nl = it / F.nfbB, b = it - nl * F.nfbB;
-                const double* G = F.grdB + ((size_t)(n0 + nl) * F.nfbB + b) * 3;
+                const double* G = grdB + ((size_t)(n0 + nl) * F.nfbB + b) * 3;
                 const double g0 = __ldg(G), g1 = __ldg(G + 1), g2 = __ldg(G + 2);
 #pragma unroll
                 for (int d = 0; d < 3; ++d)
@@ -135,7 +154,7 @@ __global__ void __launch_bounds__(128) k_element_generic(FormDev F, long long f,
             else if (F.opA == AFB_GRAD) { j0 = 3 * c; nb = 3; }
             else { j0 = 0; nb = 1; }
             double u[3];
-            if (F.opA == AFB_IDEN) u[0] = __ldg(F.phiA + (size_t)n * F.nfbA + a);
+            if (F.opA == AFB_IDEN) u[0] = __ldg(phiA + (size_t)n * F.nfbA + a);
             else if (F.opA == AFB_GRAD) {
 #pragma unroll
                 for (int d = 0; d < 3; ++d) u[d] = UbA[(d * F.qc + nl) * F.nfbA + a];
@@ -162,7 +181,7 @@ __global__ void __launch_bounds__(128) k_element_generic(FormDev F, long long f,
                 double s = acc[t];
                 if (F.opB == AFB_IDEN) {
                     for (int nl = 0; nl < qn; ++nl)
-                        s += __ldg(F.phiB + (size_t)(n0 + nl) * F.nfbB + b) * DU[(cb * F.qc + nl) * nia + ial];
+                        s += __ldg(phiB + (size_t)(n0 + nl) * F.nfbB + b) * DU[(cb * F.qc + nl) * nia + ial];
                 } else if (F.opB == AFB_GRAD) {
                     for (int nl = 0; nl < qn; ++nl)
 #pragma unroll
@@ -322,10 +341,10 @@ int launch_form(afb_ctx* ctx, const afb_form& form, const OpInfo& A, const OpInf
                 const double* x, const double* y, const double* z,
                 const int32_t* v0, const int32_t* v1, const int32_t* v2, const int32_t* v3,
                 const double* XY, double* out, long long s_e, long long s_ib, long long s_ia, int add,
-                const double* Ddev) {
+                const double* Ddev, const int32_t* face, const int32_t* item_tet) {
     if (f <= 0) return 0;
     const double *p, *w;
-    const int q = tet_rule(form.quad_order, &p, &w);
+    const int q = face ? tri_rule(form.quad_order, &p, &w) : tet_rule(form.quad_order, &p, &w);
     if (q < 0) { set_error(ctx, "quadrature order must be in 0..20"); return -7; }
     const int tt = form.tensor_type;
     if (tt < AFB_TENSOR_NULL || tt > AFB_TENSOR_GENERAL) { set_error(ctx, "bad tensor_type"); return -7; }
@@ -337,9 +356,9 @@ int launch_form(afb_ctx* ctx, const afb_form& form, const OpInfo& A, const OpInf
     if (form.coef_layout < AFB_COEF_CONST || form.coef_layout > AFB_COEF_PER_POINT) { set_error(ctx, "bad coef_layout"); return -7; }
     // element-independent tables, cached on the device per (space, rule)
     const double *dW, *dphiA, *dgrdA, *dphiB, *dgrdB;
-    int rc = get_tables(ctx, A.fem, form.quad_order, &dW, &dphiA, &dgrdA);
+    int rc = get_tables(ctx, A.fem, form.quad_order, &dW, &dphiA, &dgrdA, face != nullptr);
     if (rc) return rc;
-    rc = get_tables(ctx, B.fem, form.quad_order, &dW, &dphiB, &dgrdB);
+    rc = get_tables(ctx, B.fem, form.quad_order, &dW, &dphiB, &dgrdB, face != nullptr);
     if (rc) return rc;
 
     FormDev F;
@@ -352,6 +371,7 @@ int launch_form(afb_ctx* ctx, const afb_form& form, const OpInfo& A, const OpInf
     F.D = Ddev;
     F.alpha = form.alpha;
     F.s_e = s_e; F.s_ib = s_ib; F.s_ia = s_ia; F.row_off = form.row_off; F.col_off = form.col_off; F.add = add;
+    F.face = face; F.item_tet = item_tet;
 
     GeomSrc g;
     g.x = x; g.y = y; g.z = z; g.v0 = v0; g.v1 = v1; g.v2 = v2; g.v3 = v3;

@@ -46,6 +46,7 @@ int resolve_op(int op, int fem, int vec, OpInfo* out);
 void basis_values(int fem, int q, const double* XYL, double* phi /*[n*nf + i]*/);
 void basis_ref_grads(int fem, int q, const double* XYL, double* G /*[(n*nf + i)*3 + d]*/);
 int tet_rule(int order, const double** p, const double** w);
+int tri_rule(int order, const double** p /*3 per point*/, const double** w);
 
 }  // namespace afb
 
@@ -68,6 +69,10 @@ struct FormDev {
     long long s_e, s_ib, s_ia;
     int row_off, col_off;
     int add;             // 0: store, 1: add into out
+    // surface integrals (fem3Dface): face[e] in 0..3 selects the face {k, k+1, k+2 mod 4} of item e; the tables then hold the four
+    // lifted triangle rules one after the other (phi[face][q*nfb], grd[face][q*nfb*3]) and the measure is the face area
+    const int32_t* face;      // NULL = volume integral
+    const int32_t* item_tet;  // NULL, or the mesh element behind item e (coefficients and output stay indexed by the item)
 };
 
 struct TableEntry {
@@ -204,13 +209,14 @@ int launch_form(afb_ctx* ctx, const afb_form& form, const OpInfo& A, const OpInf
                 const double* x, const double* y, const double* z,                 // SoA nodes (or NULL)
                 const int32_t* v0, const int32_t* v1, const int32_t* v2, const int32_t* v3,
                 const double* XY /* 4 arrays 3 x f, AoS variant, or NULL */,
-                double* out, long long s_e, long long s_ib, long long s_ia, int add, const double* Ddev);
+                double* out, long long s_e, long long s_ib, long long s_ia, int add, const double* Ddev,
+                const int32_t* face = nullptr, const int32_t* item_tet = nullptr);
 int form_dlen(const afb_form& form, const OpInfo& A, const OpInfo& B);
 int launch_forms_sq(afb_ctx* ctx, const std::vector<afb_form>& fm, const std::vector<OpInfo>& oa, const std::vector<const double*>& Dd,
                     const std::vector<int>& sel, int64_t e_lo, int64_t nel, double* out, long long s_e, const double* XY = nullptr,
                     int colmajor = 0);
 // device tables W[q], phi[q*nf], G^[q*nf*3] of (space, rule); uploaded on first use (afb_ctx.cu)
-int get_tables(afb_ctx* ctx, int fem, int order, const double** W, const double** phi, const double** grd);
+int get_tables(afb_ctx* ctx, int fem, int order, const double** W, const double** phi, const double** grd, bool faces = false);
 // block-decomposed fused path of vector / mixed spaces (afb_blocks.cu)
 void blocks_clear(afb_ctx* ctx);
 void blocks_clear_dst(afb_ctx* ctx);

@@ -16,6 +16,7 @@
 
 #include "afb_internal.h"
 #include "tet_quadrature.inc"
+#include "tri_quadrature.inc"
 
 namespace afb {
 
@@ -108,7 +109,27 @@ int tet_rule(int order, const double** p, const double** w) {
     return AFB_TETQ_NPTS[order];
 }
 
+// triangle rule behind fem3Dface (reference: triangle_quadrature_formulas, fem/quadrature_formulas.cpp:109-516)
+int tri_rule(int order, const double** p, const double** w) {
+    if (order < 0 || order > AFB_TRIQ_MAX_ORDER) return -1;
+    *p = AFB_TRIQ_P + 3 * AFB_TRIQ_OFFS[order];
+    *w = AFB_TRIQ_W + AFB_TRIQ_OFFS[order];
+    return AFB_TRIQ_NPTS[order];
+}
+
 }  // namespace afb
+
+extern "C" int afb_tri_quadrature(int order, double* p, double* w, int capacity) {
+    const double *pp, *ww;
+    int q = afb::tri_rule(order, &pp, &ww);
+    if (q < 0) return -7;
+    if (p && w) {
+        if (capacity < q) return -7;
+        std::memcpy(p, pp, sizeof(double) * 3 * q);
+        std::memcpy(w, ww, sizeof(double) * q);
+    }
+    return q;
+}
 
 extern "C" int afb_op_dims(int op, int fem, int vec, int* nfa, int* dim) {
     afb::OpInfo o;

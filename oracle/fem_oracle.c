@@ -22,6 +22,7 @@
 #include <string.h>
 
 #include "../inmost-fem_b200/csrc/tet_quadrature.inc"
+#include "../inmost-fem_b200/csrc/tri_quadrature.inc"
 
 enum { OP_IDEN = 1, OP_GRAD = 2, OP_DIV = 3 };                         /* operators.h:36-44 */
 enum { FEM_P0 = 1, FEM_P1 = 2, FEM_P2 = 3, FEM_P3 = 4 };               /* operators.h:24-34 */
@@ -201,15 +202,40 @@ int orc_quad_points(int order, long f, const double* XY0, const double* XY1, con
     return q;
 }
 
-/* Element matrices for f tets. Returns 0, or <0 on bad arguments (-3 unsupported space/operator,
- * -5 identity/scalar tensor with incompatible operator dimensions: diff_tensor.h:315-317). */
-int orc_fem3dtet(const orc_form* fm, long f, const double* XY0, const double* XY1, const double* XY2, const double* XY3, double* A) {
+/* triangle rule of fem3Dface: p[3*q] barycentric, w[q] (quadrature_formulas.cpp:109-516) */
+int orc_tri_quadrature(int order, const double** p, const double** w) {
+    if (order < 0 || order > AFB_TRIQ_MAX_ORDER) return -1;
+    *p = AFB_TRIQ_P + 3 * AFB_TRIQ_OFFS[order];
+    *w = AFB_TRIQ_W + AFB_TRIQ_OFFS[order];
+    return AFB_TRIQ_NPTS[order];
+}
+
+/* area of the triangle p0 p1 p2 (fem/geometry.h:67-72) */
+static double tri_area(const double* p0, const double* p1, const double* p2) {
+    double a[3] = {p0[0] - p2[0], p0[1] - p2[1], p0[2] - p2[2]}, b[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};
+    double c[3] = {a[1] * b[2] - a[2] * b[1], -a[0] * b[2] + a[2] * b[0], a[0] * b[1] - a[1] * b[0]};
+    return sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]) / 2;
+}
+
+/* Element matrices for f tets: volume integrals (face == NULL, fem3Dtet) or surface integrals over face face[r] of tet r
+ * (fem3Dface, fem/operations/int_face.inl:160-199: the triangle rule is lifted to the face {face, face+1, face+2 mod 4} with
+ * zero barycentric weight on vertex face+3, and the measure is the face area).  Returns 0, or <0 on bad arguments (-3
+ * unsupported space/operator, -5 identity/scalar tensor with incompatible operator dimensions: diff_tensor.h:315-317). */
+static int fem3d_core(const orc_form* fm, long f, const double* XY0, const double* XY1, const double* XY2, const double* XY3, double* A,
+                      const int* face) {
     int nfa, idim, nfb, jdim;
     if (orc_op_dims(fm->opA, fm->femA, fm->vecA, &nfa, &idim)) return -3;
     if (orc_op_dims(fm->opB, fm->femB, fm->vecB, &nfb, &jdim)) return -3;
     const double *XYL, *W;
-    int q = orc_tet_quadrature(fm->quad_order, &XYL, &W);
+    int q;
+    double* XYLf = NULL;
+    if (face) {
+        q = orc_tri_quadrature(fm->quad_order, &XYL, &W);
+        if (q < 0) return -1;
+        XYLf = (double*)malloc(sizeof(double) * 4 * (size_t)q);
+    } else q = orc_tet_quadrature(fm->quad_order, &XYL, &W);
     if (q < 0) return -1;
+    const double* XYLt = XYL;   /* triangle points (face mode) */
     int tt = fm->tensor_type;
     if ((tt == T_NULL || tt == T_SCALAR) && jdim != idim && (nfa != 1 || idim != 1)) return -5;
     int same = (fm->opA == fm->opB && fm->femA == fm->femB && fm->vecA == fm->vecB);
@@ -229,6 +255,20 @@ int orc_fem3dtet(const orc_form* fm, long f, const double* XY0, const double* XY
         }
         double det = inverse3x3(XYP, PSI);
         double vol = fabs(det) / 6;
+        if (face) {
+            const int fc = face[r];
+            if (fc < 0 || fc > 3) { free(U); if (!same) free(V); free(DU); free(scratch); free(XYLf); return -7; }
+            for (int n = 0; n < q; ++n) {   /* int_face.inl:175-180 */
+                XYLf[4 * n + fc] = XYLt[3 * n + 0];
+                XYLf[4 * n + (fc + 1) % 4] = XYLt[3 * n + 1];
+                XYLf[4 * n + (fc + 2) % 4] = XYLt[3 * n + 2];
+                XYLf[4 * n + (fc + 3) % 4] = 0;
+            }
+            XYL = XYLf;
+            /* vertices relative to P0 like mem.XYP (core.inl:231-240); int_face.inl:184-187 */
+            double X[12] = {0, 0, 0, XYP[0], XYP[1], XYP[2], XYP[3], XYP[4], XYP[5], XYP[6], XYP[7], XYP[8]};
+            vol = tri_area(X + 3 * fc, X + 3 * ((fc + 1) % 4), X + 3 * ((fc + 2) % 4));
+        }
         apply_op(fm->opA, fm->femA, fm->vecA, q, XYL, PSI, U, scratch);
         if (!same) apply_op(fm->opB, fm->femB, fm->vecB, q, XYL, PSI, V, scratch);
         /* DU = w_n |T| D U  (diff_tensor.h:498-549 PerPoint path) */
@@ -262,8 +302,19 @@ int orc_fem3dtet(const orc_form* fm, long f, const double* XY0, const double* XY
                 Ar[ib + nfb * ia] = s;
             }
     }
-    free(U); if (!same) free(V); free(DU); free(scratch);
+    free(U); if (!same) free(V); free(DU); free(scratch); free(XYLf);
     return 0;
+}
+
+int orc_fem3dtet(const orc_form* fm, long f, const double* XY0, const double* XY1, const double* XY2, const double* XY3, double* A) {
+    return fem3d_core(fm, f, XY0, XY1, XY2, XY3, A, NULL);
+}
+
+/* fem3Dface for f tets, face[r] in 0..3 = face {r, r+1, r+2 mod 4} of the tet (int_face.h:49-55) */
+int orc_fem3dface(const orc_form* fm, long f, const int* face, const double* XY0, const double* XY1, const double* XY2, const double* XY3,
+                  double* A) {
+    if (!face) return -7;
+    return fem3d_core(fm, f, XY0, XY1, XY2, XY3, A, face);
 }
 
 /* U table of one operator on f tets with an explicit rule; layout U[k + dim*(n + q*(i + nfa*r))] */

@@ -53,6 +53,9 @@ def orc():
         L = ctypes.CDLL(path)
         L.orc_fem3dtet.restype = ctypes.c_int
         L.orc_fem3dtet.argtypes = [ctypes.POINTER(_Form), ctypes.c_long, _dp, _dp, _dp, _dp, _dp]
+        L.orc_fem3dface.restype = ctypes.c_int
+        L.orc_fem3dface.argtypes = [ctypes.POINTER(_Form), ctypes.c_long, _ip, _dp, _dp, _dp, _dp, _dp]
+        L.orc_tri_quadrature.argtypes = [ctypes.c_int, ctypes.POINTER(_dp), ctypes.POINTER(_dp)]
         L.orc_op_dims.argtypes = [ctypes.c_int] * 3 + [_ip, _ip]
         L.orc_quad_points.argtypes = [ctypes.c_int, ctypes.c_long, _dp, _dp, _dp, _dp, _dp]
         L.orc_operator_apply.argtypes = [ctypes.c_int] * 4 + [_dp, ctypes.c_long, _dp, _dp, _dp, _dp, _dp]
@@ -76,6 +79,11 @@ def ref():
         L.ref_tet_quadrature.argtypes = [ctypes.c_int, _dp, _dp, ctypes.c_int]
         L.ref_fem3dtet.restype = ctypes.c_int
         L.ref_fem3dtet.argtypes = [ctypes.c_int] * 9 + [_dp, ctypes.c_long] + [_dp] * 5 + [ctypes.c_int] * 3
+        if hasattr(L, "ref_fem3dface"):
+            L.ref_fem3dface.restype = ctypes.c_int
+            L.ref_fem3dface.argtypes = [ctypes.c_int] * 9 + [_dp, ctypes.c_long, _ip] + [_dp] * 5
+            L.ref_tri_quadrature.restype = ctypes.c_int
+            L.ref_tri_quadrature.argtypes = [ctypes.c_int, _dp, _dp, ctypes.c_int]
         L.ref_operator_apply.restype = ctypes.c_int
         L.ref_operator_apply.argtypes = [ctypes.c_int] * 4 + [_dp, _dp, ctypes.c_long] + [_dp] * 5
         L.ref_last_error.restype = ctypes.c_char_p
@@ -138,6 +146,41 @@ def fem3dtet(form, XY, D=None, impl="oracle", mode=0, fuse=1, nthreads=1):
                                 *[_P(x) for x in xs], _P(A), mode, fuse, nthreads)
         if rc:
             raise RuntimeError("ref_fem3dtet failed rc=%d: %s" % (rc, ref().ref_last_error().decode()))
+    return A
+
+
+def tri_quadrature(order):
+    p, w = _dp(), _dp()
+    q = orc().orc_tri_quadrature(order, ctypes.byref(p), ctypes.byref(w))
+    if q < 0:
+        raise ValueError("quadrature order out of range")
+    return (np.ctypeslib.as_array(p, shape=(3 * q,)).copy().reshape(q, 3),
+            np.ctypeslib.as_array(w, shape=(q,)).copy())
+
+
+def fem3dface(form, XY, face, D=None, impl="oracle"):
+    """Surface-integral element matrices (fem3Dface, fem/operations/int_face.inl:160-199) of `form` over face face[r] of tet r
+    (face k = vertices k, k+1, k+2 mod 4).  Layouts as fem3dtet; PER_POINT coefficients follow the triangle rule."""
+    opA, femA, vecA, opB, femB, vecB, order, ttype, layout = form
+    xs = _xy(XY)
+    f = xs[0].shape[0]
+    nfa, _ = op_dims(opA, femA, vecA)
+    nfb, _ = op_dims(opB, femB, vecB)
+    A = np.zeros((f, nfa, nfb))
+    fc = np.ascontiguousarray(np.broadcast_to(np.asarray(face, dtype=np.int32), (f,)))
+    Dc = None if D is None else np.ascontiguousarray(D, dtype=np.float64)
+    if impl == "oracle":
+        fm = _Form(opA, femA, vecA, opB, femB, vecB, order, ttype, layout, _P(Dc))
+        rc = orc().orc_fem3dface(ctypes.byref(fm), f, fc.ctypes.data_as(_ip), *[_P(x) for x in xs], _P(A))
+        if rc:
+            raise RuntimeError("orc_fem3dface failed rc=%d" % rc)
+    else:
+        if Dc is None:
+            Dc = np.zeros(1)
+        rc = ref().ref_fem3dface(opA, femA, vecA, opB, femB, vecB, order, ttype, layout, _P(Dc), f, fc.ctypes.data_as(_ip),
+                                 *[_P(x) for x in xs], _P(A))
+        if rc:
+            raise RuntimeError("ref_fem3dface failed rc=%d: %s" % (rc, ref().ref_last_error().decode()))
     return A
 
 

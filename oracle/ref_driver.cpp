@@ -306,6 +306,49 @@ int ref_tet_quadrature(int order, double* p, double* w, int cap) {
     } catch (std::exception& e) { g_err = e.what(); return -1; }
 }
 
+// triangle rule of the reference: p[3*q] barycentric, w[q]; returns q (or -1)
+int ref_tri_quadrature(int order, double* p, double* w, int cap) {
+    try {
+        auto f = triangle_quadrature_formulas(order);
+        int q = f.GetNumPoints();
+        if (p && w) {
+            if (cap < q) return -1;
+            std::memcpy(p, f.p, sizeof(double) * 3 * q);
+            std::memcpy(w, f.w, sizeof(double) * q);
+        }
+        return q;
+    } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
+
+// Surface-integral element matrices through the reference's runtime fem3Dface (fem/operations/int_face.inl:160-199), one
+// tet per call with its own face number face[r]. Layouts as ref_fem3dtet; PER_POINT coefficients are indexed by the points of
+// the triangle rule.
+int ref_fem3dface(int opA, int femA, int vecA, int opB, int femB, int vecB, int order, int ttype, int layout, const double* D,
+                  long f, const int* face, const double* XY0, const double* XY1, const double* XY2, const double* XY3, double* A) {
+    try {
+        auto oa = make_op(opA, femA, vecA), ob = make_op(opB, femB, vecB);
+        if (!oa || !ob) { g_err = "unsupported operator/space"; return -3; }
+        const long nfa = oa->Nfa(), nfb = ob->Nfa();
+        auto formula = triangle_quadrature_formulas(order);
+        TensorData td{ttype, layout, D, formula.GetNumPoints(), 0, 0};
+        TensorFunctor fn{&td};
+        std::vector<char> raw;
+        PlainMemoryX<> req;
+        if (layout == 0) req = fem3Dface_memory_requirements<DfuncTraits<PerPoint, true>>(*oa, *ob, order, 1);
+        else req = fem3Dface_memory_requirements<DfuncTraits<PerPoint, false>>(*oa, *ob, order, 1);
+        raw.resize(req.enoughRawSize());
+        req.allocateFromRaw(raw.data(), raw.size());
+        for (long t = 0; t < f; ++t) {
+            td.base_tet = t; td.calls = 0;
+            auto XYZ = make_tetras(XY0 + 3 * t, XY1 + 3 * t, XY2 + 3 * t, XY3 + 3 * t, 1);
+            DenseMatrix<> Am(A + nfa * nfb * t, nfb, nfa, nfa * nfb);
+            if (layout == 0) fem3Dface<DfuncTraits<PerPoint, true>>(XYZ, face[t], *oa, *ob, fn, Am, req, order, nullptr);
+            else fem3Dface<DfuncTraits<PerPoint, false>>(XYZ, face[t], *oa, *ob, fn, Am, req, order, nullptr);
+        }
+        return 0;
+    } catch (std::exception& e) { g_err = e.what(); return -4; }
+}
+
 int ref_op_dims(int op, int fem, int vec, int* nfa, int* dim) {
     auto o = make_op(op, fem, vec);
     if (!o) return -3;

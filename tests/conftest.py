@@ -49,6 +49,11 @@ def ref_outputs():
 
 
 @pytest.fixture(scope="session")
+def ref_face_outputs():
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "ref_face_outputs.npz")))
+
+
+@pytest.fixture(scope="session")
 def ctx(pkg):
     c = pkg.Context(0)
     yield c

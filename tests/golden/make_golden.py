@@ -10,6 +10,7 @@ Two kinds of fixture, both taken from the reference (/root/reference, read-only)
        tests/fem/operations/int_tet_test.cpp:455       rhs trick IDEN(P0) x IDEN(P2^3): {-1 x4, 4 x6} x3
        tests/fem/spaces/predefined_spaces_test.cpp:62-382   U tables of IDEN/GRAD on P0..P3, f = 2 tets
      -> reference_tests.json
+ (1b) tests/fem/operations/int_face_test.cpp:78-89   fem3Dface GRAD(P2) x IDEN(P1^3), face 1, normal-weighted tensor
  (2) outputs of the reference itself (oracle/_ref/libanifem_ref.so, built by oracle/Makefile from the
      unmodified sources) on seeded inputs for every operator/space/tensor family of SURVEY.md section 8a
      -> ref_outputs.npz  (inputs are regenerated from the seed by tests/golden_cases.py)
@@ -74,6 +75,18 @@ def extract_int_tet():
     return out
 
 
+def extract_int_face():
+    """tests/fem/operations/int_face_test.cpp:78-89: GRAD(P2) x IDEN(P1^3) over face 1 of the tet (1,1,1),(2,1,1),(1,2,1),(1,1,2),
+    order 3, tensor D(i,j) = sum_k (x[j%3] + (3i+k)/10) n_k with n the outward normal of the face (:29-56)"""
+    src = open(os.path.join(REF, "tests/fem/operations/int_face_test.cpp")).read()
+    k = src.index("A_expd = {")
+    vals = numbers(brace_block(src, k)[0])
+    assert len(vals) == 120
+    return {"grad_p2_x_iden_p1vec_face1": {"table_cols_trial_rows_test": np.array(vals).reshape(10, 12).tolist(), "face": 1, "order": 3,
+                                           "tet": [[1, 1, 1], [2, 1, 1], [1, 2, 1], [1, 1, 2]],
+                                           "tensor": "D(i,j) = sum_k (x[j%3] + (3i+k)/10) n_k, 3x3 GENERAL, n = outward normal"}}
+
+
 def extract_spaces():
     src = open(os.path.join(REF, "tests/fem/spaces/predefined_spaces_test.cpp")).read()
     end = src.index("#undef SETOP")
@@ -109,7 +122,7 @@ def extract_spaces():
 
 
 def main():
-    ref_tests = {"int_tet": extract_int_tet(), "spaces": extract_spaces()}
+    ref_tests = {"int_tet": extract_int_tet(), "int_face": extract_int_face(), "spaces": extract_spaces()}
     with open(os.path.join(HERE, "reference_tests.json"), "w") as f:
         json.dump(ref_tests, f)
     print("reference_tests.json:", list(ref_tests["int_tet"].keys()), list(ref_tests["spaces"]["tables"].keys()))
@@ -124,6 +137,12 @@ def main():
         assert np.abs(tmpl - out[name]).max() <= 1e-13 * (1 + np.abs(out[name]).max()), name
     np.savez_compressed(os.path.join(HERE, "ref_outputs.npz"), **out)
     print("ref_outputs.npz:", len(out), "cases")
+    # (3) the reference's fem3Dface on the seeded surface cases
+    outf = {}
+    for name, form, XY, face, D in golden_cases.face_cases():
+        outf[name] = O.fem3dface(form, XY, face, D, impl="ref")
+    np.savez_compressed(os.path.join(HERE, "ref_face_outputs.npz"), **outf)
+    print("ref_face_outputs.npz:", len(outf), "cases")
 
 
 if __name__ == "__main__":

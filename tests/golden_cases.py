@@ -85,3 +85,35 @@ def cases():
         D = tensor(rng, tt, lay, idim, jdim, f, q)
         out.append((name, A + B + (order, tt, lay), XY, D))
     return out
+
+
+NPTS_TRI = [1, 1, 3, 6, 6, 7, 12, 15, 16, 19, 25, 28, 33, 37, 42, 49, 55, 60, 67, 73, 79]
+
+
+def face_cases():
+    """seeded surface-integral cases (fem3Dface, fem/operations/int_face.inl): Neumann / Robin style forms, every face number"""
+    rng = np.random.default_rng(20261018)
+    spec = [
+        # name, (opA, femA, vecA), (opB, femB, vecB), order, ttype, layout, f
+        ("robin_p1_scalar_tet", (IDEN, P1, 1), (IDEN, P1, 1), 2, T_SCALAR, L_PER_TET, 9),
+        ("robin_p2_null", (IDEN, P2, 1), (IDEN, P2, 1), 4, T_NULL, L_CONST, 8),
+        ("robin_p2_scalar_pt", (IDEN, P2, 1), (IDEN, P2, 1), 5, T_SCALAR, L_PER_POINT, 6),
+        ("robin_p3_q12", (IDEN, P3, 1), (IDEN, P3, 1), 6, T_SCALAR, L_CONST, 5),
+        ("neumann_p1_rhs", (IDEN, P0, 1), (IDEN, P1, 1), 2, T_SCALAR, L_PER_POINT, 7),
+        ("neumann_p2_rhs_null", (IDEN, P0, 1), (IDEN, P2, 1), 3, T_NULL, L_CONST, 5),
+        ("neumann_p2vec_traction", (IDEN, P0, 1), (IDEN, P2, 3), 3, T_GENERAL, L_PER_TET, 6),
+        ("robin_p2vec_sym", (IDEN, P2, 3), (IDEN, P2, 3), 4, T_SYMMETRIC, L_CONST, 4),
+        ("gradp2_x_idenp1vec_gen_pt", (GRAD, P2, 1), (IDEN, P1, 3), 3, T_GENERAL, L_PER_POINT, 5),
+        ("gradp1_x_gradp1_face", (GRAD, P1, 1), (GRAD, P1, 1), 1, T_SYMMETRIC, L_PER_TET, 4),
+        ("idenp1_x_divp2vec", (IDEN, P1, 1), (DIV, P2, 3), 2, T_SCALAR, L_CONST, 4),
+        ("robin_p2_q79", (IDEN, P2, 1), (IDEN, P2, 1), 20, T_NULL, L_CONST, 2),
+    ]
+    out = []
+    for name, A, B, order, tt, lay, f in spec:
+        q = NPTS_TRI[order]
+        XY = random_tets(rng, f)
+        face = (np.arange(f) + rng.integers(0, 4)) % 4
+        idim, jdim = op_dims(*A)[1], op_dims(*B)[1]
+        D = tensor(rng, tt, lay, idim, jdim, f, q)
+        out.append((name, A + B + (order, tt, lay), XY, face.astype(np.int32), D))
+    return out

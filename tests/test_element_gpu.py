@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import golden_cases as gc
-from test_oracle_golden import TET, poly_tensor
+from test_oracle_golden import FACE_TET, TET, face_normal_tensor, poly_tensor
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-12
@@ -48,6 +48,45 @@ def test_reference_known_answer_tables(pkg, ctx, ref_tests):
     B = np.array(g["table"])
     A = ctx.fem3dtet(pkg.make_form(gc.IDEN, gc.P0, 1, gc.IDEN, gc.P2, 3, 2, gc.T_SCALAR, gc.L_CONST, np.full((1, 1), g["mu"])), TET)[0].ravel()
     assert np.linalg.norm(A - B) <= 100 * (1 + np.linalg.norm(A)) * eps
+
+
+def test_face_seeded_cases_vs_oracle_and_reference(pkg, ctx, oracle, ref_face_outputs):
+    """afb_fem3dface_batched (= Ani::fem3Dface) against the committed outputs of the reference and the oracle"""
+    worst = 0.0
+    for name, form, XY, face, D in gc.face_cases():
+        A = ctx.fem3dface(_form(pkg, form, D), XY, face)
+        ref = ref_face_outputs[name]
+        orc = oracle.fem3dface(form, XY, face, D)
+        scale = np.abs(ref).reshape(ref.shape[0], -1).max(axis=1)[:, None, None] + 1e-300
+        err = max((np.abs(A - ref) / scale).max(), (np.abs(A - orc) / scale).max())
+        worst = max(worst, err)
+        assert err <= RTOL, (name, err)
+    print("worst relative error over seeded face cases: %.2e" % worst)
+
+
+def test_face_known_answer_table_and_properties(pkg, ctx, ref_tests):
+    """the reference's own table for fem3Dface (int_face_test.cpp:78-95); triangle rules identical to the reference's; the face
+    mass matrix of P2 sums to the face area on every face of 5000 random tets; wrong face index is an error (int_face.inl:28)"""
+    g = ref_tests["int_face"]["grad_p2_x_iden_p1vec_face1"]
+    exp = np.array(g["table_cols_trial_rows_test"])
+    D = face_normal_tensor(pkg.tri_quadrature, g["face"])
+    A = ctx.fem3dface(pkg.make_form(gc.GRAD, gc.P2, 1, gc.IDEN, gc.P1, 3, g["order"], gc.T_GENERAL, gc.L_PER_POINT, D), FACE_TET, [g["face"]])[0]
+    assert np.linalg.norm(A - exp) <= 100 * (1 + np.linalg.norm(exp)) * np.finfo(float).eps
+    rng = np.random.default_rng(7)
+    f = 5000
+    XY = gc.random_tets(rng, f)
+    face = rng.integers(0, 4, f).astype(np.int32)
+    M = ctx.fem3dface(pkg.make_form(gc.IDEN, gc.P2, 1, gc.IDEN, gc.P2, 1, 4, gc.T_NULL, gc.L_CONST), XY, face)
+    idx = np.stack([(face + k) % 4 for k in range(3)], 0)
+    P = XY[idx, np.arange(f)]                        # (3, f, 3)
+    area = 0.5 * np.linalg.norm(np.cross(P[1] - P[0], P[2] - P[0]), axis=1)
+    assert np.abs(M.sum(axis=(1, 2)) - area).max() <= 1e-12 * area.max()
+    # dofs not on the face do not couple: the vertex opposite to the face and the three edges through it
+    opp = (face + 3) % 4
+    assert np.abs(M[np.arange(f), opp, :]).max() <= 1e-15 * area.max()
+    with pytest.raises(pkg.AfbError) as e:
+        ctx.fem3dface(pkg.make_form(gc.IDEN, gc.P1, 1, gc.IDEN, gc.P1, 1, 2, gc.T_NULL, gc.L_CONST), FACE_TET, [4])
+    assert e.value.code == -7 and "face" in str(e.value)
 
 
 def test_quad_points(pkg, ctx, oracle):

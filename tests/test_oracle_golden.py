@@ -97,6 +97,68 @@ def test_oracle_vs_live_reference(oracle):
         assert np.abs(a - b).max() <= 1e-13 * (1 + np.abs(b).max()), name
 
 
+FACE_TET = np.array([[1, 1, 1], [2, 1, 1], [1, 2, 1], [1, 1, 2]], float)[:, None, :]  # int_face_test.cpp:16-19
+
+
+def face_normal_tensor(tri_quadrature, face=1):
+    """the tensor of tests/fem/operations/int_face_test.cpp:29-56 at the points of the order-3 triangle rule lifted to `face`:
+    D(i,j) = sum_k (x[j%3] + (3i+k)/10) n_k, n = outward normal; user layout K(k,j) at k + 3*j"""
+    P = FACE_TET[:, 0, :]
+    p, _ = tri_quadrature(3)
+    idx = [(face + k) % 4 for k in range(3)]
+    X = p @ P[idx]                                    # (q,3) physical points on the face
+    n = np.cross(P[idx[1]] - P[idx[0]], P[idx[2]] - P[idx[0]])
+    if n @ (P[(face + 3) % 4] - P[idx[0]]) > 0:
+        n = -n
+    n /= np.linalg.norm(n)
+    q = X.shape[0]
+    D = np.zeros((q, 3, 3))                           # memory [j][i]
+    for i in range(3):
+        for j in range(3):
+            D[:, j, i] = sum((X[:, j % 3] + (3 * i + k) / 10.0) * n[k] for k in range(3))
+    return np.ascontiguousarray(D.reshape(q, 9))
+
+
+def test_int_face_table(oracle, ref_tests):
+    """fem3Dface GRAD(P2) x IDEN(P1^3) over face 1, 12x10 known-answer table (int_face_test.cpp:78-95), tol 100(1+|A|)eps"""
+    g = ref_tests["int_face"]["grad_p2_x_iden_p1vec_face1"]
+    exp = np.array(g["table_cols_trial_rows_test"])  # [ia][ib]
+    D = face_normal_tensor(oracle.tri_quadrature, g["face"])
+    form = (gc.GRAD, gc.P2, 1, gc.IDEN, gc.P1, 3, g["order"], gc.T_GENERAL, gc.L_PER_POINT)
+    A = oracle.fem3dface(form, FACE_TET, [g["face"]], D)[0]
+    assert np.linalg.norm(A - exp) <= 100 * (1 + np.linalg.norm(exp)) * np.finfo(float).eps
+
+
+def test_triangle_rules(oracle):
+    """weights sum to 1, interior points, exactness on monomials of the stated order (int_T x^a y^b = a! b! / (a+b+2)! on the unit triangle)"""
+    from math import factorial
+    for order in range(1, 21):
+        p, w = oracle.tri_quadrature(order)
+        assert p.shape[0] == gc.NPTS_TRI[order] and abs(w.sum() - 1) < 1e-14 and (p > 0).all()
+        assert np.abs(p.sum(axis=1) - 1).max() < 1e-15
+        x, y = p[:, 0], p[:, 1]
+        for a in range(order + 1):
+            b = order - a
+            num = (w * x ** a * y ** b).sum() / 2
+            assert abs(num - factorial(a) * factorial(b) / factorial(a + b + 2)) <= 1e-14, (order, a)
+
+
+def test_face_oracle_vs_committed_reference_outputs(oracle, ref_face_outputs):
+    for name, form, XY, face, D in gc.face_cases():
+        A = oracle.fem3dface(form, XY, face, D)
+        ref = ref_face_outputs[name]
+        assert np.abs(A - ref).max() <= 1e-13 * (1 + np.abs(ref).max()), name
+
+
+def test_face_oracle_vs_live_reference(oracle):
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    for name, form, XY, face, D in gc.face_cases():
+        a = oracle.fem3dface(form, XY, face, D)
+        b = oracle.fem3dface(form, XY, face, D, impl="ref")
+        assert np.abs(a - b).max() <= 1e-13 * (1 + np.abs(b).max()), name
+
+
 def test_identity_tensor_incompatible_dims(oracle):
     """TENSOR_NULL with Dim(OpA) != Dim(OpB) is an error (diff_tensor.h:315-317)"""
     form = (gc.GRAD, gc.P1, 1, gc.IDEN, gc.P1, 1, 2, gc.T_NULL, gc.L_CONST)
