@@ -183,6 +183,20 @@ int afb_priority_rows_set(afb_ctx* ctx, int64_t first_priority_row);
 int afb_assemble_phase(afb_ctx* ctx, int nforms, const afb_form* forms, int nrhs_forms, const afb_form* rhs_forms, double* csr_val,
                        double* rhs, double drop_val, int phase);
 
+/* ---- surface terms: fem3Dface inside the local assembler (examples/Fem/Ani/diffusion.cpp:215-245, lin_elast.cpp:198-217) ---- */
+/* The boundary faces that carry Neumann / Robin data: face face_num[b] (0..3, int_face.h:49-55) of mesh element face_tet[b].
+ * Copies the list; the row lists are built at the first afb_assemble_faces after a pattern change. nbf = 0 clears. */
+int afb_boundary_set(afb_ctx* ctx, int64_t nbf, const int32_t* face_tet, const int32_t* face_num, int mem_space);
+/* Adds the surface forms int_f (D OpA(u)) . OpB(v) over the listed faces INTO csr_val / rhs (call after afb_assemble, which
+ * produces the volume part; the reference's local assembler adds the face matrices to the cell matrix before the scatter).
+ * Forms as in afb_assemble with the triangle rule of quad_order; coefficient layouts: CONST, PER_TET = one record per listed
+ * face b, PER_POINT = D[len*(n + q*b)] over the points of the triangle rule.  drop_val as in afb_assemble.  Matrix forms need
+ * csr_val.  With essential conditions set (afb_dirichlet_set) the faces get the free-row part of applyDir: Dirichlet rows stay
+ * untouched, Dirichlet columns move to rhs.  Deterministic (every row sums its faces in ascending b).
+ * Returns 0 / -1 (non-finite value). */
+int afb_assemble_faces(afb_ctx* ctx, int nforms, const afb_form* forms, int nrhs_forms, const afb_form* rhs_forms,
+                       double* csr_val, double* rhs, double drop_val, int mem_space);
+
 /* Multi-GPU interface rows: dst[slot[k]] += contrib[k] for the n contributions received from ONE peer (device
  * pointers; the slots of one call are distinct, peers are applied in rank order => deterministic, no atomics).
  * Replaces the value exchange the reference avoids by recomputing ghost cells (assembler.inl:162-183). */

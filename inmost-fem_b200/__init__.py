@@ -42,7 +42,8 @@ EXPORTS = ["afb_ctx_create", "afb_ctx_destroy", "afb_last_error", "afb_sync", "a
            "afb_dofmap_set", "afb_dofmap_set_diag", "afb_dofmap_natural", "afb_dofmap_get",
            "afb_pattern_build", "afb_pattern_get", "afb_pattern_set", "afb_assemble", "afb_halo_add", "afb_last_times",
            "afb_dirichlet_set", "afb_fem3dapply_batched", "afb_eval_quadrature", "afb_priority_rows_set", "afb_assemble_phase",
-           "afb_fields_set", "afb_fem3dface_batched", "afb_tri_quadrature"]
+           "afb_fields_set", "afb_fem3dface_batched", "afb_tri_quadrature",
+           "afb_boundary_set", "afb_assemble_faces"]
 
 
 def build(verbose=False):
@@ -75,6 +76,8 @@ def lib():
         L.afb_fem3dtet_batched.argtypes = [vp, ctypes.POINTER(AfbForm), c64, vp, vp, vp, vp, vp, ci]
         L.afb_fem3dface_batched.argtypes = [vp, ctypes.POINTER(AfbForm), c64, vp, vp, vp, vp, vp, vp, ci]
         L.afb_tri_quadrature.argtypes = [ci, vp, vp, ci]
+        L.afb_boundary_set.argtypes = [vp, c64, vp, vp, ci]
+        L.afb_assemble_faces.argtypes = [vp, ci, ctypes.POINTER(AfbForm), ci, ctypes.POINTER(AfbForm), vp, vp, cd, ci]
         L.afb_op_dims.argtypes = [ci, ci, ci, ctypes.POINTER(ci), ctypes.POINTER(ci)]
         L.afb_tet_quadrature.argtypes = [ci, vp, vp, ci]
         L.afb_quad_points.argtypes = [vp, ci, c64, vp, vp, vp, vp, vp, ci]
@@ -408,6 +411,24 @@ class Context:
             assert sv == sr
         return self._ck(lib().afb_assemble(self._h, len(forms), fa, len(rhs_forms), fr, pv, pr, 1 if accumulate else 0,
                                            drop_val, space), allow=(-1,))
+
+    def boundary_set(self, face_tet, face_num):
+        """boundary faces carrying surface terms: face face_num[b] of element face_tet[b] (numpy int arrays)"""
+        ft = np.ascontiguousarray(face_tet, dtype=np.int32)
+        fn = np.ascontiguousarray(face_num, dtype=np.int32)
+        assert ft.shape == fn.shape
+        self._ck(lib().afb_boundary_set(self._h, ft.shape[0], ft.ctypes.data, fn.ctypes.data, HOST))
+
+    def assemble_faces(self, forms, rhs_forms, val=None, rhs=None, drop_val=1e-100):
+        """adds the surface forms over the faces of boundary_set into val / rhs (afb_assemble_faces)"""
+        fa = (AfbForm * max(1, len(forms)))(*forms)
+        fr = (AfbForm * max(1, len(rhs_forms)))(*rhs_forms)
+        pv, sv = _ptr(val)
+        pr, sr = _ptr(rhs)
+        space = sv if val is not None else sr
+        if val is not None and rhs is not None:
+            assert sv == sr
+        return self._ck(lib().afb_assemble_faces(self._h, len(forms), fa, len(rhs_forms), fr, pv, pr, drop_val, space), allow=(-1,))
 
     def priority_rows_set(self, first_priority_row):
         self._ck(lib().afb_priority_rows_set(self._h, int(first_priority_row)))

@@ -324,7 +324,8 @@ void afb_ctx_destroy(afb_ctx* c) {
     afb::blocks_clear(c);
     afb::DevBuf* bufs[] = {&c->x, &c->y, &c->z, &c->v[0], &c->v[1], &c->v[2], &c->v[3], &c->e2r, &c->e2c, &c->rowptr, &c->colind,
                            &c->radj_ptr, &c->radj, &c->pos, &c->stageA, &c->stageF, &c->tables, &c->coef, &c->io_val, &c->io_rhs,
-                           &c->flag, &c->tmp1, &c->tmp2, &c->tmp3, &c->xy, &c->diag_col, &c->rp_order, &c->rp_cnt, &c->rp_sptr, &c->rp_ell, &c->rp_new2old, &c->rp_old2new, &c->rp_cs, &c->rp_eptr, &c->rp_elist, &c->rp_p0, &c->rp_len, &c->rp_smax, &c->dir_flag, &c->dir_val, &c->dir_rows, &c->rp_clist};
+                           &c->flag, &c->tmp1, &c->tmp2, &c->tmp3, &c->xy, &c->diag_col, &c->rp_order, &c->rp_cnt, &c->rp_sptr, &c->rp_ell, &c->rp_new2old, &c->rp_old2new, &c->rp_cs, &c->rp_eptr, &c->rp_elist, &c->rp_p0, &c->rp_len, &c->rp_smax, &c->dir_flag, &c->dir_val, &c->dir_rows, &c->rp_clist,
+                           &c->bf_tet, &c->bf_face, &c->bf_item, &c->bf_urow, &c->bf_uoff, &c->bf_aidx};
     for (auto* b : bufs) b->release();
     for (auto& t : c->table_cache) cudaFree(t.W);
     for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -366,7 +367,7 @@ int afb_mesh_set(afb_ctx* ctx, int64_t nnode, const double* x, const double* y, 
     AFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->nnode = nnode; ctx->ntet = ntet;
     ctx->has_dofmap = false; ctx->has_pattern = false;
-    ctx->fields.clear(); ctx->fields_custom = false; afb::blocks_clear(ctx);
+    ctx->fields.clear(); ctx->fields_custom = false; afb::blocks_clear(ctx); ctx->bf_plan_valid = false;
     return 0;
 }
 
@@ -387,7 +388,7 @@ int afb_mesh_cube(afb_ctx* ctx, int nx, int ny, int nz, double size, int bx, int
     AFB_CUDA(ctx, cudaGetLastError());
     ctx->nnode = nnode; ctx->ntet = ntet;
     ctx->has_dofmap = false; ctx->has_pattern = false;
-    ctx->fields.clear(); ctx->fields_custom = false; afb::blocks_clear(ctx);
+    ctx->fields.clear(); ctx->fields_custom = false; afb::blocks_clear(ctx); ctx->bf_plan_valid = false;
     return afb_mesh_orient(ctx);
 }
 
@@ -452,7 +453,7 @@ int afb_dofmap_set(afb_ctx* ctx, int nrow_loc, int ncol_loc, const int64_t* elem
     ctx->nrow_loc = nrow_loc; ctx->ncol_loc = ncol_loc;
     ctx->row_begin = row_begin; ctx->row_end = row_end; ctx->ncols_global = ncols_global;
     ctx->has_dofmap = true; ctx->has_pattern = false; ctx->has_diag = false;
-    ctx->fields.clear(); ctx->fields_custom = false; afb::blocks_clear(ctx);
+    ctx->fields.clear(); ctx->fields_custom = false; afb::blocks_clear(ctx); ctx->bf_plan_valid = false;
     ctx->has_dirichlet = false; ctx->dir_rows_valid = false;
     return 0;
 }

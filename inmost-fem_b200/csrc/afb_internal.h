@@ -179,6 +179,15 @@ struct afb_ctx {
     afb::DevBuf dir_flag, dir_val, dir_rows;
     long long n_dir_rows = 0;
 
+    // boundary faces carrying surface terms (afb_faces.cu): face bf_face[b] of element bf_tet[b]; row -> (face, local row) lists
+    long long bf_n = 0;
+    int bf_nu = 0;                // rows touched by the listed faces
+    bool bf_plan_valid = false;
+    afb::DevBuf bf_tet, bf_face;  // int32[bf_n]
+    afb::DevBuf bf_item;          // uint32: b*nrow_loc + i, sorted by row, ascending inside a row
+    afb::DevBuf bf_urow, bf_uoff; // uint32[bf_nu] touched rows, int32[bf_nu+1] their item ranges
+    afb::DevBuf bf_aidx;          // int64 per item: row of the slot table (index into the row adjacency)
+
     // work buffers
     afb::DevBuf stageA, stageF, tables, coef, io_val, io_rhs, flag, tmp1, tmp2, tmp3, xy;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};

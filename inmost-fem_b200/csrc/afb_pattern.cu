@@ -164,6 +164,7 @@ static int pattern_impl(afb_ctx* ctx, int64_t* nnz_out, const int64_t* user_rowp
     cudaSetDevice(ctx->device);
     blocks_clear_dst(ctx);
     ctx->dir_rows_valid = false;
+    ctx->bf_plan_valid = false;
     const long long ntet = ctx->ntet, nrows = ctx->row_end - ctx->row_begin;
     const int nrl = ctx->nrow_loc, ncl = ctx->ncol_loc;
     const long long nitem = ntet * nrl;

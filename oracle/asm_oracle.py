@@ -252,6 +252,28 @@ class Problem:
         return A, F
 
 
+    def face_matrices(self, XY, face, idx=None, impl="oracle"):
+        """The same for surface integrals (fem3Dface over face face[r] of the tet XY[:, r]; forms and data of THIS Problem are
+        the face forms, per-face data indexed by idx = boundary-face indices): A (f, nloc, nloc), F (f, nloc)."""
+        f = XY.shape[1]
+        A = np.zeros((f, self.nloc, self.nloc))
+        F = np.zeros((f, self.nloc))
+        for fm in self.mat_forms:
+            fa, va = self.vars[fm["trial"]]
+            fb, vb = self.vars[fm["test"]]
+            form = (fm["opA"], fa, va, fm["opB"], fb, vb, fm["order"], fm["ttype"], fm["layout"])
+            Ae = O.fem3dface(form, XY, face, self._D(fm, idx), impl=impl)
+            ca, rb = self.var_off[fm["trial"]], self.var_off[fm["test"]]
+            A[:, ca:ca + Ae.shape[1], rb:rb + Ae.shape[2]] += fm.get("alpha", 1.0) * Ae
+        for fm in self.rhs_forms:
+            fb, vb = self.vars[fm["test"]]
+            form = (O.IDEN, O.P0, 1, fm["opB"], fb, vb, fm["order"], fm["ttype"], fm["layout"])
+            Fe = O.fem3dface(form, XY, face, self._D(fm, idx), impl=impl)
+            rb = self.var_off[fm["test"]]
+            F[:, rb:rb + Fe.shape[2]] += fm.get("alpha", 1.0) * Fe[:, 0, :]
+        return A, F
+
+
 def apply_dir(A, F, colcode, flag, value):
     """applyDir(A, F, k, bc) of fem/operations/dc_on_dof.h:27-45 for every Dirichlet local dof k of every element, as the
     reference's local assemblers do (examples/tutorials/ex1.cpp:96-105): F(i) -= A(i,k) bc; F(k) = bc; row and column k
@@ -267,9 +289,11 @@ def apply_dir(A, F, colcode, flag, value):
     A[e, k, k] = 1.0
 
 
-def assemble(problem, coords, tets, dofmap, rank=None, impl="oracle", drop_val=1e-100, chunk=200000, dirichlet=None):
+def assemble(problem, coords, tets, dofmap, rank=None, impl="oracle", drop_val=1e-100, chunk=200000, dirichlet=None, faces=None):
     """Full reference-style assembly on `rank`'s row interval: returns rowptr, colind, val, rhs.
-    dirichlet = (flag[ndof], value[ndof]): essential BCs applied to every element matrix like the reference's examples."""
+    dirichlet = (flag[ndof], value[ndof]): essential BCs applied to every element matrix like the reference's examples.
+    faces = (face_tet[nbf], face_num[nbf], Problem of the surface forms): Neumann / Robin terms added to the cell matrix by the
+    local assembler before the essential BCs (examples/Fem/Ani/diffusion.cpp:215-245)."""
     r = 0 if rank is None else rank
     row_begin, row_end = (0, dofmap.nrows) if rank is None else (int(dofmap.beg_ind[r]), int(dofmap.end_ind[r]))
     rowcode, colcode = dofmap.codes(rank)
@@ -283,6 +307,16 @@ def assemble(problem, coords, tets, dofmap, rank=None, impl="oracle", drop_val=1
         idx = sel[s:s + chunk]
         XY = coords[tets[idx]].transpose(1, 0, 2)  # (4, f, 3)
         A, F = problem.element_matrices(XY, idx=idx, impl=impl)
+        if faces is not None:
+            ft, fn, fprob = faces
+            ft = np.asarray(ft)
+            loc = np.full(tets.shape[0], -1, dtype=np.int64)
+            loc[idx] = np.arange(idx.shape[0])
+            fsel = np.nonzero(loc[ft] >= 0)[0]           # boundary faces of the cells of this chunk, ascending face index
+            if fsel.size:
+                Af, Ff = fprob.face_matrices(coords[tets[ft[fsel]]].transpose(1, 0, 2), np.asarray(fn)[fsel], idx=fsel, impl=impl)
+                np.add.at(A, loc[ft[fsel]], Af)
+                np.add.at(F, loc[ft[fsel]], Ff)
         if dirichlet is not None:
             apply_dir(A, F, colcode[s:s + chunk], np.asarray(dirichlet[0]), np.asarray(dirichlet[1], dtype=float))
         st = O.scatter_csr(rowcode[s:s + chunk], colcode[s:s + chunk], A, F, row_begin, rowptr, colind, val, rhs, drop_val)

@@ -307,6 +307,101 @@ def test_dirichlet_conditions(pkg, ctx, asm_oracle, case):
                 os.environ[k] = vv
 
 
+def _boundary_faces(co, te, sides):
+    """(tet, face number) of every face whose three vertices lie on one of the `sides` (predicates on coordinates);
+    face k = vertices k, k+1, k+2 mod 4"""
+    ft, fn = [], []
+    for k in range(4):
+        idx = [(k + m) % 4 for m in range(3)]
+        hit = np.zeros(te.shape[0], dtype=bool)
+        for side in sides:
+            hit |= side(co[te[:, idx[0]]]) & side(co[te[:, idx[1]]]) & side(co[te[:, idx[2]]])
+        sel = np.nonzero(hit)[0]
+        ft.append(sel); fn.append(np.full(sel.size, k))
+    ft, fn = np.concatenate(ft), np.concatenate(fn)
+    order = np.lexsort((fn, ft))
+    return ft[order].astype(np.int32), fn[order].astype(np.int32)
+
+
+@pytest.mark.parametrize("case", ["p2_robin_neumann", "p1_with_dirichlet", "p2vec_traction", "p3_generic"])
+def test_boundary_face_terms(pkg, ctx, asm_oracle, case):
+    """afb_boundary_set + afb_assemble_faces = the fem3Dface terms the reference's local assemblers add on labelled boundary
+    faces (examples/Fem/Ani/diffusion.cpp:215-245): Robin matrix + Neumann load on two sides of the cube, with and without
+    essential conditions on another side, scalar and vector spaces, on top of the fused and the generic volume paths"""
+    M = asm_oracle
+    variables = {"p1_with_dirichlet": [(gc.P1, 1)], "p2vec_traction": [(gc.P2, 3)], "p3_generic": [(gc.P3, 1)]}.get(case, [(gc.P2, 1)])
+    fem, vec = variables[0]
+    n = (3, 2, 2) if case in ("p2vec_traction", "p3_generic") else (4, 3, 3)
+    co, te, dm = _mesh(pkg, ctx, M, n, variables, jitter=0.0)
+    if case == "p2vec_traction":
+        _, forms, rhsf, prob = problems.c4_p2_elasticity(pkg, M, co, te)
+    elif case == "p1_with_dirichlet":
+        _, forms, rhsf, prob = problems.c1_p1_diffusion(pkg, M, co, te)
+    else:
+        rng0 = np.random.default_rng(3)
+        K = gc.tensor(rng0, gc.T_SYMMETRIC, gc.L_PER_TET, 3, 3, te.shape[0], 4)
+        _, forms, rhsf, prob = problems._mk(pkg, M, variables, [(0, 0, gc.GRAD, gc.GRAD, 2 if fem != gc.P3 else 4, gc.T_SYMMETRIC, gc.L_PER_TET, K, 1.0)],
+                                            [(0, gc.IDEN, 2, gc.T_NULL, gc.L_CONST, None, 1.0)])
+    ft, fn = _boundary_faces(co, te, [lambda X: np.abs(X[:, 0] - 1.0) < 1e-12, lambda X: np.abs(X[:, 2]) < 1e-12])
+    nbf = ft.size
+    assert nbf == 2 * (n[1] * n[2] + n[0] * n[1])
+    rng = np.random.default_rng(17)
+    order = 4
+    q = gc.NPTS_TRI[order]
+    if vec == 1:
+        alpha = gc.tensor(rng, gc.T_SCALAR, gc.L_PER_TET, 1, 1, nbf, q)        # Robin coefficient per face
+        gN = gc.tensor(rng, gc.T_SCALAR, gc.L_PER_POINT, 1, 1, nbf, q).reshape(nbf, q)   # Neumann flux per quadrature point of every face
+        fmats = [(0, 0, gc.IDEN, gc.IDEN, order, gc.T_SCALAR, gc.L_PER_TET, alpha, 1.0)]
+        frhss = [(0, gc.IDEN, order, gc.T_SCALAR, gc.L_PER_POINT, gN, 1.0)]
+    else:
+        R = gc.tensor(rng, gc.T_SYMMETRIC, gc.L_CONST, 3, 3, nbf, q)             # elastic foundation
+        t = np.ascontiguousarray(rng.standard_normal((nbf, 3)))                  # traction per face
+        fmats = [(0, 0, gc.IDEN, gc.IDEN, order, gc.T_SYMMETRIC, gc.L_CONST, R, 0.5)]
+        frhss = [(0, gc.IDEN, order, gc.T_GENERAL, gc.L_PER_TET, t, 1.0)]
+    _, fforms, frhsf, fprob = problems._mk(pkg, M, variables, fmats, frhss)
+    dirichlet = None
+    if case == "p1_with_dirichlet":
+        flag = np.zeros(dm.nrows, dtype=np.uint8)
+        flag[np.nonzero(np.abs(co[:, 1]) < 1e-12)[0]] = 1      # P1: dof = node (NATURAL numbering); y = 0 side, shares edges with x = 1 and z = 0
+        value = rng.standard_normal(dm.nrows)
+        dirichlet = (flag, value)
+    env = {"AFB_DISABLE_TENSOR_PATH": "1"} if case == "p3_generic" else {}
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        nnz = ctx.pattern_build()
+        rowptr, colind = ctx.pattern_get()
+        if dirichlet is not None:
+            ctx.dirichlet_set(*dirichlet)
+        val, rhs = np.full(nnz, np.nan), np.full(dm.nrows, np.nan)
+        assert ctx.assemble(forms, rhsf, val, rhs) == 0
+        ctx.boundary_set(ft, fn)
+        assert ctx.assemble_faces(fforms, frhsf, val, rhs) == 0
+        rp, ci, v, r, st = M.assemble(prob, co, te, dm, dirichlet=dirichlet, faces=(ft, fn, fprob))
+        assert st == 0 and np.array_equal(rowptr, rp) and np.array_equal(colind, ci)
+        rowmax = np.maximum.reduceat(np.abs(v), rp[:-1])
+        rowmax[rowmax == 0] = 1.0
+        err = (np.abs(val - v) / np.repeat(rowmax, np.diff(rp))).max()
+        rerr = np.abs(rhs - r).max() / max(np.abs(r).max(), 1.0)
+        print("%s: %d boundary faces, err A %.2e rhs %.2e" % (case, nbf, err, rerr))
+        assert err <= RTOL and rerr <= 10 * RTOL
+        # the face terms really are in there: without them the matrix differs
+        v0 = M.assemble(prob, co, te, dm, dirichlet=dirichlet)[2]
+        assert np.abs(v - v0).max() > 1e-3 * np.abs(v).max()
+        # bit-reproducible, and device buffers give the same numbers as host buffers
+        val2, rhs2 = np.full(nnz, np.nan), np.full(dm.nrows, np.nan)
+        assert ctx.assemble(forms, rhsf, val2, rhs2) == 0 and ctx.assemble_faces(fforms, frhsf, val2, rhs2) == 0
+        assert np.array_equal(val, val2) and np.array_equal(rhs, rhs2)
+    finally:
+        ctx.dirichlet_set(None, None)
+        ctx.boundary_set(np.zeros(0, np.int32), np.zeros(0, np.int32))
+        for k, vv in old.items():
+            if vv is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = vv
+
+
 @pytest.mark.parametrize("problem", ["c3", "c5"])
 def test_generic_path_in_element_chunks(pkg, ctx, asm_oracle, oracle, problem):
     """the generic staged path bounds its staging memory (AFB_STAGE_BYTES): many element chunks give the same matrix up to the
