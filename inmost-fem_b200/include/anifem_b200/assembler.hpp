@@ -22,6 +22,7 @@
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <algorithm>
 #include <vector>
 
 #include "fem.hpp"
@@ -98,7 +99,27 @@ public:
         m_rhs.push_back(afb_form{IDEN, FEM_P0, 1, OpB::op, OpB::fem, OpB::vec, order, ttype, coef_layout, coef_space, D, alpha, VarOffset(test_var), 0});
         return *this;
     }
-    void ClearForms() { m_forms.clear(); m_rhs.clear(); }
+    /// Surface terms: the fem3Dface<OpA,OpB>(XYZ, face, ...) calls a reference local assembler makes on the faces with a boundary
+    /// label (examples/Fem/Ani/diffusion.cpp:215-245).  The labelled faces are given once as (cell, face number 0..3); the
+    /// coefficient layouts are CONST, AFB_COEF_PER_TET = one record per listed face, PER_POINT = per point of the triangle rule.
+    Assembler& SetBoundaryFaces(const std::vector<int32_t>& face_cell, const std::vector<int32_t>& face_num) {
+        if (face_cell.size() != face_num.size()) throw std::runtime_error("SetBoundaryFaces: arrays differ in size");
+        ck(afb_boundary_set(m_ctx, (int64_t)face_cell.size(), face_cell.data(), face_num.data(), AFB_HOST));
+        return *this;
+    }
+    template <typename OpA, typename OpB>
+    Assembler& AddFaceMatForm(int trial_var, int test_var, int order, TensorType ttype, int coef_layout, const double* D, double alpha = 1.0,
+                              int coef_space = AFB_HOST) {
+        m_fforms.push_back(afb_form{OpA::op, OpA::fem, OpA::vec, OpB::op, OpB::fem, OpB::vec, order, ttype, coef_layout, coef_space, D, alpha,
+                                    VarOffset(test_var), VarOffset(trial_var)});
+        return *this;
+    }
+    template <typename OpB>
+    Assembler& AddFaceRhsForm(int test_var, int order, TensorType ttype, int coef_layout, const double* D, double alpha = 1.0, int coef_space = AFB_HOST) {
+        m_frhs.push_back(afb_form{IDEN, FEM_P0, 1, OpB::op, OpB::fem, OpB::vec, order, ttype, coef_layout, coef_space, D, alpha, VarOffset(test_var), 0});
+        return *this;
+    }
+    void ClearForms() { m_forms.clear(); m_rhs.clear(); m_fforms.clear(); m_frhs.clear(); }
 
     /// Essential boundary conditions: what the reference's local assemblers do with applyDir(A, F, k, bc) on every Dirichlet
     /// dof of every cell (fem/operations/dc_on_dof.h:27-45, examples/tutorials/ex1.cpp:96-105).  is_dirichlet / value are
@@ -143,18 +164,21 @@ public:
     int Assemble(CsrMatrix& matrix, std::vector<double>& rhs, const AssmOpts& opts = AssmOpts()) {
         if (m_forms.empty() && m_rhs.empty()) throw std::runtime_error("System local evaluator is not specified");
         prepare_outputs(&matrix, &rhs);
-        return ck(afb_assemble(m_ctx, (int)m_forms.size(), m_forms.data(), (int)m_rhs.size(), m_rhs.data(), matrix.val.data(), rhs.data(), 1,
-                               opts.drop_val, AFB_HOST));
+        const int st = ck(afb_assemble(m_ctx, (int)m_forms.size(), m_forms.data(), (int)m_rhs.size(), m_rhs.data(), matrix.val.data(), rhs.data(), 1,
+                                       opts.drop_val, AFB_HOST));
+        return std::min(st, faces(matrix.val.data(), rhs.data(), opts));
     }
     int AssembleMatrix(CsrMatrix& matrix, const AssmOpts& opts = AssmOpts()) {
         if (m_forms.empty()) throw std::runtime_error("Matrix local evaluator is not specified");
         prepare_outputs(&matrix, nullptr);
-        return ck(afb_assemble(m_ctx, (int)m_forms.size(), m_forms.data(), 0, nullptr, matrix.val.data(), nullptr, 1, opts.drop_val, AFB_HOST));
+        const int st = ck(afb_assemble(m_ctx, (int)m_forms.size(), m_forms.data(), 0, nullptr, matrix.val.data(), nullptr, 1, opts.drop_val, AFB_HOST));
+        return std::min(st, faces(matrix.val.data(), nullptr, opts));
     }
     int AssembleRHS(std::vector<double>& rhs, const AssmOpts& opts = AssmOpts()) {
         if (m_rhs.empty()) throw std::runtime_error("Right-hand side local evaluator is not specified");
         prepare_outputs(nullptr, &rhs);
-        return ck(afb_assemble(m_ctx, 0, nullptr, (int)m_rhs.size(), m_rhs.data(), nullptr, rhs.data(), 1, opts.drop_val, AFB_HOST));
+        const int st = ck(afb_assemble(m_ctx, 0, nullptr, (int)m_rhs.size(), m_rhs.data(), nullptr, rhs.data(), 1, opts.drop_val, AFB_HOST));
+        return std::min(st, faces(nullptr, rhs.data(), opts));
     }
     /// GetTimeEvalLocFunc-style getters (assembler.inl:949-964): ms of the last Assemble
     double GetTimeEvalLocFunc() const { double t[4]; afb_last_times(m_ctx, t); return t[0]; }
@@ -166,6 +190,10 @@ private:
         if (rc < 0 && rc != -1) throw std::runtime_error(afb_last_error(m_ctx));
         return rc;
     }
+    int faces(double* val, double* rhs, const AssmOpts& opts) {
+        if (m_fforms.empty() && m_frhs.empty()) return 0;
+        return ck(afb_assemble_faces(m_ctx, (int)m_fforms.size(), m_fforms.data(), (int)m_frhs.size(), m_frhs.data(), val, rhs, opts.drop_val, AFB_HOST));
+    }
     void need_prepared() {
         if (!m_prepared) PrepareProblem();
     }
@@ -176,7 +204,7 @@ private:
     }
     afb_ctx* m_ctx = nullptr;
     std::vector<FemVarDescr> m_vars;
-    std::vector<afb_form> m_forms, m_rhs;
+    std::vector<afb_form> m_forms, m_rhs, m_fforms, m_frhs;
     bool m_has_mesh = false, m_explicit = false, m_prepared = false;
     int64_t m_nnz = 0, m_beg = 0, m_end = 0;
 };

@@ -141,19 +141,22 @@ struct FemSpace {
 
 namespace b200 {
 /// core shared by the compile-time and the runtime front ends
+/// face_num < 0: volume integral (fem3Dtet); 0..3: surface integral over that face of every tet (fem3Dface, int_face.inl:160-199)
 template <typename Functor>
 void fem3Dtet_core(const ApplyOpBase& oa, const ApplyOpBase& ob, bool is_constant, const Tetras<const double>& XYZ, const Functor& Dfnc,
-                   DenseMatrix<double>& A, int order, void* user_data) {
+                   DenseMatrix<double>& A, int order, void* user_data, int face_num = -1) {
     const int f = XYZ.fusion;
     if (f <= 0) return;
+    if (face_num > 3) throw std::runtime_error("Wrong face index");
     const int nfa = static_cast<int>(oa.Nfa()), nfb = static_cast<int>(ob.Nfa()), idim = static_cast<int>(oa.Dim()), jdim = static_cast<int>(ob.Dim());
     if (A.size < static_cast<std::size_t>(nfa) * nfb * f)
         throw std::runtime_error("Not enough memory for local matrix, expected size = " + std::to_string(nfa * nfb * f) +
                                  " but A has size = " + std::to_string(A.size));
     A.nRow = nfb; A.nCol = static_cast<std::size_t>(nfa) * f;
     afb_ctx* ctx = default_context();
-    const int q = afb_tet_quadrature(order, nullptr, nullptr, 0);
-    if (q < 0) throw std::runtime_error("Numerical tetrahedron integration formula implemented only for 0 <= order <= 20");
+    const int q = face_num < 0 ? afb_tet_quadrature(order, nullptr, nullptr, 0) : afb_tri_quadrature(order, nullptr, nullptr, 0);
+    if (q < 0) throw std::runtime_error(face_num < 0 ? "Numerical tetrahedron integration formula implemented only for 0 <= order <= 20"
+                                                     : "Numerical triangle integration formula implemented only for 0 <= order <= 20");
     // evaluate the callback: once (constant tensor) or per quadrature point of every tet, r-major / n-minor like the
     // reference (fem/diff_tensor.h:492-520)
     const TensorDims dims{static_cast<std::size_t>(jdim), static_cast<std::size_t>(idim)};
@@ -168,7 +171,22 @@ void fem3Dtet_core(const ApplyOpBase& oa, const ApplyOpBase& ob, bool is_constan
     } else {
         layout = AFB_COEF_PER_POINT;
         std::vector<double> XYG(static_cast<std::size_t>(3) * q * f);
-        check(ctx, afb_quad_points(ctx, order, f, XYZ.XY0, XYZ.XY1, XYZ.XY2, XYZ.XY3, XYG.data(), AFB_HOST));
+        if (face_num < 0) check(ctx, afb_quad_points(ctx, order, f, XYZ.XY0, XYZ.XY1, XYZ.XY2, XYZ.XY3, XYG.data(), AFB_HOST));
+        else {
+            // points of the triangle rule lifted to the face {face, face+1, face+2 mod 4} (int_face.inl:175-180, core.inl:249-269)
+            std::vector<double> p(static_cast<std::size_t>(3) * q), w(q);
+            afb_tri_quadrature(order, p.data(), w.data(), q);
+            const double* X[4] = {XYZ.XY0, XYZ.XY1, XYZ.XY2, XYZ.XY3};
+            for (int r = 0; r < f; ++r)
+                for (int n = 0; n < q; ++n)
+                    for (int k = 0; k < 3; ++k) {
+                        double lam[4] = {0, 0, 0, 0};
+                        for (int m = 0; m < 3; ++m) lam[(face_num + m) % 4] = p[3 * n + m];
+                        double sx = X[0][k + 3 * r];
+                        for (int l = 1; l < 4; ++l) sx += lam[l] * (X[l][k + 3 * r] - X[0][k + 3 * r]);
+                        XYG[k + 3 * (n + static_cast<std::size_t>(q) * r)] = sx;
+                    }
+        }
         D.assign(dl * q * f, 0.0);
         types.reserve(static_cast<std::size_t>(q) * f);
         for (int r = 0; r < f; ++r)
@@ -201,7 +219,11 @@ void fem3Dtet_core(const ApplyOpBase& oa, const ApplyOpBase& ob, bool is_constan
         }
     }
     afb_form fm{oa.op, oa.fem, oa.vec, ob.op, ob.fem, ob.vec, order, ttype, layout, AFB_HOST, D.data(), 1.0, 0, 0};
-    check(ctx, afb_fem3dtet_batched(ctx, &fm, f, XYZ.XY0, XYZ.XY1, XYZ.XY2, XYZ.XY3, A.data, AFB_HOST));
+    if (face_num < 0) check(ctx, afb_fem3dtet_batched(ctx, &fm, f, XYZ.XY0, XYZ.XY1, XYZ.XY2, XYZ.XY3, A.data, AFB_HOST));
+    else {
+        std::vector<int32_t> faces(f, face_num);
+        check(ctx, afb_fem3dface_batched(ctx, &fm, f, faces.data(), XYZ.XY0, XYZ.XY1, XYZ.XY2, XYZ.XY3, A.data, AFB_HOST));
+    }
 }
 }  // namespace b200
 
@@ -247,6 +269,34 @@ void fem3Dtet(const Tetras<const double>& XYZ, const ApplyOpBase& applyOpU, cons
               PlainMemoryX<> /*mem*/, int order = 5, void* user_data = nullptr) {
     b200::fem3Dtet_core(applyOpU, applyOpV, FuncTraits::IsConstant::value, XYZ, Dfnc, A, order, user_data);
 }
+/// Elemental matrix of the surface integral int_f (D OpA(u)) . OpB(v) over face face_num of every tet: face k = vertices
+/// {k, k+1, k+2 mod 4} (fem/operations/int_face.h:15-29,49-66); the callback sees the points of the triangle rule on the face.
+template <typename OpA, typename OpB, typename FuncTraits = DfuncTraits<>, typename Functor>
+void fem3Dface(const Tetras<const double>& XYZ, int face_num, const Functor& Dfnc, DenseMatrix<double>& A, int order = 5, void* user_data = nullptr) {
+    if (face_num < 0) throw std::runtime_error("Wrong face index");
+    b200::fem3Dtet_core(ApplyOpBase(OpA::op, OpA::fem, OpA::vec), ApplyOpBase(OpB::op, OpB::fem, OpB::vec), FuncTraits::IsConstant::value, XYZ, Dfnc, A,
+                        order, user_data, face_num);
+}
+template <typename OpA, typename OpB, typename FuncTraits = DfuncTraits<>, typename Functor>
+void fem3Dface(const DenseMatrix<double>& XY0, const DenseMatrix<double>& XY1, const DenseMatrix<double>& XY2, const DenseMatrix<double>& XY3,
+               int face_num, const Functor& Dfnc, DenseMatrix<double>& A, int order = 5, void* user_data = nullptr) {
+    fem3Dface<OpA, OpB, FuncTraits>(make_tetras(XY0.data, XY1.data, XY2.data, XY3.data, static_cast<int>(XY0.nCol)), face_num, Dfnc, A, order, user_data);
+}
+/// caller-memory and runtime-operator overloads (int_face.h:22-29,90-93; dyn_ops.h:26-32): the memory argument is not used
+template <typename OpA, typename OpB, typename FuncTraits = DfuncTraits<>, typename Functor, typename ScalarType, typename IndexType>
+void fem3Dface(const Tetras<const double>& XYZ, int face_num, const Functor& Dfnc, DenseMatrix<double>& A, PlainMemory<ScalarType, IndexType>,
+               int order = 5, void* user_data = nullptr) {
+    fem3Dface<OpA, OpB, FuncTraits>(XYZ, face_num, Dfnc, A, order, user_data);
+}
+template <typename FuncTraits = DfuncTraits<>, typename Functor>
+void fem3Dface(const Tetras<const double>& XYZ, int face_num, const ApplyOpBase& applyOpU, const ApplyOpBase& applyOpV, const Functor& Dfnc,
+               DenseMatrix<double>& A, PlainMemoryX<> /*mem*/, int order = 5, void* user_data = nullptr) {
+    if (face_num < 0) throw std::runtime_error("Wrong face index");
+    b200::fem3Dtet_core(applyOpU, applyOpV, FuncTraits::IsConstant::value, XYZ, Dfnc, A, order, user_data, face_num);
+}
+template <typename OpA, typename OpB, typename ScalarType = double, typename IndexType = int>
+PlainMemory<ScalarType, IndexType> fem3Dface_memory_requirements(int /*order*/, int /*fusion*/ = 1) { return PlainMemory<ScalarType, IndexType>(); }
+
 /// no host scratch is needed: both sizes are zero (int_tet.h:154-160)
 template <typename OpA, typename OpB, typename ScalarType = double, typename IndexType = int>
 PlainMemory<ScalarType, IndexType> fem3Dtet_memory_requirements(int /*order*/, int /*fusion*/ = 1) { return PlainMemory<ScalarType, IndexType>(); }

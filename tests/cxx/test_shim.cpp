@@ -161,6 +161,80 @@ int main() {
         for (std::size_t k = 0; k < v1.size(); ++k) d = std::fmax(d, std::fabs(A.val[k] - 2 * v1[k]));
         EXPECT(d == 0.0);
     }
+    // --- Assembler with surface terms: Robin matrix (alpha = 1) + Neumann load (g = 2) on the whole boundary of the unit cube, P2:
+    //     1^T A_face 1 = |boundary| = 6, sum of the face load = 2 * 6 (the fem3Dface calls of Fem/Ani/diffusion.cpp:215-245)
+    {
+        Assembler discr;
+        discr.SetCubeMesh(3, 3, 3).SetProbDescr({{FEM_P2, 1}});
+        using G2 = Operator<GRAD, FemFix<FEM_P2>>; using I2 = Operator<IDEN, FemFix<FEM_P2>>;
+        const double one = 1.0, two = 2.0;
+        discr.AddMatForm<G2, G2>(0, 0, 2, TENSOR_NULL, AFB_COEF_CONST, nullptr);
+        discr.PrepareProblem();
+        int64_t nnode = 0, ntet = 0;
+        EXPECT(afb_mesh_get(discr.context(), &nnode, &ntet, nullptr, nullptr, AFB_HOST) == 0);
+        std::vector<double> xyz(3 * nnode); std::vector<int32_t> v(4 * ntet);
+        EXPECT(afb_mesh_get(discr.context(), &nnode, &ntet, xyz.data(), v.data(), AFB_HOST) == 0);
+        std::vector<int32_t> fc, fn;
+        auto on_side = [&](int node, int side) { const double c = xyz[(side % 3) * nnode + node]; return std::fabs(c - (side < 3 ? 0.0 : 1.0)) < 1e-12; };
+        for (int64_t e = 0; e < ntet; ++e)
+            for (int k = 0; k < 4; ++k)
+                for (int side = 0; side < 6; ++side)
+                    if (on_side(v[((k + 0) % 4) * ntet + e], side) && on_side(v[((k + 1) % 4) * ntet + e], side) && on_side(v[((k + 2) % 4) * ntet + e], side)) {
+                        fc.push_back((int32_t)e); fn.push_back(k);
+                    }
+        EXPECT(fc.size() == 6 * 9 * 2);
+        CsrMatrix A0; std::vector<double> b0;
+        EXPECT(discr.Assemble(A0, b0) == 0);
+        discr.SetBoundaryFaces(fc, fn);
+        discr.AddFaceMatForm<I2, I2>(0, 0, 4, TENSOR_SCALAR, AFB_COEF_CONST, &one).AddFaceRhsForm<I2>(0, 4, TENSOR_SCALAR, AFB_COEF_CONST, &two);
+        CsrMatrix A; std::vector<double> b;
+        EXPECT(discr.Assemble(A, b) == 0);
+        double sa = 0, sb = 0;
+        for (std::size_t k = 0; k < A.val.size(); ++k) sa += A.val[k] - A0.val[k];
+        for (std::size_t k = 0; k < b.size(); ++k) sb += b[k] - b0[k];
+        EXPECT(std::fabs(sa - 6.0) < 1e-11);
+        EXPECT(std::fabs(sb - 12.0) < 1e-11);
+    }
+    // --- fem3Dface: GRAD(P2) x IDEN(P1^3) over face 1, normal-weighted tensor, 12x10 table of tests/fem/operations/int_face_test.cpp:29-95
+    {
+        double P1[] = {1, 1, 1}, P2[] = {2, 1, 1}, P3[] = {1, 2, 1}, P4[] = {1, 1, 2};
+        DenseMatrix<> F1(P1, 3, 1), F2(P2, 3, 1), F3(P3, 3, 1), F4(P4, 3, 1);
+        using OP1 = Operator<GRAD, FemFix<FEM_P2>>;
+        using OP2 = Operator<IDEN, FemVec<3, FEM_P1>>;
+        const double s3 = 1.0 / std::sqrt(3.0);   // outward normal of face 1 = (1,1,1)/sqrt(3)
+        auto ddotn = [s3](const std::array<double, 3>& x, double* Dmem, TensorDims dims, void*, int) {
+            const int d1 = 3, d2 = 3;
+            if ((int)dims.first != d1 || (int)dims.second != d2) throw std::runtime_error("Error in expected tensor sizes");
+            for (int j = 0; j < d2; ++j)
+                for (int i = 0; i < d1; ++i) {
+                    double v = 0;
+                    for (int k = 0; k < 3; ++k) v += (x[j % 3] + (3 * i + k) / 10.0) * s3;
+                    Dmem[i + d1 * j] = v;
+                }
+            return TENSOR_GENERAL;
+        };
+        const double A_exp[120] = {
+            0.000, 2.150, 2.150, 2.150, 0.000, 2.600, 2.600, 2.600, 0.000, 3.050, 3.050, 3.050,
+            0.000, 0.900, 0.075, 0.075, 0.000, 1.050, 0.075, 0.075, 0.000, 1.200, 0.075, 0.075,
+            0.000, 0.075, 0.900, 0.075, 0.000, 0.075, 1.050, 0.075, 0.000, 0.075, 1.200, 0.075,
+            0.000, 0.075, 0.075, 0.900, 0.000, 0.075, 0.075, 1.050, 0.000, 0.075, 0.075, 1.200,
+            0.000,-4.300,-2.150,-2.150, 0.000,-5.200,-2.600,-2.600, 0.000,-6.100,-3.050,-3.050,
+            0.000,-2.150,-4.300,-2.150, 0.000,-2.600,-5.200,-2.600, 0.000,-3.050,-6.100,-3.050,
+            0.000,-2.150,-2.150,-4.300, 0.000,-2.600,-2.600,-5.200, 0.000,-3.050,-3.050,-6.100,
+            0.000, 2.050, 2.050, 1.300, 0.000, 2.500, 2.500, 1.600, 0.000, 2.950, 2.950, 1.900,
+            0.000, 2.050, 1.300, 2.050, 0.000, 2.500, 1.600, 2.500, 0.000, 2.950, 1.900, 2.950,
+            0.000, 1.300, 2.050, 2.050, 0.000, 1.600, 2.500, 2.500, 0.000, 1.900, 2.950, 2.950};
+        double Ad[120];
+        DenseMatrix<> A(Ad, 12, 10);
+        fem3Dface<OP1, OP2>(F1, F2, F3, F4, 1, ddotn, A, 3);
+        EXPECT(A.nRow == 12 && A.nCol == 10);
+        EXPECT(norm_diff(1, A, -1, A_exp) <= 100 * (1 + norm(A)) * DBL_EPSILON);
+        fem3Dface<DfuncTraits<>>(make_tetras(P1, P2, P3, P4, 1), 1, FemSpace(FEM_P2).getOP(GRAD), FemSpace(FEM_P1, 3).getOP(IDEN), ddotn, A, PlainMemoryX<>(), 3);
+        EXPECT(norm_diff(1, A, -1, A_exp) <= 100 * (1 + norm(A)) * DBL_EPSILON);
+        bool thrown = false;
+        try { fem3Dface<OP1, OP2>(F1, F2, F3, F4, 4, ddotn, A, 3); } catch (const std::runtime_error&) { thrown = true; }
+        EXPECT(thrown);
+    }
     std::printf(fails ? "test_shim: %d FAILED\n" : "test_shim: all passed\n", fails);
     return fails ? 1 : 0;
 }
