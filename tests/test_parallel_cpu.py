@@ -61,6 +61,33 @@ def _worker(rank, world, port, dims, variables, errq):
         assert nb.row_begin == dm.beg_ind[rank] and nb.row_end == dm.end_ind[rank] and nb.nrows_global == dm.nrows
         plan = par.InterfacePlan(nb)
         n_ext = plan.n_own + plan.n_for
+        # scalar fields for afb_fields_set: the intervals partition the local rows / the global columns, every local dof of an
+        # element lies in the intervals of its field, and the scalar position of an entity is the same in all fields of a space
+        fields = nb.fields(plan)
+        rows_seen, cols_seen = np.zeros(n_ext, dtype=int), np.zeros(nb.nrows_global, dtype=int)
+        rowcode, colcode = plan.rowcode.numpy() - 1, plan.colcode.numpy() - 1
+
+        def scalar(ids, segs):
+            out, pre = np.full(ids.shape, -1, dtype=np.int64), 0
+            for a, c in segs:
+                m = (ids >= a) & (ids < a + c)
+                out[m] = pre + ids[m] - a
+                pre += c
+            return out
+        first_of_space = {}
+        for fem, loff, rseg, cseg in fields:
+            for a, c in rseg:
+                rows_seen[a:a + c] += 1
+            for a, c in cseg:
+                cols_seen[a:a + c] += 1
+            nl = gc.NF[fem]
+            sr, sc = scalar(rowcode[:, loff:loff + nl], rseg), scalar(colcode[:, loff:loff + nl], cseg)
+            assert (sr >= 0).all() and (sc >= 0).all(), "a local dof lies outside the intervals of its field"
+            if fem in first_of_space:
+                assert np.array_equal(sr, first_of_space[fem][0]) and np.array_equal(sc, first_of_space[fem][1])
+            else:
+                first_of_space[fem] = (sr, sc)
+        assert (rows_seen == 1).all() and (cols_seen == 1).all(), "field intervals do not partition the row / column space"
         rp_l, ci_l = _local_pattern(plan.rowcode.numpy(), plan.colcode.numpy(), plan.n_own, n_ext, nb.row_begin)
         rp_e, ci_e = plan.finalize_pattern(torch.from_numpy(rp_l), torch.from_numpy(ci_l))
         # problem: stiffness (+ mass on variable 0) with per-tet coefficients, rhs load
