@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <vector>
 
+#include "enumerator.hpp"
 #include "fem.hpp"
 
 namespace Ani {
@@ -72,6 +73,9 @@ public:
         return *this;
     }
     Assembler& SetProbDescr(std::vector<FemVarDescr> vars) { m_vars = std::move(vars); m_explicit = false; m_prepared = false; return *this; }
+    /// SetEnumerator(ASSEMBLING_TYPE) (assembler.h:333-336, global_enumerator.h:393-401): NATURAL (default) is numbered on the
+    /// device; the other types are numbered on the host (enumerator.hpp, as the reference does) and go in through afb_dofmap_set
+    Assembler& SetEnumerator(ASSEMBLING_TYPE t) { m_enum_type = t; m_prepared = false; return *this; }
     /// explicit elem -> global index codes (m_indexesR / m_indexesC, assembler.inl:49-55,139-184)
     Assembler& SetDofMap(int nrow_loc, int ncol_loc, const int64_t* rowcode, const int64_t* colcode, int64_t row_begin, int64_t row_end, int64_t ncols) {
         if (!m_has_mesh) throw std::runtime_error("Mesh was not specified");
@@ -139,7 +143,18 @@ public:
             if (m_vars.empty()) throw std::runtime_error("Description of fem expression is empty, try SetProbDescr(...)");
             std::vector<int> fem, vec;
             for (auto& v : m_vars) { fem.push_back(v.fem); vec.push_back(v.vec); }
-            ck(afb_dofmap_natural(m_ctx, static_cast<int>(fem.size()), fem.data(), vec.data()));
+            if (m_enum_type == NATURAL) ck(afb_dofmap_natural(m_ctx, static_cast<int>(fem.size()), fem.data(), vec.data()));
+            else {
+                int64_t nnode = 0, ntet = 0;
+                ck(afb_mesh_get(m_ctx, &nnode, &ntet, nullptr, nullptr, AFB_HOST));
+                std::vector<int32_t> v(static_cast<std::size_t>(4) * ntet);
+                ck(afb_mesh_get(m_ctx, &nnode, &ntet, nullptr, v.data(), AFB_HOST));
+                std::vector<EnumVar> ev;
+                for (auto& d : m_vars) ev.push_back(EnumVar{d.fem, d.vec});
+                DofEnumeration en = enumerate_dofs(m_enum_type, nnode, ntet, v.data(), v.data() + ntet, v.data() + 2 * ntet, v.data() + 3 * ntet, ev);
+                for (auto& c : en.elem2dof) c += 1;   // assemble_index_encode: sign * (id + 1) (assembler.inl:49-55)
+                ck(afb_dofmap_set(m_ctx, en.nloc, en.nloc, en.elem2dof.data(), en.elem2dof.data(), 0, en.nrows, en.nrows, AFB_HOST));
+            }
         }
         ck(afb_pattern_build(m_ctx, &m_nnz));
         int nr, nc; int64_t ng;
@@ -206,6 +221,7 @@ private:
     std::vector<FemVarDescr> m_vars;
     std::vector<afb_form> m_forms, m_rhs, m_fforms, m_frhs;
     bool m_has_mesh = false, m_explicit = false, m_prepared = false;
+    ASSEMBLING_TYPE m_enum_type = NATURAL;
     int64_t m_nnz = 0, m_beg = 0, m_end = 0;
 };
 

@@ -191,6 +191,92 @@ class DofMap:
         return row, col
 
 
+# GlobEnumeration types (inmost_interface/global_enumerator.h:393-401) and the arrangement of the OrderedEnumerator tuple
+# (VAR, DIM, ELEM_TYPE, ELEM_ID, DOF_ID) each of them sets (global_enumerator.cpp:818-835)
+ENUM_TYPES = ("ANITYPE", "MINIBLOCKS", "NATURAL", "DIMUNION", "BYELEMTYPE", "ETDIMBLOCKS")
+_ARRANGEMENT = {"NATURAL": ("VAR", "DIM", "ELEM_TYPE", "ELEM_ID", "DOF_ID"),
+                "DIMUNION": ("VAR", "ELEM_TYPE", "ELEM_ID", "DOF_ID", "DIM"),
+                "BYELEMTYPE": ("ELEM_TYPE", "VAR", "DIM", "ELEM_ID", "DOF_ID"),
+                "ETDIMBLOCKS": ("ELEM_TYPE", "VAR", "ELEM_ID", "DOF_ID", "DIM")}
+
+
+def enumerate_dofs(tets, variables, enum_type="NATURAL", nnode=None):
+    """elem -> global dof table (ntet, nloc) and the number of dofs on ONE rank for every GlobEnumeration type, restated from
+    the definitions, not from closed forms:
+      * OrderedEnumerator (NATURAL, DIMUNION, BYELEMTYPE, ETDIMBLOCKS): the index of a dof is the rank of its tuple
+        (VAR, DIM, ELEM_TYPE, ELEM_ID, DOF_ID) in the lexicographic order of the type's arrangement
+        (global_enumerator.cpp:702-777: loc_emap over the tuples; DIM = di % ndim, DOF_ID = di / ndim for the di-th dof of a
+        vector variable on an entity, :727-731);
+      * SimpleEnumerator ANITYPE: InitElemIndex[edim] + (gid - BegElemID) + iodf * NumElem[edim] (:823-825), iodf = position of
+        the dof among all dofs on the entity: variables in order, component fastest inside a vector variable;
+      * SimpleEnumerator MINIBLOCKS: the layout its own inverse map decodes (:866-871): InitElemIndex[edim] + gid * nd[edim] +
+        iodf.  (The forward formula at :826 multiplies iodf by NumElem[edim], which leaves the valid range when an entity
+        carries more than one dof; the inverse and the name say dofs of one entity are adjacent.)
+    Entity ids as everywhere in this oracle: nodes by id, edges / faces in lexicographic order of their sorted node tuples.
+    Local order on the tet as in DofMap (variable, component, vertices, edges [P3 pair oriented by node ids], faces, cell)."""
+    ntet = tets.shape[0]
+    nnode = int(tets.max()) + 1 if nnode is None else nnode
+    edges, faces, te, tf = connectivity(tets)
+    ent_of_tet = [tets, te, tf, np.arange(ntet)[:, None]]
+    nent = [nnode, edges.shape[0], faces.shape[0], ntet]
+    # every dof as a record (var, comp, dim-type d, entity, k)
+    recs = []
+    for v, (fem, vec) in enumerate(variables):
+        for c in range(vec):
+            for d in range(4):
+                for k in range(NDOF[fem][d]):
+                    g = np.arange(nent[d])
+                    recs.append(np.stack([np.full(nent[d], v), np.full(nent[d], c), np.full(nent[d], d), g, np.full(nent[d], k)], 1))
+    recs = np.concatenate(recs, 0)
+    ndofs = recs.shape[0]
+    if enum_type in _ARRANGEMENT:
+        col = {"VAR": 0, "DIM": 1, "ELEM_TYPE": 2, "ELEM_ID": 3, "DOF_ID": 4}
+        keys = [recs[:, col[name]] for name in _ARRANGEMENT[enum_type]]
+        order = np.lexsort(tuple(reversed(keys)))          # lexsort: last key is the primary one
+        ids = np.empty(ndofs, dtype=np.int64)
+        ids[order] = np.arange(ndofs)
+    elif enum_type in ("ANITYPE", "MINIBLOCKS"):
+        i_nd = [sum(NDOF[fem][d] * vec for fem, vec in variables) for d in range(4)]    # dofs per entity of dimension d
+        init = np.concatenate([[0], np.cumsum([i_nd[d] * nent[d] for d in range(4)])])
+        # iodf: variables in order; inside a vector variable dof k, component c -> k * vec + c
+        shift = {}
+        for d in range(4):
+            o = 0
+            for v, (fem, vec) in enumerate(variables):
+                shift[(v, d)] = o
+                o += NDOF[fem][d] * vec
+        vecs = np.array([vec for _, vec in variables])
+        iodf = np.array([shift[(int(r[0]), int(r[2]))] for r in recs[:, :3]]) + recs[:, 4] * vecs[recs[:, 0]] + recs[:, 1]
+        d = recs[:, 2]
+        if enum_type == "ANITYPE":
+            ids = init[d] + recs[:, 3] + iodf * np.array(nent)[d]
+        else:
+            ids = init[d] + recs[:, 3] * np.array(i_nd)[d] + iodf
+    else:
+        raise ValueError("unknown enumeration type " + str(enum_type))
+    assert np.array_equal(np.sort(ids), np.arange(ndofs)), "the enumeration is not a bijection"
+    lookup = {}
+    for r, i in zip(recs, ids):
+        lookup[(int(r[0]), int(r[1]), int(r[2]), int(r[3]), int(r[4]))] = int(i)
+    cols = []
+    for v, (fem, vec) in enumerate(variables):
+        for c in range(vec):
+            for d in range(4):
+                nd = NDOF[fem][d]
+                if nd == 0:
+                    continue
+                ents = ent_of_tet[d]
+                for le in range(ents.shape[1]):
+                    ks = [np.full(ntet, k) for k in range(nd)]
+                    if d == 1 and nd == 2:   # S2 pair on an edge, oriented by the node ids (tetdofmap.inl:98-104)
+                        a, b = LOCAL_EDGES[le]
+                        flip = (tets[:, a] > tets[:, b]).astype(np.int64)
+                        ks = [flip, 1 - flip]
+                    for kk in ks:
+                        cols.append(np.array([lookup[(v, c, d, int(g), int(k))] for g, k in zip(ents[:, le], kk)], dtype=np.int64))
+    return np.stack(cols, 1), ndofs
+
+
 def template_pattern(rowcode, colcode, row_begin, row_end):
     """AssembleTemplate: sorted CSR rows over [row_begin,row_end) incl. forced diagonal"""
     ne, nrow = rowcode.shape

@@ -2,9 +2,12 @@
 import os
 import subprocess
 
+import numpy as np
 import pytest
 
 from conftest import ROOT
+
+import golden_cases as gc
 
 CXX_DIR = os.path.join(ROOT, "tests", "cxx")
 
@@ -22,3 +25,29 @@ def test_shim_runs_reference_style_tests(pkg):
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     print(out.stdout, out.stderr)
     assert out.returncode == 0 and "all passed" in out.stdout
+
+
+@pytest.mark.parametrize("variables", [[(gc.P1, 1)], [(gc.P2, 1)], [(gc.P3, 1)], [(gc.P2, 3), (gc.P1, 1)], [(gc.P0, 1), (gc.P3, 3)]])
+def test_host_enumerators_against_the_restated_definitions(asm_oracle, tmp_path, variables):
+    """anifem_b200/enumerator.hpp (closed forms) against the oracle's restatement of the GlobEnumeration definitions
+    (lexicographic rank of the (VAR, DIM, ELEM_TYPE, ELEM_ID, DOF_ID) tuple, SimpleEnumerator formulas;
+    global_enumerator.cpp:702-777,818-835) for all six ASSEMBLING_TYPEs -- bit-exact integer tables, CPU only"""
+    M = asm_oracle
+    subprocess.check_call(["make", "-s", "-C", CXX_DIR, "test_enum"])
+    co, te, _ = M.cube_mesh(3, 2, 2)
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(co.shape[0])          # scrambled node ids: exercises the P3 edge-pair orientation and the entity sort
+    te = perm[te]
+    tets_file, out_file = str(tmp_path / "tets.i32"), str(tmp_path / "out.i64")
+    np.ascontiguousarray(te.T, dtype=np.int32).tofile(tets_file)
+    args = [str(x) for fv in variables for x in fv]
+    for t, name in enumerate(M.ENUM_TYPES):
+        subprocess.check_call([os.path.join(CXX_DIR, "test_enum"), str(t), str(co.shape[0]), str(te.shape[0]), tets_file, out_file] + args)
+        raw = np.fromfile(out_file, dtype=np.int64)
+        nrows, nloc = int(raw[0]), int(raw[1])
+        table = raw[2:].reshape(te.shape[0], nloc)
+        exp, n = M.enumerate_dofs(te, variables, name, co.shape[0])
+        assert nrows == n and np.array_equal(table, exp), name
+    # NATURAL is the numbering afb_dofmap_natural builds on the device (same oracle DofMap the GPU tests compare with)
+    dm = M.DofMap(te, variables, nnode=co.shape[0])
+    assert np.array_equal(M.enumerate_dofs(te, variables, "NATURAL", co.shape[0])[0], dm.elem2dof)
