@@ -159,6 +159,23 @@ def test_face_oracle_vs_live_reference(oracle):
         assert np.abs(a - b).max() <= 1e-13 * (1 + np.abs(b).max()), name
 
 
+def test_apply_dir_reference_case(asm_oracle):
+    """applyDir(A, F, dof, bc) exactly as tests/fem/operations/dc_on_dof_test.cpp:13-41 builds its expectation:
+    A(i,j) = (i+1)(j+1), F(i) = i+1, dof 2, bc 1 -> row and column 2 zeroed, A(2,2) = 1, F -= A(:,2) bc, F(2) = bc"""
+    N, dof, bc = 4, 2, 1.0
+    A = np.array([[(i + 1) * (j + 1) for i in range(N)] for j in range(N)], float)[None]   # [e, col j, row i]
+    F = np.arange(1, N + 1, dtype=float)[None]
+    A_exp, F_exp = A.copy(), F.copy()
+    A_exp[0, dof, :] = 0; A_exp[0, :, dof] = 0; A_exp[0, dof, dof] = 1
+    F_exp[0] -= A[0, dof, :] * bc
+    F_exp[0, dof] = bc
+    flag = np.zeros(N, dtype=np.uint8); flag[dof] = 1
+    value = np.zeros(N); value[dof] = bc
+    colcode = np.arange(1, N + 1)[None]
+    asm_oracle.apply_dir(A, F, colcode, flag, value)
+    assert np.array_equal(A, A_exp) and np.array_equal(F, F_exp)
+
+
 def test_identity_tensor_incompatible_dims(oracle):
     """TENSOR_NULL with Dim(OpA) != Dim(OpB) is an error (diff_tensor.h:315-317)"""
     form = (gc.GRAD, gc.P1, 1, gc.IDEN, gc.P1, 1, 2, gc.T_NULL, gc.L_CONST)
