@@ -14,14 +14,15 @@ several blocks is owned by the lowest rank; inside a rank, owned nodes are order
 edges lexicographically by their (min,max) global node ids; NATURAL numbering inside the rank's interval.
 
 Everything here is device-agnostic torch code (runs on CPU/gloo in the tests, on CUDA/NCCL in bench.py); the
-numerics stay in the CUDA library.  Scope of round 1: variables living on nodes and edges (P1, P2, vectors of
-them, Taylor-Hood).  P3 (faces, edge pairs) is single-GPU only for now.
+numerics stay in the CUDA library.  Scope: variables living on nodes, edges and faces (P1, P2, P3, vectors of them,
+Taylor-Hood); P0 (cell dofs) is not partitioned.  P3 is covered by the CPU (gloo) tests of the numbering / exchange plan only.
 """
 import torch
 import torch.distributed as dist
 
-NDOF = {1: (0, 0), 2: (1, 0), 3: (1, 1)}  # fem -> dofs per (node, edge); P0 / P3 are not partitioned in round 1
+NDOF = {2: (1, 0, 0), 3: (1, 1, 0), 4: (1, 2, 1)}  # fem (P1, P2, P3) -> dofs per (node, edge, face); P0 (cell dofs) is not partitioned
 LOCAL_EDGES = ((0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3))
+LOCAL_FACES = ((0, 1, 2), (1, 2, 3), (2, 3, 0), (3, 0, 1))
 
 
 def proc_grid(nranks, sizes):
@@ -106,9 +107,10 @@ class Numbering:
         self.vars = list(variables)
         for fem, _ in self.vars:
             if fem not in NDOF:
-                raise NotImplementedError("multi-GPU numbering covers P1/P2-based variables in this round")
+                raise NotImplementedError("multi-GPU numbering covers P1 / P2 / P3 based variables")
         tets = tets.long()
         need_e = any(NDOF[f][1] for f, _ in self.vars)
+        need_f = any(NDOF[f][2] for f, _ in self.vars)
         # ---- local entities with canonical keys
         ent_key = [gnode.long()]
         ent_of_tet = [tets]
@@ -124,6 +126,25 @@ class Numbering:
             ent_key.append(ekeys)
             ent_of_tet.append(inv.reshape(-1, 6))
             ent_iface.append(eif)
+        if need_f:
+            # faces: canonical key = sorted global node triple as one integer (lexicographic order of the triples, like the
+            # edges); the three factors must fit 63 bits
+            if nn_global >= (1 << 21):
+                raise NotImplementedError("P3 on a partitioned mesh: face keys need more than 63 bits above 2^21 global nodes")
+            tri = torch.stack([torch.stack([gnode[tets[:, a]] for a in f], 1).long() for f in LOCAL_FACES], 1)   # (ntet, 4, 3)
+            tri = torch.sort(tri, dim=2).values
+            key = (tri[..., 0] * nn_global + tri[..., 1]) * nn_global + tri[..., 2]
+            fkeys, inv = torch.unique(key.reshape(-1), sorted=True, return_inverse=True)
+            allif = torch.stack([iface_node[tets[:, f[0]]] & iface_node[tets[:, f[1]]] & iface_node[tets[:, f[2]]] for f in LOCAL_FACES], 1).reshape(-1)
+            fif = torch.zeros(fkeys.numel(), dtype=torch.bool, device=dev)
+            fif[inv[allif]] = True
+            if not need_e:   # keep the (node, edge, face) slots aligned
+                ent_key.append(torch.zeros(0, dtype=torch.int64, device=dev))
+                ent_of_tet.append(torch.zeros((tets.shape[0], 0), dtype=torch.int64, device=dev))
+                ent_iface.append(torch.zeros(0, dtype=torch.bool, device=dev))
+            ent_key.append(fkeys)
+            ent_of_tet.append(inv.reshape(-1, 4))
+            ent_iface.append(fif)
         nd_types = len(ent_key)
         # ---- ownership: lowest rank among the ranks that hold the entity
         self.owner, self.pos = [], []
@@ -191,6 +212,13 @@ class Numbering:
                     ow = self.owner[d][ents]
                     base = beg_ind_dev[ow] + grp_off[(v, c, d)].to(dev)[ow] + self.pos[d][ents] * nd
                     for le in range(ents.shape[1]):
+                        if d == 1 and nd == 2:
+                            # the two dofs of a P3 edge follow the orientation of the edge by global node ids (tetdofmap.inl:98-104)
+                            a, b = LOCAL_EDGES[le]
+                            flip = (gnode[tets[:, a]] > gnode[tets[:, b]]).long()
+                            cols.append(base[:, le] + flip)
+                            cols.append(base[:, le] + 1 - flip)
+                            continue
                         for k in range(nd):
                             cols.append(base[:, le] + k)
         self.elem2dof = torch.stack(cols, 1).contiguous()
@@ -207,7 +235,7 @@ class Numbering:
         foreign = plan.foreign.cpu()
         for v, (fem, vec) in enumerate(self.vars):
             ds = [d for d in range(self.nd_types) if NDOF[fem][d]]
-            nl = 4 * NDOF[fem][0] + 6 * NDOF[fem][1]
+            nl = 4 * NDOF[fem][0] + 6 * NDOF[fem][1] + 4 * NDOF[fem][2]
             for c in range(vec):
                 cols = []
                 for p in range(self.world):

@@ -98,6 +98,14 @@ def test_two_gpus_taylor_hood(pkg, oracle):
     _run(2, (4, 3, 2), [(gc.P2, 3), (gc.P1, 1)])
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpus_p3(pkg, oracle):
+    """P3 (face dofs, oriented edge pairs) on two GPUs.  The numbering / exchange plan is covered on the CPU
+    (tests/test_parallel_cpu.py::test_two_ranks_p3); this GPU leg was added after the round's GPU budget was spent and has
+    not run on hardware yet."""
+    _run(2, (3, 2, 2), [(gc.P3, 1)])
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 4, reason="needs 4 GPUs")
 def test_four_gpus_p1(pkg, oracle):
     _run(4, (6, 5, 3), [(gc.P1, 1)])

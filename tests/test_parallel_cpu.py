@@ -147,5 +147,14 @@ def test_three_ranks_p1(pkg, oracle):
     _run(3, (5, 3, 2), [(gc.P1, 1)])
 
 
+def test_two_ranks_p3(pkg, oracle):
+    """P3: face dofs and the oriented pairs of edge dofs across the interface (numbering, pattern union, exchange)"""
+    _run(2, (3, 2, 2), [(gc.P3, 1)])
+
+
+def test_three_ranks_p3_p1(pkg, oracle):
+    _run(3, (3, 3, 2), [(gc.P3, 1), (gc.P1, 1)])
+
+
 def test_two_ranks_taylor_hood(pkg, oracle):
     _run(2, (3, 2, 2), [(gc.P2, 3), (gc.P1, 1)])
