@@ -1,9 +1,9 @@
 #!/usr/bin/env python3
 """CPU emulation of the slice builder of k_rows_cl (inmost-fem_b200/csrc/afb_rows.cu: k_morton, k_row_key, slices of 32 rows per
 (cluster, length bucket), visit-steps = sum over classes of the slice maximum) to put numbers on plan-level levers before they
-are built.  ANALYSIS TOOL (uses the oracle's mesh / numbering helpers); not part of the product.
+are built.  TEST-SIDE ANALYSIS TOOL (lives under tests/ because it uses the oracle's mesh / numbering helpers); not part of the product.
 
-  python tools/plan_stats.py [--n 40] [--chunk 512]
+  python tests/analysis/plan_stats.py [--n 40] [--chunk 512]
 
 Reports the fraction of real visits for
   * the current plan (10 visit classes for P2 = local row index),
@@ -16,7 +16,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as entry  # noqa: E402
 
