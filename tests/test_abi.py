@@ -41,6 +41,12 @@ def test_quadrature_tables_match_oracle(pkg, oracle):
         assert np.array_equal(p, po) and np.array_equal(w, wo)
     with pytest.raises(pkg.AfbError):
         pkg.tet_quadrature(21)
+    for order in range(0, 21):   # triangle rules of fem3Dface
+        p, w = pkg.tri_quadrature(order)
+        po, wo = oracle.tri_quadrature(order)
+        assert np.array_equal(p, po) and np.array_equal(w, wo)
+    with pytest.raises(pkg.AfbError):
+        pkg.tri_quadrature(21)
 
 
 def test_no_cpu_fallback(pkg):
