@@ -98,9 +98,16 @@ def _all_to_all_var(parts, group=None):
 class Numbering:
     """Global NATURAL numbering of the local block + owned interval, built with one metadata exchange."""
 
-    def __init__(self, tets, gnode, iface_node, variables, nn_global, group=None):
+    ENUM_TYPES = ("ANITYPE", "MINIBLOCKS", "NATURAL", "DIMUNION", "BYELEMTYPE", "ETDIMBLOCKS")   # global_enumerator.h:393-401
+
+    def __init__(self, tets, gnode, iface_node, variables, nn_global, group=None, enum_type="NATURAL"):
         """tets (ntet,4) local node ids; gnode (nnode,) global node id of each local node; iface_node (nnode,) bool:
-        node may be shared with another rank; variables [(fem, vec)]; nn_global = total number of nodes."""
+        node may be shared with another rank; variables [(fem, vec)]; nn_global = total number of nodes; enum_type: the
+        GlobEnumeration type ordering the dofs inside every rank's interval (closed forms of include/anifem_b200/enumerator.hpp
+        with the rank's own entity counts and ELEM_ID = position among the rank's owned entities)."""
+        if enum_type not in self.ENUM_TYPES:
+            raise ValueError("Faced unknown ASSEMBLING_TYPE")
+        self.enum_type = enum_type
         self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         dev = tets.device
@@ -193,12 +200,45 @@ class Numbering:
         self.end_ind = self.beg_ind + sum(num[d] * ndof_ent[d] for d in range(nd_types))
         self.nrows_global = int(sum(int(num[d].sum()) * ndof_ent[d] for d in range(nd_types)))
         grp_off, off = {}, torch.zeros(self.world, dtype=torch.int64)
-        for v, (fem, vec) in enumerate(self.vars):
-            for c in range(vec):
-                for d in range(nd_types):
-                    if NDOF[fem][d]:
-                        grp_off[(v, c, d)] = off.clone()
-                        off = off + num[d] * NDOF[fem][d]
+        et_first = enum_type in ("BYELEMTYPE", "ETDIMBLOCKS")            # ELEM_TYPE is the leading key of the arrangement
+        dim_last = enum_type in ("DIMUNION", "ETDIMBLOCKS")              # the component is the innermost key
+        groups = [(v, c, d) for v, (fem, vec) in enumerate(self.vars) for c in range(vec) for d in range(nd_types)]
+        if et_first:
+            groups.sort(key=lambda t: (t[2], t[0], t[1]))
+        if dim_last:   # one group per (variable, entity type): all components interleaved
+            groups = [t for t in groups if t[1] == 0]
+        for v, c, d in groups:
+            fem, vec = self.vars[v]
+            if NDOF[fem][d]:
+                size = num[d] * NDOF[fem][d] * (vec if dim_last else 1)
+                for cc in (range(vec) if dim_last else (c,)):
+                    grp_off[(v, cc, d)] = off.clone()
+                off = off + size
+        # SimpleEnumerator (global_enumerator.cpp:671-700,818-835): InitElemIndex per entity type, position of a dof among all
+        # dofs of its entity (variables in order, component fastest)
+        init = torch.zeros((nd_types + 1, self.world), dtype=torch.int64)
+        for d in range(nd_types):
+            init[d + 1] = init[d] + num[d] * ndof_ent[d]
+        shift = {}
+        for d in range(nd_types):
+            o = 0
+            for v, (fem, vec) in enumerate(self.vars):
+                shift[(v, d)] = o
+                o += NDOF[fem][d] * vec
+
+        def index(v, c, d, ow, pos, k):
+            """global id of dof k (int or tensor) of component c of variable v on the entities (owner ow, position pos)"""
+            fem, vec = self.vars[v]
+            ns = NDOF[fem][d]
+            if enum_type in ("NATURAL", "BYELEMTYPE"):
+                loc = grp_off[(v, c, d)].to(dev)[ow] + pos * ns + k
+            elif dim_last:
+                loc = grp_off[(v, c, d)].to(dev)[ow] + (pos * ns + k) * vec + c
+            elif enum_type == "ANITYPE":
+                loc = init[d].to(dev)[ow] + pos + (shift[(v, d)] + k * vec + c) * num[d].to(dev)[ow]
+            else:   # MINIBLOCKS: the layout the reference's inverse map decodes (:866-871)
+                loc = init[d].to(dev)[ow] + pos * ndof_ent[d] + shift[(v, d)] + k * vec + c
+            return beg_ind_dev[ow] + loc
         # ---- element -> global dof (local order: variable, component, 4 vertices, 6 edges)
         cols = []
         beg_ind_dev = self.beg_ind.to(dev)
@@ -210,17 +250,17 @@ class Numbering:
                         continue
                     ents = ent_of_tet[d]
                     ow = self.owner[d][ents]
-                    base = beg_ind_dev[ow] + grp_off[(v, c, d)].to(dev)[ow] + self.pos[d][ents] * nd
+                    ps = self.pos[d][ents]
                     for le in range(ents.shape[1]):
                         if d == 1 and nd == 2:
                             # the two dofs of a P3 edge follow the orientation of the edge by global node ids (tetdofmap.inl:98-104)
                             a, b = LOCAL_EDGES[le]
                             flip = (gnode[tets[:, a]] > gnode[tets[:, b]]).long()
-                            cols.append(base[:, le] + flip)
-                            cols.append(base[:, le] + 1 - flip)
+                            cols.append(index(v, c, d, ow[:, le], ps[:, le], flip))
+                            cols.append(index(v, c, d, ow[:, le], ps[:, le], 1 - flip))
                             continue
                         for k in range(nd):
-                            cols.append(base[:, le] + k)
+                            cols.append(index(v, c, d, ow[:, le], ps[:, le], k))
         self.elem2dof = torch.stack(cols, 1).contiguous()
         self.nloc = self.elem2dof.shape[1]
         self.row_begin, self.row_end = int(self.beg_ind[self.rank]), int(self.end_ind[self.rank])
@@ -231,6 +271,8 @@ class Numbering:
         A field is contiguous inside every rank's interval (NATURAL: VAR, component, DIM, ... global_enumerator.cpp:702-777):
         its global columns are one interval per rank; its local rows are the own interval followed by the runs of its
         dofs inside the sorted list of foreign rows (one run per peer)."""
+        if self.enum_type != "NATURAL":
+            return []   # other arrangements interleave components or split a field by entity type: no field intervals, generic path
         out, loff = [], 0
         foreign = plan.foreign.cpu()
         for v, (fem, vec) in enumerate(self.vars):
@@ -364,7 +406,7 @@ class DistributedAssembler:
     """One rank of a multi-GPU assembly on the cube: local block mesh, global numbering, final pattern, exchange.
     Mirrors what a reference user gets from GenerateCube + Assembler::PrepareProblem under mpirun."""
 
-    def __init__(self, ctx, dims, variables, group=None):
+    def __init__(self, ctx, dims, variables, group=None, enum_type="NATURAL"):
         import torch
         self.ctx, self.group = ctx, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
@@ -381,7 +423,7 @@ class DistributedAssembler:
         iface = (((ii == 0) & (bx > 0)) | ((ii == lx) & (bx + lx < nx)) | ((jj == 0) & (by > 0)) | ((jj == ly) & (by + ly < ny)) |
                  ((kk == 0) & (bz > 0)) | ((kk == lz) & (bz + lz < nz))).reshape(-1)
         nn_global = (nx + 1) * (ny + 1) * (nz + 1)
-        self.numbering = nb = Numbering(self.tets, gnode, iface, variables, nn_global, group)
+        self.numbering = nb = Numbering(self.tets, gnode, iface, variables, nn_global, group, enum_type)
         self.plan = plan = InterfacePlan(nb)
         n_ext = plan.n_own + plan.n_for
         ctx.dofmap_set_any(plan.rowcode, plan.colcode, 0, n_ext, nb.nrows_global, plan.diag_col)

@@ -104,9 +104,11 @@ def connectivity(tets):
 
 
 class DofMap:
-    """elem->dof tables for a list of variables [(fem, vecdim), ...] under NATURAL numbering."""
+    """elem->dof tables for a list of variables [(fem, vecdim), ...]; NATURAL numbering unless enum_type names another
+    GlobEnumeration type (then the index inside every rank's interval is the rank of the dof's tuple among the dofs the rank
+    owns, restated from the definitions like enumerate_dofs; ELEM_ID = GlobalID - BegElemID of the rank)."""
 
-    def __init__(self, tets, variables, cell_rank=None, nranks=1, nnode=None):
+    def __init__(self, tets, variables, cell_rank=None, nranks=1, nnode=None, enum_type="NATURAL"):
         self.tets = tets
         self.vars = list(variables)
         ntet = tets.shape[0]
@@ -170,6 +172,8 @@ class DofMap:
                                 cols.append(base[:, le] + k)
         self.elem2dof = np.stack(cols, axis=1)  # (ntet, nloc) global ids
         self.nloc = self.elem2dof.shape[1]
+        if enum_type != "NATURAL":
+            self._renumber(enum_type, owner, gid, beg, num, nent)
         # owner rank of every local dof's entity (for row codes)
         owc = []
         for v, (fem, vec) in enumerate(self.vars):
@@ -180,6 +184,56 @@ class DofMap:
                         for k in range(nd):
                             owc.append(owner[d][ent_of_tet[d][:, le]])
         self.dof_owner = np.stack(owc, axis=1)
+
+    def _renumber(self, enum_type, owner, gid, beg, num, nent):
+        """replace the NATURAL ids by those of enum_type: old NATURAL id -> new id, rank by rank, from the definitions"""
+        new_of_old = np.full(self.nrows, -1, dtype=np.int64)
+        col = {"VAR": 0, "DIM": 1, "ELEM_TYPE": 2, "ELEM_ID": 3, "DOF_ID": 4}
+        for r in range(self.nranks):
+            recs, old = [], []
+            for v, (fem, vec) in enumerate(self.vars):
+                for c in range(vec):
+                    for d in range(4):
+                        nd = NDOF[fem][d]
+                        ents = np.nonzero(owner[d] == r)[0]
+                        if nd == 0 or ents.size == 0:
+                            continue
+                        g = gid[d][ents] - beg[d][r]
+                        for k in range(nd):
+                            recs.append(np.stack([np.full(g.size, v), np.full(g.size, c), np.full(g.size, d), g, np.full(g.size, k)], 1))
+                            old.append(self.beg_ind[r] + self.grp_off[(v, c, d)][r] + g * nd + k)
+            if not recs:
+                continue
+            recs, old = np.concatenate(recs, 0), np.concatenate(old)
+            n = recs.shape[0]
+            if enum_type in _ARRANGEMENT:
+                keys = [recs[:, col[name]] for name in _ARRANGEMENT[enum_type]]
+                order = np.lexsort(tuple(reversed(keys)))
+                loc = np.empty(n, dtype=np.int64)
+                loc[order] = np.arange(n)
+            else:
+                i_nd = [sum(NDOF[fem][d] * vec for fem, vec in self.vars) for d in range(4)]
+                cnt = [int(num[d][r]) for d in range(4)]
+                init = np.concatenate([[0], np.cumsum([i_nd[d] * cnt[d] for d in range(4)])])
+                shift = {}
+                for d in range(4):
+                    o = 0
+                    for v, (fem, vec) in enumerate(self.vars):
+                        shift[(v, d)] = o
+                        o += NDOF[fem][d] * vec
+                vecs = np.array([vec for _, vec in self.vars])
+                iodf = np.array([shift[(int(a), int(b))] for a, b in recs[:, [0, 2]]]) + recs[:, 4] * vecs[recs[:, 0]] + recs[:, 1]
+                d = recs[:, 2]
+                if enum_type == "ANITYPE":
+                    loc = init[d] + recs[:, 3] + iodf * np.array(cnt)[d]
+                elif enum_type == "MINIBLOCKS":
+                    loc = init[d] + recs[:, 3] * np.array(i_nd)[d] + iodf
+                else:
+                    raise ValueError("unknown enumeration type " + str(enum_type))
+            assert np.array_equal(np.sort(loc), np.arange(n))
+            new_of_old[old] = self.beg_ind[r] + loc
+        assert (new_of_old >= 0).all()
+        self.elem2dof = new_of_old[self.elem2dof]
 
     def codes(self, rank=None):
         """(rowcode, colcode) as assemble_index_encode: sign*(id+1); rows of entities not owned by

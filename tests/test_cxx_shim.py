@@ -48,6 +48,8 @@ def test_host_enumerators_against_the_restated_definitions(asm_oracle, tmp_path,
         table = raw[2:].reshape(te.shape[0], nloc)
         exp, n = M.enumerate_dofs(te, variables, name, co.shape[0])
         assert nrows == n and np.array_equal(table, exp), name
+        # the per-rank restatement used by the multi-rank tests agrees on one rank
+        assert np.array_equal(M.DofMap(te, variables, nnode=co.shape[0], enum_type=name).elem2dof, exp), name
     # NATURAL is the numbering afb_dofmap_natural builds on the device (same oracle DofMap the GPU tests compare with)
     dm = M.DofMap(te, variables, nnode=co.shape[0])
     assert np.array_equal(M.enumerate_dofs(te, variables, "NATURAL", co.shape[0])[0], dm.elem2dof)

@@ -31,7 +31,7 @@ def _local_pattern(rowcode, colcode, n_own, n_ext, row_begin):
     return np.cumsum(rowptr), (key % NC).astype(np.int32)
 
 
-def _worker(rank, world, port, dims, variables, errq):
+def _worker(rank, world, port, dims, variables, errq, enum_type="NATURAL"):
     try:
         os.environ["MASTER_ADDR"] = "127.0.0.1"
         os.environ["MASTER_PORT"] = str(port)
@@ -45,7 +45,7 @@ def _worker(rank, world, port, dims, variables, errq):
         import importlib
         par = importlib.import_module("inmost_fem_b200.parallel")
         co, te, cr = M.cube_mesh(*dims, nranks=world)
-        dm = M.DofMap(te, variables, cr, world, nnode=co.shape[0])
+        dm = M.DofMap(te, variables, cr, world, nnode=co.shape[0], enum_type=enum_type)
         # block / grid restatement agrees with the oracle's cell -> rank map
         bx, by, bz, lx, ly, lz = par.block_of_rank(rank, world, dims)
         assert 6 * lx * ly * lz == int((cr == rank).sum())
@@ -56,7 +56,7 @@ def _worker(rank, world, port, dims, variables, errq):
         # nodes that also belong to cells of another rank
         other = np.zeros(co.shape[0], dtype=bool)
         other[np.unique(te[cr != rank])] = True
-        nb = par.Numbering(torch.from_numpy(ltl), torch.from_numpy(gn), torch.from_numpy(other[gn]), variables, co.shape[0])
+        nb = par.Numbering(torch.from_numpy(ltl), torch.from_numpy(gn), torch.from_numpy(other[gn]), variables, co.shape[0], enum_type=enum_type)
         assert np.array_equal(nb.elem2dof.numpy(), dm.elem2dof[mine]), "global numbering differs from the oracle"
         assert nb.row_begin == dm.beg_ind[rank] and nb.row_end == dm.end_ind[rank] and nb.nrows_global == dm.nrows
         plan = par.InterfacePlan(nb)
@@ -87,7 +87,10 @@ def _worker(rank, world, port, dims, variables, errq):
                 assert np.array_equal(sr, first_of_space[fem][0]) and np.array_equal(sc, first_of_space[fem][1])
             else:
                 first_of_space[fem] = (sr, sc)
-        assert (rows_seen == 1).all() and (cols_seen == 1).all(), "field intervals do not partition the row / column space"
+        if enum_type == "NATURAL":
+            assert (rows_seen == 1).all() and (cols_seen == 1).all(), "field intervals do not partition the row / column space"
+        else:
+            assert fields == []   # no field intervals under the other arrangements: the generic path assembles them
         rp_l, ci_l = _local_pattern(plan.rowcode.numpy(), plan.colcode.numpy(), plan.n_own, n_ext, nb.row_begin)
         rp_e, ci_e = plan.finalize_pattern(torch.from_numpy(rp_l), torch.from_numpy(ci_l))
         # problem: stiffness (+ mass on variable 0) with per-tet coefficients, rhs load
@@ -123,11 +126,11 @@ def _worker(rank, world, port, dims, variables, errq):
         errq.put("rank %d:\n%s" % (rank, traceback.format_exc()))
 
 
-def _run(world, dims, variables):
+def _run(world, dims, variables, enum_type="NATURAL"):
     ctx = mp.get_context("spawn")
     errq = ctx.Queue()
     port = 29500 + (os.getpid() % 2000) + world
-    procs = [ctx.Process(target=_worker, args=(r, world, port, dims, variables, errq)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, dims, variables, errq, enum_type)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
@@ -154,6 +157,13 @@ def test_two_ranks_p3(pkg, oracle):
 
 def test_three_ranks_p3_p1(pkg, oracle):
     _run(3, (3, 3, 2), [(gc.P3, 1), (gc.P1, 1)])
+
+
+@pytest.mark.parametrize("enum_type", ["ANITYPE", "MINIBLOCKS", "DIMUNION", "BYELEMTYPE", "ETDIMBLOCKS"])
+def test_two_ranks_other_enumerators(pkg, oracle, enum_type):
+    """the other GlobEnumeration types across ranks (Taylor-Hood: vector + scalar variable, node and edge dofs): numbering against the
+    oracle's per-rank restatement of the definitions, pattern union and exchange in that numbering"""
+    _run(2, (3, 2, 2), [(gc.P2, 3), (gc.P1, 1)], enum_type)
 
 
 def test_two_ranks_taylor_hood(pkg, oracle):
