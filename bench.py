@@ -148,6 +148,7 @@ def main():
     ap.add_argument("--config", default="c2", choices=["c2", "c4", "c5"],
                     help="multi-GPU runs only: c4 = FemVec<3,P2> elasticity, c5 = Taylor-Hood Stokes (single GPU: bench_configs.py); the contract line is c2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="N>1: skip the oracle comparison of small cubes that precedes the timed region")
     ap.add_argument("--no-secondary", action="store_true", help="skip the quick C1/C3/C4/C5 measurements")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

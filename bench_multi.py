@@ -13,8 +13,77 @@ import torch.distributed as dist
 import bench
 
 
+PARITY_CASES = (("p2", (12, 10, 8)), ("taylor_hood", (6, 5, 4)), ("p3", (5, 4, 3)))
+
+
+def parity_check(pkg, par, rank, world, local_rank):
+    """Correctness of the path the timed region measures, on the same process group: small cubes (P2, Taylor-Hood, P3) are
+    assembled by all ranks and every rank's owned rows are compared with the CPU oracle's per-rank matrices
+    (oracle/asm_oracle.py, used here as the checker only): numbering and CSR pattern bit-exact, values / rhs relative to the
+    largest entry of the row <= 1e-12.  Returns the dict for the JSON line; `ok` is the AND over all ranks and cases."""
+    import numpy as np
+    import golden_cases as gc
+    import problems
+    O, M = bench.entry.load_oracle()
+    checked, worst, ok = [], 0.0, True
+    for name, dims in PARITY_CASES:
+        variables = {"p2": [(gc.P2, 1)], "taylor_hood": [(gc.P2, 3), (gc.P1, 1)], "p3": [(gc.P3, 1)]}[name]
+        ctx = pkg.Context(local_rank, torch.cuda.current_stream().cuda_stream)
+        case_ok, err = True, 0.0
+        try:
+            da = par.DistributedAssembler(ctx, dims, variables)
+            co, te, cr = M.cube_mesh(*dims, nranks=world)
+            dm = M.DofMap(te, variables, cr, world, nnode=co.shape[0])
+            mine = np.nonzero(cr == rank)[0]
+            case_ok &= bool(np.array_equal(da.numbering.elem2dof.cpu().numpy(), dm.elem2dof[mine]))
+            xc = co[te].mean(axis=1)
+            if name == "taylor_hood":
+                _, forms, rhsf, prob = problems.c5_stokes(pkg, M, co, te)
+            else:
+                fem = variables[0][0]
+                mats = [(0, 0, gc.GRAD, gc.GRAD, 2, gc.T_SYMMETRIC, gc.L_PER_TET, problems.sym_K(xc), 1.0)]
+                rhss = [(0, gc.IDEN, 2, gc.T_NULL, gc.L_CONST, None, 1.0)]
+                _, _, _, prob = problems._mk(pkg, M, variables, mats, rhss)
+                K_loc = torch.from_numpy(problems.sym_K(xc[mine])).cuda()
+                forms = [pkg.make_form(gc.GRAD, fem, 1, gc.GRAD, fem, 1, 2, gc.T_SYMMETRIC, gc.L_PER_TET, K_loc)]
+                rhsf = [pkg.make_form(gc.IDEN, gc.P0, 1, gc.IDEN, fem, 1, 2, gc.T_NULL, gc.L_CONST)]
+            rp_o, ci_o, v_o, r_o, _ = M.assemble(prob, co, te, dm, rank=rank)
+            case_ok &= bool(np.array_equal(da.rowptr.cpu().numpy(), rp_o) and np.array_equal(da.colind.cpu().numpy(), ci_o))
+            if case_ok:
+                assert da.assemble(forms, rhsf) == 0
+                torch.cuda.synchronize()
+                val = da.val[:da.plan.nnz_own].cpu().numpy()
+                rhs = da.rhs[:da.plan.n_own].cpu().numpy()
+                rowmax = np.maximum.reduceat(np.abs(v_o), rp_o[:-1])
+                err = float((np.abs(val - v_o) / np.repeat(rowmax, np.diff(rp_o))).max())
+                err = max(err, float(np.abs(rhs - r_o).max() / np.abs(r_o).max()))
+                case_ok &= err <= 1e-12
+        except Exception as exc:  # noqa: BLE001 -- a failing case is reported (and fails the run), it must not hang the other ranks
+            case_ok, err = False, float("inf")
+            if rank == 0:
+                print("parity case %s raised: %r" % (name, exc), flush=True)
+        finally:
+            ctx.close()
+        t = torch.tensor([0.0 if case_ok else 1.0, err if err == err and err != float("inf") else 1e300], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ok &= t[0].item() == 0.0
+        worst = max(worst, t[1].item())
+        checked.append({"case": name, "hexes": list(dims), "ok": t[0].item() == 0.0, "max_rel_err": t[1].item()})
+    return {"ok": ok, "checked": checked, "max_rel_err": worst, "tolerance": 1e-12, "pattern": "bit-exact vs oracle/asm_oracle.py per rank",
+            "ranks": world}
+
+
 def run(args, pkg, rank, world, local_rank):
     par = importlib.import_module("inmost_fem_b200.parallel")
+    parity = None
+    if not getattr(args, "no_parity", False):
+        parity = parity_check(pkg, par, rank, world, local_rank)
+        if not parity["ok"]:
+            if rank == 0:
+                print(json.dumps({"error": "multi-GPU parity check failed", "parity": parity}))
+            dist.barrier()
+            dist.destroy_process_group()
+            return 3
     n = args.n
     if args.global_n:
         # strong scaling: the global mesh is fixed, the blocks shrink with the number of GPUs
@@ -123,7 +192,7 @@ def run(args, pkg, rank, world, local_rank):
                 "roofline": {"bound": "hbm", "achieved": gbs / world, "peak": peak_gbs, "unit": "GB/s", "frac": gbs / world / peak_gbs, "traffic": None,
                              "kernel": "whole step per GPU (%s + %s + exchange)" % (times["element_kernel"], times["gather_kernel"]),
                              "algorithmic_bytes_per_launch": alg_bytes // world},
-                "clocks": sampler.summary()}
+                "clocks": sampler.summary(), "parity": parity}
         if config != "c2":
             line["config"]["workload"] = metric + ", per-GPU block %d^3 hexes x 6 tets, structural pattern pre-built" % n
         print(json.dumps(line))

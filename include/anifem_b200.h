@@ -56,7 +56,8 @@ typedef struct afb_form {
     int coef_layout;       /* AFB_COEF_* */
     int coef_space;        /* AFB_HOST / AFB_DEVICE: where D lives */
     const double* D;
-    double alpha;          /* the block is scaled by alpha before it is added */
+    double alpha;          /* the block is scaled by alpha before it is added; used as given by EVERY entry point
+                            * (0 contributes nothing): set it to 1.0 explicitly, a zero-initialised struct is a zero form */
     int row_off, col_off;  /* offset of the block inside the (nrow_loc x ncol_loc) element matrix */
 } afb_form;
 
@@ -68,6 +69,9 @@ const char* afb_last_error(const afb_ctx* ctx); /* ctx may be NULL: last error o
 int afb_sync(afb_ctx* ctx);
 /* number of kernels this library launched on the context since the last reset (bench evidence) */
 int64_t afb_launch_count(afb_ctx* ctx, int reset);
+/* the cudaStream_t every kernel / copy of this context is issued on (the one given to afb_ctx_create or the private one):
+ * work issued by the caller around afb_assemble_phase (NCCL exchange, afb_halo_add inputs) must be ordered against it. */
+void* afb_stream_get(afb_ctx* ctx);
 
 /* ---- element level: replaces Ani::fem3Dtet (fem/operations/int_tet.inl:3-57) ------------------ */
 /* Batched element matrices: XYk are 3 x f col-major (fem/geometry.h:108-122), A is nfB x (nfA*f)

@@ -36,7 +36,7 @@ class AfbForm(ctypes.Structure):
                 ("row_off", ctypes.c_int), ("col_off", ctypes.c_int)]
 
 
-EXPORTS = ["afb_ctx_create", "afb_ctx_destroy", "afb_last_error", "afb_sync", "afb_launch_count",
+EXPORTS = ["afb_ctx_create", "afb_ctx_destroy", "afb_last_error", "afb_sync", "afb_launch_count", "afb_stream_get",
            "afb_fem3dtet_batched", "afb_op_dims", "afb_tet_quadrature", "afb_quad_points",
            "afb_mesh_set", "afb_mesh_cube", "afb_mesh_orient", "afb_mesh_get",
            "afb_dofmap_set", "afb_dofmap_set_diag", "afb_dofmap_natural", "afb_dofmap_get",
@@ -73,6 +73,8 @@ def lib():
         L.afb_sync.argtypes = [vp]
         L.afb_launch_count.argtypes = [vp, ci]
         L.afb_launch_count.restype = c64
+        L.afb_stream_get.argtypes = [vp]
+        L.afb_stream_get.restype = vp
         L.afb_fem3dtet_batched.argtypes = [vp, ctypes.POINTER(AfbForm), c64, vp, vp, vp, vp, vp, ci]
         L.afb_fem3dface_batched.argtypes = [vp, ctypes.POINTER(AfbForm), c64, vp, vp, vp, vp, vp, vp, ci]
         L.afb_tri_quadrature.argtypes = [ci, vp, vp, ci]
@@ -185,6 +187,10 @@ class Context:
 
     def sync(self):
         self._ck(lib().afb_sync(self._h))
+
+    def stream_handle(self):
+        """cudaStream_t (integer) every kernel of this context is issued on"""
+        return int(lib().afb_stream_get(self._h) or 0)
 
     def launch_count(self, reset=False):
         return int(lib().afb_launch_count(self._h, 1 if reset else 0))

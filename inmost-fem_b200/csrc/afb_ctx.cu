@@ -236,13 +236,18 @@ __global__ void k_natural(long long ntet, NatDesc nd, const int32_t* v0, const i
 }
 
 // int64 AoS codes [i + nloc*e] -> int32 SoA codes [i*ntet + e], rows rebased to row_begin
-__global__ void k_codes_in(long long ntet, int nloc, const long long* src, long long rebase, int32_t* dst, int* any_neg) {
+// lo/hi: legal range of |code| - 1 (rows: [row_begin, row_end), 0 = ghost row; columns: [0, ncols_global), never 0): the reference
+// aborts on an index outside its interval (assembler.inl:399-412); any_neg[1] reports it here
+__global__ void k_codes_in(long long ntet, int nloc, const long long* src, long long rebase, long long lo, long long hi, int zero_ok,
+                           int32_t* dst, int* any_neg) {
     const long long n = ntet * nloc;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
         const long long e = t / nloc;
         const int i = (int)(t - e * nloc);
         const long long c = src[t];
         long long o = 0;
+        const long long id = (c > 0 ? c : -c) - 1;
+        if (c == 0 ? !zero_ok : (id < lo || id >= hi)) { any_neg[1] = 1; dst[(long long)i * ntet + e] = 0; continue; }
         if (c > 0) o = c - rebase;
         else if (c < 0) { o = c + rebase; *any_neg = 1; }
         dst[(long long)i * ntet + e] = (int32_t)o;
@@ -348,6 +353,8 @@ int64_t afb_launch_count(afb_ctx* ctx, int reset) {
     return n;
 }
 
+void* afb_stream_get(afb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
 int afb_mesh_set(afb_ctx* ctx, int64_t nnode, const double* x, const double* y, const double* z,
                  int64_t ntet, const int32_t* v0, const int32_t* v1, const int32_t* v2, const int32_t* v3, int mem_space) {
     if (!ctx) return -7;
@@ -442,13 +449,20 @@ int afb_dofmap_set(afb_ctx* ctx, int nrow_loc, int ncol_loc, const int64_t* elem
             src = ctx->tmp1.as<long long>();
         }
         if (ntet)
-            k_codes_in<<<grid_for(ntet * nloc), 256, 0, ctx->stream>>>(ntet, nloc, src, side ? 0 : row_begin, side ? ctx->e2c.as<int32_t>() : ctx->e2r.as<int32_t>(), ctx->flag.as<int>());
+            k_codes_in<<<grid_for(ntet * nloc), 256, 0, ctx->stream>>>(ntet, nloc, src, side ? 0 : row_begin, side ? 0 : row_begin, side ? ncols_global : row_end,
+                                                                       side ? 0 : 1, side ? ctx->e2c.as<int32_t>() : ctx->e2r.as<int32_t>(), ctx->flag.as<int>());
         ctx->launches++;
         AFB_CUDA(ctx, cudaGetLastError());
         AFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
-    int neg = 0;
-    AFB_CUDA(ctx, cudaMemcpy(&neg, ctx->flag.p, sizeof(int), cudaMemcpyDeviceToHost));
+    int negbad[2] = {0, 0};
+    AFB_CUDA(ctx, cudaMemcpy(negbad, ctx->flag.p, 2 * sizeof(int), cudaMemcpyDeviceToHost));
+    if (negbad[1]) {
+        ctx->has_dofmap = false; ctx->has_pattern = false;
+        set_error(ctx, "afb_dofmap_set: index code outside its range (rows: 0 or [row_begin,row_end); columns: [1,ncols_global], never 0)");
+        return -7;
+    }
+    const int neg = negbad[0];
     ctx->has_signs = neg != 0;
     ctx->nrow_loc = nrow_loc; ctx->ncol_loc = ncol_loc;
     ctx->row_begin = row_begin; ctx->row_end = row_end; ctx->ncols_global = ncols_global;
@@ -748,7 +762,7 @@ int afb_fem3dtet_batched(afb_ctx* ctx, const afb_form* form, int64_t f, const do
     }
     afb_form fm = *form;
     fm.row_off = 0; fm.col_off = 0;
-    if (fm.alpha == 0.0) fm.alpha = 1.0;
+    // alpha is used as given (0 contributes nothing), exactly like afb_assemble
     // reference layout A[ib + nfB*(ia + nfA*r)]
     // square scalar forms with the same operator on both sides: the register-tiled kernel (afb_element.cu, k_element_sq)
     {
@@ -822,7 +836,7 @@ int afb_fem3dface_batched(afb_ctx* ctx, const afb_form* form, int64_t f, const i
     }
     afb_form fm = *form;
     fm.row_off = 0; fm.col_off = 0;
-    if (fm.alpha == 0.0) fm.alpha = 1.0;
+    // alpha is used as given (0 contributes nothing), exactly like afb_assemble
     int rc = afb::launch_form(ctx, fm, oa, ob, f, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ctx->xy.as<double>(),
                               out, (long long)oa.nfa * ob.nfa, 1, ob.nfa, 0, Dd, dface, nullptr);
     if (rc) return rc;

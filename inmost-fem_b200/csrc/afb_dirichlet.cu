@@ -27,15 +27,31 @@ inline unsigned grid_for(long long n, int block = 256) {
 
 // rows [0,nrows): flag = 1 when the row is Dirichlet or has a Dirichlet column
 __global__ void k_dir_rows(long long nrows, long long row_begin, const long long* __restrict__ rowptr, const int32_t* __restrict__ colind,
-                           const unsigned char* __restrict__ isdir, const int32_t* __restrict__ diag_col, unsigned char* flag) {
+                           const unsigned char* __restrict__ isdir, const int32_t* __restrict__ diag_col, const int32_t* __restrict__ row_gid,
+                           unsigned char* flag) {
     const int lane = threadIdx.x & 31;
     const long long wglob = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long r = wglob; r < nrows; r += nw) {
-        const long long gcol = diag_col ? diag_col[r] : row_begin + r;   // global id of the row's own dof (-1: foreign row without diagonal)
+        // global id of the row's own dof: explicit table (extended row space of a partitioned mesh), else the forced-diagonal column
+        const long long gcol = row_gid ? row_gid[r] : (diag_col ? diag_col[r] : row_begin + r);
         bool any = gcol >= 0 && isdir[gcol];
         for (long long k = rowptr[r] + lane; k < rowptr[r + 1]; k += 32) any |= isdir[colind[k]] != 0;
         any = __any_sync(0xffffffffu, any);
         if (lane == 0) flag[r] = any ? 1 : 0;
+    }
+}
+
+// global dof id of every local row of an explicit dof map whose test and trial sides share the local numbering: the row code and
+// the column code of local dof i of an element name the same dof (assembler.inl:139-184 fills indexesR / indexesC from one
+// template).  Rows without elements keep the default.  All writers of a row store the same value.
+__global__ void k_row_gid_default(long long nrows, long long row_begin, const int32_t* __restrict__ diag_col, int32_t* gid) {
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < nrows; r += (long long)gridDim.x * blockDim.x)
+        gid[r] = (diag_col && diag_col[r] >= 0) ? diag_col[r] : (int32_t)(row_begin + r);
+}
+__global__ void k_row_gid_fill(long long n /* nloc*ntet */, const int32_t* __restrict__ e2r, const int32_t* __restrict__ e2c, int32_t* gid) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const int rc = e2r[t], cc = e2c[t];
+        if (rc != 0 && cc != 0) gid[(rc > 0 ? rc : -rc) - 1] = (cc > 0 ? cc : -cc) - 1;
     }
 }
 
@@ -90,9 +106,20 @@ static int dirichlet_rows(afb_ctx* ctx) {
     D_CUDA(idx.reserve(std::max<long long>(1, nrows) * 4));
     D_CUDA(ctx->dir_rows.reserve(std::max<long long>(1, nrows) * 4));
     D_CUDA(nsel.reserve(8));
+    // explicit dof maps with forced-diagonal tables (the extended row space of parallel.InterfacePlan has rows whose own dof lives
+    // on another rank: diag_col = -1): the global id of every row comes from the element codes
+    ctx->row_gid_valid = false;
+    if (ctx->has_diag && ctx->nrow_loc == ctx->ncol_loc) {
+        D_CUDA(ctx->row_gid.reserve(std::max<long long>(1, nrows) * 4));
+        k_row_gid_default<<<grid_for(nrows), 256, 0, st>>>(nrows, ctx->row_begin, ctx->diag_col.as<int32_t>(), ctx->row_gid.as<int32_t>());
+        const long long nn = (long long)ctx->nrow_loc * ctx->ntet;
+        k_row_gid_fill<<<grid_for(nn), 256, 0, st>>>(nn, ctx->e2r.as<int32_t>(), ctx->e2c.as<int32_t>(), ctx->row_gid.as<int32_t>());
+        ctx->launches += 2;
+        ctx->row_gid_valid = true;
+    }
     k_dir_rows<<<grid_for(nrows * 32), 256, 0, st>>>(nrows, ctx->row_begin, ctx->rowptr.as<long long>(), ctx->colind.as<int32_t>(),
                                                     ctx->dir_flag.as<unsigned char>(), ctx->has_diag ? ctx->diag_col.as<int32_t>() : nullptr,
-                                                    flag.as<unsigned char>());
+                                                    ctx->row_gid_valid ? ctx->row_gid.as<int32_t>() : nullptr, flag.as<unsigned char>());
     k_iota<<<grid_for(nrows), 256, 0, st>>>(nrows, idx.as<int>());
     size_t tb = 0;
     cub::DeviceSelect::Flagged(nullptr, tb, idx.as<int>(), flag.as<unsigned char>(), ctx->dir_rows.as<int>(), nsel.as<long long>(), nrows, st);
@@ -109,6 +136,11 @@ static int dirichlet_rows(afb_ctx* ctx) {
     return 0;
 }
 
+int dirichlet_prepare(afb_ctx* ctx) {
+    if (!ctx->has_dirichlet || ctx->dir_rows_valid) return 0;
+    return dirichlet_rows(ctx);
+}
+
 // applied by afb_assemble to this call's contribution (val / rhs may be NULL)
 int dirichlet_apply(afb_ctx* ctx, double* val, double* rhs) {
     if (!ctx->has_dirichlet) return 0;
@@ -120,7 +152,7 @@ int dirichlet_apply(afb_ctx* ctx, double* val, double* rhs) {
     k_apply_dir<<<grid_for(ctx->n_dir_rows * 32), 256, 0, ctx->stream>>>(
         ctx->n_dir_rows, ctx->dir_rows.as<int>(), ctx->row_begin, ctx->rowptr.as<long long>(), ctx->colind.as<int32_t>(),
         ctx->radj_ptr.as<long long>(), ctx->dir_flag.as<unsigned char>(), ctx->dir_val.as<double>(),
-        ctx->has_diag ? ctx->diag_col.as<int32_t>() : nullptr, nullptr, val, rhs);
+        ctx->has_diag ? ctx->diag_col.as<int32_t>() : nullptr, ctx->row_gid_valid ? ctx->row_gid.as<int32_t>() : nullptr, val, rhs);
     ctx->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(ctx, e, "k_apply_dir launch");

@@ -68,12 +68,13 @@ __global__ void k_bf_gather(int nu, const unsigned* __restrict__ urow, const int
                             const long long* __restrict__ aidx, int nrl, int ncl, long long ntet, const int32_t* __restrict__ bf_tet,
                             const double* __restrict__ sA, const double* __restrict__ sF, const PosT* __restrict__ pos,
                             const long long* __restrict__ rowptr, const int32_t* __restrict__ e2c, long long row_begin,
-                            const int32_t* __restrict__ diag_col, const unsigned char* __restrict__ isdir, const double* __restrict__ bc,
+                            const int32_t* __restrict__ diag_col, const int32_t* __restrict__ row_gid, const unsigned char* __restrict__ isdir,
+                            const double* __restrict__ bc,
                             double* val, double* rhs, double drop, int* status) {
     GRID_STRIDE(u, nu) {
         const long long r = urow[u];
         if (isdir) {
-            const long long gid = (diag_col && diag_col[r] >= 0) ? diag_col[r] : row_begin + r;
+            const long long gid = row_gid ? row_gid[r] : ((diag_col && diag_col[r] >= 0) ? diag_col[r] : row_begin + r);
             if (isdir[gid]) continue;   // Dirichlet row: stays deg * identity (applyDir zeroes the row of every cell matrix)
         }
         const long long p0 = rowptr[r];
@@ -228,7 +229,7 @@ extern "C" int afb_assemble_faces(afb_ctx* ctx, int nforms, const afb_form* form
             set_error(ctx, "form block outside the element matrix");
             return -7;
         }
-        if (fm[k].alpha == 0.0) fm[k].alpha = 1.0;
+
         const int dlen = form_dlen(fm[k], oa[k], ob[k]);
         const int q = afb_tri_quadrature(fm[k].quad_order, nullptr, nullptr, 0);
         if (q < 0) { set_error(ctx, "quadrature order must be in 0..20"); return -7; }
@@ -287,15 +288,17 @@ extern "C" int afb_assemble_faces(afb_ctx* ctx, int nforms, const afb_form* form
     const unsigned char* isdir = dir ? ctx->dir_flag.as<unsigned char>() : nullptr;
     const double* bc = dir ? ctx->dir_val.as<double>() : nullptr;
     const int32_t* dcol = ctx->has_diag ? ctx->diag_col.as<int32_t>() : nullptr;
+    if (dir) { const int rc = dirichlet_prepare(ctx); if (rc) return rc; }
+    const int32_t* rgid = (dir && ctx->row_gid_valid) ? ctx->row_gid.as<int32_t>() : nullptr;
     if (ctx->bf_nu > 0) {
         if (ctx->pos_bytes == 1)
             k_bf_gather<unsigned char><<<grid_for(ctx->bf_nu), 128, 0, st>>>(ctx->bf_nu, ctx->bf_urow.as<unsigned>(), ctx->bf_uoff.as<int>(), ctx->bf_item.as<unsigned>(),
                 ctx->bf_aidx.as<long long>(), nrl, ncl, ctx->ntet, ctx->bf_tet.as<int32_t>(), sA, sF, ctx->pos.as<unsigned char>(),
-                ctx->rowptr.as<long long>(), ctx->e2c.as<int32_t>(), ctx->row_begin, dcol, isdir, bc, dval, drhs, drop_val, ctx->flag.as<int>());
+                ctx->rowptr.as<long long>(), ctx->e2c.as<int32_t>(), ctx->row_begin, dcol, rgid, isdir, bc, dval, drhs, drop_val, ctx->flag.as<int>());
         else
             k_bf_gather<unsigned short><<<grid_for(ctx->bf_nu), 128, 0, st>>>(ctx->bf_nu, ctx->bf_urow.as<unsigned>(), ctx->bf_uoff.as<int>(), ctx->bf_item.as<unsigned>(),
                 ctx->bf_aidx.as<long long>(), nrl, ncl, ctx->ntet, ctx->bf_tet.as<int32_t>(), sA, sF, ctx->pos.as<unsigned short>(),
-                ctx->rowptr.as<long long>(), ctx->e2c.as<int32_t>(), ctx->row_begin, dcol, isdir, bc, dval, drhs, drop_val, ctx->flag.as<int>());
+                ctx->rowptr.as<long long>(), ctx->e2c.as<int32_t>(), ctx->row_begin, dcol, rgid, isdir, bc, dval, drhs, drop_val, ctx->flag.as<int>());
         ctx->launches++;
         AFB_CUDA(ctx, cudaGetLastError());
     }

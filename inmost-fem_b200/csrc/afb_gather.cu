@@ -127,7 +127,9 @@ int assemble_tensor_path(afb_ctx* ctx, int nfA, int nfF, const std::vector<afb_f
 
 int launch_gather(afb_ctx* ctx, const double* stageA, const double* stageF, double* val, double* rhs, int accumulate, double drop_val,
                   int* status_flag, long long e_lo, long long e_hi) {
-    const size_t need = (size_t)(256 / 32) * std::max(1, ctx->max_row_len) * sizeof(double);
+    // rows per block = 256 / G with the lane-group size G the dispatch below selects (4, 8, 16 or 32 lanes per row)
+    const int Gsel = ctx->ncol_loc <= 4 ? 4 : (ctx->ncol_loc <= 8 ? 8 : (ctx->ncol_loc <= 16 ? 16 : 32));
+    const size_t need = (size_t)(256 / Gsel) * std::max(1, ctx->max_row_len) * sizeof(double);
     if (need > 200 * 1024) { set_error(ctx, "afb_assemble: matrix rows too long for the shared-memory row image"); return -3; }
     cudaError_t e;
     const int nc = ctx->ncol_loc;

@@ -177,6 +177,8 @@ struct afb_ctx {
     // essential boundary conditions (afb_dirichlet.cu): per global dof flag + value, list of affected rows
     bool has_dirichlet = false, dir_rows_valid = false;
     afb::DevBuf dir_flag, dir_val, dir_rows;
+    afb::DevBuf row_gid;          // int32[nrows]: global dof of every local row (explicit dof maps with diag tables), built with dir_rows
+    bool row_gid_valid = false;
     long long n_dir_rows = 0;
 
     // boundary faces carrying surface terms (afb_faces.cu): face bf_face[b] of element bf_tet[b]; row -> (face, local row) lists
@@ -235,6 +237,7 @@ int assemble_block_path(afb_ctx* ctx, int nfA, int nfF, const std::vector<afb_fo
                         double drop_val, int* status_flag);
 // essential boundary conditions (afb_dirichlet.cu)
 int dirichlet_apply(afb_ctx* ctx, double* val, double* rhs);
+int dirichlet_prepare(afb_ctx* ctx);   // row list + row -> global dof table for the current pattern
 // thread-per-row gather + its plan (afb_rows.cu)
 int build_rows_plan(afb_ctx* ctx);
 bool rows_supports(const afb_ctx* ctx, int nga, int ngf);

@@ -28,6 +28,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 
 #include "afb_internal.h"
 
@@ -699,7 +700,9 @@ template <int NLOC, int NC, int NGA, int NGF>
 int launch_rows_t(afb_ctx* ctx, const double* TA, const double* TF, const double* gbuf, double* val, double* rhs, int accumulate,
                   double drop_val, int* status, const long long* p0_override, int phase, const int* tix, const unsigned short* rtab, const int* rdst) {
     constexpr int NGP = (NGA + NGF + 1) & ~1;
-    static RowTab<NLOC, NC, NGA, NGF> T;  // host staging of the parameter (copied by value at launch)
+    // host staging of the kernel parameter (copied by value at launch); per call, so that contexts on different threads do not share it
+    std::unique_ptr<RowTab<NLOC, NC, NGA, NGF>> Tp(new RowTab<NLOC, NC, NGA, NGF>());
+    RowTab<NLOC, NC, NGA, NGF>& T = *Tp;
     // TA is [c][i][j], TF is [c][i]
     for (int i = 0; i < NLOC; ++i)
         for (int j = 0; j < NC; ++j)

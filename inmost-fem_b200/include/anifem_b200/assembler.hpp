@@ -132,6 +132,11 @@ public:
         if (!m_prepared) throw std::runtime_error("SetDirichlet: call PrepareProblem first");
         if (is_dirichlet.empty()) { ck(afb_dirichlet_set(m_ctx, nullptr, nullptr, AFB_HOST)); return *this; }
         if (is_dirichlet.size() != value.size()) throw std::runtime_error("SetDirichlet: flag and value arrays differ in size");
+        {   // the library copies one entry per global dof: the arrays must cover the whole column space
+            int64_t ng = 0;
+            ck(afb_dofmap_get(m_ctx, nullptr, nullptr, nullptr, nullptr, &ng, nullptr, nullptr, AFB_HOST));
+            if ((int64_t)is_dirichlet.size() != ng) throw std::runtime_error("SetDirichlet: arrays must have one entry per global dof");
+        }
         ck(afb_dirichlet_set(m_ctx, is_dirichlet.data(), value.data(), AFB_HOST));
         return *this;
     }

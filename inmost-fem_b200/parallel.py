@@ -455,9 +455,33 @@ class DistributedAssembler:
     def colind(self):
         return self.colind_ext[:self.plan.nnz_own]
 
+    def _ctx_stream(self):
+        """torch stream context that makes the context's CUDA stream torch's current stream: the NCCL exchange and the halo
+        additions are ordered against the assembly kernels only through torch's current stream, so the whole sequence must be
+        issued on the stream the library launches on (a Context created without a stream owns a private one)."""
+        import contextlib
+        if not self.val_is_cuda():
+            return contextlib.nullcontext()
+        h = self.ctx.stream_handle()
+        cur = torch.cuda.current_stream()
+        if h == cur.cuda_stream:
+            return contextlib.nullcontext()
+        ext = torch.cuda.ExternalStream(h)
+        ext.wait_stream(cur)          # inputs produced on the caller's stream are visible to the assembly
+        self._ext_stream = ext
+        return torch.cuda.stream(ext)
+
     def assemble(self, forms, rhs_forms, drop_val=1e-100):
         """Assemble the owned rows [row_begin,row_end): local element contributions + interface contributions of peers.
         Results: self.val[:nnz_own] (CSR values of the owned rows), self.rhs[:n_own]."""
+        self._ext_stream = None
+        with self._ctx_stream():
+            st = self._assemble(forms, rhs_forms, drop_val)
+        if self._ext_stream is not None:   # results are consumed on the caller's stream
+            torch.cuda.current_stream().wait_stream(self._ext_stream)
+        return st
+
+    def _assemble(self, forms, rhs_forms, drop_val):
         if self.phased:
             self.ctx.assemble_phase(forms, rhs_forms, self.val, self.rhs, 1, drop_val=drop_val)
             works = self.plan.exchange_start(self.val, self.rhs)

@@ -235,6 +235,64 @@ int main() {
         try { fem3Dface<OP1, OP2>(F1, F2, F3, F4, 4, ddotn, A, 3); } catch (const std::runtime_error&) { thrown = true; }
         EXPECT(thrown);
     }
+    // --- SetEnumerator(ANITYPE ... ETDIMBLOCKS) (assembler.h:333-336, global_enumerator.h:393-401): the matrix assembled under every
+    //     numbering is the NATURAL one with rows / columns permuted by the map between the two dof tables (Taylor-Hood P2^3 x P1)
+    {
+        using GU = Operator<GRAD, FemVec<3, FEM_P2>>; using DU = Operator<DIV, FemVec<3, FEM_P2>>; using IP = Operator<IDEN, FemFix<FEM_P1>>;
+        using IU = Operator<IDEN, FemVec<3, FEM_P2>>;
+        const double fz[3] = {0.0, 0.0, -1.0};
+        auto build = [&](Assembler& d, ASSEMBLING_TYPE t) {
+            d.SetCubeMesh(3, 2, 2).SetProbDescr({{FEM_P2, 3}, {FEM_P1, 1}}).SetEnumerator(t);
+            d.AddMatForm<GU, GU>(0, 0, 2, TENSOR_NULL, AFB_COEF_CONST, nullptr).AddMatForm<IP, DU>(1, 0, 2, TENSOR_NULL, AFB_COEF_CONST, nullptr, -1.0);
+            d.AddMatForm<DU, IP>(0, 1, 2, TENSOR_NULL, AFB_COEF_CONST, nullptr, -1.0).AddRhsForm<IU>(0, 2, TENSOR_GENERAL, AFB_COEF_CONST, fz);
+            d.PrepareProblem();
+        };
+        Assembler nat;
+        build(nat, NATURAL);
+        CsrMatrix An; std::vector<double> bn;
+        EXPECT(nat.Assemble(An, bn) == 0);
+        int64_t nnode = 0, ntet = 0;
+        EXPECT(afb_mesh_get(nat.context(), &nnode, &ntet, nullptr, nullptr, AFB_HOST) == 0);
+        std::vector<int32_t> v(4 * ntet);
+        EXPECT(afb_mesh_get(nat.context(), &nnode, &ntet, nullptr, v.data(), AFB_HOST) == 0);
+        const std::vector<EnumVar> ev = {{FEM_P2, 3}, {FEM_P1, 1}};
+        const DofEnumeration en0 = enumerate_dofs(NATURAL, nnode, ntet, v.data(), v.data() + ntet, v.data() + 2 * ntet, v.data() + 3 * ntet, ev);
+        {   // the host NATURAL table is the one the device numbering produced
+            std::vector<int64_t> rc((std::size_t)ntet * en0.nloc), cc(rc.size());
+            int nr, nc; int64_t rb, re, ng;
+            EXPECT(afb_dofmap_get(nat.context(), &nr, &nc, &rb, &re, &ng, rc.data(), cc.data(), AFB_HOST) == 0);
+            bool same = nr == en0.nloc;
+            for (std::size_t k = 0; same && k < rc.size(); ++k) same = cc[k] == en0.elem2dof[k] + 1;
+            EXPECT(same);
+        }
+        const ASSEMBLING_TYPE types[5] = {ANITYPE, MINIBLOCKS, DIMUNION, BYELEMTYPE, ETDIMBLOCKS};
+        for (ASSEMBLING_TYPE t : types) {
+            Assembler d;
+            build(d, t);
+            CsrMatrix A; std::vector<double> b;
+            EXPECT(d.Assemble(A, b) == 0);
+            EXPECT(A.val.size() == An.val.size() && b.size() == bn.size());
+            const DofEnumeration en = enumerate_dofs(t, nnode, ntet, v.data(), v.data() + ntet, v.data() + 2 * ntet, v.data() + 3 * ntet, ev);
+            std::vector<int64_t> perm(en0.nrows, -1);   // NATURAL id -> id under t
+            for (std::size_t k = 0; k < en.elem2dof.size(); ++k) perm[en0.elem2dof[k]] = en.elem2dof[k];
+            double scale = 0, err = 0, errb = 0;
+            for (double x : An.val) scale = std::fmax(scale, std::fabs(x));
+            bool found_all = true;
+            for (int64_t r = 0; r + 1 < (int64_t)An.rowptr.size(); ++r) {
+                const int64_t pr = perm[r];
+                errb = std::fmax(errb, std::fabs(b[pr] - bn[r]));
+                for (int64_t k = An.rowptr[r]; k < An.rowptr[r + 1]; ++k) {
+                    const int32_t pc = (int32_t)perm[An.colind[k]];
+                    const int32_t* lo = std::lower_bound(A.colind.data() + A.rowptr[pr], A.colind.data() + A.rowptr[pr + 1], pc);
+                    if (lo == A.colind.data() + A.rowptr[pr + 1] || *lo != pc) { found_all = false; continue; }
+                    err = std::fmax(err, std::fabs(A.val[lo - A.colind.data()] - An.val[k]));
+                }
+                if (A.rowptr[pr + 1] - A.rowptr[pr] != An.rowptr[r + 1] - An.rowptr[r]) found_all = false;
+            }
+            EXPECT(found_all);
+            EXPECT(err <= 1e-12 * scale && errb <= 1e-13);
+        }
+    }
     std::printf(fails ? "test_shim: %d FAILED\n" : "test_shim: all passed\n", fails);
     return fails ? 1 : 0;
 }

@@ -194,3 +194,52 @@ def test_unstructured_mesh_and_unoriented_tets(pkg, ctx, asm_oracle):
     _, forms, rhsf, prob = problems._mk(pkg, M, variables, [(0, 0, gc.GRAD, gc.GRAD, 4, gc.T_SYMMETRIC, gc.L_PER_TET, K, 1.0)],
                                         [(0, gc.IDEN, 3, gc.T_NULL, gc.L_CONST, None, 1.0)])
     _check(ctx, M, prob, forms, rhsf, co, te, dm, "unstructured P3")
+
+
+def test_negative_sign_codes(pkg, ctx, asm_oracle, oracle):
+    """oriented dofs: index codes sign*(id+1) with negative signs (assembler.inl:49-55, :155-159); the scatter multiplies every
+    contribution by s_row * s_col and the load entry by s_row (assembler.inl:407, :416-418).  Signs are per (cell, local dof) like
+    the reference's OrderTempl sign slot; same sign on the row and the column code of a local dof."""
+    M, O = asm_oracle, oracle
+    rng = np.random.default_rng(11)
+    co, te, _ = M.cube_mesh(4, 3, 2)
+    for variables, fem in (([(gc.P2, 1)], gc.P2), ([(gc.P1, 1)], gc.P1)):
+        dm = M.DofMap(te, variables, nnode=co.shape[0])
+        rowcode, colcode = dm.codes(None)
+        sgn = np.where(rng.random(rowcode.shape) < 0.4, -1, 1).astype(np.int64)
+        rowcode, colcode = rowcode * sgn, colcode * sgn
+        K = problems.sym_K(co[te].mean(axis=1))
+        _, forms, rhsf, prob = problems._mk(pkg, M, variables, [(0, 0, gc.GRAD, gc.GRAD, 2, gc.T_SYMMETRIC, gc.L_PER_TET, K, 1.0)],
+                                            [(0, gc.IDEN, 2, gc.T_SCALAR, gc.L_PER_TET, 1 + co[te].mean(axis=1)[:, :1].copy(), 1.0)])
+        ctx.mesh_set(co, te)
+        ctx.dofmap_set(rowcode, colcode, 0, dm.nrows, dm.nrows)
+        nnz = ctx.pattern_build()
+        rowptr, colind = ctx.pattern_get()
+        rp, ci = M.template_pattern(rowcode, colcode, 0, dm.nrows)
+        assert np.array_equal(rowptr, rp) and np.array_equal(colind, ci)
+        A, F = prob.element_matrices(co[te].transpose(1, 0, 2), idx=np.arange(te.shape[0]))
+        v, r = np.zeros(ci.size), np.zeros(dm.nrows)
+        assert O.scatter_csr(rowcode, colcode, A, F, 0, rp, ci, v, r) == 0
+        val, rhs = np.full(nnz, np.nan), np.full(dm.nrows, np.nan)
+        assert ctx.assemble(forms, rhsf, val, rhs) == 0
+        _compare(val, rhs, v, r, rp, te, nnz, "signed codes fem %d" % fem)
+        # all signs positive gives a different matrix: the signs were honoured, not dropped
+        v0 = np.zeros(ci.size)
+        O.scatter_csr(np.abs(rowcode), np.abs(colcode), A, None, 0, rp, ci, v0, None)
+        assert np.abs(v0 - v).max() > 1e-3 * np.abs(v).max()
+
+
+def test_dofmap_rejects_out_of_range_codes(pkg, ctx, asm_oracle):
+    """an index outside its interval aborts the reference (assembler.inl:399-412); here afb_dofmap_set fails with -7"""
+    M = asm_oracle
+    co, te, _ = M.cube_mesh(2, 2, 2)
+    dm = M.DofMap(te, [(gc.P1, 1)], nnode=co.shape[0])
+    rowcode, colcode = dm.codes(None)
+    ctx.mesh_set(co, te)
+    for which, bad in (("row", dm.nrows + 1), ("col", dm.nrows + 1), ("col", 0)):
+        rc, cc = rowcode.copy(), colcode.copy()
+        (rc if which == "row" else cc)[3, 1] = bad
+        with pytest.raises(pkg.AfbError) as e:
+            ctx.dofmap_set(rc, cc, 0, dm.nrows, dm.nrows)
+        assert e.value.code == -7
+    ctx.dofmap_set(rowcode, colcode, 0, dm.nrows, dm.nrows)   # the valid table is still accepted
