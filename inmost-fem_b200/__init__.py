@@ -451,5 +451,5 @@ class Context:
     def last_times(self):
         t = (ctypes.c_double * 4)()
         lib().afb_last_times(self._h, t)
-        kern = {0: ("k_element_generic", "k_gather"), 1: ("k_geom", "k_gather_tensor"), 2: ("k_geom", "k_rows_cl")}[int(t[3])]
+        kern = {0: ("k_element_generic", "k_gather"), 1: ("k_geom", "k_gather_tensor"), 2: ("k_geom", "k_rows_cl"), 3: ("k_geom", "k_rings")}[int(t[3])]
         return {"element_ms": t[0], "gather_ms": t[1], "copy_ms": t[2], "fused_path": bool(t[3]), "element_kernel": kern[0], "gather_kernel": kern[1]}

@@ -159,8 +159,10 @@ int afb_priority_rows_set(afb_ctx* ctx, int64_t first_priority_row) {
     if (!ctx->has_pattern) { set_error(ctx, "pattern was not built"); return -6; }
     cudaSetDevice(ctx->device);
     ctx->priority_row = first_priority_row;
-    if (first_priority_row < 0) { ctx->rp_prio_valid = false; return 0; }
-    return rows_priority_build(ctx, first_priority_row);
+    if (first_priority_row < 0) { ctx->rp_prio_valid = false; ctx->rg_prio_valid = false; return 0; }
+    const int rc = rows_priority_build(ctx, first_priority_row);
+    if (rc) return rc;
+    return rings_priority_build(ctx, first_priority_row);
 }
 
 int afb_assemble_phase(afb_ctx* ctx, int nforms, const afb_form* forms, int nrhs, const afb_form* rhs_forms, double* csr_val, double* rhs,
@@ -279,8 +281,8 @@ static int assemble_impl(afb_ctx* ctx, int nforms, const afb_form* forms, int nr
     if (handled < 0) return handled;
     if (!handled) handled = assemble_tensor_path(ctx, nfA, nfF, fm, oa, ob, Dd, fval, frhs, accumulate, drop_val, ctx->flag.as<int>(), ph);
     if (handled < 0) return handled;
-    if (ph == 1 && handled == 2) { ctx->phase_done = false; return 0; }   // phase 2 follows
-    if (ph == 2 && handled != 2) { set_error(ctx, "afb_assemble_phase: phase 2 does not match phase 1"); return -6; }
+    if (ph == 1 && (handled == 2 || handled == 3)) { ctx->phase_done = false; return 0; }   // phase 2 follows
+    if (ph == 2 && handled != 2 && handled != 3) { set_error(ctx, "afb_assemble_phase: phase 2 does not match phase 1"); return -6; }
     if (handled && !accumulate) {
         if (doA && !fval && ctx->nnz) AFB_CUDA(ctx, cudaMemsetAsync(dval, 0, ctx->nnz * sizeof(double), st));
         if (doF && !frhs && nrows) AFB_CUDA(ctx, cudaMemsetAsync(drhs, 0, nrows * sizeof(double), st));

@@ -174,6 +174,14 @@ struct afb_ctx {
     int phase_status = 0;
     long long rp_nprio = 0, priority_row = -1;
 
+    // ring plan of square P2 problems (afb_rings.cu, afb_ring_plan.h)
+    bool has_ring_plan = false, rg_prio_valid = false;
+    long long rg_ncl = 0, rg_nslices = 0, rg_nsteps = 0, rg_nvert = 0, rg_nz = 0, rg_nprio = 0, rg_vsplit = 0;
+    int rg_gcap = 0, rg_imgcap = 0;
+    afb::DevBuf rg_cs, rg_eptr, rg_elist, rg_sptr, rg_hdr, rg_steps, rg_dptr, rg_desc, rg_vimg, rg_xptr, rg_xpos, rg_xbase;
+    afb::DevBuf rg_vptr, rg_vlist, rg_vdpos, rg_vrow, rg_zlist, rg_scratch, rg_clist;
+    std::vector<unsigned> rg_maxrow, rg_vrow_host;   // largest row a cluster writes to; rows of the vertex list (ascending)
+
     // essential boundary conditions (afb_dirichlet.cu): per global dof flag + value, list of affected rows
     bool has_dirichlet = false, dir_rows_valid = false;
     afb::DevBuf dir_flag, dir_val, dir_rows;
@@ -245,6 +253,12 @@ int launch_rows(afb_ctx* ctx, int nga, int ngf, const double* TA, const double* 
                 int accumulate, double drop_val, int* status, const long long* p0_override = nullptr, int phase = 0,
                 const int* tix = nullptr, const unsigned short* rtab = nullptr, const int* rdst = nullptr);
 int rows_priority_build(afb_ctx* ctx, long long first_priority_row);
+// ring-traversal assembly of square P2 problems + its plan (afb_rings.cu)
+int build_ring_plan(afb_ctx* ctx);
+int rings_priority_build(afb_ctx* ctx, long long first_priority_row);
+bool rings_supports(const afb_ctx* ctx, int nstiff, int nmass, int nload);
+int launch_rings(afb_ctx* ctx, const double* TG, const double* Tm, const double* Tf, const double* gbuf, double* val, double* rhs,
+                 int accumulate, double drop_val, int* status, int phase);
 // gather (afb_gather.cu)
 int launch_gather(afb_ctx* ctx, const double* stageA, const double* stageF, double* val, double* rhs,
                   int accumulate, double drop_val, int* status_flag, long long e_lo, long long e_hi);

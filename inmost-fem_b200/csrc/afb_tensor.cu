@@ -25,6 +25,7 @@
 #include <cstring>
 
 #include "afb_internal.h"
+#include "afb_ring_plan.h"
 
 using namespace afb;
 
@@ -39,6 +40,7 @@ struct TFormDev {
     int dstride;   // doubles per element record of D (PER_TET)
     int kidx[9];   // position of every tensor value inside the record; -1 = the value 0, -2 = the value 1
     int goff, ng;  // components [goff, goff+ng) of g_e
+    int bary;      // kind 0, ng 6: store the off-diagonal barycentric coefficients (G01,G23,G02,G13,G03,G12) of the ring kernel instead of M
     double alpha;
     const double* D;
 };
@@ -46,6 +48,7 @@ struct GeomParams {
     int nforms;
     int ngpad;  // doubles per element in gbuf (even)
     int ngtot;  // components actually used; the pad slot is zeroed
+    int zero_all;  // records have fixed slots some of which no form fills (ring kernel): zero the whole record first
     TFormDev f[MAX_TFORMS];
 };
 
@@ -94,6 +97,7 @@ __global__ void __launch_bounds__(256) k_geom(long long ntet, GeomParams gp, con
     for (int k = 0; k < 4; ++k) { P[k][0] = __ldg(x + nn[k]); P[k][1] = __ldg(y + nn[k]); P[k][2] = __ldg(z + nn[k]); }
     const double vol = fabs(jac_inv(P, PSI)) * (1.0 / 6.0);
     if (gp.ngpad > gp.ngtot) g[gp.ngtot] = 0.0;
+    if (gp.zero_all) for (int k = 0; k < gp.ngpad; ++k) g[k] = 0.0;
     for (int f = 0; f < gp.nforms; ++f) {
         const TFormDev& F = gp.f[f];
         const double* D = F.D;
@@ -132,6 +136,14 @@ __global__ void __launch_bounds__(256) k_geom(long long ntet, GeomParams gp, con
                 o[3] = c * (PSI[0] * PSI[1] + PSI[3] * PSI[4] + PSI[6] * PSI[7]);
                 o[4] = c * (PSI[0] * PSI[2] + PSI[3] * PSI[5] + PSI[6] * PSI[8]);
                 o[5] = c * (PSI[1] * PSI[2] + PSI[4] * PSI[5] + PSI[7] * PSI[8]);
+            }
+            if (F.bary) {
+                // M = G restricted to the vertices 1..3 (reference gradients d/dxi_a = grad l_a, a = 1..3); the barycentric gradients
+                // sum to zero, so G_0b = -(M_1b + M_2b + M_3b).  Record order of the ring kernel: (G01,G23), (G02,G13), (G03,G12)
+                const double m00 = o[0], m11 = o[1], m22 = o[2], m01 = o[3], m02 = o[4], m12 = o[5];
+                o[0] = -(m00 + m01 + m02); o[1] = m12;
+                o[2] = -(m01 + m11 + m12); o[3] = m02;
+                o[4] = -(m02 + m12 + m22); o[5] = m01;
             }
         } else if (F.kind == 1) {
             o[0] = s * coef_value(D, F.kidx[0]);
@@ -501,6 +513,56 @@ int fused_group(afb_ctx* ctx, afb_ctx* plan, const std::vector<SForm>& mat, cons
         (ismat ? offA : offF) += f.ng;
     }
     cudaStream_t st = ctx->stream;
+    // ---- ring-traversal kernel (afb_rings.cu): square P2 problems with one symmetric stiffness form (+ mass, + load)
+    {
+        int is = -1, im = -1, nother = 0;
+        for (int k = 0; k < nfA; ++k) {
+            const SForm& f = mat[k];
+            const bool p2 = f.nfa == 10 && f.nfb == 10 && f.row_off == 0 && f.col_off == 0;
+            if (p2 && f.kind == 0 && f.ng == 6 && is < 0) is = k;
+            else if (p2 && f.kind == 1 && im < 0) im = k;
+            else ++nother;
+        }
+        const bool load_ok = nfF == 0 || (nfF == 1 && rhsf[0].kind == 1 && rhsf[0].ng == 1 && rhsf[0].nfb == 10 && rhsf[0].row_off == 0);
+        if (plan == ctx && !p0_override && !tix && !rtab && !rdst && dval && is >= 0 && nother == 0 && load_ok && (nfF == 0 || drhs) &&
+            rings_supports(ctx, 1, im >= 0 ? 1 : 0, nfF)) {
+            std::vector<double> TM, TG(600), Tm, Tf;
+            build_form_table(mat[is], TM);
+            ring_table_from_M(TM.data(), 10, TG.data());
+            if (ring_table_symmetry_defect(TG.data()) < 1e-12) {
+                if (im >= 0) build_form_table(mat[im], Tm);
+                if (nfF) build_form_table(rhsf[0], Tf);
+                GeomParams gr;
+                std::memset(&gr, 0, sizeof(gr));
+                gr.ngpad = 8; gr.ngtot = 8; gr.zero_all = 1;
+                auto add = [&](const SForm& f, int goff, int bary) {
+                    TFormDev& d = gr.f[gr.nforms++];
+                    d.kind = f.kind; d.full = f.full; d.layout = f.layout; d.dstride = f.dstride;
+                    for (int t = 0; t < 9; ++t) d.kidx[t] = f.kidx[t];
+                    d.goff = goff; d.ng = f.ng; d.bary = bary; d.alpha = f.alpha; d.D = f.D;
+                };
+                add(mat[is], 0, 1);
+                if (im >= 0) add(mat[im], 6, 0);
+                if (nfF) add(rhsf[0], 7, 0);
+                AFB_CUDA(ctx, ctx->stageF.reserve((size_t)ctx->ntet * 8 * sizeof(double)));
+                double* gb = ctx->stageF.as<double>();
+                if (record_events) cudaEventRecord(ctx->ev[1], st);
+                if (phase != 2) {
+                    k_geom<<<(unsigned)((ctx->ntet + 255) / 256), 256, (size_t)256 * 8 * sizeof(double), st>>>(
+                        ctx->ntet, gr, ctx->x.as<double>(), ctx->y.as<double>(), ctx->z.as<double>(), ctx->v[0].as<int32_t>(), ctx->v[1].as<int32_t>(),
+                        ctx->v[2].as<int32_t>(), ctx->v[3].as<int32_t>(), gb, ctx->rp_old2new.as<unsigned>());
+                    ctx->launches++;
+                    AFB_CUDA(ctx, cudaGetLastError());
+                }
+                if (record_events) cudaEventRecord(ctx->ev[2], st);
+                const int rc = launch_rings(ctx, TG.data(), im >= 0 ? Tm.data() : nullptr, nfF ? Tf.data() : nullptr, gb, dval, drhs, accumulate, drop_val,
+                                            status_flag, phase);
+                if (rc < 0) return rc;
+                if (record_events) cudaEventRecord(ctx->ev[3], st);
+                return 3;
+            }
+        }
+    }
     AFB_CUDA(ctx, ctx->stageF.reserve((size_t)ctx->ntet * ngpad * sizeof(double)));  // g_e buffer
     double* gbuf = ctx->stageF.as<double>();
 

@@ -17,6 +17,15 @@ def test_shim_builds(pkg):
     assert os.path.exists(os.path.join(CXX_DIR, "test_shim"))
 
 
+def test_ring_plan_and_kernel_emulation_on_cpu(pkg):
+    """tests/cxx/test_ring_plan.cpp: the host plan builder of the ring kernel (afb_ring_plan.cpp) + a scalar emulation of k_rings on
+    that plan reproduce the plain scatter of the same element matrices (closed / open rings, every frame, drop rule, accumulate)"""
+    subprocess.check_call(["make", "-s", "-C", CXX_DIR, "test_ring_plan"])
+    out = subprocess.run([os.path.join(CXX_DIR, "test_ring_plan")], capture_output=True, text=True, timeout=300)
+    print(out.stdout, out.stderr)
+    assert out.returncode == 0 and "all passed" in out.stdout
+
+
 @pytest.mark.gpu
 def test_shim_runs_reference_style_tests(pkg):
     exe = os.path.join(CXX_DIR, "test_shim")

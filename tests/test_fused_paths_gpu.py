@@ -77,7 +77,9 @@ def test_cluster_gather_many_clusters(pkg, ctx, asm_oracle, chunk, space):
                                         [(0, 0, gc.GRAD, gc.GRAD, 2, gc.T_SYMMETRIC, gc.L_PER_TET, K, 1.0),
                                          (0, 0, gc.IDEN, gc.IDEN, 3, gc.T_SCALAR, gc.L_PER_TET, c, 0.5)],
                                         [(0, gc.IDEN, 2, gc.T_SCALAR, gc.L_PER_TET, c, 2.0)])
-    _, _, path = _oracle_compare(ctx, M, prob, forms, rhsf, co, te, dm, "%s chunk %d" % (space, chunk), {"AFB_ROWS_CHUNK": str(chunk)})
+    # the ring kernel (afb_rings.cu, tests/test_rings_gpu.py) would take the P2 case: this test is about the row gather
+    _, _, path = _oracle_compare(ctx, M, prob, forms, rhsf, co, te, dm, "%s chunk %d" % (space, chunk),
+                                 {"AFB_ROWS_CHUNK": str(chunk), "AFB_DISABLE_RING_KERNEL": "1"})
     assert path["gather_kernel"] == "k_rows_cl"
 
 
