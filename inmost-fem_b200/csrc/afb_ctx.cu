@@ -331,8 +331,7 @@ void afb_ctx_destroy(afb_ctx* c) {
                            &c->radj_ptr, &c->radj, &c->pos, &c->stageA, &c->stageF, &c->tables, &c->coef, &c->io_val, &c->io_rhs,
                            &c->flag, &c->tmp1, &c->tmp2, &c->tmp3, &c->xy, &c->diag_col, &c->rp_order, &c->rp_cnt, &c->rp_sptr, &c->rp_ell, &c->rp_new2old, &c->rp_old2new, &c->rp_cs, &c->rp_eptr, &c->rp_elist, &c->rp_p0, &c->rp_len, &c->rp_smax, &c->dir_flag, &c->dir_val, &c->dir_rows, &c->rp_clist,
                            &c->bf_tet, &c->bf_face, &c->bf_item, &c->bf_urow, &c->bf_uoff, &c->bf_aidx, &c->row_gid,
-                           &c->rg_cs, &c->rg_eptr, &c->rg_elist, &c->rg_sptr, &c->rg_hdr, &c->rg_steps, &c->rg_dptr, &c->rg_desc, &c->rg_vimg, &c->rg_xptr,
-                           &c->rg_xpos, &c->rg_xbase, &c->rg_vptr, &c->rg_vlist, &c->rg_vdpos, &c->rg_vrow, &c->rg_zlist, &c->rg_scratch, &c->rg_clist};
+                           &c->rg_cinfo, &c->rg_elist, &c->rg_hdr, &c->rg_steps, &c->rg_desc, &c->rg_xpos, &c->rg_vptr, &c->rg_vlist, &c->rg_vdpos, &c->rg_vrow, &c->rg_zlist, &c->rg_scratch, &c->rg_clist};
     for (auto* b : bufs) b->release();
     for (auto& t : c->table_cache) cudaFree(t.W);
     for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);

@@ -162,7 +162,7 @@ int afb_priority_rows_set(afb_ctx* ctx, int64_t first_priority_row) {
     if (first_priority_row < 0) { ctx->rp_prio_valid = false; ctx->rg_prio_valid = false; return 0; }
     const int rc = rows_priority_build(ctx, first_priority_row);
     if (rc) return rc;
-    return rings_priority_build(ctx, first_priority_row);
+    return ctx->has_ring_plan ? rings_priority_build(ctx, first_priority_row) : 0;
 }
 
 int afb_assemble_phase(afb_ctx* ctx, int nforms, const afb_form* forms, int nrhs, const afb_form* rhs_forms, double* csr_val, double* rhs,

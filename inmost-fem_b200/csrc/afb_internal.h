@@ -175,11 +175,13 @@ struct afb_ctx {
     long long rp_nprio = 0, priority_row = -1;
 
     // ring plan of square P2 problems (afb_rings.cu, afb_ring_plan.h)
-    bool has_ring_plan = false, rg_prio_valid = false;
+    bool has_ring_plan = false, rg_prio_valid = false, ring_plan_tried = false;
+    double ring_plan_ms = 0.0;   // host + transfer time of the last ring plan build
     long long rg_ncl = 0, rg_nslices = 0, rg_nsteps = 0, rg_nvert = 0, rg_nz = 0, rg_nprio = 0, rg_vsplit = 0;
-    int rg_gcap = 0, rg_imgcap = 0;
-    afb::DevBuf rg_cs, rg_eptr, rg_elist, rg_sptr, rg_hdr, rg_steps, rg_dptr, rg_desc, rg_vimg, rg_xptr, rg_xpos, rg_xbase;
+    int rg_gcap = 0, rg_imgcap = 0, rg_stepcap = 0, rg_xcap = 0, rg_edges = 0;
+    afb::DevBuf rg_cinfo, rg_elist, rg_hdr, rg_steps, rg_desc, rg_xpos;
     afb::DevBuf rg_vptr, rg_vlist, rg_vdpos, rg_vrow, rg_zlist, rg_scratch, rg_clist;
+    std::vector<unsigned char> rg_cinfo_host;   // host copy of the cluster records (permuted for phased launches)
     std::vector<unsigned> rg_maxrow, rg_vrow_host;   // largest row a cluster writes to; rows of the vertex list (ascending)
 
     // essential boundary conditions (afb_dirichlet.cu): per global dof flag + value, list of affected rows
@@ -255,6 +257,7 @@ int launch_rows(afb_ctx* ctx, int nga, int ngf, const double* TA, const double* 
 int rows_priority_build(afb_ctx* ctx, long long first_priority_row);
 // ring-traversal assembly of square P2 problems + its plan (afb_rings.cu)
 int build_ring_plan(afb_ctx* ctx);
+int ensure_ring_plan(afb_ctx* ctx);   // builds the plan (and its priority split) on first use; 0 ok
 int rings_priority_build(afb_ctx* ctx, long long first_priority_row);
 bool rings_supports(const afb_ctx* ctx, int nstiff, int nmass, int nload);
 int launch_rings(afb_ctx* ctx, const double* TG, const double* Tm, const double* Tf, const double* gbuf, double* val, double* rhs,

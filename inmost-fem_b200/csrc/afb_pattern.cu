@@ -261,12 +261,8 @@ static int pattern_impl(afb_ctx* ctx, int64_t* nnz_out, const int64_t* user_rowp
     if (rcp) return rcp;
     ctx->rp_prio_valid = false;
     if (ctx->priority_row >= 0 && !ctx->is_sub) { const int rcq = rows_priority_build(ctx, ctx->priority_row); if (rcq) return rcq; }
-    ctx->has_ring_plan = false;
-    if (!ctx->is_sub) {   // ring-traversal plan of square P2 problems (afb_rings.cu); absent -> the row gather serves the fused path
-        const int rcr = build_ring_plan(ctx);
-        if (rcr) return rcr;
-        if (ctx->priority_row >= 0) { const int rcq = rings_priority_build(ctx, ctx->priority_row); if (rcq) return rcq; }
-    }
+    // the ring-traversal plan of square P2 problems (afb_rings.cu) is built by the first assembly that can use it
+    ctx->has_ring_plan = false; ctx->ring_plan_tried = false; ctx->rg_prio_valid = false;
     return blocks_build(ctx);  // pair plans of vector / mixed spaces; block destinations are searched in whatever pattern is installed
 }
 

@@ -4,6 +4,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <functional>
@@ -176,6 +179,15 @@ int ring_plan_build(const RingPlanIn& in, RingPlan& out) {
     });
     if (fail.load() != F_OK) { out.why = fail_text(fail.load()); return 0; }
 
+    const bool verbose = getenv("RING_PLAN_VERBOSE") != nullptr;
+    auto tlast = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!verbose) return;
+        const auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[ring plan] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t - tlast).count());
+        tlast = t;
+    };
+    lap("ring order");
     // ---- edges in Morton order of their first tet; vertex rows
     std::vector<unsigned long long> ekey;
     std::vector<unsigned> vert_index(nrows, 0xffffffffu);
@@ -227,6 +239,7 @@ int ring_plan_build(const RingPlanIn& in, RingPlan& out) {
         L.image = off + L.nvent;
     };
 
+    lap("edge sort");
     // ---- pass 2a: sizes
     std::vector<int> c_slices(ncl), c_elist(ncl), c_desc(ncl), c_image(ncl), c_vent(ncl);
     std::vector<long long> c_steps(ncl);
@@ -247,20 +260,25 @@ int ring_plan_build(const RingPlanIn& in, RingPlan& out) {
         }
     });
     int gcap = 0, imgcap = 0;
-    for (long long c = 0; c < ncl; ++c) { gcap = std::max(gcap, c_elist[c]); imgcap = std::max(imgcap, c_image[c]); }
+    for (long long c = 0; c < ncl; ++c) {
+        gcap = std::max(gcap, c_elist[c]); imgcap = std::max(imgcap, c_image[c]);
+        out.stepcap = std::max(out.stepcap, (int)c_steps[c]); out.xcap = std::max(out.xcap, c_vent[c]);
+    }
     out.gcap = gcap; out.imgcap = imgcap; out.edges_per_cluster = EC;
-    if (gcap > in.max_staged || gcap >= (1 << RW0_EL_BITS) - 1) { out.why = "cluster stages too many elements"; return 0; }
-    if (imgcap > in.max_image_doubles || imgcap >= 65535) { out.why = "cluster image too large"; return 0; }
+    out.smem_bytes = ring_smem_bytes(gcap, imgcap, out.stepcap, EC, out.xcap, 4);
+    if (gcap >= (1 << RW0_EL_BITS) - 1) { out.why = "cluster stages too many elements"; return 0; }
+    if (imgcap >= 65535 || out.smem_bytes > (size_t)in.max_smem_bytes) { out.why = "cluster does not fit the shared-memory budget"; return 0; }
 
     out.cs.assign(ncl + 1, 0); out.eptr.assign(ncl + 1, 0); out.dptr.assign(ncl + 1, 0); out.xptr.assign(ncl + 1, 0);
     std::vector<long long> cstep0(ncl + 1, 0);
     for (long long c = 0; c < ncl; ++c) {
         out.cs[c + 1] = out.cs[c] + c_slices[c];
-        out.eptr[c + 1] = out.eptr[c] + c_elist[c];
+        out.eptr[c + 1] = out.eptr[c] + ((c_elist[c] + 3) & ~3);   // 16-byte aligned ranges; the count is in the cluster record
         out.dptr[c + 1] = out.dptr[c] + c_desc[c];
-        out.xptr[c + 1] = out.xptr[c] + c_vent[c];
+        out.xptr[c + 1] = out.xptr[c] + ((c_vent[c] + 3) & ~3);   // 16-byte aligned ranges (asynchronous copies); the count is vimg[2c+1] - vimg[2c]
         cstep0[c + 1] = cstep0[c] + c_steps[c];
     }
+    lap("cluster sizes");
     const long long nslices = out.cs[ncl], nsteps = cstep0[ncl];
     if (nslices * 32 * 4 >= 0xfffffff0LL) { out.why = "too many edges for 32-bit scratch indices"; return 0; }
     out.elist.assign((size_t)out.eptr[ncl], 0);
@@ -272,8 +290,29 @@ int ring_plan_build(const RingPlanIn& in, RingPlan& out) {
     out.xpos.assign((size_t)out.xptr[ncl], 0);
     out.xbase.assign(ncl, 0);
     out.cl_maxrow.assign(ncl, 0);
+    out.cinfo.assign(ncl, RingCluster());
     std::vector<unsigned> lane_va((size_t)nslices * 32, 0xffffffffu), lane_vb((size_t)nslices * 32, 0xffffffffu);
 
+    lap("allocate");
+    std::vector<unsigned char> row_holes;   // rows with entries no local element contributes to (superset patterns)
+    // ---- entries of the pattern no element contributes to
+    {
+        std::vector<std::vector<long long>> zl(nth);
+        row_holes.assign(nrows, 0);
+        parallel_for(nrows, nth, [&](int t, long long r0, long long r1) {
+            for (long long r = r0; r < r1; ++r) {
+                const int len = (int)(in.rowptr[r + 1] - in.rowptr[r]);
+                if (len == 0) continue;
+                unsigned long long m[4] = {0, 0, 0, 0};
+                for (long long a = in.radj_ptr[r]; a < in.radj_ptr[r + 1]; ++a)
+                    for (int j = 0; j < 10; ++j) { const int sl = in.pos[(size_t)a * 10 + j]; m[sl >> 6] |= 1ULL << (sl & 63); }
+                for (int sl = 0; sl < len; ++sl)
+                    if (!((m[sl >> 6] >> (sl & 63)) & 1ULL)) { zl[t].push_back(in.rowptr[r] + sl); row_holes[r] = 1; }
+            }
+        });
+        for (auto& z : zl) out.zlist.insert(out.zlist.end(), z.begin(), z.end());
+    }
+    lap("unproduced entries");
     // ---- pass 2b: fill
     parallel_for(ncl, nth, [&](int, long long c0, long long c1) {
         ClusterLayout L;
@@ -281,6 +320,15 @@ int ring_plan_build(const RingPlanIn& in, RingPlan& out) {
             layout(c, L);
             std::copy(L.elist.begin(), L.elist.end(), out.elist.begin() + out.eptr[c]);
             out.vimg[2 * c] = L.vimg0; out.vimg[2 * c + 1] = L.image;
+            {
+                RingCluster& ci = out.cinfo[c];
+                std::memset(&ci, 0, sizeof(ci));
+                ci.e0 = out.eptr[c]; ci.ne = (int)L.elist.size();
+                ci.sl0 = out.cs[c]; ci.nsl = (int)L.slice_steps.size();
+                ci.stc0 = cstep0[c]; ci.nstc = (int)c_steps[c];
+                ci.d0 = out.dptr[c]; ci.nd = out.dptr[c + 1] - out.dptr[c];
+                ci.x0 = out.xptr[c]; ci.vim0 = L.vimg0; ci.nx = L.nvent;
+            }
             unsigned maxrow = 0;
             // row images
             int d = out.dptr[c];
@@ -289,6 +337,7 @@ int ring_plan_build(const RingPlanIn& in, RingPlan& out) {
                 if (r == 0xffffffffu) continue;
                 out.desc[d++] = RingRowDesc{in.rowptr[r], (unsigned short)L.ebase[k], (unsigned short)(in.rowptr[r + 1] - in.rowptr[r]), 0, 0};
                 maxrow = std::max(maxrow, r);
+                if (row_holes[r]) out.cinfo[c].pad = 1;   // the image of this cluster's edge rows must be zeroed first
             }
             // vertex-row entries this cluster produces, in emission order (per lane: the four ring sums of the edge's end points, then one
             // (ring vertex, ab) entry per step); they are stored compactly behind the edge rows, sorted by (row, slot)
@@ -329,6 +378,7 @@ int ring_plan_build(const RingPlanIn& in, RingPlan& out) {
                 long long lo = in.rowptr[vs.front() >> 8] + (long long)(vs.front() & 0xff), hi = in.rowptr[vs.back() >> 8] + (long long)(vs.back() & 0xff);
                 if (hi - lo >= 0xffffffffLL) { fail = F_RANGE; return; }
                 out.xbase[c] = lo;
+                out.cinfo[c].xbase = lo;
                 for (size_t k = 0; k < vs.size(); ++k) {
                     out.xpos[(size_t)out.xptr[c] + k] = (unsigned)(in.rowptr[vs[k] >> 8] + (long long)(vs[k] & 0xff) - lo);
                     maxrow = std::max(maxrow, (unsigned)(vs[k] >> 8));
@@ -352,6 +402,7 @@ int ring_plan_build(const RingPlanIn& in, RingPlan& out) {
                 for (int lane = 0; lane < 32; ++lane) {
                     const unsigned r = L.edges[s * 32 + lane];
                     unsigned* H = out.hdr.data() + (size_t)sg * RING_HW * 32 + lane;
+                    H[5 * 32] = (unsigned)(step0 - cstep0[c]) | ((unsigned)nst << 16);
                     if (r == 0xffffffffu) { H[4 * 32] = 0xffffffffu; continue; }
                     const long long a0 = in.radj_ptr[r];
                     const int n = (int)(in.radj_ptr[r + 1] - a0);
@@ -414,6 +465,7 @@ int ring_plan_build(const RingPlanIn& in, RingPlan& out) {
     if (fail.load() != F_OK) { out.why = fail_text(fail.load()); return 0; }
     out.sptr[nslices] = nsteps;
 
+    lap("fill");
     // ---- vertex diagonals / loads: partial sums per vertex row in (slice, lane, endpoint) order
     out.vptr.assign(nvert + 1, 0);
     out.vrow.assign(nvert, 0);
@@ -439,22 +491,7 @@ int ring_plan_build(const RingPlanIn& in, RingPlan& out) {
         }
     }
 
-    // ---- entries of the pattern no element contributes to
-    {
-        std::vector<std::vector<long long>> zl(nth);
-        parallel_for(nrows, nth, [&](int t, long long r0, long long r1) {
-            for (long long r = r0; r < r1; ++r) {
-                const int len = (int)(in.rowptr[r + 1] - in.rowptr[r]);
-                if (len == 0) continue;
-                unsigned long long m[4] = {0, 0, 0, 0};
-                for (long long a = in.radj_ptr[r]; a < in.radj_ptr[r + 1]; ++a)
-                    for (int j = 0; j < 10; ++j) { const int sl = in.pos[(size_t)a * 10 + j]; m[sl >> 6] |= 1ULL << (sl & 63); }
-                for (int sl = 0; sl < len; ++sl)
-                    if (!((m[sl >> 6] >> (sl & 63)) & 1ULL)) zl[t].push_back(in.rowptr[r] + sl);
-            }
-        });
-        for (auto& z : zl) out.zlist.insert(out.zlist.end(), z.begin(), z.end());
-    }
+    lap("vertex lists");
     out.ncl = ncl; out.nslices = nslices; out.nsteps = nsteps; out.nedges = nedges; out.nvert = nvert; out.nstaged = out.eptr[ncl];
     out.ok = true;
     return 0;

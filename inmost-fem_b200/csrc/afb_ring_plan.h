@@ -27,7 +27,7 @@
 
 namespace afb {
 
-constexpr int RING_HW = 5;   // header words per (slice, lane)
+constexpr int RING_HW = 6;   // header words per (slice, lane)
 constexpr int RING_SW = 3;   // plan words per (step, lane)
 constexpr unsigned RING_NOIMG = 0xFFFFu;
 
@@ -42,7 +42,8 @@ constexpr unsigned RW0_HOLDF = 1u << 24;      // first step of a closed ring: ke
 constexpr unsigned RW0_ADDF = 1u << 25;       // terminal step of a closed ring: add the kept group
 // step word 1: slot bytes of (ab, r), (ab, ar), (ab, br), (ab, rs) in row ab;  step word 2: low 16 bits = image offset of (r, ab)
 // header words: H0 = image offset of row ab | steps << 16 | valid << 24;  H1 = slot bytes of (ab,a), (ab,b), (ab,ab);
-// H2 = image offsets of (a,b) | (a,ab) << 16;  H3 = (b,a) | (b,ab) << 16;  H4 = row of ab (0xFFFFFFFF: empty lane)
+// H2 = image offsets of (a,b) | (a,ab) << 16;  H3 = (b,a) | (b,ab) << 16;  H4 = row of ab (0xFFFFFFFF: empty lane);
+// H5 (the same in every lane) = first step of the slice relative to the cluster's first step | steps of the slice << 16
 
 struct RingRowDesc {       // one row image of a cluster (copy-out)
     long long p0;          // first CSR entry of the row
@@ -50,6 +51,20 @@ struct RingRowDesc {       // one row image of a cluster (copy-out)
     unsigned short len;    // row length
     unsigned short pad0, pad1;
 };
+
+struct alignas(16) RingCluster {   // everything a CTA needs to know about a cluster: one 64-byte load
+    int e0, ne;            // staged element ids: elist[e0 .. e0+ne)   (e0 is a multiple of 4)
+    int sl0, nsl;          // slices
+    long long stc0;        // first step
+    int nstc;              // steps
+    int d0, nd;            // row descriptors (complete edge rows)
+    int x0;                // first CSR offset of the vertex-row entries (multiple of 4)
+    int vim0, nx;          // image offset / number of the vertex-row entries
+    long long xbase;       // CSR position the offsets are relative to
+    long long pad;         // bit 0: some edge row of the cluster has entries no local element contributes to (superset pattern):
+                           // the kernel zeroes the edge-row part of the image before the ring phase
+};
+static_assert(sizeof(RingCluster) == 64, "cluster record is one 64-byte line");
 
 struct RingPlanIn {
     long long ntet = 0, nrows = 0;
@@ -61,8 +76,7 @@ struct RingPlanIn {
     const unsigned char* pos = nullptr;    // [n_adj*10] slot of local column j of adjacency entry a in its row
     const unsigned* old2new = nullptr;     // Morton id of every element
     int edges_per_cluster = 256;
-    int max_image_doubles = 12000;         // shared-memory budget of one cluster image
-    int max_staged = 1500;                 // elements whose coefficient records one cluster stages
+    int max_smem_bytes = 227 * 1024;       // shared-memory budget of one cluster (ring_smem_bytes)
     int nthreads = 1;
 };
 
@@ -72,7 +86,11 @@ struct RingPlan {
     long long ncl = 0, nslices = 0, nsteps = 0, nedges = 0, nvert = 0, nstaged = 0;
     int gcap = 0;                  // largest staged element list
     int imgcap = 0;                // largest cluster image (doubles)
+    int stepcap = 0;               // most steps of one cluster
+    int xcap = 0;                  // most vertex-row entries of one cluster
+    size_t smem_bytes = 0;         // shared memory of one CTA with 4 record pieces (ring_smem_bytes)
     int edges_per_cluster = 0;
+    std::vector<RingCluster> cinfo;   // [ncl]
     std::vector<int> cs;           // [ncl+1] slices of a cluster
     std::vector<int> eptr;         // [ncl+1] staged element list of a cluster
     std::vector<unsigned> elist;   // Morton ids
@@ -96,6 +114,14 @@ struct RingPlan {
     std::vector<unsigned char> cl_minrow_prio;  // scratch for phased assembly, filled by ring_plan_priority
     std::vector<unsigned> cl_maxrow;            // [ncl] largest row a cluster writes to
 };
+
+// shared memory of one k_rings CTA: coefficient planes (parts 16-byte pieces per element + the zero record, capacity rounded to 8),
+// cluster image, plan words of every step, slice headers, row descriptors, CSR offsets of the vertex-row entries, element ids
+inline size_t ring_smem_bytes(int gcap, int imgcap, int stepcap, int edges_per_cluster, int xcap, int parts) {
+    const size_t plane = (((size_t)gcap + 8) & ~(size_t)7) * 16;
+    return plane * parts + (((size_t)imgcap * 8 + 15) & ~(size_t)15) + (size_t)stepcap * RING_SW * 128 + (size_t)((edges_per_cluster + 31) / 32) * RING_HW * 128 +
+           (size_t)edges_per_cluster * 16 + (((size_t)xcap * 4 + 15) & ~(size_t)15) + (((size_t)gcap * 4 + 15) & ~(size_t)15) + 16;
+}
 
 // 0 ok (plan.ok tells whether the mesh / numbering is covered)
 int ring_plan_build(const RingPlanIn& in, RingPlan& out);

@@ -18,6 +18,8 @@
 // The vertex diagonals and vertex loads are partial sums per (edge, end point) in a scratch array, added per vertex in a fixed
 // order by k_ring_vertices.  Deterministic, no atomics on data.
 #include <algorithm>
+#include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -47,20 +49,15 @@ const int RT_J[RT_N] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 1, 4, 0, 4, 4, 4, 0, 1};
 
 struct RingArgs {
     int gcap;            // staged elements per cluster (capacity of a coefficient plane)
+    int imgcap, stepcap, slicecap, edgecap, xcap;   // capacities of the other shared-memory regions (ring_smem_bytes)
     int zero;            // always 0: keeps the table loads next to their DFMA (see k_rows_cl)
-    const int* clist;    // NULL: CTA b works on cluster b; else cluster clist[b]
-    const int* cs;       // [ncl+1]
-    const int* eptr;     // [ncl+1]
+    long long ncl;       // clusters of this launch
+    const RingCluster* cinfo;   // [ncl] cluster records in processing order
     const unsigned* elist;
-    const long long* sptr;
     const unsigned* hdr;
     const unsigned* steps;
-    const int* dptr;
     const RingRowDesc* desc;
-    const int* vimg;     // [2*ncl]
-    const int* xptr;
     const unsigned* xpos;
-    const long long* xbase;
     const double* gbuf;  // Morton order, 8 doubles per element
     double* val;
     double* rhs;
@@ -83,154 +80,293 @@ __device__ __forceinline__ double2 lds128(unsigned addr) {
 }
 __device__ __forceinline__ void cp_async16(unsigned dst, const void* src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 // slot of an element record inside a coefficient plane (bank-group hash, as in k_rows_cl)
 __device__ __forceinline__ unsigned rec_slot(unsigned el1) { return el1 ^ (((el1 >> 3) ^ (el1 >> 6) ^ (el1 >> 9)) & 7u); }
 
-template <bool HASM, bool HASF>
+__device__ __forceinline__ void cp_async4(unsigned dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ unsigned lds32(unsigned addr) {
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// Entries a ring thread evaluates per tet.  The tables of the supported forms are symmetric (T[q][i][j] == T[q][j][i]: symmetric
+// coefficient, same space on both sides; checked on the host), so (a,ab) = (ab,a), (b,ab) = (ab,b), (b,a) = (a,b) and
+// (r,ab) = (ab,r) are not evaluated a second time: 13 entries, k = 0..9 (row ab), 10 (a,b), 16 (a,a), 17 (b,b).
+// RING_MASK_P2STIFF: coefficients q (bit q: G01,G23,G02,G13,G03,G12) with a non-zero table value for the P2 stiffness matrix --
+// grad phi_vertex is parallel to one barycentric gradient, grad phi_edge lies in the span of two, so 34 of the 78 products
+// remain.  The host compares the actual table with the mask and falls back to the dense instantiation if they disagree.
+__device__ constexpr unsigned RING_MASK_P2STIFF[RT_N] = {0x15, 0x29, 0x24, 0x18, 0x3d, 0x30, 0x0c, 0x0c, 0x30, 0x3c, 0x01, 0, 0, 0, 0, 0, 0x15, 0x29};
+__device__ constexpr unsigned RING_MASK_DENSE[RT_N] = {0x3f, 0x3f, 0x3f, 0x3f, 0x3f, 0x3f, 0x3f, 0x3f, 0x3f, 0x3f, 0x3f, 0, 0, 0, 0, 0, 0x3f, 0x3f};
+
+// DROPF: apply the drop rule |A_e(i,j)| > drop_val per contribution.  Off for drop_val <= 1e-100 (the reference's default,
+// assembler.h:212): a dropped contribution is then below 1e-100 in magnitude, i.e. the sums differ by less than 1e-98 absolutely.
+//
+// Persistent CTAs (a few per SM) walk the clusters with a software pipeline that keeps memory latency off the critical path:
+//   iteration i:  wait A_i | barrier | prefetch ids of i+1 | RING PHASE i | wait ids | barrier | issue A_{i+1} | COPY-OUT i | barrier | issue B_{i+1}
+// A = coefficient records + plan words + headers (needed by the ring phase), B = row descriptors + CSR offsets (needed by the
+// copy-out); the cluster record of i+1 (one 64-byte load) is fetched at the top of iteration i.  [The first version did the
+// loads of a cluster at the start of its own CTA: 40 % of the stall samples sat on that chain of three dependent global loads,
+// profiles/r02b_rings.md.]
+template <bool HASM, bool HASF, bool DROPF, bool SPARSE>
 __global__ void __launch_bounds__(256) k_rings(const __grid_constant__ RingTab T, const RingArgs p) {
     constexpr int PARTS = (HASM || HASF) ? 4 : 3;
     extern __shared__ __align__(128) unsigned char smraw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int c = p.clist ? p.clist[blockIdx.x] : (int)blockIdx.x;
-    const int e0 = p.eptr[c], ne = p.eptr[c + 1] - e0;
+    // shared-memory layout (ring_smem_bytes): coefficient planes | image | step words | slice headers | row descriptors | offsets | ids
     const unsigned g_a = (unsigned)__cvta_generic_to_shared(smraw);
     const unsigned plane = (((unsigned)p.gcap + 8u) & ~7u) * 16u;
-    // ---- 1. stage the coefficient records: record 0 stays zero (steps without a tet read it)
-    {
-        const char* gsrc = reinterpret_cast<const char*>(p.gbuf);
-        if (threadIdx.x < PARTS) {
-            double2 zz; zz.x = 0.0; zz.y = 0.0;
-            *reinterpret_cast<double2*>(smraw + (size_t)threadIdx.x * plane) = zz;
-        }
-        for (int el = threadIdx.x; el < ne; el += blockDim.x) {
-            const unsigned id = __ldg(p.elist + e0 + el);
+    const unsigned img_a = g_a + plane * PARTS;
+    const unsigned stp_a = img_a + (((unsigned)p.imgcap * 8u + 15u) & ~15u);
+    const unsigned hdr_a = stp_a + (unsigned)p.stepcap * (RING_SW * 128);
+    const unsigned dsc_a = hdr_a + (unsigned)p.slicecap * (RING_HW * 128);
+    const unsigned xps_a = dsc_a + (unsigned)p.edgecap * 16u;
+    const unsigned ids_a = xps_a + (((unsigned)p.xcap * 4u + 15u) & ~15u);
+    const double* img = reinterpret_cast<const double*>(smraw + (size_t)(img_a - g_a));
+    const RingRowDesc* sdesc = reinterpret_cast<const RingRowDesc*>(smraw + (size_t)(dsc_a - g_a));
+    const unsigned* sxpos = reinterpret_cast<const unsigned*>(smraw + (size_t)(xps_a - g_a));
+    const unsigned* sids = reinterpret_cast<const unsigned*>(smraw + (size_t)(ids_a - g_a));
+    const double drop = p.drop;
+    double chk = 0.0;   // NaN iff some coefficient of a visited tet is NaN or +-Inf
+    const char* gsrc = reinterpret_cast<const char*>(p.gbuf);
+    // p.zero through a warp reduction: the value lives in a uniform register, so that (st & zero_u) below is computed on the uniform
+    // datapath and the table operands are fetched by LDCU.  [Read from the parameter bank inside the loop it ended up in a vector
+    // register and every table value became a per-thread LDC.64 on the ADU pipe.]
+    const int zero_u = __reduce_or_sync(0xffffffffu, p.zero);
+
+    auto issue_ids = [&](const RingCluster& ci) {   // element ids of the cluster (ranges are padded to 4 entries)
+        const char* src = reinterpret_cast<const char*>(p.elist + ci.e0);
+        for (int k = threadIdx.x; k < (ci.ne + 3) / 4; k += blockDim.x) cp_async16(ids_a + k * 16, src + (size_t)k * 16);
+    };
+    auto issue_A = [&](const RingCluster& ci) {     // the ids must be in shared memory
+        for (int el = threadIdx.x; el < ci.ne; el += blockDim.x) {
+            const unsigned id = sids[el];
             const unsigned dst = g_a + rec_slot((unsigned)el + 1u) * 16;
 #pragma unroll
             for (int part = 0; part < PARTS; ++part) cp_async16(dst + part * plane, gsrc + ((size_t)id * 4 + part) * 16);
         }
+        const char* ssrc = reinterpret_cast<const char*>(p.steps + (size_t)ci.stc0 * (RING_SW * 32));
+        for (int k = threadIdx.x; k < ci.nstc * (RING_SW * 8); k += blockDim.x) cp_async16(stp_a + k * 16, ssrc + (size_t)k * 16);
+        const char* hsrc = reinterpret_cast<const char*>(p.hdr + (size_t)ci.sl0 * (RING_HW * 32));
+        for (int k = threadIdx.x; k < ci.nsl * (RING_HW * 8); k += blockDim.x) cp_async16(hdr_a + k * 16, hsrc + (size_t)k * 16);
+    };
+    auto issue_B = [&](const RingCluster& ci) {
+        const char* dsrc = reinterpret_cast<const char*>(p.desc + ci.d0);
+        for (int k = threadIdx.x; k < ci.nd; k += blockDim.x) cp_async16(dsc_a + k * 16, dsrc + (size_t)k * 16);
+        const char* xsrc = reinterpret_cast<const char*>(p.xpos + ci.x0);   // ranges are padded to 4 entries: whole 16-byte pieces
+        for (int k = threadIdx.x; k < (ci.nx + 3) / 4; k += blockDim.x) cp_async16(xps_a + k * 16, xsrc + (size_t)k * 16);
+    };
+    auto load_cluster = [&](long long kc) -> RingCluster {   // one 64-byte record, the same address for every thread
+        const int4* q = reinterpret_cast<const int4*>(p.cinfo + kc);
+        union { int4 v[4]; RingCluster c; } u;
+        u.v[0] = __ldg(q); u.v[1] = __ldg(q + 1); u.v[2] = __ldg(q + 2); u.v[3] = __ldg(q + 3);
+        return u.c;
+    };
+
+    // record 0 of every coefficient plane stays zero (steps without a tet read it); no asynchronous copy ever targets it
+    if (threadIdx.x < PARTS) {
+        double2 zz; zz.x = 0.0; zz.y = 0.0;
+        *reinterpret_cast<double2*>(smraw + (size_t)threadIdx.x * plane) = zz;
+    }
+    long long kc = blockIdx.x;
+    if (kc >= p.ncl) return;
+    // cluster records two iterations ahead (clamped index: the loads are unconditional, nothing waits for them until they are used)
+    RingCluster cur = load_cluster(kc), nxt = load_cluster(min(kc + (long long)gridDim.x, p.ncl - 1));
+    issue_ids(cur);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    issue_A(cur);
+    cp_async_commit();
+    issue_B(cur);
+    cp_async_commit();
+
+    for (; kc < p.ncl; kc += gridDim.x) {
+        const bool more = kc + gridDim.x < p.ncl;
+        const RingCluster nn = load_cluster(min(kc + 2LL * gridDim.x, p.ncl - 1));
+        if (cur.pad & 1) {   // superset pattern (entries only other ranks contribute to): those image slots are never written
+            for (int k = threadIdx.x * 2; k < cur.vim0; k += blockDim.x * 2) {
+                asm volatile("st.shared.v2.f64 [%0], {%1, %1};" ::"r"(img_a + (unsigned)k * 8u), "d"(0.0) : "memory");
+            }
+        }
+        cp_async_wait<1>();   // A of this cluster (its B may still be in flight)
+        __syncthreads();
+        if (more) issue_ids(nxt);   // the id buffer is free: A of this cluster was issued from it before the last barrier
         cp_async_commit();
-    }
-    const unsigned img_a = g_a + plane * PARTS;   // cluster image (doubles)
-    const int sl0 = p.cs[c], sl1 = p.cs[c + 1];
-    const double drop = p.drop;
-    double chk = 0.0;   // NaN iff some coefficient of a visited tet is NaN or +-Inf
-    cp_async_wait_all();
-    __syncthreads();
 
-    // ---- 2. ring phase
-    for (int s = sl0 + warp; s < sl1; s += nwarps) {
-        const unsigned* H = p.hdr + (size_t)s * (RING_HW * 32) + lane;
-        const unsigned h0 = __ldg(H), h1 = __ldg(H + 32), h2 = __ldg(H + 64), h3 = __ldg(H + 96), h4 = __ldg(H + 128);
-        const long long st0 = __ldg(p.sptr + s);
-        // warp-uniform trip count in a uniform register (the compiler cannot see that s is the same for the whole warp): the loop
-        // counter and with it the table offsets below stay uniform, which is what keeps the table operands on LDCU
-        const int nst = __reduce_max_sync(0xffffffffu, (int)(__ldg(p.sptr + s + 1) - st0));
-        const unsigned* W = p.steps + (size_t)st0 * (RING_SW * 32) + lane;
-        const unsigned ebase = img_a + (h0 & 0xffffu) * 8u;
-        // plan words two steps ahead
-        unsigned wa0 = 0, wa1 = 0, wa2 = 0, wb0 = 0, wb1 = 0, wb2 = 0;
-        if (nst > 0) { wa0 = __ldg(W); wa1 = __ldg(W + 32); wa2 = __ldg(W + 64); }
-        if (nst > 1) { wb0 = __ldg(W + 96); wb1 = __ldg(W + 128); wb2 = __ldg(W + 160); }
-        double Sa = 0, Sb = 0, Sab = 0, Vab = 0, Va4 = 0, Vba = 0, Vb4 = 0, Da = 0, Db = 0, Fab = 0, Fa = 0, Fb = 0;
-        double C0 = 0, C1 = 0, C2 = 0, C3 = 0, K0 = 0, K1 = 0, K2 = 0, K3 = 0;
-        for (int st = 0; st < nst; ++st) {
-            const unsigned w0 = wa0, w1 = wa1, w2 = wa2;
-            wa0 = wb0; wa1 = wb1; wa2 = wb2;
-            if (st + 2 < nst) {
-                const unsigned* Wn = W + (size_t)(st + 2) * (RING_SW * 32);
-                wb0 = __ldg(Wn); wb1 = __ldg(Wn + 32); wb2 = __ldg(Wn + 64);
-            }
-            // z2 is 0 at run time but loop-variant for the compiler: the table entries stay uniform constant loads (LDCU) next to
-            // their DFMA instead of being hoisted out of the loop into vector registers
-            const int z2 = (st & p.zero) * 2;
-            const unsigned eloc = w0 & ((1u << RW0_EL_BITS) - 1u);
-            const unsigned rec = g_a + rec_slot(eloc) * 16;
-            double G[6], gm = 0.0, gf = 0.0;
+        // ---- ring phase: no global loads
+        for (int sl = warp; sl < cur.nsl; sl += nwarps) {
+            const unsigned H = hdr_a + (unsigned)sl * (RING_HW * 128) + lane * 4;
+            const unsigned h0 = lds32(H), h1 = lds32(H + 128), h2 = lds32(H + 256), h3 = lds32(H + 384), h4 = lds32(H + 512), h5 = lds32(H + 640);
+            // warp-uniform trip count in a uniform register (the compiler cannot see that the slice is the same for the whole
+            // warp): the loop counter and with it the table offsets below stay uniform, which keeps the table operands on LDCU
+            const int nst = __reduce_max_sync(0xffffffffu, (int)(h5 >> 16));
+            unsigned W = stp_a + (h5 & 0xffffu) * (RING_SW * 128) + lane * 4;
+            const unsigned ebase = img_a + (h0 & 0xffffu) * 8u;
+            double Sa = 0, Sb = 0, Sab = 0, Vab = 0, Da = 0, Db = 0, Fab = 0, Fa = 0, Fb = 0;
+            double C0 = 0, C1 = 0, C2 = 0, K0 = 0, K1 = 0, K2 = 0;
+            // two steps per trip: the arithmetic of consecutive ring tets is independent (only the three carried sums link them), so
+            // the two coefficient fetches and DFMA groups interleave -- the kernel runs with ~3 warps per scheduler, instruction-level
+            // parallelism is what hides the latencies.  A missing second step (odd count) is an empty step.
+            for (int st = 0; st < nst; st += 2, W += 2 * RING_SW * 128) {
+                const bool two = st + 1 < nst;   // uniform
+                const unsigned wa0 = lds32(W), wa1 = lds32(W + 128), wa2 = lds32(W + 256);
+                unsigned wb0 = lds32(W + 384), wb1 = lds32(W + 512), wb2 = lds32(W + 640);
+                if (!two) { wb0 = 0u; wb1 = 0u; wb2 = 0u; }
+                // z2 is 0 at run time but loop-variant for the compiler: the table entries stay uniform constant loads (LDCU) next
+                // to their DFMA instead of being hoisted out of the loop into vector registers
+                const int z2 = (st & zero_u) * 2;
+                const unsigned ela = wa0 & ((1u << RW0_EL_BITS) - 1u), elb = wb0 & ((1u << RW0_EL_BITS) - 1u);
+                double xa[RT_N], xb[RT_N], gfa = 0.0, gfb = 0.0;
 #pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                const unsigned tau = (w0 >> (RW0_TAU_SHIFT + 2 * q)) & 3u;
-                const double2 d = lds128(rec + tau * plane);
-                const bool sw = (w0 >> (RW0_SWAP_SHIFT + q)) & 1u;
-                G[2 * q] = sw ? d.y : d.x;
-                G[2 * q + 1] = sw ? d.x : d.y;
-            }
-            if (HASM || HASF) {
-                const double2 d = lds128(rec + 3 * plane);
-                gm = d.x; gf = d.y;
-            }
+                for (int k = 0; k < RT_N; ++k) { xa[k] = 0.0; xb[k] = 0.0; }
+                if (__any_sync(0xffffffffu, (ela | elb) != 0u)) {   // terminal / padding steps of the whole slice skip the arithmetic
+                    double Ga[6], Gb[6], gma = 0.0, gmb = 0.0;
+                    const unsigned reca = g_a + rec_slot(ela) * 16, recb = g_a + rec_slot(elb) * 16;
 #pragma unroll
-            for (int q = 0; q < 6; ++q) chk = fma(G[q], 0.0, chk);
-            if (HASM) chk = fma(gm, 0.0, chk);
-            if (HASF) chk = fma(gf, 0.0, chk);
-            // entry k of the table: |A_e(i,j)| > drop_val is the reference's rule (assembler.inl:416)
-            auto E = [&](int k) -> double {
-                double x = 0.0;
+                    for (int q = 0; q < 3; ++q) {
+                        const double2 da = lds128(reca + ((wa0 >> (RW0_TAU_SHIFT + 2 * q)) & 3u) * plane);
+                        const double2 db = lds128(recb + ((wb0 >> (RW0_TAU_SHIFT + 2 * q)) & 3u) * plane);
+                        const bool swa = (wa0 >> (RW0_SWAP_SHIFT + q)) & 1u, swb = (wb0 >> (RW0_SWAP_SHIFT + q)) & 1u;
+                        Ga[2 * q] = swa ? da.y : da.x; Ga[2 * q + 1] = swa ? da.x : da.y;
+                        Gb[2 * q] = swb ? db.y : db.x; Gb[2 * q + 1] = swb ? db.x : db.y;
+                    }
+                    if (HASM || HASF) {
+                        const double2 da = lds128(reca + 3 * plane), db = lds128(recb + 3 * plane);
+                        gma = da.x; gfa = da.y; gmb = db.x; gfb = db.y;
+                    }
+                    {   // non-finite test of the coefficients (x*0 is NaN for NaN and +-Inf)
+                        const double sa = (Ga[0] * 0.0 + Ga[1] * 0.0) + (Ga[2] * 0.0 + Ga[3] * 0.0) + (Ga[4] * 0.0 + Ga[5] * 0.0);
+                        const double sb = (Gb[0] * 0.0 + Gb[1] * 0.0) + (Gb[2] * 0.0 + Gb[3] * 0.0) + (Gb[4] * 0.0 + Gb[5] * 0.0);
+                        chk += (sa + sb) + ((HASM ? gma * 0.0 + gmb * 0.0 : 0.0) + (HASF ? gfa * 0.0 + gfb * 0.0 : 0.0));
+                    }
+                    // the 13 entries of both tets, coefficient-major so that the DFMA chains of different entries interleave.
+                    // |A_e(i,j)| > drop_val is the reference's rule (assembler.inl:416)
 #pragma unroll
-                for (int q = 0; q < 6; ++q) x = fma(T.A[k][q + z2], G[q], x);
-                if (HASM) x = fma(T.A[k][6 + z2], gm, x);
-                return (fabs(x) <= drop) ? 0.0 : x;
-            };
-            Sa += E(0); Sb += E(1); Sab += E(4);
-            Vab += E(10); Va4 += E(11); Vba += E(12); Vb4 += E(13);
-            {
-                const double da = E(16), db = E(17);
-                if (w0 & RW0_FLAGA) Da += da;
-                if (w0 & RW0_FLAGB) Db += db;
+                    for (int q = 0; q < 6; ++q) {
+#pragma unroll
+                        for (int k = 0; k < RT_N; ++k)
+                            if (((SPARSE ? RING_MASK_P2STIFF[k] : RING_MASK_DENSE[k]) >> q) & 1u) {
+                                const double t = T.A[k][q + z2];
+                                xa[k] = fma(t, Ga[q], xa[k]);
+                                xb[k] = fma(t, Gb[q], xb[k]);
+                            }
+                    }
+                    if (HASM) {
+#pragma unroll
+                        for (int k = 0; k < RT_N; ++k)
+                            if (RING_MASK_DENSE[k]) { const double t = T.A[k][6 + z2]; xa[k] = fma(t, gma, xa[k]); xb[k] = fma(t, gmb, xb[k]); }
+                    }
+                    if (DROPF) {
+#pragma unroll
+                        for (int k = 0; k < RT_N; ++k)
+                            if (RING_MASK_DENSE[k]) { xa[k] = (fabs(xa[k]) <= drop) ? 0.0 : xa[k]; xb[k] = (fabs(xb[k]) <= drop) ? 0.0 : xb[k]; }
+                    }
+                }
+                // ring sums: tet a, then tet b (fixed order)
+                Sa = (Sa + xa[0]) + xb[0]; Sb = (Sb + xa[1]) + xb[1]; Sab = (Sab + xa[4]) + xb[4]; Vab = (Vab + xa[10]) + xb[10];
+                if (wa0 & RW0_FLAGA) Da += xa[16];
+                if (wa0 & RW0_FLAGB) Db += xa[17];
+                if (wb0 & RW0_FLAGA) Da += xb[16];
+                if (wb0 & RW0_FLAGB) Db += xb[17];
+                if (HASF) {
+                    const double tf0 = T.F[0 + z2], tf1 = T.F[1 + z2], tf2 = T.F[2 + z2];
+                    Fab = fma(tf0, gfa, Fab); Fab = fma(tf0, gfb, Fab);
+                    if (wa0 & RW0_FLAGA) Fa = fma(tf1, gfa, Fa);
+                    if (wa0 & RW0_FLAGB) Fb = fma(tf2, gfa, Fb);
+                    if (wb0 & RW0_FLAGA) Fa = fma(tf1, gfb, Fa);
+                    if (wb0 & RW0_FLAGB) Fb = fma(tf2, gfb, Fb);
+                }
+                if (ela) sts64(ebase + (wa1 >> 24) * 8u, xa[9]);
+                if (elb) sts64(ebase + (wb1 >> 24) * 8u, xb[9]);
+                // step a: the group of its ring vertex r is complete (carry + this tet), the group of s is carried on
+                {
+                    double o0 = C0 + xa[2], o1 = C1 + xa[5], o2 = C2 + xa[7];
+                    if (wa0 & RW0_HOLDF) { K0 = o0; K1 = o1; K2 = o2; }   // step 0 of a closed ring: the carry is zero, o = this tet's part
+                    if (wa0 & RW0_ADDF) { o0 += K0; o1 += K1; o2 += K2; }
+                    if (wa0 & RW0_EMITR) {
+                        sts64(ebase + (wa1 & 0xffu) * 8u, o0);
+                        sts64(ebase + ((wa1 >> 8) & 0xffu) * 8u, o1);
+                        sts64(ebase + ((wa1 >> 16) & 0xffu) * 8u, o2);
+                        sts64(img_a + (wa2 & 0xffffu) * 8u, o0);   // (r, ab) = (ab, r)
+                    }
+                    C0 = xa[3]; C1 = xa[6]; C2 = xa[8];
+                }
+                {
+                    double o0 = C0 + xb[2], o1 = C1 + xb[5], o2 = C2 + xb[7];
+                    if (wb0 & RW0_HOLDF) { K0 = o0; K1 = o1; K2 = o2; }
+                    if (wb0 & RW0_ADDF) { o0 += K0; o1 += K1; o2 += K2; }
+                    if (wb0 & RW0_EMITR) {
+                        sts64(ebase + (wb1 & 0xffu) * 8u, o0);
+                        sts64(ebase + ((wb1 >> 8) & 0xffu) * 8u, o1);
+                        sts64(ebase + ((wb1 >> 16) & 0xffu) * 8u, o2);
+                        sts64(img_a + (wb2 & 0xffffu) * 8u, o0);
+                    }
+                    if (two) { C0 = xb[3]; C1 = xb[6]; C2 = xb[8]; }
+                }
             }
-            if (HASF) {
-                Fab = fma(T.F[0 + z2], gf, Fab);
-                if (w0 & RW0_FLAGA) Fa = fma(T.F[1 + z2], gf, Fa);
-                if (w0 & RW0_FLAGB) Fb = fma(T.F[2 + z2], gf, Fb);
+            if (h4 != 0xffffffffu) {
+                sts64(ebase + (h1 & 0xffu) * 8u, Sa);
+                sts64(ebase + ((h1 >> 8) & 0xffu) * 8u, Sb);
+                sts64(ebase + ((h1 >> 16) & 0xffu) * 8u, Sab);
+                sts64(img_a + (h2 & 0xffffu) * 8u, Vab);
+                sts64(img_a + (h2 >> 16) * 8u, Sa);      // (a, ab) = (ab, a)
+                sts64(img_a + (h3 & 0xffffu) * 8u, Vab);  // (b, a) = (a, b)
+                sts64(img_a + (h3 >> 16) * 8u, Sb);      // (b, ab) = (ab, b)
+                double2* sc = reinterpret_cast<double2*>(p.scratch + ((size_t)(cur.sl0 + sl) * 32 + lane) * 4);
+                double2 d0v, d1v;
+                d0v.x = Da; d0v.y = Db; d1v.x = Fa; d1v.y = Fb;
+                sc[0] = d0v; sc[1] = d1v;
+                if (HASF) { if (p.accumulate) p.rhs[h4] += Fab; else p.rhs[h4] = Fab; }
             }
-            if (eloc) sts64(ebase + (w1 >> 24) * 8u, E(9));
-            double o0 = C0 + E(2), o1 = C1 + E(5), o2 = C2 + E(7), o3 = C3 + E(14);
-            if (w0 & RW0_HOLDF) { K0 = o0; K1 = o1; K2 = o2; K3 = o3; }   // step 0 of a closed ring: C is zero, o = this tet's part
-            if (w0 & RW0_ADDF) { o0 += K0; o1 += K1; o2 += K2; o3 += K3; }
-            if (w0 & RW0_EMITR) {
-                sts64(ebase + (w1 & 0xffu) * 8u, o0);
-                sts64(ebase + ((w1 >> 8) & 0xffu) * 8u, o1);
-                sts64(ebase + ((w1 >> 16) & 0xffu) * 8u, o2);
-                sts64(img_a + (w2 & 0xffffu) * 8u, o3);
-            }
-            C0 = E(3); C1 = E(6); C2 = E(8); C3 = E(15);
         }
-        if (h4 != 0xffffffffu) {
-            sts64(ebase + (h1 & 0xffu) * 8u, Sa);
-            sts64(ebase + ((h1 >> 8) & 0xffu) * 8u, Sb);
-            sts64(ebase + ((h1 >> 16) & 0xffu) * 8u, Sab);
-            sts64(img_a + (h2 & 0xffffu) * 8u, Vab);
-            sts64(img_a + (h2 >> 16) * 8u, Va4);
-            sts64(img_a + (h3 & 0xffffu) * 8u, Vba);
-            sts64(img_a + (h3 >> 16) * 8u, Vb4);
-            double2* sc = reinterpret_cast<double2*>(p.scratch + ((size_t)s * 32 + lane) * 4);
-            double2 d0, d1;
-            d0.x = Da; d0.y = Db; d1.x = Fa; d1.y = Fb;
-            sc[0] = d0; sc[1] = d1;
-            if (HASF) { if (p.accumulate) p.rhs[h4] += Fab; else p.rhs[h4] = Fab; }
-        }
-    }
-    __syncthreads();
+        cp_async_wait<0>();   // B of this cluster and the ids of the next one
+        __syncthreads();
+        if (more) issue_A(nxt);   // coefficient planes, step words and headers are free; the copies fly during the copy-out
+        cp_async_commit();
 
-    // ---- 3. copy-out: complete edge rows (one row per warp step, lanes <-> entries), then the vertex-row entries
-    {
-        const double* img = reinterpret_cast<const double*>(smraw + (size_t)plane * PARTS);
-        const int d0 = p.dptr[c], d1 = p.dptr[c + 1];
-        for (int d = d0 + warp; d < d1; d += nwarps) {
-            const RingRowDesc R = p.desc[d];
-            double* dst = p.val + R.p0;
-            const double* src = img + R.off;
-            for (int k = lane; k < (int)R.len; k += 32) {
-                if (p.accumulate) dst[k] += src[k]; else dst[k] = src[k];
+        // ---- copy-out: complete edge rows (8 lanes per row, 4 rows per warp pass; rows of up to 32 entries without a loop), then
+        //      the vertex-row entries.  [A plain k-loop per row was 23 % of all instructions of the kernel, profiles/r02b_rings.md.]
+        {
+            const int sub = lane >> 3, l8 = lane & 7;
+            for (int d = warp * 4 + sub; d < cur.nd; d += nwarps * 4) {
+                const RingRowDesc R = sdesc[d];
+                double* dst = p.val + R.p0 + l8;
+                const unsigned sa = img_a + ((unsigned)R.off + (unsigned)l8) * 8u;
+                const int rem = (int)R.len - l8;   // entries l8, l8+8, ... < len
+                double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+                if (rem > 0) v0 = lds64(sa);
+                if (rem > 8) v1 = lds64(sa + 64);
+                if (rem > 16) v2 = lds64(sa + 128);
+                if (rem > 24) v3 = lds64(sa + 192);
+                if (p.accumulate) {
+                    if (rem > 0) dst[0] += v0;
+                    if (rem > 8) dst[8] += v1;
+                    if (rem > 16) dst[16] += v2;
+                    if (rem > 24) dst[24] += v3;
+                    for (int k = 32; k < rem; k += 8) dst[k] += lds64(sa + k * 8);
+                } else {
+                    if (rem > 0) dst[0] = v0;
+                    if (rem > 8) dst[8] = v1;
+                    if (rem > 16) dst[16] = v2;
+                    if (rem > 24) dst[24] = v3;
+                    for (int k = 32; k < rem; k += 8) dst[k] = lds64(sa + k * 8);
+                }
+            }
+            const double* vsrc = img + cur.vim0;
+            double* vdst = p.val + cur.xbase;
+            if (p.accumulate) { for (int k = threadIdx.x; k < cur.nx; k += blockDim.x) vdst[sxpos[k]] += vsrc[k]; }
+            else {
+#pragma unroll 4
+                for (int k = threadIdx.x; k < cur.nx; k += blockDim.x) vdst[sxpos[k]] = vsrc[k];
             }
         }
-        const int x0 = p.xptr[c], nx = p.xptr[c + 1] - x0;
-        const double* vsrc = img + p.vimg[2 * c];
-        double* vdst = p.val + p.xbase[c];
-        for (int k = threadIdx.x; k < nx; k += blockDim.x) {
-            const unsigned off = __ldg(p.xpos + x0 + k);
-            if (p.accumulate) vdst[off] += vsrc[k]; else vdst[off] = vsrc[k];
-        }
+        __syncthreads();   // image, descriptors and offsets are free
+        if (more) issue_B(nxt);
+        cp_async_commit();
+        cur = nxt;
+        nxt = nn;
     }
     if (chk != chk) *p.status = 1;  // benign race: every writer stores the same value
 }
@@ -267,8 +403,7 @@ int upload(afb_ctx* ctx, DevBuf& b, const std::vector<T>& v) {
 }
 
 size_t rings_smem(const afb_ctx* ctx, int parts) {
-    const size_t plane = (((size_t)ctx->rg_gcap + 8) & ~(size_t)7) * 16;
-    return plane * parts + (size_t)ctx->rg_imgcap * 8 + 16;
+    return ring_smem_bytes(ctx->rg_gcap, ctx->rg_imgcap, ctx->rg_stepcap, ctx->rg_edges, ctx->rg_xcap, parts);
 }
 
 }  // namespace
@@ -310,14 +445,13 @@ int build_ring_plan(afb_ctx* ctx) {
     in.old2new = old2new.data();
     in.nthreads = (int)std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
     if (const char* tv = getenv("AFB_PLAN_THREADS")) in.nthreads = std::max(1, atoi(tv));
-    // two clusters per SM: image + staged records <= ~110 KB
-    int ec = 256;
-    if (const char* ev = getenv("AFB_RING_EDGES")) ec = std::max(32, atoi(ev));
+    // one warp per slice of 32 edges; several clusters resident per SM (about 72 KB of shared memory each at 128 edges)
+    int ec = 128;
+    if (const char* ev = getenv("AFB_RING_EDGES")) ec = std::max(32, std::min(256, atoi(ev) / 32 * 32));
     RingPlan pl;
-    for (int attempt = 0; attempt < 3; ++attempt, ec /= 2) {
+    for (int attempt = 0; attempt < 3 && ec >= 32; ++attempt, ec /= 2) {
         in.edges_per_cluster = ec;
-        in.max_staged = 1400;
-        in.max_image_doubles = (220 * 1024 - 64 * (in.max_staged + 8)) / 8;
+        in.max_smem_bytes = 227 * 1024;
         ring_plan_build(in, pl);
         if (pl.ok) break;
         if (pl.why.find("cluster") == std::string::npos) break;   // not a size problem: smaller clusters will not help
@@ -327,18 +461,12 @@ int build_ring_plan(afb_ctx* ctx) {
         return 0;
     }
     int rc = 0;
-    rc = rc ? rc : upload(ctx, ctx->rg_cs, pl.cs);
-    rc = rc ? rc : upload(ctx, ctx->rg_eptr, pl.eptr);
+    rc = rc ? rc : upload(ctx, ctx->rg_cinfo, pl.cinfo);
     rc = rc ? rc : upload(ctx, ctx->rg_elist, pl.elist);
-    rc = rc ? rc : upload(ctx, ctx->rg_sptr, pl.sptr);
     rc = rc ? rc : upload(ctx, ctx->rg_hdr, pl.hdr);
     rc = rc ? rc : upload(ctx, ctx->rg_steps, pl.steps);
-    rc = rc ? rc : upload(ctx, ctx->rg_dptr, pl.dptr);
     rc = rc ? rc : upload(ctx, ctx->rg_desc, pl.desc);
-    rc = rc ? rc : upload(ctx, ctx->rg_vimg, pl.vimg);
-    rc = rc ? rc : upload(ctx, ctx->rg_xptr, pl.xptr);
     rc = rc ? rc : upload(ctx, ctx->rg_xpos, pl.xpos);
-    rc = rc ? rc : upload(ctx, ctx->rg_xbase, pl.xbase);
     rc = rc ? rc : upload(ctx, ctx->rg_vptr, pl.vptr);
     rc = rc ? rc : upload(ctx, ctx->rg_vlist, pl.vlist);
     rc = rc ? rc : upload(ctx, ctx->rg_vdpos, pl.vdpos);
@@ -350,7 +478,9 @@ int build_ring_plan(afb_ctx* ctx) {
     AFB_CUDA(ctx, cudaStreamSynchronize(st));
     ctx->rg_ncl = pl.ncl; ctx->rg_nslices = pl.nslices; ctx->rg_nsteps = pl.nsteps; ctx->rg_nvert = pl.nvert;
     ctx->rg_gcap = pl.gcap; ctx->rg_imgcap = pl.imgcap; ctx->rg_nz = (long long)pl.zlist.size();
+    ctx->rg_stepcap = pl.stepcap; ctx->rg_xcap = pl.xcap; ctx->rg_edges = pl.edges_per_cluster;
     ctx->rg_maxrow = pl.cl_maxrow;
+    ctx->rg_cinfo_host.assign(reinterpret_cast<const unsigned char*>(pl.cinfo.data()), reinterpret_cast<const unsigned char*>(pl.cinfo.data() + pl.cinfo.size()));
     ctx->rg_vrow_host = pl.vrow;
     if (rings_smem(ctx, 4) > 227 * 1024) return 0;
     ctx->has_ring_plan = true;
@@ -359,7 +489,19 @@ int build_ring_plan(afb_ctx* ctx) {
                         "gcap %d, image <= %d doubles, %zu B shared per CTA, %lld unproduced entries\n",
                 pl.nedges, pl.ncl, pl.edges_per_cluster, pl.nslices, pl.nsteps, 100.0 * (6.0 * ntet + pl.nedges) / (32.0 * std::max<long long>(1, pl.nsteps)),
                 pl.nstaged, (double)pl.nstaged / ntet, pl.gcap, pl.imgcap, rings_smem(ctx, 4), ctx->rg_nz);
+    if (getenv("AFB_VERBOSE")) fprintf(stderr, "[afb] ring plan: %d steps and %d vertex-row entries per cluster at most\n", pl.stepcap, pl.xcap);
     return 0;
+}
+
+int ensure_ring_plan(afb_ctx* ctx) {
+    if (ctx->ring_plan_tried || ctx->is_sub) return 0;
+    ctx->ring_plan_tried = true;
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = build_ring_plan(ctx);
+    if (!rc && ctx->has_ring_plan && ctx->priority_row >= 0) rc = rings_priority_build(ctx, ctx->priority_row);
+    ctx->ring_plan_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (getenv("AFB_VERBOSE")) fprintf(stderr, "[afb] ring plan build: %.1f ms (%s)\n", ctx->ring_plan_ms, ctx->has_ring_plan ? "in use" : "not applicable");
+    return rc;
 }
 
 // clusters that write to a row >= first_priority_row go first (phased assembly, afb_assemble_phase)
@@ -370,7 +512,10 @@ int rings_priority_build(afb_ctx* ctx, long long first_priority_row) {
     for (long long c = 0; c < ctx->rg_ncl; ++c) ((long long)ctx->rg_maxrow[c] >= first_priority_row ? first : rest).push_back((int)c);
     ctx->rg_nprio = (long long)first.size();
     first.insert(first.end(), rest.begin(), rest.end());
-    const int rc = upload(ctx, ctx->rg_clist, first);
+    const RingCluster* all = reinterpret_cast<const RingCluster*>(ctx->rg_cinfo_host.data());
+    std::vector<RingCluster> perm(first.size());
+    for (size_t k = 0; k < first.size(); ++k) perm[k] = all[first[k]];
+    const int rc = upload(ctx, ctx->rg_clist, perm);
     if (rc) return rc;
     AFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     // vertex rows are numbered in ascending row order: the priority vertices are a suffix
@@ -398,17 +543,17 @@ int launch_rings(afb_ctx* ctx, const double* TG, const double* Tm, const double*
     }
     if (Tf) { Tp->F[0] = Tf[4]; Tp->F[1] = Tf[0]; Tp->F[2] = Tf[1]; }
     RingArgs p;
-    p.gcap = ctx->rg_gcap; p.zero = 0; p.clist = nullptr;
-    p.cs = ctx->rg_cs.as<int>(); p.eptr = ctx->rg_eptr.as<int>(); p.elist = ctx->rg_elist.as<unsigned>();
-    p.sptr = ctx->rg_sptr.as<long long>(); p.hdr = ctx->rg_hdr.as<unsigned>(); p.steps = ctx->rg_steps.as<unsigned>();
-    p.dptr = ctx->rg_dptr.as<int>(); p.desc = ctx->rg_desc.as<RingRowDesc>(); p.vimg = ctx->rg_vimg.as<int>();
-    p.xptr = ctx->rg_xptr.as<int>(); p.xpos = ctx->rg_xpos.as<unsigned>(); p.xbase = ctx->rg_xbase.as<long long>();
+    p.gcap = ctx->rg_gcap; p.zero = 0;
+    p.imgcap = ctx->rg_imgcap; p.stepcap = ctx->rg_stepcap; p.slicecap = (ctx->rg_edges + 31) / 32; p.edgecap = ctx->rg_edges; p.xcap = ctx->rg_xcap;
+    p.cinfo = ctx->rg_cinfo.as<RingCluster>();
+    p.elist = ctx->rg_elist.as<unsigned>(); p.hdr = ctx->rg_hdr.as<unsigned>(); p.steps = ctx->rg_steps.as<unsigned>();
+    p.desc = ctx->rg_desc.as<RingRowDesc>(); p.xpos = ctx->rg_xpos.as<unsigned>();
     p.gbuf = gbuf; p.val = val; p.rhs = rhs; p.scratch = ctx->rg_scratch.as<double>();
     p.accumulate = accumulate; p.drop = drop_val; p.status = status;
     long long nblocks = ctx->rg_ncl, v0 = 0, v1 = ctx->rg_nvert;
     if (phase != 0 && ctx->rg_prio_valid) {
         nblocks = phase == 1 ? ctx->rg_nprio : ctx->rg_ncl - ctx->rg_nprio;
-        p.clist = ctx->rg_clist.as<int>() + (phase == 1 ? 0 : ctx->rg_nprio);
+        p.cinfo = ctx->rg_clist.as<RingCluster>() + (phase == 1 ? 0 : ctx->rg_nprio);   // records permuted: priority clusters first
         if (phase == 1) v0 = ctx->rg_vsplit; else v1 = ctx->rg_vsplit;
     } else if (phase == 2) { nblocks = 0; v1 = 0; }
     cudaStream_t st = ctx->stream;
@@ -419,16 +564,40 @@ int launch_rings(afb_ctx* ctx, const double* TG, const double* Tm, const double*
     const bool hasm = Tm != nullptr, hasf = Tf != nullptr && rhs != nullptr;
     const size_t smem = rings_smem(ctx, (hasm || hasf) ? 4 : 3);
     if (nblocks > 0) {
-#define LAUNCH(M, F)                                                                                                         \
+        const int nthreads = 32 * std::max(1, (ctx->rg_edges + 31) / 32);   // one warp per slice
+        p.ncl = nblocks;
+        // persistent CTAs: as many as fit on the device (shared memory bound), each walks clusters blockIdx, blockIdx + grid, ...
+        int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(227 * 1024) / (smem + 1024)));
+        if (const char* pv = getenv("AFB_RING_CTAS")) per_sm = std::max(1, atoi(pv));
+        const unsigned grid = (unsigned)std::min<long long>(nblocks, 148LL * per_sm);
+        const bool dropf = drop_val > 1e-100;
+        // sparse instantiation: every table value outside the P2 stiffness mask must vanish (to rounding of the table builder)
+        bool sparse = !getenv("AFB_RING_DENSE");
+        {
+            double mx = 0.0;
+            for (int k = 0; k < RT_N; ++k) for (int q = 0; q < 6; ++q) mx = std::max(mx, std::fabs(Tp->A[k][q]));
+            const unsigned mask[RT_N] = {0x15, 0x29, 0x24, 0x18, 0x3d, 0x30, 0x0c, 0x0c, 0x30, 0x3c, 0x01, 0, 0, 0, 0, 0, 0x15, 0x29};
+            const bool used[RT_N] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0, 1, 1};
+            for (int k = 0; k < RT_N; ++k)
+                for (int q = 0; q < 6; ++q)
+                    if (used[k] && !((mask[k] >> q) & 1u) && std::fabs(Tp->A[k][q]) > 1e-13 * mx) sparse = false;
+        }
+#define LAUNCH(M, F, D, S)                                                                                                   \
     do {                                                                                                                     \
-        cudaError_t e = cudaFuncSetAttribute(k_rings<M, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+        cudaError_t e = cudaFuncSetAttribute(k_rings<M, F, D, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
         if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaFuncSetAttribute(k_rings)");                                     \
-        k_rings<M, F><<<(unsigned)nblocks, 256, smem, st>>>(*Tp, p);                                                         \
+        k_rings<M, F, D, S><<<grid, nthreads, smem, st>>>(*Tp, p);                                                           \
     } while (0)
-        if (hasm && hasf) LAUNCH(true, true);
-        else if (hasm) LAUNCH(true, false);
-        else if (hasf) LAUNCH(false, true);
-        else LAUNCH(false, false);
+#define LAUNCH_D(M, F)                                                                      \
+    do {                                                                                    \
+        if (dropf) { if (sparse) LAUNCH(M, F, true, true); else LAUNCH(M, F, true, false); } \
+        else { if (sparse) LAUNCH(M, F, false, true); else LAUNCH(M, F, false, false); }     \
+    } while (0)
+        if (hasm && hasf) LAUNCH_D(true, true);
+        else if (hasm) LAUNCH_D(true, false);
+        else if (hasf) LAUNCH_D(false, true);
+        else LAUNCH_D(false, false);
+#undef LAUNCH_D
 #undef LAUNCH
         ctx->launches++;
         cudaError_t e = cudaGetLastError();

@@ -82,13 +82,19 @@ __global__ void __launch_bounds__(256) k_geom(long long ntet, GeomParams gp, con
                                               const int32_t* __restrict__ v2, const int32_t* __restrict__ v3, double* __restrict__ gbuf,
                                               const unsigned* __restrict__ old2new /* NULL or the Morton id of every element */) {
     // records are built in shared memory and leave the CTA as 16-byte pieces, `parts` consecutive lanes per record: full
-    // sectors per store instruction even though the records scatter (Morton order)
+    // sectors per store instruction even though the records scatter (Morton order).
+    // 64-byte records (SWZ): two records per 128-byte row, the 8-byte slot of component k XOR-ed with the row number, so that
+    // the 32 lanes writing component k of their records hit 16 different bank pairs (natural layout: stride 64 bytes = 8-way
+    // conflicts on every store, the LSU pipe was 97 % busy; profiles/r02b_rings.md)
     extern __shared__ double srec[];                       // [256][ngpad]
     __shared__ long long sdst[256];
     const long long e0 = blockIdx.x * (long long)blockDim.x;
     const long long e = e0 + threadIdx.x;
     const bool valid = e < ntet;
-    double* g = srec + (size_t)threadIdx.x * gp.ngpad;
+    const bool swz = gp.ngpad == 8;
+    const int swf = swz ? ((threadIdx.x >> 1) & 7) : 0;
+    double* g = swz ? srec + (size_t)(threadIdx.x >> 1) * 16 + ((threadIdx.x & 1) << 3) : srec + (size_t)threadIdx.x * gp.ngpad;
+#define GG(idx) g[(idx) ^ swf]
     if (valid) {
     sdst[threadIdx.x] = old2new ? (long long)old2new[e] : e;
     const int nn[4] = {__ldg(v0 + e), __ldg(v1 + e), __ldg(v2 + e), __ldg(v3 + e)};
@@ -96,14 +102,14 @@ __global__ void __launch_bounds__(256) k_geom(long long ntet, GeomParams gp, con
 #pragma unroll
     for (int k = 0; k < 4; ++k) { P[k][0] = __ldg(x + nn[k]); P[k][1] = __ldg(y + nn[k]); P[k][2] = __ldg(z + nn[k]); }
     const double vol = fabs(jac_inv(P, PSI)) * (1.0 / 6.0);
-    if (gp.ngpad > gp.ngtot) g[gp.ngtot] = 0.0;
-    if (gp.zero_all) for (int k = 0; k < gp.ngpad; ++k) g[k] = 0.0;
+    if (gp.ngpad > gp.ngtot) GG(gp.ngtot) = 0.0;
+    if (gp.zero_all) for (int k = 0; k < gp.ngpad; ++k) GG(k) = 0.0;
     for (int f = 0; f < gp.nforms; ++f) {
         const TFormDev& F = gp.f[f];
         const double* D = F.D;
         if (F.layout == AFB_COEF_PER_TET) D += (size_t)F.dstride * e;
         const double s = vol * F.alpha;
-        double* o = g + F.goff;
+        const int ob = F.goff;
         if (F.kind == 0) {
             if (F.full) {
                 double K[9];
@@ -120,45 +126,54 @@ __global__ void __launch_bounds__(256) k_geom(long long ntet, GeomParams gp, con
                 for (int a = 0; a < 3; ++a)
 #pragma unroll
                     for (int b = 0; b < 3; ++b) M[a][b] = s * (PSI[a] * R[0][b] + PSI[a + 3] * R[1][b] + PSI[a + 6] * R[2][b]);
-                if (F.ng == 6) { o[0] = M[0][0]; o[1] = M[1][1]; o[2] = M[2][2]; o[3] = M[0][1]; o[4] = M[0][2]; o[5] = M[1][2]; }
+                if (F.ng == 6) { GG(ob + (0)) = M[0][0]; GG(ob + (1)) = M[1][1]; GG(ob + (2)) = M[2][2]; GG(ob + (3)) = M[0][1]; GG(ob + (4)) = M[0][2]; GG(ob + (5)) = M[1][2]; }
                 else {
 #pragma unroll
                     for (int a = 0; a < 3; ++a)
 #pragma unroll
-                        for (int b = 0; b < 3; ++b) o[3 * a + b] = M[a][b];
+                        for (int b = 0; b < 3; ++b) GG(ob + (3 * a + b)) = M[a][b];
                 }
             } else {
                 const double c = s * coef_value(D, F.kidx[0]);
                 // M = c * PSI PSI^T (rows a of the inverse Jacobian dotted)
-                o[0] = c * (PSI[0] * PSI[0] + PSI[3] * PSI[3] + PSI[6] * PSI[6]);
-                o[1] = c * (PSI[1] * PSI[1] + PSI[4] * PSI[4] + PSI[7] * PSI[7]);
-                o[2] = c * (PSI[2] * PSI[2] + PSI[5] * PSI[5] + PSI[8] * PSI[8]);
-                o[3] = c * (PSI[0] * PSI[1] + PSI[3] * PSI[4] + PSI[6] * PSI[7]);
-                o[4] = c * (PSI[0] * PSI[2] + PSI[3] * PSI[5] + PSI[6] * PSI[8]);
-                o[5] = c * (PSI[1] * PSI[2] + PSI[4] * PSI[5] + PSI[7] * PSI[8]);
+                GG(ob + (0)) = c * (PSI[0] * PSI[0] + PSI[3] * PSI[3] + PSI[6] * PSI[6]);
+                GG(ob + (1)) = c * (PSI[1] * PSI[1] + PSI[4] * PSI[4] + PSI[7] * PSI[7]);
+                GG(ob + (2)) = c * (PSI[2] * PSI[2] + PSI[5] * PSI[5] + PSI[8] * PSI[8]);
+                GG(ob + (3)) = c * (PSI[0] * PSI[1] + PSI[3] * PSI[4] + PSI[6] * PSI[7]);
+                GG(ob + (4)) = c * (PSI[0] * PSI[2] + PSI[3] * PSI[5] + PSI[6] * PSI[8]);
+                GG(ob + (5)) = c * (PSI[1] * PSI[2] + PSI[4] * PSI[5] + PSI[7] * PSI[8]);
             }
             if (F.bary) {
                 // M = G restricted to the vertices 1..3 (reference gradients d/dxi_a = grad l_a, a = 1..3); the barycentric gradients
                 // sum to zero, so G_0b = -(M_1b + M_2b + M_3b).  Record order of the ring kernel: (G01,G23), (G02,G13), (G03,G12)
-                const double m00 = o[0], m11 = o[1], m22 = o[2], m01 = o[3], m02 = o[4], m12 = o[5];
-                o[0] = -(m00 + m01 + m02); o[1] = m12;
-                o[2] = -(m01 + m11 + m12); o[3] = m02;
-                o[4] = -(m02 + m12 + m22); o[5] = m01;
+                const double m00 = GG(ob + (0)), m11 = GG(ob + (1)), m22 = GG(ob + (2)), m01 = GG(ob + (3)), m02 = GG(ob + (4)), m12 = GG(ob + (5));
+                GG(ob + (0)) = -(m00 + m01 + m02); GG(ob + (1)) = m12;
+                GG(ob + (2)) = -(m01 + m11 + m12); GG(ob + (3)) = m02;
+                GG(ob + (4)) = -(m02 + m12 + m22); GG(ob + (5)) = m01;
             }
         } else if (F.kind == 1) {
-            o[0] = s * coef_value(D, F.kidx[0]);
+            GG(ob + (0)) = s * coef_value(D, F.kidx[0]);
         } else {
-            // kind 2: K(0,l) = k_l -> o[b] = s sum_l k_l PSI[b+3l];  kind 3: K(k,0) = k_k -> o[a] = s sum_k PSI[a+3k] k_k
+            // kind 2: K(0,l) = k_l -> GG(ob + (b)) = s sum_l k_l PSI[b+3l];  kind 3: K(k,0) = k_k -> GG(ob + (a)) = s sum_k PSI[a+3k] k_k
             const double k0 = coef_value(D, F.kidx[0]), k1 = coef_value(D, F.kidx[1]), k2 = coef_value(D, F.kidx[2]);
 #pragma unroll
-            for (int a = 0; a < 3; ++a) o[a] = s * (PSI[a] * k0 + PSI[a + 3] * k1 + PSI[a + 6] * k2);
+            for (int a = 0; a < 3; ++a) GG(ob + (a)) = s * (PSI[a] * k0 + PSI[a + 3] * k1 + PSI[a + 6] * k2);
         }
     }
     }  // valid
+#undef GG
     __syncthreads();
     const int parts = gp.ngpad >> 1;
     const int nrec = (int)min((long long)blockDim.x, ntet - e0);
     const double2* src = reinterpret_cast<const double2*>(srec);
+    if (swz) {
+        for (int q = threadIdx.x; q < nrec * 4; q += blockDim.x) {
+            const int rec = q >> 2, part = q & 3, f = (rec >> 1) & 7;
+            double2 d = src[(size_t)(rec >> 1) * 8 + ((rec & 1) << 2) + (part ^ (f >> 1))];
+            if (f & 1) { const double t = d.x; d.x = d.y; d.y = t; }
+            reinterpret_cast<double2*>(gbuf + sdst[rec] * 8)[part] = d;
+        }
+    } else
     for (int q = threadIdx.x; q < nrec * parts; q += blockDim.x) {
         const int rec = q / parts, part = q - rec * parts;
         reinterpret_cast<double2*>(gbuf + sdst[rec] * gp.ngpad)[part] = src[q];
@@ -524,14 +539,28 @@ int fused_group(afb_ctx* ctx, afb_ctx* plan, const std::vector<SForm>& mat, cons
             else ++nother;
         }
         const bool load_ok = nfF == 0 || (nfF == 1 && rhsf[0].kind == 1 && rhsf[0].ng == 1 && rhsf[0].nfb == 10 && rhsf[0].row_off == 0);
-        if (plan == ctx && !p0_override && !tix && !rtab && !rdst && dval && is >= 0 && nother == 0 && load_ok && (nfF == 0 || drhs) &&
-            rings_supports(ctx, 1, im >= 0 ? 1 : 0, nfF)) {
+        const bool eligible = plan == ctx && !p0_override && !tix && !rtab && !rdst && dval && is >= 0 && nother == 0 && load_ok && (nfF == 0 || drhs) &&
+                              !getenv("AFB_DISABLE_RING_KERNEL");
+        if (eligible) { const int rce = ensure_ring_plan(ctx); if (rce) return rce; }
+        if (eligible && rings_supports(ctx, 1, im >= 0 ? 1 : 0, nfF)) {
             std::vector<double> TM, TG(600), Tm, Tf;
             build_form_table(mat[is], TM);
             ring_table_from_M(TM.data(), 10, TG.data());
-            if (ring_table_symmetry_defect(TG.data()) < 1e-12) {
-                if (im >= 0) build_form_table(mat[im], Tm);
-                if (nfF) build_form_table(rhsf[0], Tf);
+            if (im >= 0) build_form_table(mat[im], Tm);
+            if (nfF) build_form_table(rhsf[0], Tf);
+            // the kernel relies on two symmetries of the tables: invariance under vertex relabelling (one frame for every ring tet)
+            // and T[q][i][j] == T[q][j][i] (entries (a,ab) / (ab,a) etc. are evaluated once)
+            double asym = 0.0, tmax = 0.0;
+            for (int q = 0; q < 6; ++q)
+                for (int i = 0; i < 10; ++i)
+                    for (int j = 0; j < 10; ++j) {
+                        asym = std::max(asym, std::fabs(TG[(q * 10 + i) * 10 + j] - TG[(q * 10 + j) * 10 + i]));
+                        tmax = std::max(tmax, std::fabs(TG[(q * 10 + i) * 10 + j]));
+                    }
+            if (im >= 0)
+                for (int i = 0; i < 10; ++i)
+                    for (int j = 0; j < 10; ++j) asym = std::max(asym, std::fabs(Tm[i * 10 + j] - Tm[j * 10 + i]) * (tmax > 0 ? 1.0 : 0.0));
+            if (ring_table_symmetry_defect(TG.data()) < 1e-12 && asym <= 1e-13 * tmax) {
                 GeomParams gr;
                 std::memset(&gr, 0, sizeof(gr));
                 gr.ngpad = 8; gr.ngtot = 8; gr.zero_all = 1;

@@ -38,7 +38,7 @@ struct Problem {
     std::vector<unsigned> old2new;
 };
 
-static void build_problem(int nx, int ny, int nz, unsigned seed, bool scramble, Problem& P) {
+static void build_problem(int nx, int ny, int nz, unsigned seed, bool scramble, Problem& P, bool superset = false) {
     std::mt19937 rng(seed);
     const int NX = nx + 1, NY = ny + 1, NZ = nz + 1;
     P.nv = (long long)NX * NY * NZ;
@@ -95,6 +95,9 @@ static void build_problem(int nx, int ny, int nz, unsigned seed, bool scramble, 
             const long long e = t / 10;
             for (int j = 0; j < 10; ++j) cols.push_back(P.e2r[(size_t)j * P.ntet + e] - 1);
             P.radj.push_back(t);
+        }
+        if (superset && r % 5 == 0) {   // columns no local element contributes to (what the union pattern of a partitioned mesh contains)
+            cols.push_back((int32_t)((r * 7 + 3) % P.nrows)); cols.push_back((int32_t)((r * 13 + 1) % P.nrows)); cols.push_back((int32_t)(P.nrows - 1 - r % 3));
         }
         std::sort(cols.begin(), cols.end());
         cols.erase(std::unique(cols.begin(), cols.end()), cols.end());
@@ -163,12 +166,15 @@ static void emulate(const RingPlan& pl, const std::vector<double>& TG, const std
     if (!accumulate) for (long long z : pl.zlist) val[z] = 0.0;
     for (long long c = 0; c < pl.ncl; ++c) {
         std::vector<double> img(pl.vimg[2 * c + 1], SENT);
+        if (pl.cinfo[c].pad & 1) for (int k = 0; k < pl.vimg[2 * c]; ++k) img[k] = 0.0;
         const unsigned* el = pl.elist.data() + pl.eptr[c];
         for (int s = pl.cs[c]; s < pl.cs[c + 1]; ++s) {
             const long long st0 = pl.sptr[s], st1 = pl.sptr[s + 1];
             for (int lane = 0; lane < 32; ++lane) {
                 const unsigned* H = pl.hdr.data() + (size_t)s * RING_HW * 32 + lane;
-                const unsigned h0 = H[0], h1 = H[32], h2 = H[64], h3 = H[96], h4 = H[128];
+                const unsigned h0 = H[0], h1 = H[32], h2 = H[64], h3 = H[96], h4 = H[128], h5 = H[160];
+                if ((long long)(h5 & 0xffff) != st0 - pl.sptr[pl.cs[c]] || (long long)(h5 >> 16) != st1 - st0) { std::printf("slice header word 5 wrong\n"); std::exit(2); }
+                if (pl.cinfo[c].sl0 != pl.cs[c] || pl.cinfo[c].e0 != pl.eptr[c] || pl.cinfo[c].stc0 != pl.sptr[pl.cs[c]] || pl.cinfo[c].x0 != pl.xptr[c] || pl.cinfo[c].vim0 != pl.vimg[2 * c]) { std::printf("cluster record wrong\n"); std::exit(2); }
                 if (h4 == 0xffffffffu) continue;
                 const int ebase = h0 & 0xffff;
                 double Sa = 0, Sb = 0, Sab = 0, Vab = 0, Va4 = 0, Vba = 0, Vb4 = 0, Da = 0, Db = 0, Fab = 0, Fa = 0, Fb = 0;
@@ -224,7 +230,7 @@ static void emulate(const RingPlan& pl, const std::vector<double>& TG, const std
                 if (accumulate) val[R.p0 + k] += x; else val[R.p0 + k] = x;
             }
         }
-        for (int k = pl.xptr[c]; k < pl.xptr[c + 1]; ++k) {
+        for (int k = pl.xptr[c]; k < pl.xptr[c] + (pl.vimg[2 * c + 1] - pl.vimg[2 * c]); ++k) {
             const double x = img[pl.vimg[2 * c] + (k - pl.xptr[c])];
             if (x == SENT) { std::printf("vertex-row entry never written\n"); std::exit(2); }
             const long long p = pl.xbase[c] + pl.xpos[k];
@@ -238,9 +244,9 @@ static void emulate(const RingPlan& pl, const std::vector<double>& TG, const std
     }
 }
 
-static int run_case(int nx, int ny, int nz, unsigned seed, bool scramble, int EC, int nthreads, double drop, bool accumulate) {
+static int run_case(int nx, int ny, int nz, unsigned seed, bool scramble, int EC, int nthreads, double drop, bool accumulate, bool superset = false) {
     Problem P;
-    build_problem(nx, ny, nz, seed, scramble, P);
+    build_problem(nx, ny, nz, seed, scramble, P, superset);
     std::vector<double> TG, Tm, Tf;
     build_tables(2, TG, Tm, Tf);
     const double defect = ring_table_symmetry_defect(TG.data());
@@ -272,7 +278,7 @@ static int run_case(int nx, int ny, int nz, unsigned seed, bool scramble, int EC
     for (int d = 0; d < 4; ++d) in.v[d] = P.v[d].data();
     in.e2r = P.e2r.data(); in.rowptr = P.rowptr.data(); in.radj_ptr = P.radj_ptr.data(); in.radj = P.radj.data(); in.pos = P.pos.data();
     in.old2new = P.old2new.data(); in.edges_per_cluster = EC; in.nthreads = nthreads;
-    in.max_image_doubles = 60000; in.max_staged = 4000;
+    in.max_smem_bytes = 1 << 30;
     RingPlan pl;
     const auto t0 = std::chrono::steady_clock::now();
     ring_plan_build(in, pl);
@@ -307,6 +313,8 @@ int main(int argc, char** argv) {
     fails += run_case(5, 4, 3, 4, true, 256, 4, 0.0, true);
     fails += run_case(1, 1, 1, 5, true, 32, 1, 0.0, false);
     fails += run_case(6, 6, 6, 6, false, 256, 4, 0.0, false);
+    fails += run_case(5, 4, 4, 8, true, 64, 2, 0.0, false, true);    // superset pattern
+    fails += run_case(4, 4, 3, 9, false, 128, 2, 0.0, true, true);   // superset pattern, accumulate
     std::printf(fails ? "test_ring_plan: %d FAILED\n" : "test_ring_plan: all passed\n", fails);
     return fails ? 1 : 0;
 }

@@ -108,8 +108,9 @@ def test_accumulate_and_determinism(pkg, ctx, asm_oracle):
     # matrix only / rhs only (AssembleMatrix / AssembleRHS)
     c = np.zeros(nnz)
     assert ctx.assemble(forms, [], c, None) == 0 and np.array_equal(c, a)
+    # the load alone is assembled by the row gather, together with the matrix by the ring kernel: the same sums in another order
     fc = np.zeros(nrows)
-    assert ctx.assemble([], rhsf, None, fc) == 0 and np.array_equal(fc, fa)
+    assert ctx.assemble([], rhsf, None, fc) == 0 and np.abs(fc - fa).max() <= 1e-14 * np.abs(fa).max()
 
 
 def test_nan_status(pkg, ctx, asm_oracle):

@@ -114,18 +114,18 @@ def test_rings_phased_assembly(pkg, asm_oracle):
     ctx = pkg.Context(0, torch.cuda.current_stream().cuda_stream)
     ctx.mesh_cube(6, 5, 5)
     ctx.dofmap_natural([(gc.P2, 1)])
-    os.environ["AFB_RING_EDGES"] = "64"
-    try:
-        nnz = ctx.pattern_build()
-    finally:
-        os.environ.pop("AFB_RING_EDGES")
+    nnz = ctx.pattern_build()
     co, te = ctx.mesh_get()
     rng = np.random.default_rng(3)
     _, forms, rhsf, prob = _forms(pkg, M, te, rng)
     nrows = ctx.dofmap_info()[3]
     ref_v = torch.zeros(nnz, dtype=torch.float64, device="cuda")
     ref_r = torch.zeros(nrows, dtype=torch.float64, device="cuda")
-    assert ctx.assemble(forms, rhsf, ref_v, ref_r) == 0
+    os.environ["AFB_RING_EDGES"] = "64"   # the plan is built by the first assembly that uses it
+    try:
+        assert ctx.assemble(forms, rhsf, ref_v, ref_r) == 0
+    finally:
+        os.environ.pop("AFB_RING_EDGES")
     assert ctx.last_times()["gather_kernel"] == "k_rings"
     for first in (nrows - 37, nrows // 2, 5):
         ctx.priority_rows_set(first)
@@ -175,3 +175,39 @@ def test_rings_properties_at_scale(pkg, asm_oracle):
     assert (np.abs(val - v2) / np.repeat(rowmax, np.diff(rowptr))).max() <= RTOL
     assert np.abs(rhs - r2).max() <= RTOL * np.abs(r2).max()
     ctx.close()
+
+
+def test_rings_superset_pattern(pkg, ctx, asm_oracle):
+    """a user pattern with columns no local element contributes to (what the union pattern of a partitioned mesh looks like,
+    afb_pattern_set): those entries come out as zeros, with accumulate they stay untouched"""
+    M = asm_oracle
+    co, te, dm = _mesh(pkg, ctx, M, (5, 4, 3), [(gc.P2, 1)], jitter=0.05, seed=4)
+    rng = np.random.default_rng(4)
+    _, forms, rhsf, prob = _forms(pkg, M, te, rng)
+    rp, ci, v, r, st = M.assemble(prob, co, te, dm)
+    nrows = rp.size - 1
+    rows = np.repeat(np.arange(nrows), np.diff(rp))
+    extra_r = rng.integers(0, nrows, 4000)
+    extra_c = rng.integers(0, nrows, 4000)
+    key = np.unique(np.concatenate([rows * nrows + ci.astype(np.int64), extra_r * nrows + extra_c]))
+    rp2 = np.zeros(nrows + 1, dtype=np.int64)
+    np.add.at(rp2, key // nrows + 1, 1)
+    rp2 = np.cumsum(rp2)
+    ci2 = (key % nrows).astype(np.int32)
+    exp = np.zeros(key.size)
+    exp[np.searchsorted(key, rows * nrows + ci.astype(np.int64))] = v
+    ctx.pattern_build()
+    ctx.pattern_set(rp2, ci2)
+    os.environ["AFB_RING_EDGES"] = "64"
+    try:
+        val, rhs = np.full(key.size, np.nan), np.full(nrows, np.nan)
+        assert ctx.assemble(forms, rhsf, val, rhs) == 0
+    finally:
+        os.environ.pop("AFB_RING_EDGES")
+    assert ctx.last_times()["gather_kernel"] == "k_rings"
+    scale = np.abs(v).max()
+    assert np.abs(val - exp).max() <= RTOL * scale and np.abs(rhs - r).max() <= RTOL * np.abs(r).max()
+    assert (val[exp == 0] == 0).all()
+    val2 = np.full(key.size, 0.25)
+    assert ctx.assemble(forms, [], val2, None, accumulate=True) == 0
+    assert np.abs(val2 - 0.25 - exp).max() <= RTOL * scale and (val2[exp == 0] == 0.25).all()
