@@ -14,8 +14,9 @@
 //   ANITYPE      InitElemIndex[et] + g + iodf * NumElem[et]              (global_enumerator.cpp:823-825)
 //   MINIBLOCKS   InitElemIndex[et] + g * nd[et] + iodf                   (the layout the inverse map decodes, :866-871)
 // with ns = dofs of the scalar base space per entity, ndim = components, off[..] = number of dofs whose tuple precedes the group
-// in the lexicographic order of the arrangement, iodf = position among all dofs on the entity (variables in order, component
-// fastest inside a vector variable, :727-731), nd[et] = dofs per entity over all variables.
+// in the lexicographic order of the arrangement, iodf = position among all dofs on the entity = GetElemDofId (variables in order,
+// inside a vector variable component-major: c * ns + k, global_enumerator.h:76, .cpp:262-274; pinned against the reference's
+// own SimpleEnumerator compiled on oracle/mock_inmost), nd[et] = dofs per entity over all variables.
 // Entity ids (our stand-in for INMOST GlobalIDs, as in afb_dofmap_natural): nodes by id, edges and faces in lexicographic order of
 // their sorted node tuples, cells by id.  Local order on the tet: variable, component, 4 vertices, 6 edges (01,02,03,12,13,23;
 // the two dofs of a P3 edge ordered by the node ids, tetdofmap.inl:98-104), 4 faces (012,123,230,301), cell (fem_space.h:27-69).
@@ -125,8 +126,8 @@ inline DofEnumeration enumerate_dofs(ASSEMBLING_TYPE type, int64_t nnode, int64_
         switch (type) {
             case NATURAL: case BYELEMTYPE: return off[((size_t)v * 3 + c) * 4 + d] + g * ns + k;
             case DIMUNION: case ETDIMBLOCKS: return off2[(size_t)v * 4 + d] + (g * ns + k) * ndim + c;
-            case ANITYPE: return init[d] + g + (shift[(size_t)v * 4 + d] + (int64_t)k * ndim + c) * nent[d];
-            default: return init[d] + g * nd[d] + shift[(size_t)v * 4 + d] + (int64_t)k * ndim + c;   // MINIBLOCKS
+            case ANITYPE: return init[d] + g + (shift[(size_t)v * 4 + d] + (int64_t)c * ns + k) * nent[d];
+            default: return init[d] + g * nd[d] + shift[(size_t)v * 4 + d] + (int64_t)c * ns + k;   // MINIBLOCKS
         }
     };
     // ---- elem -> dof

@@ -215,7 +215,7 @@ class Numbering:
                     grp_off[(v, cc, d)] = off.clone()
                 off = off + size
         # SimpleEnumerator (global_enumerator.cpp:671-700,818-835): InitElemIndex per entity type, position of a dof among all
-        # dofs of its entity (variables in order, component fastest)
+        # dofs of its entity (GetElemDofId: variables in order, component-major inside a vector variable)
         init = torch.zeros((nd_types + 1, self.world), dtype=torch.int64)
         for d in range(nd_types):
             init[d + 1] = init[d] + num[d] * ndof_ent[d]
@@ -235,9 +235,9 @@ class Numbering:
             elif dim_last:
                 loc = grp_off[(v, c, d)].to(dev)[ow] + (pos * ns + k) * vec + c
             elif enum_type == "ANITYPE":
-                loc = init[d].to(dev)[ow] + pos + (shift[(v, d)] + k * vec + c) * num[d].to(dev)[ow]
+                loc = init[d].to(dev)[ow] + pos + (shift[(v, d)] + c * ns + k) * num[d].to(dev)[ow]
             else:   # MINIBLOCKS: the layout the reference's inverse map decodes (:866-871)
-                loc = init[d].to(dev)[ow] + pos * ndof_ent[d] + shift[(v, d)] + k * vec + c
+                loc = init[d].to(dev)[ow] + pos * ndof_ent[d] + shift[(v, d)] + c * ns + k
             return beg_ind_dev[ow] + loc
         # ---- element -> global dof (local order: variable, component, 4 vertices, 6 edges)
         cols = []

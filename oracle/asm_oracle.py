@@ -222,7 +222,10 @@ class DofMap:
                         shift[(v, d)] = o
                         o += NDOF[fem][d] * vec
                 vecs = np.array([vec for _, vec in self.vars])
-                iodf = np.array([shift[(int(a), int(b))] for a, b in recs[:, [0, 2]]]) + recs[:, 4] * vecs[recs[:, 0]] + recs[:, 1]
+                # position of a dof among all dofs of its entity = GetElemDofId (global_enumerator.h:76, .cpp:262-274): variables in
+                # order, inside a vector variable component-major (dim_dof_shift = nd * dim_id, then the dof of the component)
+                ns_rec = np.array([NDOF[self.vars[int(a)][0]][int(b)] for a, b in recs[:, [0, 2]]])
+                iodf = np.array([shift[(int(a), int(b))] for a, b in recs[:, [0, 2]]]) + recs[:, 1] * ns_rec + recs[:, 4]
                 d = recs[:, 2]
                 if enum_type == "ANITYPE":
                     loc = init[d] + recs[:, 3] + iodf * np.array(cnt)[d]
@@ -292,7 +295,8 @@ def enumerate_dofs(tets, variables, enum_type="NATURAL", nnode=None):
     elif enum_type in ("ANITYPE", "MINIBLOCKS"):
         i_nd = [sum(NDOF[fem][d] * vec for fem, vec in variables) for d in range(4)]    # dofs per entity of dimension d
         init = np.concatenate([[0], np.cumsum([i_nd[d] * nent[d] for d in range(4)])])
-        # iodf: variables in order; inside a vector variable dof k, component c -> k * vec + c
+        # iodf = GetElemDofId (global_enumerator.h:76, .cpp:262-274): variables in order; inside a vector variable component c,
+        # dof k of the component -> c * nd + k (dim_dof_shift = nd * dim_id)
         shift = {}
         for d in range(4):
             o = 0
@@ -300,7 +304,8 @@ def enumerate_dofs(tets, variables, enum_type="NATURAL", nnode=None):
                 shift[(v, d)] = o
                 o += NDOF[fem][d] * vec
         vecs = np.array([vec for _, vec in variables])
-        iodf = np.array([shift[(int(r[0]), int(r[2]))] for r in recs[:, :3]]) + recs[:, 4] * vecs[recs[:, 0]] + recs[:, 1]
+        ns_rec = np.array([NDOF[variables[int(r[0])][0]][int(r[2])] for r in recs[:, :3]])
+        iodf = np.array([shift[(int(r[0]), int(r[2]))] for r in recs[:, :3]]) + recs[:, 1] * ns_rec + recs[:, 4]
         d = recs[:, 2]
         if enum_type == "ANITYPE":
             ids = init[d] + recs[:, 3] + iodf * np.array(nent)[d]

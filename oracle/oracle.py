@@ -256,3 +256,91 @@ def ref_assemble_csr(problem, coords, tets, codes, row_begin, rowptr, colind, va
     if rc not in (0, -1):
         raise RuntimeError("ref_assemble_csr failed rc=%d: %s" % (rc, L.ref_last_error().decode()))
     return rc
+
+
+# ---- the reference's own global assembler on the mock INMOST (oracle/ref_asm_driver.cpp, oracle/mock_inmost/inmost.h) ----------
+_refasm = None
+
+
+def have_refasm():
+    return os.path.exists(os.path.join(HERE, "_ref", "libanifem_refasm.so"))
+
+
+def refasm():
+    global _refasm
+    if _refasm is None:
+        L = ctypes.CDLL(os.path.join(HERE, "_ref", "libanifem_refasm.so"))
+        L.ref_last_error.restype = ctypes.c_char_p
+        L.refasm_setup.restype = ctypes.c_int
+        L.refasm_setup.argtypes = [ctypes.c_int, ctypes.c_int, _ip, _ip, ctypes.c_long, _dp, ctypes.c_long, _lp, _lp, _lp, _lp]
+        L.refasm_template.restype = ctypes.c_long
+        L.refasm_assemble.restype = ctypes.c_int
+        L.refasm_assemble.argtypes = [ctypes.c_int, ctypes.POINTER(_RefForm), ctypes.c_double, ctypes.c_int, _lp, _lp]
+        L.refasm_get.argtypes = [_lp, _ip, _dp, _dp]
+        _refasm = L
+    return _refasm
+
+
+def _ref_forms(problem):
+    forms, keep = [], []
+    for fm in problem.mat_forms:
+        fa, va = problem.vars[fm["trial"]]
+        fb, vb = problem.vars[fm["test"]]
+        D = None if fm.get("D") is None else np.ascontiguousarray(fm["D"], dtype=np.float64)
+        keep.append(D)
+        forms.append(_RefForm(fm["opA"], fa, va, fm["opB"], fb, vb, fm["order"], fm["ttype"], fm["layout"], 0, _P(D),
+                              fm.get("alpha", 1.0), problem.var_off[fm["test"]], problem.var_off[fm["trial"]]))
+    for fm in problem.rhs_forms:
+        fb, vb = problem.vars[fm["test"]]
+        D = None if fm.get("D") is None else np.ascontiguousarray(fm["D"], dtype=np.float64)
+        keep.append(D)
+        forms.append(_RefForm(IDEN, P0, 1, fm["opB"], fb, vb, fm["order"], fm["ttype"], fm["layout"], 1, _P(D),
+                              fm.get("alpha", 1.0), problem.var_off[fm["test"]], 0))
+    return (_RefForm * max(1, len(forms)))(*forms), len(forms), keep
+
+
+class RefAssembler:
+    """The reference's Ani::Assembler (unmodified inmost_interface sources) on a tetrahedral mesh held by the mock INMOST:
+    numbering of a GlobEnumeration type, index codes of fill_assemble_templates, AssembleTemplate, Assemble."""
+
+    ENUM = ("ANITYPE", "MINIBLOCKS", "NATURAL", "DIMUNION", "BYELEMTYPE", "ETDIMBLOCKS")   # global_enumerator.h:393-401
+
+    def __init__(self, coords, tets, variables, enum_type="NATURAL"):
+        L = refasm()
+        coords = np.ascontiguousarray(coords, dtype=np.float64)
+        tets = np.ascontiguousarray(tets, dtype=np.int64)
+        nv = len(variables)
+        fem = (ctypes.c_int * nv)(*[int(v[0]) for v in variables])
+        vec = (ctypes.c_int * nv)(*[int(v[1]) for v in variables])
+        nloc = sum(op_dims(IDEN, f, v)[0] for f, v in variables)
+        self.codesC = np.zeros((tets.shape[0], nloc), dtype=np.int64)
+        self.codesR = np.zeros((tets.shape[0], nloc), dtype=np.int64)
+        nrows = ctypes.c_long()
+        rc = L.refasm_setup(self.ENUM.index(enum_type), nv, fem, vec, coords.shape[0], _P(coords), tets.shape[0], tets.ctypes.data_as(_lp),
+                            ctypes.byref(nrows), self.codesC.ctypes.data_as(_lp), self.codesR.ctypes.data_as(_lp))
+        if rc != nloc:
+            raise RuntimeError("refasm_setup failed rc=%d: %s" % (rc, L.ref_last_error().decode()))
+        self.nrows, self.nloc = nrows.value, nloc
+
+    def _get(self, nnz, with_rhs):
+        rowptr = np.zeros(self.nrows + 1, dtype=np.int64)
+        colind = np.zeros(nnz, dtype=np.int32)
+        val = np.zeros(nnz)
+        rhs = np.zeros(self.nrows) if with_rhs else None
+        refasm().refasm_get(rowptr.ctypes.data_as(_lp), colind.ctypes.data_as(_ip), _P(val), _P(rhs))
+        return rowptr, colind, val, rhs
+
+    def template(self):
+        nnz = refasm().refasm_template()
+        if nnz < 0:
+            raise RuntimeError("AssembleTemplate failed: %s" % refasm().ref_last_error().decode())
+        return self._get(nnz, False)[:2]
+
+    def assemble(self, problem, drop_val=1e-100, include_template=False, ordered_insert=False):
+        """Assemble(matrix, rhs, opts): returns (status, rowptr, colind, val, rhs) with the rows sorted by column"""
+        arr, n, keep = _ref_forms(problem)
+        nnz = ctypes.c_long()
+        st = refasm().refasm_assemble(n, arr, drop_val, (1 if include_template else 0) | (2 if ordered_insert else 0), None, ctypes.byref(nnz))
+        if st not in (0, -1):
+            raise RuntimeError("Assemble failed rc=%d: %s" % (st, refasm().ref_last_error().decode()))
+        return (st,) + self._get(nnz.value, True)

@@ -1,9 +1,12 @@
 """CPU tests (no GPU): the oracle restatement against the reference's own known-answer tables, the
 committed reference outputs, and -- when it was built here -- the reference itself."""
+import os
+
 import numpy as np
 import pytest
 
 import golden_cases as gc
+from conftest import ROOT
 
 TET = np.array([[0, 0, 0], [2, 1, 1], [1, 2, 1], [2, 1, 2]], float)[:, None, :]  # (4,1,3)
 
@@ -181,3 +184,102 @@ def test_identity_tensor_incompatible_dims(oracle):
     form = (gc.GRAD, gc.P1, 1, gc.IDEN, gc.P1, 1, 2, gc.T_NULL, gc.L_CONST)
     with pytest.raises(RuntimeError):
         oracle.fem3dtet(form, TET, None)
+
+
+# ---- assembler level: oracle/asm_oracle.py pinned to the reference's OWN Assembler -------------------------------------------
+# (unmodified anifem++/inmost_interface/{assembler.inl, global_enumerator.cpp, ordering.inl, elemental_assembler.cpp} compiled on
+# oracle/mock_inmost/inmost.h by `make -C oracle refasm`; its outputs for the cases of tests/asm_cases.py are committed as
+# tests/golden/ref_assembler.npz by tests/golden/make_golden_asm.py)
+import asm_cases  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def ref_asm_golden():
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "ref_assembler.npz")))
+
+
+def _multi_dof_entities(M, variables):
+    nd = np.zeros(4, dtype=int)
+    for fem, vec in variables:
+        nd += np.array(M.NDOF[fem]) * vec
+    return (nd > 1).any()
+
+
+@pytest.mark.parametrize("live", [False, True])
+def test_numbering_vs_reference_enumerators(asm_oracle, oracle, ref_asm_golden, live):
+    """all six GlobEnumeration types (global_enumerator.cpp:562-605, 671-777, 818-835) + fill_assemble_templates
+    (assembler.inl:139-184): index codes bit-exact on a cube and on a mesh with scrambled node ids / element order.
+    MINIBLOCKS: the reference's forward formula (:826) is not a bijection once an entity carries more than one dof (two strides are
+    mixed) -- asserted here; the oracle and the product follow the layout its inverse map decodes (:866-871) in that case."""
+    M = asm_oracle
+    if live and not oracle.have_refasm():
+        pytest.skip("oracle/_ref/libanifem_refasm.so not built (reference tree absent)")
+    for name, co, te, variables in asm_cases.numbering_cases(M):
+        for et in M.ENUM_TYPES:
+            if live:
+                R = oracle.RefAssembler(co, te, variables, et)
+                codes, nrows = R.codesC, R.nrows
+            else:
+                codes, nrows = ref_asm_golden["num/%s/%s/codes" % (name, et)], int(ref_asm_golden["num/%s/%s/nrows" % (name, et)][0])
+            exp, n = M.enumerate_dofs(te, variables, et, co.shape[0])
+            assert n == nrows, (name, et)
+            ref = np.abs(codes) - 1
+            if et == "MINIBLOCKS" and _multi_dof_entities(M, variables):
+                assert np.unique(ref).size < nrows, "the reference's MINIBLOCKS forward map became a bijection: re-pin"
+                continue
+            assert np.array_equal(ref, exp), (name, et)
+            assert (codes > 0).all()   # Lagrange spaces: no oriented dofs, all signs +
+            assert np.array_equal(M.DofMap(te, variables, nnode=co.shape[0], enum_type=et).elem2dof, exp)
+
+
+@pytest.mark.parametrize("live", [False, True])
+def test_assembly_vs_reference_assembler(asm_oracle, oracle, ref_asm_golden, live):
+    """AssembleTemplate (assembler.inl:589-695): pattern bit-exact.  Assemble (:313-488) in its default mode (unsorted rows,
+    find-or-append, drop_val decides what enters the pattern) and in the is_mtx_include_template + use_ordered_insert mode
+    (:428-438): values / rhs within 1e-13 of the row scale; the default-mode pattern is the subset of the template whose
+    omitted entries are exactly the ones every cell dropped."""
+    M = asm_oracle
+    if live and not oracle.have_refasm():
+        pytest.skip("oracle/_ref/libanifem_refasm.so not built (reference tree absent)")
+    for name, co, te, variables, prob, kw in asm_cases.assembly_cases(M, oracle):
+        dm = M.DofMap(te, variables, nnode=co.shape[0])
+        drop = kw.get("drop_val", 1e-100)
+        rp, ci, v, r, st = M.assemble(prob, co, te, dm, drop_val=drop)
+        nrows = rp.size - 1
+        key = np.repeat(np.arange(nrows), np.diff(rp)) * nrows + ci
+        R = oracle.RefAssembler(co, te, variables, "NATURAL") if live else None
+        trp, tci = R.template() if live else (ref_asm_golden["asm/%s/template_rowptr" % name], ref_asm_golden["asm/%s/template_colind" % name])
+        assert np.array_equal(trp, rp) and np.array_equal(tci, ci), name + ": template pattern"
+        for mode, opts in (("plain", {}), ("templ", dict(include_template=True, ordered_insert=True))):
+            if live:
+                st2, rp2, ci2, v2, r2 = R.assemble(prob, drop_val=drop, **opts)
+            else:
+                g = lambda k: ref_asm_golden["asm/%s/%s/%s" % (name, mode, k)]
+                st2, rp2, ci2, v2, r2 = int(g("status")[0]), g("rowptr"), g("colind"), g("val"), g("rhs")
+            assert st2 == st == 0
+            key2 = np.repeat(np.arange(nrows), np.diff(rp2)) * nrows + ci2
+            assert np.isin(key2, key).all(), name + ": reference entry outside the template"
+            if mode == "templ":
+                assert np.array_equal(key2, key)
+            pos = np.searchsorted(key, key2)
+            rowmax = np.repeat(np.maximum.reduceat(np.abs(v), rp[:-1]), np.diff(rp))
+            assert (np.abs(v[pos] - v2) <= 1e-13 * rowmax[pos]).all(), name
+            miss = np.ones(key.size, bool)
+            miss[pos] = False
+            assert (v[miss] == 0).all(), name + ": an entry the reference never inserted is non-zero in the oracle"
+            assert np.abs(r - r2).max() <= 1e-13 * max(np.abs(r).max(), 1e-300)
+
+
+def test_reference_assembler_status_codes(asm_oracle, oracle):
+    """non-finite local value -> -1 (assembler.inl:419-424, 475-479), same as the oracle"""
+    if not oracle.have_refasm():
+        pytest.skip("oracle/_ref/libanifem_refasm.so not built (reference tree absent)")
+    M = asm_oracle
+    co, te, _ = M.cube_mesh(2, 2, 1)
+    variables = [(gc.P1, 1)]
+    K = np.ones((te.shape[0], 1))
+    K[3, 0] = np.nan
+    prob = M.Problem(variables, [dict(trial=0, test=0, opA=gc.GRAD, opB=gc.GRAD, order=2, ttype=gc.T_SCALAR, layout=gc.L_PER_TET, D=K)], [])
+    R = oracle.RefAssembler(co, te, variables, "NATURAL")
+    assert R.assemble(prob)[0] == -1
+    assert M.assemble(prob, co, te, M.DofMap(te, variables, nnode=co.shape[0]))[4] == -1
