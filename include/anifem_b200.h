@@ -170,6 +170,16 @@ int afb_pattern_set(afb_ctx* ctx, const int64_t* rowptr /*nrows+1*/, const int32
 int afb_assemble(afb_ctx* ctx, int nforms, const afb_form* forms, int nrhs_forms, const afb_form* rhs_forms,
                  double* csr_val, double* rhs, int accumulate, double drop_val, int mem_space);
 
+/* The element-evaluator plug-in point of the reference (MatFuncWrap, inmost_interface/func_wrap.h:96-187, installed with
+ * AssemblerT::SetMatFunc / SetRHSFunc / SetMatRHSFunc, assembler.h:326-328): the caller evaluates the local matrices itself (a
+ * host lambda per cell, e.g. examples/tutorials/ex1.cpp:83-106) and hands them over for the cells [e_lo, e_lo + nel) of the
+ * context's mesh: A_elem = nel matrices in the reference's layout m_A[j*nRows + i] (column-major nrow_loc x ncol_loc,
+ * assembler.inl:417), F_elem = nel local right-hand sides; either may be NULL; elem_space says where they live.  The
+ * contributions are ADDED into csr_val / rhs (mem_space) with the scatter rule of assembler.inl:397-481 (|A| > drop_val, signs
+ * of the index codes; essential conditions are whatever the lambda did with applyDir).  Returns 0 / -1 like afb_assemble. */
+int afb_assemble_elemental(afb_ctx* ctx, int64_t e_lo, int64_t nel, const double* A_elem, const double* F_elem, int elem_space,
+                           double* csr_val, double* rhs, double drop_val, int mem_space);
+
 /* Essential (Dirichlet) boundary conditions = applyDir(A, F, k, bc) on every Dirichlet dof of every cell, as the reference's local
  * assemblers do (fem/operations/dc_on_dof.h:27-45; examples/tutorials/ex1.cpp:96-105).  is_dirichlet[ncols_global] (0/1) and
  * value[ncols_global] are indexed by the global dof; NULL clears.  Every following afb_assemble then returns constrained rows:

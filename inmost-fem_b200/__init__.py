@@ -43,7 +43,7 @@ EXPORTS = ["afb_ctx_create", "afb_ctx_destroy", "afb_last_error", "afb_sync", "a
            "afb_pattern_build", "afb_pattern_get", "afb_pattern_set", "afb_assemble", "afb_halo_add", "afb_last_times",
            "afb_dirichlet_set", "afb_fem3dapply_batched", "afb_eval_quadrature", "afb_priority_rows_set", "afb_assemble_phase",
            "afb_fields_set", "afb_fem3dface_batched", "afb_tri_quadrature",
-           "afb_boundary_set", "afb_assemble_faces"]
+           "afb_boundary_set", "afb_assemble_faces", "afb_assemble_elemental"]
 
 
 def build(verbose=False):
@@ -98,6 +98,7 @@ def lib():
         L.afb_pattern_get.argtypes = [vp, vp, vp, ci]
         L.afb_assemble.argtypes = [vp, ci, ctypes.POINTER(AfbForm), ci, ctypes.POINTER(AfbForm), vp, vp, ci, cd, ci]
         L.afb_last_times.argtypes = [vp, _dp]
+        L.afb_assemble_elemental.argtypes = [vp, c64, c64, vp, vp, ci, vp, vp, cd, ci]
         L.afb_dirichlet_set.argtypes = [vp, vp, vp, ci]
         L.afb_priority_rows_set.argtypes = [vp, c64]
         L.afb_assemble_phase.argtypes = [vp, ci, ctypes.POINTER(AfbForm), ci, ctypes.POINTER(AfbForm), vp, vp, cd, ci]
@@ -417,6 +418,18 @@ class Context:
             assert sv == sr
         return self._ck(lib().afb_assemble(self._h, len(forms), fa, len(rhs_forms), fr, pv, pr, 1 if accumulate else 0,
                                            drop_val, space), allow=(-1,))
+
+    def assemble_elemental(self, e_lo, A_elem, F_elem, val=None, rhs=None, drop_val=1e-100):
+        """afb_assemble_elemental: adds caller-evaluated local matrices A_elem (nel, ncol_loc, nrow_loc) = the reference's
+        column-major m_A per cell, and local right-hand sides F_elem (nel, nrow_loc), of the cells e_lo.. into val / rhs"""
+        nel = (A_elem if A_elem is not None else F_elem).shape[0]
+        pa, sa = _ptr(A_elem)
+        pf, sf = _ptr(F_elem)
+        pv, sv = _ptr(val)
+        pr, sr = _ptr(rhs)
+        espace = sa if A_elem is not None else sf
+        space = sv if val is not None else sr
+        return self._ck(lib().afb_assemble_elemental(self._h, int(e_lo), int(nel), pa, pf, espace, pv, pr, drop_val, space), allow=(-1,))
 
     def boundary_set(self, face_tet, face_num):
         """boundary faces carrying surface terms: face face_num[b] of element face_tet[b] (numpy int arrays)"""

@@ -107,6 +107,15 @@ cudaError_t launch_g(afb_ctx* c, const double* sA, const double* sF, double* val
 }  // namespace
 
 namespace {
+// A_in[e][j][i] (column-major nrl x ncl per element, the reference's m_A[j*nRows + i]) -> A_out[e][i][j]
+__global__ void k_elem_transpose(long long nel, int nrl, int ncl, const double* __restrict__ in, double* __restrict__ out) {
+    const long long n = nel * nrl * ncl;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const long long e = t / (nrl * ncl);
+        const int k = (int)(t - e * nrl * ncl), i = k / ncl, j = k - i * ncl;
+        out[t] = in[e * nrl * ncl + (long long)j * nrl + i];
+    }
+}
 __global__ void k_axpy(long long n, const double* __restrict__ x, double* __restrict__ y) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] += x[i];
 }
@@ -403,6 +412,72 @@ static int assemble_impl(afb_ctx* ctx, int nforms, const afb_form* forms, int nr
     if (bad) set_error(ctx, "not a number in local matrix or rhs");
     if (phase_req == 1) { ctx->phase_done = true; ctx->phase_status = status; }   // everything was done in phase 1
     return status;
+}
+
+// Scatter of element matrices the CALLER evaluated (the MatFuncWrap plug-in point: a host lambda per cell, func_wrap.h:96-187,
+// installed with AssemblerT::SetMatRHSFunc, assembler.h:326-328): A_elem holds, for the cells [e_lo, e_lo + nel) of the context's
+// mesh, the local matrices in the reference's layout m_A[j*nRows + i] (column-major nrow_loc x ncol_loc, assembler.inl:417),
+// F_elem the local right-hand sides.  They are ADDED into csr_val / rhs with the reference's rule (|A| > drop_val, signs of the
+// index codes, non-finite value -> -1); the kernels are the row gather of the generic path.
+int afb_assemble_elemental(afb_ctx* ctx, int64_t e_lo, int64_t nel, const double* A_elem, const double* F_elem, int elem_space,
+                           double* csr_val, double* rhs, double drop_val, int mem_space) {
+    if (!ctx) return -7;
+    if (!ctx->has_dofmap) { set_error(ctx, "Description of fem expression is empty (no dof map)"); return -6; }
+    if (!ctx->has_pattern) { set_error(ctx, "pattern was not built (afb_pattern_build)"); return -6; }
+    if (e_lo < 0 || nel < 0 || e_lo + nel > ctx->ntet || (!A_elem && !F_elem) || (A_elem && !csr_val) || (F_elem && !rhs)) {
+        set_error(ctx, "afb_assemble_elemental: bad arguments");
+        return -7;
+    }
+    if (nel == 0) return 0;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) { set_error(ctx, "no CUDA device (the library has no CPU fallback)"); return -4; }
+    cudaStream_t st = ctx->stream;
+    const int nrl = ctx->nrow_loc, ncl = ctx->ncol_loc;
+    const long long nrows = ctx->row_end - ctx->row_begin;
+    const cudaMemcpyKind kin = elem_space == AFB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    double *sA = nullptr, *sF = nullptr;
+    if (A_elem) {
+        const size_t n = (size_t)nel * nrl * ncl;
+        AFB_CUDA(ctx, ctx->tmp2.reserve(n * sizeof(double)));
+        AFB_CUDA(ctx, ctx->stageA.reserve(n * sizeof(double)));
+        AFB_CUDA(ctx, cudaMemcpyAsync(ctx->tmp2.p, A_elem, n * sizeof(double), kin, st));
+        sA = ctx->stageA.as<double>();
+        // column-major (reference) -> row-major staging of the gather
+        k_elem_transpose<<<(unsigned)std::max<long long>(1, std::min<long long>(((long long)n + 255) / 256, 148LL * 32)), 256, 0, st>>>(
+            (long long)nel, nrl, ncl, ctx->tmp2.as<double>(), sA);
+        ctx->launches++;
+    }
+    if (F_elem) {
+        const size_t n = (size_t)nel * nrl;
+        AFB_CUDA(ctx, ctx->stageF.reserve(n * sizeof(double)));
+        AFB_CUDA(ctx, cudaMemcpyAsync(ctx->stageF.p, F_elem, n * sizeof(double), kin, st));
+        sF = ctx->stageF.as<double>();
+    }
+    double *dval = csr_val, *drhs = rhs;
+    if (mem_space == AFB_HOST) {
+        if (sA) {
+            AFB_CUDA(ctx, ctx->io_val.reserve(std::max<long long>(1, ctx->nnz) * sizeof(double)));
+            dval = ctx->io_val.as<double>();
+            AFB_CUDA(ctx, cudaMemcpyAsync(dval, csr_val, ctx->nnz * sizeof(double), cudaMemcpyHostToDevice, st));
+        }
+        if (sF) {
+            AFB_CUDA(ctx, ctx->io_rhs.reserve(std::max<long long>(1, nrows) * sizeof(double)));
+            drhs = ctx->io_rhs.as<double>();
+            AFB_CUDA(ctx, cudaMemcpyAsync(drhs, rhs, nrows * sizeof(double), cudaMemcpyHostToDevice, st));
+        }
+    }
+    AFB_CUDA(ctx, ctx->flag.reserve(64));
+    AFB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p, 0, 64, st));
+    const int rc = launch_gather(ctx, sA, sF, sA ? dval : nullptr, sF ? drhs : nullptr, 1, drop_val, ctx->flag.as<int>(), e_lo, e_lo + nel);
+    if (rc) return rc;
+    if (mem_space == AFB_HOST) {
+        if (sA) AFB_CUDA(ctx, cudaMemcpyAsync(csr_val, dval, ctx->nnz * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (sF) AFB_CUDA(ctx, cudaMemcpyAsync(rhs, drhs, nrows * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    int bad = 0;
+    AFB_CUDA(ctx, cudaMemcpyAsync(&bad, ctx->flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    AFB_CUDA(ctx, cudaStreamSynchronize(st));
+    if (bad) set_error(ctx, "not a number in local matrix or rhs");
+    return bad ? -1 : 0;
 }
 
 int afb_last_times(afb_ctx* ctx, double* ms4) {

@@ -25,18 +25,23 @@
 #include <algorithm>
 #include <vector>
 
+#include <thread>
+
 #include "enumerator.hpp"
 #include "fem.hpp"
+#include "func_wrap.hpp"
 
 namespace Ani {
 
 /// assembler.h:210-231
 struct AssmOpts {
+    void* user_data = nullptr;       ///< handed to the data gatherer / local evaluator of the MatFuncWrap path
     double drop_val = 1e-100;
     bool is_mtx_sorted = true;
     bool is_mtx_include_template = true;
     bool use_ordered_insert = true;
     AssmOpts& SetDropVal(double v) { drop_val = v; return *this; }
+    AssmOpts& SetUserData(void* p) { user_data = p; return *this; }
 };
 
 /// stand-in for INMOST::Sparse::Matrix over [BegInd, EndInd): sorted CSR
@@ -52,6 +57,15 @@ struct FemVarDescr { int fem; int vec; };
 
 class Assembler {
 public:
+    /// assembler.h:297-302
+    struct AssembleMode {
+        bool reorder_nodes = true;
+        bool prepare_edges = true;
+        bool prepare_faces = true;
+        int num_threads = -1;   ///< host threads evaluating the local assembler of the MatFuncWrap path; < 0 = all cores
+    };
+    AssembleMode m_assm_traits;
+
     explicit Assembler(int device = 0) {
         if (afb_ctx_create(device, nullptr, &m_ctx) != 0) throw std::runtime_error(std::string("anifem_b200: ") + afb_last_error(nullptr));
     }
@@ -89,6 +103,17 @@ public:
         for (int k = 0; k < v; ++k) o += b200_detail::base_nf(m_vars[k].fem) * m_vars[k].vec;
         return o;
     }
+    /// The element-evaluator plug-in point of the reference (assembler.h:326-328, func_wrap.h:310-347): a host callback per cell.
+    /// Compatibility path: the callback runs on host threads, the scatter on the GPU (afb_assemble_elemental).
+    Assembler& SetMatFunc(MatFuncWrapDynamic<> f) { mat_func = std::make_shared<MatFuncWrapDynamic<>>(std::move(f)); return *this; }
+    Assembler& SetRHSFunc(MatFuncWrapDynamic<> f) { rhs_func = std::make_shared<MatFuncWrapDynamic<>>(std::move(f)); return *this; }
+    Assembler& SetMatRHSFunc(MatFuncWrapDynamic<> f) { mat_rhs_func = std::make_shared<MatFuncWrapDynamic<>>(std::move(f)); return *this; }
+    /// assembler.h:324: the handler that gathers per-cell data and calls p.compute(args, user_data); default = ex1.cpp:108-118
+    /// without the label lookup: args = the four vertices, user_data = AssmOpts::user_data
+    Assembler& SetDataGatherer(std::function<void(ElementalAssembler&)> h) { m_prob_handler = std::move(h); return *this; }
+    std::shared_ptr<MatFuncWrap<>> mat_func, rhs_func, mat_rhs_func;
+    std::function<void(ElementalAssembler&)> m_prob_handler;
+
     /// one fem3Dtet<OpA,OpB> term of the local matrix; D in the user-callback layout (col-major Dim(OpB) x Dim(OpA))
     template <typename OpA, typename OpB>
     Assembler& AddMatForm(int trial_var, int test_var, int order, TensorType ttype, int coef_layout, const double* D, double alpha = 1.0,
@@ -182,6 +207,7 @@ public:
     }
     /// assembler.inl:313-488. matrix <- matrix + assembled, rhs <- rhs + assembled. Returns 0, or -1 on NaN/Inf.
     int Assemble(CsrMatrix& matrix, std::vector<double>& rhs, const AssmOpts& opts = AssmOpts()) {
+        if (mat_rhs_func || (mat_func && rhs_func)) { prepare_outputs(&matrix, &rhs); return assemble_elemental(&matrix, &rhs, opts); }
         if (m_forms.empty() && m_rhs.empty()) throw std::runtime_error("System local evaluator is not specified");
         prepare_outputs(&matrix, &rhs);
         const int st = ck(afb_assemble(m_ctx, (int)m_forms.size(), m_forms.data(), (int)m_rhs.size(), m_rhs.data(), matrix.val.data(), rhs.data(), 1,
@@ -189,12 +215,14 @@ public:
         return std::min(st, faces(matrix.val.data(), rhs.data(), opts));
     }
     int AssembleMatrix(CsrMatrix& matrix, const AssmOpts& opts = AssmOpts()) {
+        if (mat_func || mat_rhs_func) { prepare_outputs(&matrix, nullptr); return assemble_elemental(&matrix, nullptr, opts); }
         if (m_forms.empty()) throw std::runtime_error("Matrix local evaluator is not specified");
         prepare_outputs(&matrix, nullptr);
         const int st = ck(afb_assemble(m_ctx, (int)m_forms.size(), m_forms.data(), 0, nullptr, matrix.val.data(), nullptr, 1, opts.drop_val, AFB_HOST));
         return std::min(st, faces(matrix.val.data(), nullptr, opts));
     }
     int AssembleRHS(std::vector<double>& rhs, const AssmOpts& opts = AssmOpts()) {
+        if (rhs_func || mat_rhs_func) { prepare_outputs(nullptr, &rhs); return assemble_elemental(nullptr, &rhs, opts); }
         if (m_rhs.empty()) throw std::runtime_error("Right-hand side local evaluator is not specified");
         prepare_outputs(nullptr, &rhs);
         const int st = ck(afb_assemble(m_ctx, 0, nullptr, (int)m_rhs.size(), m_rhs.data(), nullptr, rhs.data(), 1, opts.drop_val, AFB_HOST));
@@ -216,6 +244,80 @@ private:
     }
     void need_prepared() {
         if (!m_prepared) PrepareProblem();
+    }
+    /// The cell loop of AssemblerT::Assemble (assembler.inl:349-483) with the user's evaluator: cell ranges over std::threads
+    /// (ThreadPar::parallel_for<STD>, fem/mutex_type.h:110-131), local matrices staged per chunk, scatter on the device.
+    int assemble_elemental(CsrMatrix* matrix, std::vector<double>* rhs, const AssmOpts& opts) {
+        int nrl = 0, ncl = 0; int64_t rb, re, ng;
+        ck(afb_dofmap_get(m_ctx, &nrl, &ncl, &rb, &re, &ng, nullptr, nullptr, AFB_HOST));
+        int64_t nnode = 0, ntet = 0;
+        ck(afb_mesh_get(m_ctx, &nnode, &ntet, nullptr, nullptr, AFB_HOST));
+        std::vector<double> xyz(static_cast<std::size_t>(3) * nnode);
+        std::vector<int32_t> v(static_cast<std::size_t>(4) * ntet);
+        ck(afb_mesh_get(m_ctx, &nnode, &ntet, xyz.data(), v.data(), AFB_HOST));
+        const bool doA = matrix != nullptr, doF = rhs != nullptr;
+        // which evaluator fills what: the combined one when present (generate_mat_rhs_func, assembler.inl), else the single ones
+        const MatFuncWrap<>* fA = doA ? (mat_rhs_func && (doF || !mat_func) ? mat_rhs_func.get() : mat_func.get()) : nullptr;
+        const MatFuncWrap<>* fF = doF ? (mat_rhs_func && (doA || !rhs_func) ? mat_rhs_func.get() : rhs_func.get()) : nullptr;
+        const bool combined = (doA && fA == mat_rhs_func.get()) || (doF && fF == mat_rhs_func.get());
+        const std::size_t per = static_cast<std::size_t>(nrl) * ncl + nrl;
+        const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(ntet, static_cast<int64_t>((std::size_t(512) << 20) / (per * sizeof(double)))));
+        int nth = m_assm_traits.num_threads < 0 ? static_cast<int>(std::thread::hardware_concurrency()) : m_assm_traits.num_threads;
+        nth = std::max(1, nth);
+        std::vector<double> Abuf(static_cast<std::size_t>(chunk) * nrl * ncl), Fbuf(static_cast<std::size_t>(chunk) * nrl);
+        int status = 0;
+        for (int64_t e_lo = 0; e_lo < ntet; e_lo += chunk) {
+            const int64_t nel = std::min<int64_t>(chunk, ntet - e_lo);
+            std::vector<std::string> errs(nth);
+            auto work = [&](int t) {
+                try {
+                    std::size_t sa, sr, sw, siw;
+                    const MatFuncWrap<>* any = combined ? mat_rhs_func.get() : (fA ? fA : fF);
+                    any->working_sizes(sa, sr, sw, siw);
+                    std::vector<double> w(sw + 1), Atmp(static_cast<std::size_t>(nrl) * ncl), Ftmp(nrl);
+                    std::vector<long> iw(siw + 1);
+                    ElementalAssembler p;
+                    p.nRows = nrl; p.nCols = ncl; p.m_w = w.data(); p.m_iw = iw.data(); p.m_thread = t; p.user_data = opts.user_data;
+                    for (int64_t k = nel * t / nth; k < nel * (t + 1) / nth; ++k) {
+                        const int64_t e = e_lo + k;
+                        p.cell_id = e;
+                        for (int n = 0; n < 4; ++n) {
+                            p.node_ids[n] = v[static_cast<std::size_t>(n) * ntet + e];
+                            for (int d = 0; d < 3; ++d) p.m_nn_p[3 * n + d] = xyz[static_cast<std::size_t>(d) * nnode + p.node_ids[n]];
+                        }
+                        double* Ae = Abuf.data() + static_cast<std::size_t>(k) * nrl * ncl;
+                        double* Fe = Fbuf.data() + static_cast<std::size_t>(k) * nrl;
+                        auto run = [&](const MatFuncWrap<>* f, double* A, double* F) {
+                            // ElementalAssembler::update (elemental_assembler.cpp:105-117): local A, F start from zero
+                            if (A) std::fill(A, A + static_cast<std::size_t>(nrl) * ncl, 0.0);
+                            if (F) std::fill(F, F + nrl, 0.0);
+                            p.m_func = f; p.m_A = A; p.m_F = F;
+                            if (m_prob_handler) m_prob_handler(p);
+                            else {
+                                const double* args[4] = {p.m_nn_p.data(), p.m_nn_p.data() + 3, p.m_nn_p.data() + 6, p.m_nn_p.data() + 9};
+                                p.compute(args, opts.user_data);
+                            }
+                        };
+                        if (combined) run(mat_rhs_func.get(), doA ? Ae : Atmp.data(), doF ? Fe : Ftmp.data());
+                        else {
+                            if (fA) run(fA, Ae, nullptr);
+                            if (fF) run(fF, nullptr, Fe);
+                        }
+                    }
+                } catch (std::exception& ex) { errs[t] = ex.what(); if (errs[t].empty()) errs[t] = "error in the local evaluator"; }
+            };
+            if (nth == 1) work(0);
+            else {
+                std::vector<std::thread> ths;
+                for (int t = 0; t < nth; ++t) ths.emplace_back(work, t);
+                for (auto& th : ths) th.join();
+            }
+            for (auto& er : errs) if (!er.empty()) throw std::runtime_error(er);
+            const int st = ck(afb_assemble_elemental(m_ctx, e_lo, nel, doA ? Abuf.data() : nullptr, doF ? Fbuf.data() : nullptr, AFB_HOST,
+                                                     doA ? matrix->val.data() : nullptr, doF ? rhs->data() : nullptr, opts.drop_val, AFB_HOST));
+            status = std::min(status, st);
+        }
+        return status;
     }
     void prepare_outputs(CsrMatrix* m, std::vector<double>* rhs) {
         need_prepared();

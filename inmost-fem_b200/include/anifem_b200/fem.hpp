@@ -68,6 +68,27 @@ struct DenseMatrix {
     void SetZero() { for (std::size_t i = 0; i < nRow * nCol; ++i) data[i] = 0; }
 };
 
+/// fem/operations/dc_on_dof.h:13-52: essential conditions on a local matrix / rhs (host-side helpers of a local assembler)
+template <typename Scalar>
+inline void applyDirNonExists(DenseMatrix<Scalar>& A, int k) {
+    for (std::size_t i = 0; i < A.nRow; ++i) A.data[i + A.nRow * k] = 0;
+    for (std::size_t i = 0; i < A.nCol; ++i) A.data[k + A.nRow * i] = 0;
+}
+template <typename Scalar>
+inline void applyDirMatrix(DenseMatrix<Scalar>& A, int k) {
+    applyDirNonExists(A, k);
+    A.data[k + A.nRow * k] = 1.0;
+}
+/// F(i) -= A(i,k) * bc for all i;  F(k) = bc;  row and column k of A zeroed;  A(k,k) = 1   (dc_on_dof.h:27-45)
+template <typename Scalar>
+inline void applyDir(DenseMatrix<Scalar>& A, DenseMatrix<Scalar>& F, int k, Scalar bc) {
+    for (std::size_t i = 0; i < A.nRow; ++i) F.data[i] -= A.data[i + A.nRow * k] * bc;
+    F.data[k] = bc;
+    applyDirMatrix(A, k);
+}
+template <typename Scalar>
+inline void applyDirResidual(DenseMatrix<Scalar>& F, int k) { F.data[k] = 0.0; }
+
 // coordinates of `fusion` tetrahedra: XYk is 3 x fusion col-major (fem/geometry.h:96-200)
 template <typename ScalarType = const double>
 struct Tetras {
@@ -79,16 +100,23 @@ inline Tetras<const double> make_tetras(const double* XY0, const double* XY1, co
 }
 
 namespace b200 {
-// process-wide context used by the free functions (one GPU, device 0 unless ANIFEM_B200_DEVICE is set)
-inline afb_ctx* default_context() {
-    static afb_ctx* ctx = [] {
-        afb_ctx* c = nullptr;
+// context used by the free functions: one per calling thread (a context is single-owner: one stream, its own buffers), so that
+// local assemblers evaluated concurrently (Assembler with num_threads > 1, like the reference's AssemblerP) may call fem3Dtet;
+// device 0 unless ANIFEM_B200_DEVICE is set
+struct ContextHolder {
+    afb_ctx* c = nullptr;
+    ContextHolder() {
         int dev = 0;
         if (const char* s = std::getenv("ANIFEM_B200_DEVICE")) dev = std::atoi(s);
         if (afb_ctx_create(dev, nullptr, &c) != 0) throw std::runtime_error(std::string("anifem_b200: ") + afb_last_error(nullptr));
-        return c;
-    }();
-    return ctx;
+    }
+    ~ContextHolder() { if (c) afb_ctx_destroy(c); }
+    ContextHolder(const ContextHolder&) = delete;
+    ContextHolder& operator=(const ContextHolder&) = delete;
+};
+inline afb_ctx* default_context() {
+    static thread_local ContextHolder holder;
+    return holder.c;
 }
 inline void check(afb_ctx* c, int rc) {
     if (rc < 0 && rc != -1) throw std::runtime_error(afb_last_error(c));

@@ -3,6 +3,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <functional>
 
 #include "anifem_b200/assembler.hpp"
 
@@ -233,6 +234,103 @@ int main() {
         EXPECT(norm_diff(1, A, -1, A_exp) <= 100 * (1 + norm(A)) * DBL_EPSILON);
         bool thrown = false;
         try { fem3Dface<OP1, OP2>(F1, F2, F3, F4, 4, ddotn, A, 3); } catch (const std::runtime_error&) { thrown = true; }
+        EXPECT(thrown);
+    }
+    // --- the MatFuncWrap plug-in point (func_wrap.h:310-347, assembler.h:326-328): the local assembler lambda of
+    //     examples/tutorials/ex1.cpp:83-106 unchanged (P1, D(x) = 1 + x^2 per quadrature point, F = 1, Dirichlet u = 0 on the
+    //     boundary through applyDir), installed with SetMatRHSFunc(GenerateElemMatRhs(...)) + a data gatherer; the result equals
+    //     the declarative description (AddMatForm with the coefficient at the quadrature points + SetDirichlet)
+    {
+        using UFem = FemFix<FEM_P1>;
+        constexpr int UNF = 4;
+        const int order = 2;
+        auto D_tensor = [](const std::array<double, 3>& X, double* D, TensorDims, void*, int) { D[0] = 1 + X[0] * X[0]; return TENSOR_SCALAR; };
+        auto F_tensor = [](const std::array<double, 3>&, double* F, TensorDims, void*, int) { F[0] = 1; return TENSOR_SCALAR; };
+        struct ProbLocData { std::array<int, 4> nlbl = {{0, 0, 0, 0}}; };
+        std::function<void(const double**, double*, double*, void*)> local_assembler =
+            [&D_tensor, &F_tensor, order](const double** XY, double* Adat, double* Fdat, void* user_data) -> void {
+            DenseMatrix<> A(Adat, UNF, UNF), F(Fdat, UNF, 1);
+            A.SetZero(); F.SetZero();
+            DenseMatrix<> X0(const_cast<double*>(XY[0]), 3, 1), X1(const_cast<double*>(XY[1]), 3, 1), X2(const_cast<double*>(XY[2]), 3, 1), X3(const_cast<double*>(XY[3]), 3, 1);
+            fem3Dtet<Operator<GRAD, UFem>, Operator<GRAD, UFem>, DfuncTraits<TENSOR_SCALAR, false>>(X0, X1, X2, X3, D_tensor, A, order);
+            fem3Dtet<Operator<IDEN, FemFix<FEM_P0>>, Operator<IDEN, UFem>, DfuncTraits<TENSOR_SCALAR, true>>(X0, X1, X2, X3, F_tensor, F, order);
+            auto& dat = *static_cast<ProbLocData*>(user_data);
+            for (int i = 0; i < 4; ++i)
+                if (dat.nlbl[i] > 0) applyDir(A, F, i, 0.0);
+        };
+        Assembler discr;
+        discr.SetCubeMesh(3, 3, 2).SetProbDescr({{FEM_P1, 1}});
+        discr.PrepareProblem();
+        int64_t nnode = 0, ntet = 0;
+        EXPECT(afb_mesh_get(discr.context(), &nnode, &ntet, nullptr, nullptr, AFB_HOST) == 0);
+        std::vector<double> xyz(3 * nnode); std::vector<int32_t> v(4 * ntet);
+        EXPECT(afb_mesh_get(discr.context(), &nnode, &ntet, xyz.data(), v.data(), AFB_HOST) == 0);
+        std::vector<int> label(nnode, 0);
+        for (int64_t n = 0; n < nnode; ++n)
+            for (int k = 0; k < 3; ++k) {
+                if (std::fabs(xyz[k * nnode + n] - 0) < 1e-12) label[n] |= 1 << (2 * k);
+                if (std::fabs(xyz[k * nnode + n] - 1) < 1e-12) label[n] |= 1 << (2 * k + 1);
+            }
+        auto local_data_gatherer = [&label](ElementalAssembler& p) -> void {
+            double* nn_p = p.get_nodes();
+            const double* args[] = {nn_p, nn_p + 3, nn_p + 6, nn_p + 9};
+            ProbLocData data;
+            for (unsigned i = 0; i < data.nlbl.size(); ++i) data.nlbl[i] = label[p.node_ids[i]];
+            p.compute(args, &data);
+        };
+        discr.SetMatRHSFunc(GenerateElemMatRhs(local_assembler, UNF, UNF));
+        discr.SetDataGatherer(local_data_gatherer);
+        CsrMatrix A1, A4; std::vector<double> b1, b4;
+        discr.m_assm_traits.num_threads = 1;
+        EXPECT(discr.Assemble(A1, b1) == 0);
+        discr.m_assm_traits.num_threads = 4;
+        EXPECT(discr.Assemble(A4, b4) == 0);
+        EXPECT(A1.val == A4.val && b1 == b4);   // the scatter is deterministic whatever the number of host threads
+        // the same problem described declaratively
+        Assembler decl;
+        decl.SetCubeMesh(3, 3, 2).SetProbDescr({{FEM_P1, 1}});
+        const int q = afb_tet_quadrature(order, nullptr, nullptr, 0);
+        std::vector<double> X[4];
+        for (int k = 0; k < 4; ++k) {
+            X[k].resize(3 * ntet);
+            for (int64_t e = 0; e < ntet; ++e) for (int d = 0; d < 3; ++d) X[k][3 * e + d] = xyz[d * nnode + v[k * ntet + e]];
+        }
+        std::vector<double> XYG(3 * q * ntet), Dq(q * ntet);
+        EXPECT(afb_quad_points(decl.context(), order, ntet, X[0].data(), X[1].data(), X[2].data(), X[3].data(), XYG.data(), AFB_HOST) == 0);
+        for (int64_t k = 0; k < q * ntet; ++k) Dq[k] = 1 + XYG[3 * k] * XYG[3 * k];
+        const double one = 1.0;
+        using G1 = Operator<GRAD, UFem>; using I1 = Operator<IDEN, UFem>;
+        decl.AddMatForm<G1, G1>(0, 0, order, TENSOR_SCALAR, AFB_COEF_PER_POINT, Dq.data()).AddRhsForm<I1>(0, order, TENSOR_SCALAR, AFB_COEF_CONST, &one);
+        decl.PrepareProblem();
+        std::vector<unsigned char> flag(nnode, 0); std::vector<double> bc(nnode, 0.0);
+        for (int64_t n = 0; n < nnode; ++n) flag[n] = label[n] > 0;
+        decl.SetDirichlet(flag, bc);
+        CsrMatrix Ad; std::vector<double> bd;
+        EXPECT(decl.Assemble(Ad, bd) == 0);
+        EXPECT(Ad.colind == A1.colind && Ad.rowptr == A1.rowptr);
+        double scale = 0, err = 0, errb = 0;
+        for (double x : Ad.val) scale = std::fmax(scale, std::fabs(x));
+        for (std::size_t k = 0; k < Ad.val.size(); ++k) err = std::fmax(err, std::fabs(Ad.val[k] - A1.val[k]));
+        for (std::size_t k = 0; k < bd.size(); ++k) errb = std::fmax(errb, std::fabs(bd[k] - b1[k]));
+        EXPECT(err <= 1e-12 * scale && errb <= 1e-13);
+        // matrix only / rhs only evaluators and the accumulate semantics of Assemble (assembler.inl:305-306)
+        Assembler sep;
+        sep.SetCubeMesh(3, 3, 2).SetProbDescr({{FEM_P1, 1}});
+        sep.SetMatFunc(GenerateElemMat([&](const double** XY, double* Adat, void* ud) { double Ftmp[UNF]; local_assembler(XY, Adat, Ftmp, ud); }, UNF, UNF));
+        sep.SetRHSFunc(GenerateElemRhs([&](const double** XY, double* Fdat, void* ud) { double Atmp[UNF * UNF]; local_assembler(XY, Atmp, Fdat, ud); }, UNF));
+        sep.SetDataGatherer(local_data_gatherer);
+        CsrMatrix As; std::vector<double> bs;
+        EXPECT(sep.AssembleMatrix(As) == 0);
+        EXPECT(sep.AssembleRHS(bs) == 0);
+        EXPECT(As.val == A1.val && bs == b1);
+        EXPECT(sep.Assemble(As, bs) == 0);
+        double d2 = 0;
+        for (std::size_t k = 0; k < As.val.size(); ++k) d2 = std::fmax(d2, std::fabs(As.val[k] - 2 * A1.val[k]));
+        EXPECT(d2 == 0.0);
+        Assembler none;
+        none.SetCubeMesh(2, 2, 2).SetProbDescr({{FEM_P1, 1}});
+        bool thrown = false;
+        try { CsrMatrix An; std::vector<double> bn; none.Assemble(An, bn); } catch (std::runtime_error&) { thrown = true; }   // "System local evaluator is not specified"
         EXPECT(thrown);
     }
     // --- SetEnumerator(ANITYPE ... ETDIMBLOCKS) (assembler.h:333-336, global_enumerator.h:393-401): the matrix assembled under every
