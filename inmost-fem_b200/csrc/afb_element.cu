@@ -10,7 +10,9 @@
 //   A(ib,ia)   -> sum_n sum_d Vb[d][n][b] * DU[band(ib)+d][n][ia], entries strided over lanes,
 //                 accumulators in registers, quadrature points processed in shared-memory chunks
 // The reference tables phi / G^ are element independent and come from afb_tables.cpp.
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "afb_internal.h"
@@ -316,6 +318,140 @@ __global__ void __launch_bounds__(128) k_element_sq(SqParams P, long long ntet, 
         }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// k_element_mma: the same contraction as k_element_sq on the FP64 tensor path (north_star: "DMMA ... only for the high-order or
+// vector-valued spaces where ncu shows the contraction dominates").  k_element_sq was bound by the shared-memory operand
+// loads of its rank-1 updates (LSU 73 %, FP64 pipe 35 %, profiles/r01d_c3_c4_kernels.md): with mma.sync.m8n8k4.f64 one operand
+// pair per lane feeds 256 FMAs, and the operands never pass through shared memory at all:
+//     A_e(i,j) = sum_k V[k][i] * DU[k][j],   k = (quadrature point n, direction d)
+// is a sum of 8x8 tiles D += A(8x4) B(4x8) with A[i][k] = V[k][i] (row operand: lane (gid, tig) holds V[n0+tig][8ti+gid]) and
+// B[k][j] = DU[k][j] (column operand: the same lane holds DU[n0+tig][8tj+gid]).  Both operands of a lane belong to the SAME
+// (point, basis function) pairs, so the lane computes its physical gradients u = PSI^T grad_ref (3 coalesced table loads from the
+// lane-ordered shared-memory copy of the reference table, 9 DFMA) and its DU = w_n |T| K_n u once per group of four points and
+// feeds them to the tiles of 3 directions x NT x NT (symmetric forms: upper tiles only, mirrored at the store).
+// One warp per tetrahedron, grid-stride; accumulators: 2 registers per tile.
+template <int NF, bool SYM>
+__global__ void __launch_bounds__(128) k_element_mma(SqParams P, long long ntet, GeomSrc g, double* __restrict__ out, long long s_e, int s_i, int s_j) {
+    constexpr int NT = (NF + 7) / 8;
+    extern __shared__ double smt[];   // per form: weights [groups][32], then grad [groups][NT][3][32] or iden [groups][NT][32]
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
+    int tab_off[SQ_MAXF];
+    {
+        int off = 0;
+        for (int fi = 0; fi < P.nforms; ++fi) {
+            const SqForm& F = P.f[fi];
+            const int groups = (F.q + 3) / 4;
+            tab_off[fi] = off;
+            const int per = F.grad ? NT * 3 : NT;
+            for (int it = threadIdx.x; it < groups * 32; it += blockDim.x) {
+                const int n = (it >> 5) * 4 + (it & 3);
+                smt[off + it] = n < F.q ? __ldg(F.W + n) * F.alpha : 0.0;
+            }
+            double* tb = smt + off + groups * 32;
+            for (int it = threadIdx.x; it < groups * per * 32; it += blockDim.x) {
+                const int l32 = it & 31, r = it >> 5;
+                const int gg = r / per, rr = r - gg * per;
+                const int n = gg * 4 + (l32 & 3);
+                double v = 0.0;
+                if (F.grad) {
+                    const int t = rr / 3, l = rr - 3 * t, i = 8 * t + (l32 >> 2);
+                    if (n < F.q && i < NF) v = __ldg(F.grd + ((size_t)n * NF + i) * 3 + l);
+                } else {
+                    const int i = 8 * rr + (l32 >> 2);
+                    if (n < F.q && i < NF) v = __ldg(F.phi + (size_t)n * NF + i);
+                }
+                tb[it] = v;
+            }
+            off += groups * 32 * (1 + per);
+        }
+    }
+    __syncthreads();
+    for (long long e = (long long)blockIdx.x * 4 + wib; e < ntet; e += (long long)gridDim.x * 4) {
+        double Pt[4][3], PSI[9];
+        load_tet(g, e, Pt);
+        const double vol = fabs(jacobian_inverse(Pt, PSI)) * (1.0 / 6.0);
+        double c0[NT][NT], c1[NT][NT];
+#pragma unroll
+        for (int a = 0; a < NT; ++a)
+#pragma unroll
+            for (int b = 0; b < NT; ++b) { c0[a][b] = 0.0; c1[a][b] = 0.0; }
+        for (int fi = 0; fi < P.nforms; ++fi) {
+            const SqForm& F = P.f[fi];
+            const int groups = (F.q + 3) / 4;
+            const double* wt = smt + tab_off[fi];
+            const double* tb = wt + groups * 32;
+            for (int gg = 0; gg < groups; ++gg) {
+                const int n = min(gg * 4 + tig, F.q - 1);   // padding points carry weight 0; their coefficient is read from the last point
+                const double wv = wt[gg * 32 + lane] * vol;
+                const double* Dn = F.D;
+                if (F.layout == AFB_COEF_PER_TET) Dn += (size_t)F.dlen * e;
+                else if (F.layout == AFB_COEF_PER_POINT) Dn += (size_t)F.dlen * (n + (size_t)F.q * e);
+                if (F.grad) {
+                    double u[NT][3], du[NT][3];
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) {
+                        const double g0 = tb[((gg * NT + t) * 3 + 0) * 32 + lane], g1 = tb[((gg * NT + t) * 3 + 1) * 32 + lane],
+                                     g2 = tb[((gg * NT + t) * 3 + 2) * 32 + lane];
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) u[t][d] = PSI[0 + 3 * d] * g0 + PSI[1 + 3 * d] * g1 + PSI[2 + 3 * d] * g2;
+                    }
+                    if (F.ttype >= AFB_TENSOR_SYMMETRIC) {
+                        double K[9];
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) K[k] = wv * __ldg(Dn + k);
+#pragma unroll
+                        for (int t = 0; t < NT; ++t)
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) du[t][k] = K[k] * u[t][0] + K[k + 3] * u[t][1] + K[k + 6] * u[t][2];   // K(k,l) at k + 3l
+                    } else {
+                        const double c = F.ttype == AFB_TENSOR_SCALAR ? wv * __ldg(Dn) : wv;
+#pragma unroll
+                        for (int t = 0; t < NT; ++t)
+#pragma unroll
+                            for (int d = 0; d < 3; ++d) du[t][d] = c * u[t][d];
+                    }
+#pragma unroll
+                    for (int d = 0; d < 3; ++d)
+#pragma unroll
+                        for (int a = 0; a < NT; ++a)
+#pragma unroll
+                            for (int b = SYM ? a : 0; b < NT; ++b)
+                                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                             : "+d"(c0[a][b]), "+d"(c1[a][b]) : "d"(u[a][d]), "d"(du[b][d]));
+                } else {
+                    const double c = F.ttype >= AFB_TENSOR_SCALAR ? wv * __ldg(Dn) : wv;
+                    double ph[NT], dp[NT];
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) { ph[t] = tb[(gg * NT + t) * 32 + lane]; dp[t] = c * ph[t]; }
+#pragma unroll
+                    for (int a = 0; a < NT; ++a)
+#pragma unroll
+                        for (int b = SYM ? a : 0; b < NT; ++b)
+                            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                         : "+d"(c0[a][b]), "+d"(c1[a][b]) : "d"(ph[a]), "d"(dp[b]));
+                }
+            }
+        }
+        // tile (a, b): this lane holds (i, j) and (i, j + 1) with i = 8a + gid, j = 8b + 2 tig
+        double* o = out + e * s_e;
+#pragma unroll
+        for (int a = 0; a < NT; ++a)
+#pragma unroll
+            for (int b = SYM ? a : 0; b < NT; ++b) {
+                const int i = 8 * a + gid, j = 8 * b + 2 * tig;
+                if (i < NF && j < NF) {
+                    o[i * s_i + j * s_j] = c0[a][b];
+                    if (j + 1 < NF) o[i * s_i + (j + 1) * s_j] = c1[a][b];
+                    if (SYM && a != b) {
+                        o[j * s_i + i * s_j] = c0[a][b];
+                        if (j + 1 < NF) o[(j + 1) * s_i + i * s_j] = c1[a][b];
+                    }
+                }
+            }
+    }
+}
+
 template <int ACC>
 cudaError_t launch_generic(const FormDev& F, long long f, const GeomSrc& g, double* out, int ia0, int nia, int words, cudaStream_t st) {
     const int warps = 4;
@@ -438,6 +574,34 @@ int launch_forms_sq(afb_ctx* ctx, const std::vector<afb_form>& fm, const std::ve
     }
     const int s_i = colmajor ? 1 : nf, s_j = colmajor ? nf : 1;
     const unsigned blocks = (unsigned)((ntet + 3) / 4);
+    // P2 / P3: FP64 tensor path (k_element_mma).  Symmetric instantiation when every form promises a symmetric product
+    // (no tensor, scalar, or TENSOR_SYMMETRIC = "symmetric tensor, may be used to optimize calculations", diff_tensor.h:20).
+    if ((nf == 10 || nf == 20) && !getenv("AFB_DISABLE_MMA_ELEMENT")) {
+        bool sym = !getenv("AFB_MMA_NOSYM");
+        size_t words = 0;
+        for (int k = 0; k < P.nforms; ++k) {
+            if (P.f[k].ttype == AFB_TENSOR_GENERAL) sym = false;
+            const int groups = (P.f[k].q + 3) / 4, nt = (nf + 7) / 8;
+            words += (size_t)groups * 32 * (1 + (P.f[k].grad ? 3 * nt : nt));
+        }
+        const size_t smem = words * sizeof(double);
+        if (smem <= 200 * 1024) {
+            const unsigned grid = (unsigned)std::min<long long>(blocks, 148LL * 16);
+#define LAUNCH_MMA(NFV, S)                                                                                                         \
+    do {                                                                                                                           \
+        cudaError_t ea = cudaFuncSetAttribute(k_element_mma<NFV, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+        if (ea != cudaSuccess) return cuda_fail(ctx, ea, "cudaFuncSetAttribute(k_element_mma)");                                   \
+        k_element_mma<NFV, S><<<grid, 128, smem, ctx->stream>>>(P, ntet, g, out, s_e, s_i, s_j);                                   \
+    } while (0)
+            if (nf == 10) { if (sym) LAUNCH_MMA(10, true); else LAUNCH_MMA(10, false); }
+            else { if (sym) LAUNCH_MMA(20, true); else LAUNCH_MMA(20, false); }
+#undef LAUNCH_MMA
+            ctx->launches++;
+            cudaError_t em = cudaGetLastError();
+            if (em != cudaSuccess) return cuda_fail(ctx, em, "k_element_mma launch");
+            return 0;
+        }
+    }
     if (nf == 4) k_element_sq<4><<<blocks, 128, 0, ctx->stream>>>(P, ntet, g, out, s_e, s_i, s_j);
     else if (nf == 10) k_element_sq<10><<<blocks, 128, 0, ctx->stream>>>(P, ntet, g, out, s_e, s_i, s_j);
     else if (nf == 20) k_element_sq<20><<<blocks, 128, 0, ctx->stream>>>(P, ntet, g, out, s_e, s_i, s_j);

@@ -296,7 +296,7 @@ int main() {
             for (int64_t e = 0; e < ntet; ++e) for (int d = 0; d < 3; ++d) X[k][3 * e + d] = xyz[d * nnode + v[k * ntet + e]];
         }
         std::vector<double> XYG(3 * q * ntet), Dq(q * ntet);
-        EXPECT(afb_quad_points(decl.context(), order, ntet, X[0].data(), X[1].data(), X[2].data(), X[3].data(), XYG.data(), AFB_HOST) == 0);
+        EXPECT(afb_quad_points(decl.context(), order, ntet, X[0].data(), X[1].data(), X[2].data(), X[3].data(), XYG.data(), AFB_HOST) == q);
         for (int64_t k = 0; k < q * ntet; ++k) Dq[k] = 1 + XYG[3 * k] * XYG[3 * k];
         const double one = 1.0;
         using G1 = Operator<GRAD, UFem>; using I1 = Operator<IDEN, UFem>;
