@@ -216,6 +216,36 @@ int afb_assemble_faces(afb_ctx* ctx, int nforms, const afb_form* forms, int nrhs
  * Replaces the value exchange the reference avoids by recomputing ghost cells (assembler.inl:162-183). */
 int afb_halo_add(afb_ctx* ctx, int64_t n, const int64_t* slot, const double* contrib, double* dst);
 
+/* ---- multi-GPU: communicator and interface exchange inside the library ("afb_ctx_create(device, nccl_comm, ...)",
+ * "afb_halo_exchange(ctx)").  One process (MPI rank) per GPU.  The reference exchanges only the numbering under MPI
+ * (global_enumerator.cpp:594-604, :698, :754) and recomputes ghost cells (assembler.inl:162-183); here every rank assembles its own
+ * elements into (owned rows ++ interface rows of other ranks) and the interface contributions travel to their owners over NCCL.
+ * NCCL is loaded at run time (dlopen "libnccl.so.2", override with AFB_NCCL_LIB); errors of NCCL return -8. */
+#define AFB_COMM_ID_BYTES 128
+/* ncclGetUniqueId: rank 0 calls it, the application hands the 128 bytes to every rank (MPI_Bcast in an MPI code) */
+int afb_comm_unique_id(void* id128);
+/* ncclCommInitRank on the context's device (collective over the nranks contexts); the context owns the communicator */
+int afb_comm_init(afb_ctx* ctx, const void* id128, int rank, int nranks);
+/* adopt an ncclComm_t owned by the application instead */
+int afb_comm_set(afb_ctx* ctx, void* nccl_comm, int rank, int nranks);
+/* Exchange plan of the extended row space [owned rows 0..n_own) ++ [interface rows of other ranks, sorted by owner]: the values of
+ * the interface rows start at entry nnz_own of the extended CSR arrays and are sent to their owners as they lie (send_val[p] values,
+ * send_rhs[p] rhs entries for rank p); recv_val[p] / recv_rhs[p] entries arrive from rank p and are added at val_slots / rhs_slots
+ * (positions in the extended arrays, concatenated over the peers in rank order; mem_space says where the two slot arrays live). */
+int afb_halo_plan_set(afb_ctx* ctx, int nranks, int64_t n_own, int64_t nnz_own, const int64_t* send_val, const int64_t* send_rhs,
+                      const int64_t* recv_val, const int64_t* recv_rhs, const int64_t* val_slots, const int64_t* rhs_slots, int mem_space);
+/* grouped ncclSend / ncclRecv on the context's communication stream, ordered after the work already issued on the context's
+ * stream; _finish orders the context's stream after the transfers and adds the received contributions peer by peer in rank order
+ * (deterministic, no atomics).  val_ext / rhs_ext: device pointers, either may be NULL.  afb_halo_exchange = start + finish. */
+int afb_halo_exchange_start(afb_ctx* ctx, double* val_ext, double* rhs_ext);
+int afb_halo_exchange_finish(afb_ctx* ctx, double* val_ext, double* rhs_ext);
+int afb_halo_exchange(afb_ctx* ctx, double* val_ext, double* rhs_ext);
+/* One assembly of a partitioned problem: interface rows first (afb_priority_rows_set(ctx, n_own)), their exchange overlapped with
+ * the remaining clusters, additions in rank order.  Device pointers; returns 0 / -1 like afb_assemble, results complete in stream
+ * order of the context's stream. */
+int afb_assemble_distributed(afb_ctx* ctx, int nforms, const afb_form* forms, int nrhs_forms, const afb_form* rhs_forms,
+                             double* val_ext, double* rhs_ext, double drop_val);
+
 /* phase times of the last afb_assemble in ms (CUDA events on the context stream):
  * [0] element kernels (k_element_generic / k_geom), [1] gather/scatter (k_gather / k_gather_tensor / k_rows_cl),
  * [2] coefficient copies, [3] = path: 0 generic staged (k_element_generic + k_gather), 1 fused tensor representation with the

@@ -43,7 +43,9 @@ EXPORTS = ["afb_ctx_create", "afb_ctx_destroy", "afb_last_error", "afb_sync", "a
            "afb_pattern_build", "afb_pattern_get", "afb_pattern_set", "afb_assemble", "afb_halo_add", "afb_last_times",
            "afb_dirichlet_set", "afb_fem3dapply_batched", "afb_eval_quadrature", "afb_priority_rows_set", "afb_assemble_phase",
            "afb_fields_set", "afb_fem3dface_batched", "afb_tri_quadrature",
-           "afb_boundary_set", "afb_assemble_faces", "afb_assemble_elemental"]
+           "afb_boundary_set", "afb_assemble_faces", "afb_assemble_elemental",
+           "afb_comm_unique_id", "afb_comm_init", "afb_comm_set", "afb_halo_plan_set", "afb_halo_exchange_start",
+           "afb_halo_exchange_finish", "afb_halo_exchange", "afb_assemble_distributed"]
 
 
 def build(verbose=False):
@@ -99,6 +101,14 @@ def lib():
         L.afb_assemble.argtypes = [vp, ci, ctypes.POINTER(AfbForm), ci, ctypes.POINTER(AfbForm), vp, vp, ci, cd, ci]
         L.afb_last_times.argtypes = [vp, _dp]
         L.afb_assemble_elemental.argtypes = [vp, c64, c64, vp, vp, ci, vp, vp, cd, ci]
+        L.afb_comm_unique_id.argtypes = [vp]
+        L.afb_comm_init.argtypes = [vp, vp, ci, ci]
+        L.afb_comm_set.argtypes = [vp, vp, ci, ci]
+        L.afb_halo_plan_set.argtypes = [vp, ci, c64, c64, vp, vp, vp, vp, vp, vp, ci]
+        L.afb_halo_exchange_start.argtypes = [vp, vp, vp]
+        L.afb_halo_exchange_finish.argtypes = [vp, vp, vp]
+        L.afb_halo_exchange.argtypes = [vp, vp, vp]
+        L.afb_assemble_distributed.argtypes = [vp, ci, ctypes.POINTER(AfbForm), ci, ctypes.POINTER(AfbForm), vp, vp, cd]
         L.afb_dirichlet_set.argtypes = [vp, vp, vp, ci]
         L.afb_priority_rows_set.argtypes = [vp, c64]
         L.afb_assemble_phase.argtypes = [vp, ci, ctypes.POINTER(AfbForm), ci, ctypes.POINTER(AfbForm), vp, vp, cd, ci]

@@ -326,6 +326,7 @@ void afb_ctx_destroy(afb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    afb::comm_release(c);
     afb::blocks_clear(c);
     afb::DevBuf* bufs[] = {&c->x, &c->y, &c->z, &c->v[0], &c->v[1], &c->v[2], &c->v[3], &c->e2r, &c->e2c, &c->rowptr, &c->colind,
                            &c->radj_ptr, &c->radj, &c->pos, &c->stageA, &c->stageF, &c->tables, &c->coef, &c->io_val, &c->io_rhs,

@@ -381,55 +381,81 @@ __global__ void __launch_bounds__(128) k_element_mma(SqParams P, long long ntet,
             const int groups = (F.q + 3) / 4;
             const double* wt = smt + tab_off[fi];
             const double* tb = wt + groups * 32;
-            for (int gg = 0; gg < groups; ++gg) {
-                const int n = min(gg * 4 + tig, F.q - 1);   // padding points carry weight 0; their coefficient is read from the last point
-                const double wv = wt[gg * 32 + lane] * vol;
-                const double* Dn = F.D;
-                if (F.layout == AFB_COEF_PER_TET) Dn += (size_t)F.dlen * e;
-                else if (F.layout == AFB_COEF_PER_POINT) Dn += (size_t)F.dlen * (n + (size_t)F.q * e);
-                if (F.grad) {
-                    double u[NT][3], du[NT][3];
+            // Coefficients are fetched ahead of their use: the scalar coefficients of four groups of points at once, a tensor one
+            // group ahead (double buffer).  [Loaded inside the group they were the top stall: 35 % of the samples waited for the
+            // global load in front of the DMUL w_n |T| c_n, profiles/r02/r02d_element_mma.md.]
+            const bool tens = F.ttype >= AFB_TENSOR_SYMMETRIC && F.grad;
+            const bool scal = F.ttype >= AFB_TENSOR_SCALAR && !tens;
+            const size_t pstride = F.layout == AFB_COEF_PER_POINT ? (size_t)F.dlen : 0;
+            const double* Dbase = F.D;
+            if (F.layout == AFB_COEF_PER_TET) Dbase += (size_t)F.dlen * e;
+            else if (F.layout == AFB_COEF_PER_POINT) Dbase += (size_t)F.dlen * F.q * e;
+            // padding points carry weight 0; their coefficient is read from the last point
+            auto dptr = [&](int gg) { return Dbase + pstride * (size_t)min(gg * 4 + tig, F.q - 1); };
+            double Kn[9];
+            if (tens) {
+                const double* Dn = dptr(0);
 #pragma unroll
-                    for (int t = 0; t < NT; ++t) {
-                        const double g0 = tb[((gg * NT + t) * 3 + 0) * 32 + lane], g1 = tb[((gg * NT + t) * 3 + 1) * 32 + lane],
-                                     g2 = tb[((gg * NT + t) * 3 + 2) * 32 + lane];
+                for (int k = 0; k < 9; ++k) Kn[k] = __ldg(Dn + k);
+            }
+            for (int g0 = 0; g0 < groups; g0 += 4) {
+                double cf[4];
 #pragma unroll
-                        for (int d = 0; d < 3; ++d) u[t][d] = PSI[0 + 3 * d] * g0 + PSI[1 + 3 * d] * g1 + PSI[2 + 3 * d] * g2;
-                    }
-                    if (F.ttype >= AFB_TENSOR_SYMMETRIC) {
-                        double K[9];
+                for (int k = 0; k < 4; ++k) cf[k] = (scal && g0 + k < groups) ? __ldg(dptr(g0 + k)) : 1.0;
 #pragma unroll
-                        for (int k = 0; k < 9; ++k) K[k] = wv * __ldg(Dn + k);
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    const int gg = g0 + k4;
+                    if (gg >= groups) break;
+                    const double wv = wt[gg * 32 + lane] * vol;
+                    if (F.grad) {
+                        double u[NT][3], du[NT][3];
 #pragma unroll
-                        for (int t = 0; t < NT; ++t)
+                        for (int t = 0; t < NT; ++t) {
+                            const double g0v = tb[((gg * NT + t) * 3 + 0) * 32 + lane], g1v = tb[((gg * NT + t) * 3 + 1) * 32 + lane],
+                                         g2v = tb[((gg * NT + t) * 3 + 2) * 32 + lane];
 #pragma unroll
-                            for (int k = 0; k < 3; ++k) du[t][k] = K[k] * u[t][0] + K[k + 3] * u[t][1] + K[k + 6] * u[t][2];   // K(k,l) at k + 3l
+                            for (int d = 0; d < 3; ++d) u[t][d] = PSI[0 + 3 * d] * g0v + PSI[1 + 3 * d] * g1v + PSI[2 + 3 * d] * g2v;
+                        }
+                        if (tens) {
+                            double K[9];
+#pragma unroll
+                            for (int k = 0; k < 9; ++k) K[k] = wv * Kn[k];
+                            if (gg + 1 < groups) {
+                                const double* Dn = dptr(gg + 1);
+#pragma unroll
+                                for (int k = 0; k < 9; ++k) Kn[k] = __ldg(Dn + k);
+                            }
+#pragma unroll
+                            for (int t = 0; t < NT; ++t)
+#pragma unroll
+                                for (int k = 0; k < 3; ++k) du[t][k] = K[k] * u[t][0] + K[k + 3] * u[t][1] + K[k + 6] * u[t][2];   // K(k,l) at k + 3l
+                        } else {
+                            const double c = wv * cf[k4];
+#pragma unroll
+                            for (int t = 0; t < NT; ++t)
+#pragma unroll
+                                for (int d = 0; d < 3; ++d) du[t][d] = c * u[t][d];
+                        }
+#pragma unroll
+                        for (int d = 0; d < 3; ++d)
+#pragma unroll
+                            for (int a = 0; a < NT; ++a)
+#pragma unroll
+                                for (int b = SYM ? a : 0; b < NT; ++b)
+                                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                                 : "+d"(c0[a][b]), "+d"(c1[a][b]) : "d"(u[a][d]), "d"(du[b][d]));
                     } else {
-                        const double c = F.ttype == AFB_TENSOR_SCALAR ? wv * __ldg(Dn) : wv;
+                        const double c = wv * cf[k4];
+                        double ph[NT], dp[NT];
 #pragma unroll
-                        for (int t = 0; t < NT; ++t)
-#pragma unroll
-                            for (int d = 0; d < 3; ++d) du[t][d] = c * u[t][d];
-                    }
-#pragma unroll
-                    for (int d = 0; d < 3; ++d)
+                        for (int t = 0; t < NT; ++t) { ph[t] = tb[(gg * NT + t) * 32 + lane]; dp[t] = c * ph[t]; }
 #pragma unroll
                         for (int a = 0; a < NT; ++a)
 #pragma unroll
                             for (int b = SYM ? a : 0; b < NT; ++b)
                                 asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                                             : "+d"(c0[a][b]), "+d"(c1[a][b]) : "d"(u[a][d]), "d"(du[b][d]));
-                } else {
-                    const double c = F.ttype >= AFB_TENSOR_SCALAR ? wv * __ldg(Dn) : wv;
-                    double ph[NT], dp[NT];
-#pragma unroll
-                    for (int t = 0; t < NT; ++t) { ph[t] = tb[(gg * NT + t) * 32 + lane]; dp[t] = c * ph[t]; }
-#pragma unroll
-                    for (int a = 0; a < NT; ++a)
-#pragma unroll
-                        for (int b = SYM ? a : 0; b < NT; ++b)
-                            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                                         : "+d"(c0[a][b]), "+d"(c1[a][b]) : "d"(ph[a]), "d"(dp[b]));
+                                             : "+d"(c0[a][b]), "+d"(c1[a][b]) : "d"(ph[a]), "d"(dp[b]));
+                    }
                 }
             }
         }

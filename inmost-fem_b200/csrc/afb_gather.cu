@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(256) k_gather(long long nrows, long long ntet,
                                                 const int32_t* __restrict__ e2r, const int32_t* __restrict__ e2c,
                                                 const double* __restrict__ stageA, const double* __restrict__ stageF,
                                                 double* __restrict__ val, double* __restrict__ rhs, int accumulate, double drop_val,
-                                                int* __restrict__ status, long long e_lo, long long e_hi) {
+                                                int* __restrict__ status, long long e_lo, long long e_hi, int len_lo) {
     extern __shared__ double sacc[];
     const int gl = threadIdx.x % G;                    // lane inside the group
     const int gib = threadIdx.x / G;                   // group inside the block
@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(256) k_gather(long long nrows, long long ntet,
     for (long long r = (long long)blockIdx.x * gpb + gib; r < nrows; r += (long long)gridDim.x * gpb) {
         const long long p0 = rowptr[r];
         const int len = (int)(rowptr[r + 1] - p0);
+        if (len <= len_lo) continue;   // rows of at most len_lo entries were done by k_gather_cols (group-uniform)
         const long long a0 = radj_ptr[r], a1 = radj_ptr[r + 1];
         double fsum = 0.0;
         if (stageA) {
@@ -80,8 +81,229 @@ __global__ void __launch_bounds__(256) k_gather(long long nrows, long long ntet,
     if (bad) *status = 1;  // benign race: every writer stores the same value
 }
 
+// k_gather_flat: the same row gather with the (adjacency entry, local column) pairs of a row flattened over the 32 lanes of a warp.
+// k_gather gives a row to a group of 2^k lanes and walks the adjacency list entry by entry: with 20 local columns (P3) 12 of 32
+// lanes idle and every entry costs one dependent round trip (adjacency word -> staged row + slots -> shared-memory add).  Here a
+// lane fetches U items k = lane, lane + 32, ... ahead (values, slots), so 4 x 32 loads are in flight per warp and all lanes work;
+// the adds then run entry by entry in ascending element order (one __syncwarp per entry), i.e. in exactly the order of k_gather:
+// the results are bit-identical.
+template <bool SIGNS, typename PosT>
+__global__ void __launch_bounds__(256) k_gather_flat(long long nrows, long long ntet, int nrow_loc, int ncol_loc, int max_len,
+                                                     const long long* __restrict__ rowptr, const long long* __restrict__ radj_ptr,
+                                                     const unsigned* __restrict__ radj, const PosT* __restrict__ pos,
+                                                     const int32_t* __restrict__ e2r, const int32_t* __restrict__ e2c,
+                                                     const double* __restrict__ stageA, const double* __restrict__ stageF,
+                                                     double* __restrict__ val, double* __restrict__ rhs, int accumulate, double drop_val,
+                                                     int* __restrict__ status, long long e_lo, long long e_hi) {
+    constexpr int U = 4;
+    extern __shared__ double sacc[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    double* acc = sacc + (size_t)wib * max_len;
+    bool bad = false;
+    for (long long r = (long long)blockIdx.x * wpb + wib; r < nrows; r += (long long)gridDim.x * wpb) {
+        const long long p0 = rowptr[r];
+        const int len = (int)(rowptr[r + 1] - p0);
+        const long long a0 = radj_ptr[r];
+        const int nadj = (int)(radj_ptr[r + 1] - a0);
+        if (stageF) {   // load contributions: fetched 32 at a time, added in adjacency order
+            double fsum = 0.0;
+            for (int b = 0; b < nadj; b += 32) {
+                double fv = 0.0;
+                if (b + lane < nadj) {
+                    const unsigned t = __ldg(radj + a0 + b + lane);
+                    const long long e = t / nrow_loc;
+                    if (e >= e_lo && e < e_hi) {
+                        fv = __ldg(stageF + ((long long)t - e_lo * nrow_loc));
+                        bad |= !isfinite(fv);
+                        if (SIGNS && e2r[(long long)(t - e * nrow_loc) * ntet + e] < 0) fv = -fv;
+                    }
+                }
+                const int cnt = min(32, nadj - b);
+                for (int i = 0; i < cnt; ++i) fsum += __shfl_sync(0xffffffffu, fv, i);
+            }
+            if (lane == 0) { if (accumulate) rhs[r] += fsum; else rhs[r] = fsum; }
+        }
+        if (!stageA) continue;
+        for (int s = lane; s < len; s += 32) acc[s] = 0.0;
+        __syncwarp();
+        const int nitems = nadj * ncol_loc;
+        int a = 0, j = lane;   // item of this lane: adjacency entry a, local column j
+        while (j >= ncol_loc) { j -= ncol_loc; ++a; }
+        for (int base = 0; base < nitems; base += 32 * U) {
+            double v[U];
+            int pp[U], ai[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                v[u] = 0.0; pp[u] = -1; ai[u] = a;
+                if (a < nadj) {
+                    const unsigned t = __ldg(radj + a0 + a);
+                    const long long e = t / nrow_loc;
+                    if (e >= e_lo && e < e_hi) {
+                        double x = __ldg(stageA + ((long long)t - e_lo * nrow_loc) * ncol_loc + j);
+                        const int p = pos[(a0 + a) * ncol_loc + j];
+                        bad |= !isfinite(x);
+                        if (SIGNS) {
+                            const int i = (int)(t - e * nrow_loc);
+                            if ((e2r[(long long)i * ntet + e] < 0) != (e2c[(long long)j * ntet + e] < 0)) x = -x;
+                        }
+                        if (fabs(x) > drop_val) { v[u] = x; pp[u] = p; }
+                    }
+                }
+                j += 32;
+                while (j >= ncol_loc) { j -= ncol_loc; ++a; }
+            }
+            const int afirst = base / ncol_loc, alast = min(nadj - 1, (base + 32 * U - 1) / ncol_loc);
+            for (int ac = afirst; ac <= alast; ++ac) {
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (ai[u] == ac && pp[u] >= 0) acc[pp[u]] += v[u];
+                __syncwarp();
+            }
+        }
+        if (accumulate) for (int s = lane; s < len; s += 32) val[p0 + s] += acc[s];
+        else for (int s = lane; s < len; s += 32) val[p0 + s] = acc[s];
+        __syncwarp();
+    }
+    if (bad) *status = 1;  // benign race: every writer stores the same value
+}
+
+// k_gather_cols: lane-group gather for local matrices with NC = 10 or 20 columns (P2 / P3 through the staged path).  A group of
+// G = NC / 5 lanes owns a row (8 or 16 rows per warp), every lane handles 5 columns of an adjacency entry and two entries are
+// fetched per trip, so a warp keeps 2 x 5 x 32 value loads in flight where the warp-per-row gather has one dependent load per
+// entry and 12 of 32 lanes idle.  Rows longer than `len_hi` entries are left to the warp-per-row kernel (len_lo there): the row
+// images of this kernel are sized for the short rows (edge and face dofs: 95 % of the rows of a P3 problem).
+// Same summation order as k_gather (ascending element per row): bit-identical results.
+template <int G, int NC, bool SIGNS, typename PosT>
+__global__ void __launch_bounds__(256) k_gather_cols(long long nrows, long long ntet, int img_len, int len_hi,
+                                                     const long long* __restrict__ rowptr, const long long* __restrict__ radj_ptr,
+                                                     const unsigned* __restrict__ radj, const PosT* __restrict__ pos,
+                                                     const int32_t* __restrict__ e2r, const int32_t* __restrict__ e2c,
+                                                     const double* __restrict__ stageA, const double* __restrict__ stageF,
+                                                     double* __restrict__ val, double* __restrict__ rhs, int accumulate, double drop_val,
+                                                     int* __restrict__ status, long long e_lo, long long e_hi) {
+    constexpr int PER = NC / G;
+    extern __shared__ double sacc[];
+    const int gl = threadIdx.x % G, gib = threadIdx.x / G, gpb = blockDim.x / G;
+    const unsigned gmask = ((1u << G) - 1u) << ((threadIdx.x & 31) / G * G);
+    double* acc = sacc + (size_t)gib * img_len;
+    bool bad = false;
+    for (long long r = (long long)blockIdx.x * gpb + gib; r < nrows; r += (long long)gridDim.x * gpb) {
+        const long long p0 = rowptr[r];
+        const int len = (int)(rowptr[r + 1] - p0);
+        if (len > len_hi) continue;   // group-uniform
+        const long long a0 = radj_ptr[r], a1 = radj_ptr[r + 1];
+        double fsum = 0.0;
+        if (stageA) {
+            for (int s = gl; s < len; s += G) acc[s] = 0.0;
+            __syncwarp(gmask);
+        }
+        for (long long a = a0; a < a1; a += 2) {
+            const bool two = a + 1 < a1;
+            const unsigned t0 = __ldg(radj + a), t1 = two ? __ldg(radj + a + 1) : t0;
+            const long long ea = t0 / NC, eb = t1 / NC;
+            const bool ina = ea >= e_lo && ea < e_hi, inb = two && eb >= e_lo && eb < e_hi;
+            const long long tla = (long long)t0 - e_lo * NC, tlb = (long long)t1 - e_lo * NC;
+            double va[PER], vb[PER];
+            int pa[PER], pb[PER];
+#pragma unroll
+            for (int k = 0; k < PER; ++k) {
+                const int j = gl * PER + k;
+                va[k] = (ina && stageA) ? __ldg(stageA + tla * NC + j) : 0.0;
+                vb[k] = (inb && stageA) ? __ldg(stageA + tlb * NC + j) : 0.0;
+                pa[k] = pos[a * NC + j];
+                pb[k] = two ? pos[(a + 1) * NC + j] : 0;
+            }
+            double sra = 1.0, srb = 1.0;
+            if (SIGNS) {
+                sra = e2r[(long long)(t0 - ea * NC) * ntet + ea] < 0 ? -1.0 : 1.0;
+                srb = e2r[(long long)(t1 - eb * NC) * ntet + eb] < 0 ? -1.0 : 1.0;
+            }
+            if (stageF && gl == 0) {
+                if (ina) { const double fv = __ldg(stageF + tla); bad |= !isfinite(fv); fsum += sra * fv; }
+                if (inb) { const double fv = __ldg(stageF + tlb); bad |= !isfinite(fv); fsum += srb * fv; }
+            }
+            if (stageA) {
+                if (ina) {
+#pragma unroll
+                    for (int k = 0; k < PER; ++k) {
+                        double v = va[k];
+                        bad |= !isfinite(v);
+                        if (SIGNS) v *= sra * (e2c[(long long)(gl * PER + k) * ntet + ea] < 0 ? -1.0 : 1.0);
+                        if (fabs(v) > drop_val) acc[pa[k]] += v;
+                    }
+                }
+                __syncwarp(gmask);
+                if (inb) {
+#pragma unroll
+                    for (int k = 0; k < PER; ++k) {
+                        double v = vb[k];
+                        bad |= !isfinite(v);
+                        if (SIGNS) v *= srb * (e2c[(long long)(gl * PER + k) * ntet + eb] < 0 ? -1.0 : 1.0);
+                        if (fabs(v) > drop_val) acc[pb[k]] += v;
+                    }
+                }
+                __syncwarp(gmask);
+            }
+        }
+        if (stageA) {
+            if (accumulate) for (int s = gl; s < len; s += G) val[p0 + s] += acc[s];
+            else for (int s = gl; s < len; s += G) val[p0 + s] = acc[s];
+            __syncwarp(gmask);
+        }
+        if (stageF && gl == 0) {
+            if (accumulate) rhs[r] += fsum; else rhs[r] = fsum;
+        }
+    }
+    if (bad) *status = 1;  // benign race: every writer stores the same value
+}
+
+template <int G, int NC, bool SIGNS, typename PosT>
+cudaError_t launch_cols3(afb_ctx* c, int len_hi, const double* sA, const double* sF, double* val, double* rhs, int accumulate, double drop, int* status, long long e_lo, long long e_hi) {
+    const long long nrows = c->row_end - c->row_begin;
+    const int gpb = 256 / G;
+    const size_t smem = (size_t)gpb * len_hi * sizeof(double);
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((nrows + gpb - 1) / gpb, 148LL * 64));
+    cudaError_t e = cudaFuncSetAttribute(k_gather_cols<G, NC, SIGNS, PosT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_gather_cols<G, NC, SIGNS, PosT><<<grid, 256, smem, c->stream>>>(nrows, c->ntet, len_hi, len_hi, c->rowptr.as<long long>(), c->radj_ptr.as<long long>(),
+                                                                    c->radj.as<unsigned>(), c->pos.as<PosT>(), c->e2r.as<int32_t>(), c->e2c.as<int32_t>(), sA, sF,
+                                                                    val, rhs, accumulate, drop, status, e_lo, e_hi);
+    return cudaGetLastError();
+}
+template <int G, int NC>
+cudaError_t launch_cols(afb_ctx* c, int len_hi, const double* sA, const double* sF, double* val, double* rhs, int accumulate, double drop, int* status, long long e_lo, long long e_hi) {
+    if (c->has_signs) {
+        if (c->pos_bytes == 1) return launch_cols3<G, NC, true, unsigned char>(c, len_hi, sA, sF, val, rhs, accumulate, drop, status, e_lo, e_hi);
+        return launch_cols3<G, NC, true, unsigned short>(c, len_hi, sA, sF, val, rhs, accumulate, drop, status, e_lo, e_hi);
+    }
+    if (c->pos_bytes == 1) return launch_cols3<G, NC, false, unsigned char>(c, len_hi, sA, sF, val, rhs, accumulate, drop, status, e_lo, e_hi);
+    return launch_cols3<G, NC, false, unsigned short>(c, len_hi, sA, sF, val, rhs, accumulate, drop, status, e_lo, e_hi);
+}
+
+template <bool SIGNS, typename PosT>
+cudaError_t launch_flat2(afb_ctx* c, const double* sA, const double* sF, double* val, double* rhs, int accumulate, double drop, int* status, long long e_lo, long long e_hi) {
+    const long long nrows = c->row_end - c->row_begin;
+    const int wpb = 8;
+    const size_t smem = (size_t)wpb * std::max(1, c->max_row_len) * sizeof(double);
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((nrows + wpb - 1) / wpb, 148LL * 64));
+    cudaError_t e = cudaFuncSetAttribute(k_gather_flat<SIGNS, PosT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_gather_flat<SIGNS, PosT><<<grid, 256, smem, c->stream>>>(nrows, c->ntet, c->nrow_loc, c->ncol_loc, std::max(1, c->max_row_len), c->rowptr.as<long long>(),
+                                                               c->radj_ptr.as<long long>(), c->radj.as<unsigned>(), c->pos.as<PosT>(), c->e2r.as<int32_t>(),
+                                                               c->e2c.as<int32_t>(), sA, sF, val, rhs, accumulate, drop, status, e_lo, e_hi);
+    return cudaGetLastError();
+}
+cudaError_t launch_flat(afb_ctx* c, const double* sA, const double* sF, double* val, double* rhs, int accumulate, double drop, int* status, long long e_lo, long long e_hi) {
+    if (c->has_signs) {
+        if (c->pos_bytes == 1) return launch_flat2<true, unsigned char>(c, sA, sF, val, rhs, accumulate, drop, status, e_lo, e_hi);
+        return launch_flat2<true, unsigned short>(c, sA, sF, val, rhs, accumulate, drop, status, e_lo, e_hi);
+    }
+    if (c->pos_bytes == 1) return launch_flat2<false, unsigned char>(c, sA, sF, val, rhs, accumulate, drop, status, e_lo, e_hi);
+    return launch_flat2<false, unsigned short>(c, sA, sF, val, rhs, accumulate, drop, status, e_lo, e_hi);
+}
+
 template <int G, bool SIGNS, typename PosT>
-cudaError_t launch_g2(afb_ctx* c, const double* sA, const double* sF, double* val, double* rhs, int accumulate, double drop, int* status, long long e_lo, long long e_hi) {
+cudaError_t launch_g2(afb_ctx* c, const double* sA, const double* sF, double* val, double* rhs, int accumulate, double drop, int* status, long long e_lo, long long e_hi, int len_lo) {
     const long long nrows = c->row_end - c->row_begin;
     const int gpb = 256 / G;
     const size_t smem = (size_t)gpb * std::max(1, c->max_row_len) * sizeof(double);
@@ -90,18 +312,18 @@ cudaError_t launch_g2(afb_ctx* c, const double* sA, const double* sF, double* va
     if (e != cudaSuccess) return e;
     k_gather<G, SIGNS, PosT><<<grid, 256, smem, c->stream>>>(nrows, c->ntet, c->nrow_loc, c->ncol_loc, std::max(1, c->max_row_len), c->rowptr.as<long long>(),
                                                              c->radj_ptr.as<long long>(), c->radj.as<unsigned>(), c->pos.as<PosT>(), c->e2r.as<int32_t>(),
-                                                             c->e2c.as<int32_t>(), sA, sF, val, rhs, accumulate, drop, status, e_lo, e_hi);
+                                                             c->e2c.as<int32_t>(), sA, sF, val, rhs, accumulate, drop, status, e_lo, e_hi, len_lo);
     return cudaGetLastError();
 }
 
 template <int G>
-cudaError_t launch_g(afb_ctx* c, const double* sA, const double* sF, double* val, double* rhs, int accumulate, double drop, int* status, long long e_lo, long long e_hi) {
+cudaError_t launch_g(afb_ctx* c, const double* sA, const double* sF, double* val, double* rhs, int accumulate, double drop, int* status, long long e_lo, long long e_hi, int len_lo = -1) {
     if (c->has_signs) {
-        if (c->pos_bytes == 1) return launch_g2<G, true, unsigned char>(c, sA, sF, val, rhs, accumulate, drop, status, e_lo, e_hi);
-        return launch_g2<G, true, unsigned short>(c, sA, sF, val, rhs, accumulate, drop, status, e_lo, e_hi);
+        if (c->pos_bytes == 1) return launch_g2<G, true, unsigned char>(c, sA, sF, val, rhs, accumulate, drop, status, e_lo, e_hi, len_lo);
+        return launch_g2<G, true, unsigned short>(c, sA, sF, val, rhs, accumulate, drop, status, e_lo, e_hi, len_lo);
     }
-    if (c->pos_bytes == 1) return launch_g2<G, false, unsigned char>(c, sA, sF, val, rhs, accumulate, drop, status, e_lo, e_hi);
-    return launch_g2<G, false, unsigned short>(c, sA, sF, val, rhs, accumulate, drop, status, e_lo, e_hi);
+    if (c->pos_bytes == 1) return launch_g2<G, false, unsigned char>(c, sA, sF, val, rhs, accumulate, drop, status, e_lo, e_hi, len_lo);
+    return launch_g2<G, false, unsigned short>(c, sA, sF, val, rhs, accumulate, drop, status, e_lo, e_hi, len_lo);
 }
 
 }  // namespace
@@ -142,6 +364,28 @@ int launch_gather(afb_ctx* ctx, const double* stageA, const double* stageF, doub
     if (need > 200 * 1024) { set_error(ctx, "afb_assemble: matrix rows too long for the shared-memory row image"); return -3; }
     cudaError_t e;
     const int nc = ctx->ncol_loc;
+    // P2 / P3 local matrices: rows of up to 128 entries (all edge / face dofs) through k_gather_cols, the long rows after them
+    // through the warp-per-row kernel
+    if ((nc == 10 || nc == 20) && ctx->nrow_loc == nc && !getenv("AFB_GATHER_GROUPS")) {
+        if (getenv("AFB_GATHER_FLAT")) {
+            e = launch_flat(ctx, stageA, stageF, val, rhs, accumulate, drop_val, status_flag, e_lo, e_hi);
+            ctx->launches++;
+            if (e != cudaSuccess) return cuda_fail(ctx, e, "k_gather_flat launch");
+            return 0;
+        }
+        const int len_hi = nc == 20 ? 128 : 48;   // 64 KB / 48 KB of row images per 256-thread block
+        e = nc == 20 ? launch_cols<4, 20>(ctx, len_hi, stageA, stageF, val, rhs, accumulate, drop_val, status_flag, e_lo, e_hi)
+                     : launch_cols<2, 10>(ctx, len_hi, stageA, stageF, val, rhs, accumulate, drop_val, status_flag, e_lo, e_hi);
+        ctx->launches++;
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "k_gather_cols launch");
+        if (ctx->max_row_len > len_hi) {
+            e = nc == 20 ? launch_g<32>(ctx, stageA, stageF, val, rhs, accumulate, drop_val, status_flag, e_lo, e_hi, len_hi)
+                         : launch_g<16>(ctx, stageA, stageF, val, rhs, accumulate, drop_val, status_flag, e_lo, e_hi, len_hi);
+            ctx->launches++;
+            if (e != cudaSuccess) return cuda_fail(ctx, e, "k_gather launch");
+        }
+        return 0;
+    }
     if (nc <= 4) e = launch_g<4>(ctx, stageA, stageF, val, rhs, accumulate, drop_val, status_flag, e_lo, e_hi);
     else if (nc <= 8) e = launch_g<8>(ctx, stageA, stageF, val, rhs, accumulate, drop_val, status_flag, e_lo, e_hi);
     else if (nc <= 16) e = launch_g<16>(ctx, stageA, stageF, val, rhs, accumulate, drop_val, status_flag, e_lo, e_hi);
@@ -301,7 +545,17 @@ static int assemble_impl(afb_ctx* ctx, int nforms, const afb_form* forms, int nr
     // the staged matrices of all elements may not fit (P2^3 x P1 at 12.6 M tets = 116 GB): elements are processed in chunks
     // of bounded staging size, every chunk gathered with accumulate (the row sums stay in ascending element order)
     double *sA = nullptr, *sF = nullptr;
+    // Every chunk after the first walks all rows again and adds into the CSR values (read + write), so one chunk is the goal:
+    // the staging buffer may take what is free on the device minus a reserve (P3 at 10.1 M tets: 32 GB of 180 GB).
     size_t stage_cap = (size_t)8 << 30;
+    {
+        size_t mfree = 0, mtotal = 0;
+        if (cudaMemGetInfo(&mfree, &mtotal) == cudaSuccess) {
+            const size_t have = ctx->stageA.cap + ctx->stageF.cap;   // already reserved by an earlier call
+            const size_t avail = mfree + have;
+            if (avail > ((size_t)12 << 30)) stage_cap = std::max(stage_cap, avail - ((size_t)8 << 30));
+        }
+    }
     if (const char* sc = getenv("AFB_STAGE_BYTES")) stage_cap = (size_t)std::max(1LL, atoll(sc));
     const size_t per_elem = ((doA ? (size_t)nrl * ncl : 0) + (doF ? (size_t)nrl : 0)) * sizeof(double);
     const long long chunk = std::max<long long>(1, std::min<long long>(ntet, (long long)(stage_cap / std::max<size_t>(1, per_elem))));

@@ -181,6 +181,17 @@ struct afb_ctx {
     int rg_gcap = 0, rg_imgcap = 0, rg_stepcap = 0, rg_xcap = 0, rg_edges = 0;
     afb::DevBuf rg_cinfo, rg_elist, rg_hdr, rg_steps, rg_desc, rg_xpos;
     afb::DevBuf rg_vptr, rg_vlist, rg_vdpos, rg_vrow, rg_zlist, rg_scratch, rg_clist;
+
+    // multi-GPU interface exchange (afb_comm.cu): NCCL communicator (void* = ncclComm_t), halo plan
+    void* comm = nullptr;
+    bool own_comm = false;
+    int comm_rank = 0, comm_size = 1;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t comm_ev[2] = {nullptr, nullptr};   // [0] context stream -> exchange, [1] exchange -> context stream
+    bool has_halo_plan = false, halo_in_flight = false;
+    int64_t halo_n_own = 0, halo_nnz_own = 0;
+    std::vector<int64_t> halo_send_val, halo_send_rhs, halo_recv_val, halo_recv_rhs;   // [comm_size] counts per peer
+    afb::DevBuf halo_val_slots, halo_rhs_slots, halo_val_recv, halo_rhs_recv;
     std::vector<unsigned char> rg_cinfo_host;   // host copy of the cluster records (permuted for phased launches)
     std::vector<unsigned> rg_maxrow, rg_vrow_host;   // largest row a cluster writes to; rows of the vertex list (ascending)
 
@@ -265,4 +276,6 @@ int launch_rings(afb_ctx* ctx, const double* TG, const double* Tm, const double*
 // gather (afb_gather.cu)
 int launch_gather(afb_ctx* ctx, const double* stageA, const double* stageF, double* val, double* rhs,
                   int accumulate, double drop_val, int* status_flag, long long e_lo, long long e_hi);
+// afb_comm.cu: destroys an owned NCCL communicator, the exchange stream / events and the halo plan buffers
+void comm_release(afb_ctx* ctx);
 }  // namespace afb
