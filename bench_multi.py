@@ -73,6 +73,60 @@ def parity_check(pkg, par, rank, world, local_rank):
             "ranks": world}
 
 
+def strong_leg(args, pkg, par, rank, world, local_rank, global_n):
+    """Second measurement of the contract line for N > 1: STRONG scaling of C2 on the north-star mesh (global_n^3 hexes x 6 tets
+    = 100.66 M tets at 256), blocks shrinking with the number of GPUs.  Device-resident steps only (CUDA events, max over ranks)."""
+    dims = (global_n,) * 3
+    ppa = par.proc_grid(world, dims)
+    stream = torch.cuda.current_stream()
+    ctx = pkg.Context(local_rank, stream.cuda_stream)
+    t0 = time.perf_counter()
+    da = par.DistributedAssembler(ctx, dims, [(pkg.P2, 1)])
+    torch.cuda.synchronize()
+    setup_ms = (time.perf_counter() - t0) * 1e3
+    ntet = da.ntet
+    xc = da.coords[da.tets.long()].mean(dim=1)
+    K_dev = torch.zeros((ntet, 9), dtype=torch.float64, device="cuda")
+    K_dev[:, 0] = 2 + xc[:, 0]; K_dev[:, 4] = 1; K_dev[:, 8] = 3
+    K_dev[:, 1] = K_dev[:, 3] = 0.5
+    K_dev[:, 5] = K_dev[:, 7] = -0.25
+    del xc
+    forms = [pkg.make_form(pkg.GRAD, pkg.P2, 1, pkg.GRAD, pkg.P2, 1, 2, pkg.TENSOR_SYMMETRIC, pkg.COEF_PER_TET, K_dev)]
+    rhsf = [pkg.make_form(pkg.IDEN, pkg.P0, 1, pkg.IDEN, pkg.P2, 1, 2, pkg.TENSOR_NULL, pkg.COEF_CONST)]
+    for _ in range(args.warmup):
+        assert da.assemble(forms, rhsf) == 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        assert da.assemble(forms, rhsf) == 0
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1) / args.steps], device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    tot = torch.tensor([ntet, da.plan.n_own, da.plan.nnz_own], dtype=torch.int64, device="cuda")
+    dist.all_reduce(tot)
+    ntet_all, nrows_all, nnz_all = [int(v) for v in tot.tolist()]
+    nn_all = (global_n + 1) ** 3
+    alg_bytes = 40 * ntet_all + 24 * nn_all + 72 * ntet_all + 8 * nnz_all + 8 * nrows_all
+    out = {"scaling": "strong", "global_hexes": list(dims), "proc_grid": ppa, "ntet": ntet_all, "nrows": nrows_all, "nnz": nnz_all,
+           "ms_per_step": ms.item(), "value": ntet_all / (ms.item() * 1e-3), "unit": bench.UNIT, "dof_per_s": nrows_all / (ms.item() * 1e-3),
+           "hbm_frac_per_gpu": alg_bytes / world / (ms.item() * 1e-3) / 1e9 / bench_peak(), "setup_ms_rank0": setup_ms, "steps": args.steps}
+    ctx.close()
+    del da, K_dev
+    torch.cuda.empty_cache()
+    return out
+
+
+def bench_peak():
+    try:
+        return json.load(open(os.path.join(bench.ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0)
+    except Exception:
+        return 6650.0
+
+
 def run(args, pkg, rank, world, local_rank):
     par = importlib.import_module("inmost_fem_b200.parallel")
     parity = None
@@ -161,6 +215,17 @@ def run(args, pkg, rank, world, local_rank):
     dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
     tot = torch.tensor([ntet, n_own, nnz_own, da.plan.n_for, sum(da.plan.send_nnz)], dtype=torch.int64, device="cuda")
     dist.all_reduce(tot)
+    times = ctx.last_times()
+    c_exch = bool(getattr(da, "c_exchange", False))
+    strong = None
+    if config == "c2" and not args.global_n and getattr(args, "strong_n", 0) > 0:
+        if rank == 0:
+            sampler.stop_flag = True
+            sampler.join(timeout=2)
+        ctx.close()
+        del da, K_dev, K_host, val_host, rhs_host, forms_d, rhsf_d, forms_h, rhsf_h, mk, xc
+        torch.cuda.empty_cache()
+        strong = strong_leg(args, pkg, par, rank, world, local_rank, args.strong_n)
     if rank == 0:
         sampler.stop_flag = True
         sampler.join(timeout=2)
@@ -174,7 +239,6 @@ def run(args, pkg, rank, world, local_rank):
         nn_all = (dims[0] + 1) * (dims[1] + 1) * (dims[2] + 1)
         nloc = sum({pkg.P1: 4, pkg.P2: 10}[f] * v for f, v in variables)
         alg_bytes = 4 * nloc * ntet_all + 24 * nn_all + (72 * ntet_all if config == "c2" else 0) + 8 * nnz_all + 8 * nrows_all
-        times = ctx.last_times()
         gbs = alg_bytes / (ms.item() * 1e-3) / 1e9
         metric = bench.METRIC if config == "c2" else "assembled tets/sec (%s, FP64, CSR values + rhs)" % (
             "C4: FemVec<3,P2> linear elasticity, constant 9x9 tensor" if config == "c4" else "C5: Taylor-Hood P2^3 x P1 Stokes")
@@ -183,7 +247,7 @@ def run(args, pkg, rank, world, local_rank):
                 "dtype": "f64", "data": "synthetic",
                 "config": bench.config_dict(n, {"global_hexes": list(dims), "proc_grid": ppa, "ntet": ntet_all, "nrows": nrows_all, "nnz": nnz_all,
                                                 "interface_rows_sent": nfor_all, "interface_values_sent_per_step": nsend_all,
-                                                "exchange": "NCCL all_to_all_single of packed FP64 interface contributions + afb_halo_add in rank order",
+                                                "exchange": ("grouped ncclSend/ncclRecv issued by the library (afb_assemble_distributed) + additions in rank order" if c_exch else "NCCL all_to_all_single of packed FP64 interface contributions + afb_halo_add in rank order"),
                                                 "setup_ms_rank0": setup_ms}),
                 "dof_per_s": nrows_all / (ms.item() * 1e-3),
                 "e2e": {"value": ntet_all / (ms_e2e.item() * 1e-3), "unit": bench.UNIT, "ms_per_step": ms_e2e.item(), "steps": e2e_steps,
@@ -193,10 +257,14 @@ def run(args, pkg, rank, world, local_rank):
                              "kernel": "whole step per GPU (%s + %s + exchange)" % (times["element_kernel"], times["gather_kernel"]),
                              "algorithmic_bytes_per_launch": alg_bytes // world},
                 "clocks": sampler.summary(), "parity": parity}
+        if strong is not None:
+            # second key: strong scaling on the north-star mesh (the contract line above is weak scaling: fixed per-GPU block)
+            line["strong_scaling"] = strong
         if config != "c2":
             line["config"]["workload"] = metric + ", per-GPU block %d^3 hexes x 6 tets, structural pattern pre-built" % n
         print(json.dumps(line))
-    ctx.close()
+    if strong is None:
+        ctx.close()
     dist.barrier()
     dist.destroy_process_group()
     return 0

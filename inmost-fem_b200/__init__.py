@@ -362,6 +362,42 @@ class Context:
         self.nnz = int(colind.shape[0])
         self._ck(lib().afb_pattern_set(self._h, pr, pc, self.nnz, sr))
 
+    # ---- multi-GPU exchange inside the library (afb_comm.cu)
+    @staticmethod
+    def comm_unique_id():
+        """128 bytes from ncclGetUniqueId (rank 0 creates them, every rank passes them to comm_init)"""
+        buf = ctypes.create_string_buffer(128)
+        rc = lib().afb_comm_unique_id(buf)
+        if rc:
+            raise AfbError(rc, lib().afb_last_error(None).decode())
+        return buf.raw
+
+    def comm_init(self, id128, rank, nranks):
+        self._ck(lib().afb_comm_init(self._h, ctypes.c_char_p(bytes(id128)), int(rank), int(nranks)))
+
+    def halo_plan_set(self, n_own, nnz_own, send_val, send_rhs, recv_val, recv_rhs, val_slots, rhs_slots):
+        """counts: python lists per rank; val_slots / rhs_slots: int64 torch cuda tensors (concatenated in rank order)"""
+        n = len(send_val)
+        arr = lambda v: (ctypes.c_int64 * n)(*[int(x) for x in v])
+        sv, sr, rv, rr = arr(send_val), arr(send_rhs), arr(recv_val), arr(recv_rhs)
+        pv = val_slots.data_ptr() if val_slots is not None and val_slots.numel() else None
+        pr = rhs_slots.data_ptr() if rhs_slots is not None and rhs_slots.numel() else None
+        self._ck(lib().afb_halo_plan_set(self._h, n, int(n_own), int(nnz_own), sv, sr, rv, rr, pv, pr, DEVICE))
+
+    def halo_exchange(self, val, rhs):
+        pv, _ = _ptr(val)
+        pr, _ = _ptr(rhs)
+        self._ck(lib().afb_halo_exchange(self._h, pv, pr))
+
+    def assemble_distributed(self, forms, rhs_forms, val, rhs, drop_val=1e-100):
+        """afb_assemble_distributed on torch cuda tensors (extended arrays): phased assembly + NCCL exchange + additions"""
+        fa = (AfbForm * max(1, len(forms)))(*forms)
+        fr = (AfbForm * max(1, len(rhs_forms)))(*rhs_forms)
+        pv, sv = _ptr(val)
+        pr, sr = _ptr(rhs)
+        assert (val is None or sv == DEVICE) and (rhs is None or sr == DEVICE)
+        return self._ck(lib().afb_assemble_distributed(self._h, len(forms), fa, len(rhs_forms), fr, pv, pr, drop_val), allow=(-1,))
+
     def halo_add(self, slot, contrib, dst):
         """dst[slot] += contrib for the contributions of one peer (torch cuda tensors; slot int64, distinct)"""
         self._ck(lib().afb_halo_add(self._h, int(slot.shape[0]), slot.data_ptr(), contrib.data_ptr(), dst.data_ptr()))

@@ -17,6 +17,8 @@ Everything here is device-agnostic torch code (runs on CPU/gloo in the tests, on
 numerics stay in the CUDA library.  Scope: variables living on nodes, edges and faces (P1, P2, P3, vectors of them,
 Taylor-Hood); P0 (cell dofs) is not partitioned.  P3 is covered by the CPU (gloo) tests of the numbering / exchange plan only.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -443,6 +445,17 @@ class DistributedAssembler:
         self.val = torch.zeros(plan.nnz_ext, dtype=torch.float64, device=dev)
         self.rhs = torch.zeros(n_ext, dtype=torch.float64, device=dev)
         self.ntet = int(self.tets.shape[0])
+        # data path of the exchange inside the library (afb_comm.cu: NCCL send / recv + additions issued from C); torch only
+        # carries the 128-byte NCCL id to the ranks.  AFB_PY_EXCHANGE=1 keeps the torch.distributed exchange (A/B); tensors on the
+        # CPU (gloo tests of the host logic) always use it.
+        self.c_exchange = bool(self.val_is_cuda()) and self.world > 1 and not os.environ.get("AFB_PY_EXCHANGE") and hasattr(ctx, "comm_init")
+        if self.c_exchange:
+            ids = [ctx.comm_unique_id() if self.rank == 0 else None]
+            dist.broadcast_object_list(ids, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            ctx.comm_init(ids[0], self.rank, self.world)
+            cat = lambda ts: torch.cat([t.reshape(-1) for t in ts]).contiguous() if len(ts) else None
+            ctx.halo_plan_set(plan.n_own, plan.nnz_own, plan.send_nnz, plan.for_per_peer, plan.recv_nnz,
+                              [int(r.numel()) for r in plan.rhs_slots], cat(plan.val_slots), cat(plan.rhs_slots))
 
     def val_is_cuda(self):
         return self.tets.is_cuda
@@ -482,6 +495,8 @@ class DistributedAssembler:
         return st
 
     def _assemble(self, forms, rhs_forms, drop_val):
+        if self.c_exchange:
+            return self.ctx.assemble_distributed(forms, rhs_forms, self.val, self.rhs, drop_val=drop_val)
         if self.phased:
             self.ctx.assemble_phase(forms, rhs_forms, self.val, self.rhs, 1, drop_val=drop_val)
             works = self.plan.exchange_start(self.val, self.rhs)
