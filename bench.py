@@ -249,16 +249,17 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
     alg_bytes = 4 * 10 * ntet + 24 * nnode + 72 * ntet + 8 * nnz + 8 * nrows
     dom_name, dom_ms = (names[0], el_ms) if el_ms >= ga_ms else (names[1], ga_ms)
-    traffic = None
+    traffic, traffic_src = None, None   # measured under ncu (never inside this run): per launch, stamped with kernel + commit
     try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = prof.get(dom_name, {}).get("dram_bytes_per_launch")
+        prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom_name, {})
+        traffic = prof.get("dram_bytes_per_launch")
+        traffic_src = "%s @ %s, %s" % (prof.get("kernel"), prof.get("git_sha"), prof.get("report")) if traffic else None
     except Exception:
         pass
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
     step_gbs = alg_bytes / (ms_dev * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic,
-                "kernel": dom_name, "kernel_ms": dom_ms, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                "traffic_source": traffic_src, "kernel": dom_name, "kernel_ms": dom_ms, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "step": {"achieved": step_gbs, "frac": step_gbs / peak_gbs, "element_ms": el_ms, "gather_ms": ga_ms, "path": "fused tensor-representation" if fused else "generic staged",
                          "note": "whole step = element kernels + gather; frac of the step is the honest end figure"}}
 
