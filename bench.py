@@ -145,8 +145,9 @@ def main():
     ap.add_argument("--n", "--hexes-per-axis", dest="n", type=int, default=119,
                     help="hexes per axis per GPU block (119 -> 10,110,954 tets); under torchrun use the long spelling (--n is ambiguous for its parser)")
     ap.add_argument("--global-n", type=int, default=0, help="strong scaling: fix the GLOBAL mesh to this many hexes per axis (default: weak scaling, --n per GPU)")
-    ap.add_argument("--strong-n", type=int, default=256, help="N>1: also measure STRONG scaling of C2 on a fixed global mesh of this many hexes per axis "
-                    "(256 -> 100,663,296 tets, the north-star mesh), reported under the key strong_scaling; 0 = skip")
+    ap.add_argument("--strong-n", type=int, default=0, help="N>1: also measure STRONG scaling of C2 on a fixed global mesh of this many hexes per axis "
+                    "(256 -> 100,663,296 tets, the north-star mesh; needs N >= 4), reported under the key strong_scaling; 0 (default) = skip: "
+                    "the contract line is weak scaling")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-n", type=int, default=64, help="hexes per axis of the CPU sample (64 -> 1,572,864 tets)")
     ap.add_argument("--ref-reps", type=int, default=12, help="timed passes of the CPU sample in the cpu_baseline leg (about 10-20 core-seconds)")
@@ -170,7 +171,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the assembly path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        # a rank that dies must not leave the others waiting for the default 10 minutes of the NCCL watchdog
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
     pkg = entry.load_package()
     if world > 1:
         import bench_multi

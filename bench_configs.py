@@ -79,6 +79,17 @@ def run_config(pkg, name, n, steps, stream, peak):
            "gather_ms": t["gather_ms"], "kernels": [t["element_kernel"], t["gather_kernel"]],
            "path": "fused tensor-representation" if t["fused_path"] else "generic staged",
            "algorithmic_bytes_per_tet": alg / ntet, "hbm_frac": alg / (ms * 1e-3) / 1e9 / peak, "pattern_build_ms": t_pat}
+    if name == "c3":
+        # contraction-bound case: useful FLOPs of fem3Dtet for the full 20 x 20 matrix (stiffness q = 14: 3 x 400 + 180 FMA per
+        # point, mass q = 24: 400 FMA per point) against the FP64 peak measured with tools/fp64_peak.cu on this pool's B200
+        flop = 2.0 * (14 * (3 * 400 + 180) + 24 * 400)
+        fp64_peak = 36.74e12
+        try:
+            fp64_peak = json.load(open(os.path.join(ROOT, "profiles", "r02", "r02c_fp64_peak.json")))["dfma_tflops"] * 1e12
+        except Exception:
+            pass
+        out["fp64"] = {"useful_flop_per_tet": flop, "peak_tflops": fp64_peak / 1e12, "peak_source": "tools/fp64_peak.cu (profiles/r02/r02c_fp64_peak.json)",
+                       "frac_element_stage": flop * ntet / (t["element_ms"] * 1e-3) / fp64_peak, "frac_assembly": flop * ntet / (ms * 1e-3) / fp64_peak}
     ctx.close()
     del val, rhs, dev
     return out

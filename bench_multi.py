@@ -4,6 +4,7 @@ exchanged over NCCL (owner-computes + exchange, inmost-fem_b200/parallel.py).  W
 the N=1 workload (n^3 hexes), so the global mesh grows with the number of GPUs."""
 import importlib
 import json
+import sys
 import os
 import time
 
@@ -29,7 +30,7 @@ def parity_check(pkg, par, rank, world, local_rank):
     for name, dims in PARITY_CASES:
         variables = {"p2": [(gc.P2, 1)], "taylor_hood": [(gc.P2, 3), (gc.P1, 1)], "p3": [(gc.P3, 1)]}[name]
         ctx = pkg.Context(local_rank, torch.cuda.current_stream().cuda_stream)
-        case_ok, err = True, 0.0
+        case_ok, err, agreed = True, 0.0, False
         try:
             da = par.DistributedAssembler(ctx, dims, variables)
             co, te, cr = M.cube_mesh(*dims, nranks=world)
@@ -49,7 +50,12 @@ def parity_check(pkg, par, rank, world, local_rank):
                 rhsf = [pkg.make_form(gc.IDEN, gc.P0, 1, gc.IDEN, fem, 1, 2, gc.T_NULL, gc.L_CONST)]
             rp_o, ci_o, v_o, r_o, _ = M.assemble(prob, co, te, dm, rank=rank)
             case_ok &= bool(np.array_equal(da.rowptr.cpu().numpy(), rp_o) and np.array_equal(da.colind.cpu().numpy(), ci_o))
-            if case_ok:
+            # the assembly contains an exchange: every rank enters it or none does (a rank that failed a check on its own must
+            # not leave its peers waiting in the exchange)
+            agree = torch.tensor([1.0 if case_ok else 0.0], device="cuda")
+            dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+            agreed = True
+            if case_ok and agree.item() == 1.0:
                 assert da.assemble(forms, rhsf) == 0
                 torch.cuda.synchronize()
                 val = da.val[:da.plan.nnz_own].cpu().numpy()
@@ -60,8 +66,10 @@ def parity_check(pkg, par, rank, world, local_rank):
                 case_ok &= err <= 1e-12
         except Exception as exc:  # noqa: BLE001 -- a failing case is reported (and fails the run), it must not hang the other ranks
             case_ok, err = False, float("inf")
-            if rank == 0:
-                print("parity case %s raised: %r" % (name, exc), flush=True)
+            print("parity case %s raised on rank %d: %r" % (name, rank, exc), file=sys.stderr, flush=True)
+            if not agreed:   # keep the collective sequence of the other ranks matched
+                agree = torch.tensor([0.0], device="cuda")
+                dist.all_reduce(agree, op=dist.ReduceOp.MIN)
         finally:
             ctx.close()
         t = torch.tensor([0.0 if case_ok else 1.0, err if err == err and err != float("inf") else 1e300], dtype=torch.float64, device="cuda")
@@ -225,7 +233,17 @@ def run(args, pkg, rank, world, local_rank):
         ctx.close()
         del da, K_dev, K_host, val_host, rhs_host, forms_d, rhsf_d, forms_h, rhsf_h, mk, xc
         torch.cuda.empty_cache()
-        strong = strong_leg(args, pkg, par, rank, world, local_rank, args.strong_n)
+        # guard: the setup (pattern union in torch: several int64 arrays per non-zero) peaks near 3.8 kB per local tet -- measured:
+        # 50.3 M tets per GPU (N = 2) runs out of the 180 GB, 12.6 M (N = 8) fits.  Every rank takes the same decision.
+        ntet_loc = 6 * args.strong_n ** 3 // world
+        free_b, _ = torch.cuda.mem_get_info()
+        fits = torch.tensor([1.0 if 3800.0 * ntet_loc < 0.8 * free_b else 0.0], device="cuda")
+        dist.all_reduce(fits, op=dist.ReduceOp.MIN)
+        if fits.item() == 1.0:
+            strong = strong_leg(args, pkg, par, rank, world, local_rank, args.strong_n)
+        else:
+            strong = {"scaling": "strong", "global_hexes": [args.strong_n] * 3, "skipped": "%.1f M tets per GPU do not fit the setup's peak memory "
+                      "(about 3.8 kB per tet in the torch pattern union); run with more GPUs" % (ntet_loc / 1e6)}
     if rank == 0:
         sampler.stop_flag = True
         sampler.join(timeout=2)

@@ -252,6 +252,9 @@ int afb_assemble_distributed(afb_ctx* ctx, int nforms, const afb_form* forms, in
  * lane-group gather (k_geom + k_gather_tensor), 2 fused with the cluster-tiled thread-per-row gather (k_geom + k_rows_cl);
  * mirrors the GetTimeEvalLocFunc / GetTimeFillMapTemplate style getters (assembler.inl:949-964) */
 int afb_last_times(afb_ctx* ctx, double* ms4);
+/* "element kernel|gather kernel" of the generic staged path that ran last (k_element_generic / k_element_sq / k_element_mma,
+ * k_gather / k_gather_cols (+ k_gather) / k_gather_flat): evidence for the bench lines */
+int afb_last_kernels(afb_ctx* ctx, char* buf, int capacity);
 
 #ifdef __cplusplus
 }

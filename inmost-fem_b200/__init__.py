@@ -45,7 +45,7 @@ EXPORTS = ["afb_ctx_create", "afb_ctx_destroy", "afb_last_error", "afb_sync", "a
            "afb_fields_set", "afb_fem3dface_batched", "afb_tri_quadrature",
            "afb_boundary_set", "afb_assemble_faces", "afb_assemble_elemental",
            "afb_comm_unique_id", "afb_comm_init", "afb_comm_set", "afb_halo_plan_set", "afb_halo_exchange_start",
-           "afb_halo_exchange_finish", "afb_halo_exchange", "afb_assemble_distributed"]
+           "afb_halo_exchange_finish", "afb_halo_exchange", "afb_assemble_distributed", "afb_last_kernels"]
 
 
 def build(verbose=False):
@@ -100,6 +100,7 @@ def lib():
         L.afb_pattern_get.argtypes = [vp, vp, vp, ci]
         L.afb_assemble.argtypes = [vp, ci, ctypes.POINTER(AfbForm), ci, ctypes.POINTER(AfbForm), vp, vp, ci, cd, ci]
         L.afb_last_times.argtypes = [vp, _dp]
+        L.afb_last_kernels.argtypes = [vp, ctypes.c_char_p, ci]
         L.afb_assemble_elemental.argtypes = [vp, c64, c64, vp, vp, ci, vp, vp, cd, ci]
         L.afb_comm_unique_id.argtypes = [vp]
         L.afb_comm_init.argtypes = [vp, vp, ci, ci]
@@ -511,4 +512,10 @@ class Context:
         t = (ctypes.c_double * 4)()
         lib().afb_last_times(self._h, t)
         kern = {0: ("k_element_generic", "k_gather"), 1: ("k_geom", "k_gather_tensor"), 2: ("k_geom", "k_rows_cl"), 3: ("k_geom", "k_rings")}[int(t[3])]
+        if int(t[3]) == 0:   # generic staged path: the library names the kernels that ran
+            buf = ctypes.create_string_buffer(128)
+            lib().afb_last_kernels(self._h, buf, 128)
+            names = buf.value.decode().split("|")
+            if len(names) == 2 and names[0] and names[1]:
+                kern = (names[0], names[1])
         return {"element_ms": t[0], "gather_ms": t[1], "copy_ms": t[2], "fused_path": bool(t[3]), "element_kernel": kern[0], "gather_kernel": kern[1]}

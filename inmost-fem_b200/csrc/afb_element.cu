@@ -623,6 +623,7 @@ int launch_forms_sq(afb_ctx* ctx, const std::vector<afb_form>& fm, const std::ve
             else { if (sym) LAUNCH_MMA(20, true); else LAUNCH_MMA(20, false); }
 #undef LAUNCH_MMA
             ctx->launches++;
+            ctx->k_elem = "k_element_mma";
             cudaError_t em = cudaGetLastError();
             if (em != cudaSuccess) return cuda_fail(ctx, em, "k_element_mma launch");
             return 0;
@@ -635,6 +636,7 @@ int launch_forms_sq(afb_ctx* ctx, const std::vector<afb_form>& fm, const std::ve
     ctx->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(ctx, e, "k_element_sq launch");
+    ctx->k_elem = "k_element_sq";
     return 0;
 }
 

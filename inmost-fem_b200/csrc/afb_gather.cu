@@ -10,6 +10,7 @@
 // CSR row at the precomputed slots; the finished row is written once, coalesced.  No atomics, bit-reproducible.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 
 #include "afb_internal.h"
 
@@ -371,6 +372,7 @@ int launch_gather(afb_ctx* ctx, const double* stageA, const double* stageF, doub
             e = launch_flat(ctx, stageA, stageF, val, rhs, accumulate, drop_val, status_flag, e_lo, e_hi);
             ctx->launches++;
             if (e != cudaSuccess) return cuda_fail(ctx, e, "k_gather_flat launch");
+            ctx->k_gath = "k_gather_flat";
             return 0;
         }
         const int len_hi = nc == 20 ? 128 : 48;   // 64 KB / 48 KB of row images per 256-thread block
@@ -378,6 +380,7 @@ int launch_gather(afb_ctx* ctx, const double* stageA, const double* stageF, doub
                      : launch_cols<2, 10>(ctx, len_hi, stageA, stageF, val, rhs, accumulate, drop_val, status_flag, e_lo, e_hi);
         ctx->launches++;
         if (e != cudaSuccess) return cuda_fail(ctx, e, "k_gather_cols launch");
+        ctx->k_gath = ctx->max_row_len > len_hi ? "k_gather_cols + k_gather" : "k_gather_cols";
         if (ctx->max_row_len > len_hi) {
             e = nc == 20 ? launch_g<32>(ctx, stageA, stageF, val, rhs, accumulate, drop_val, status_flag, e_lo, e_hi, len_hi)
                          : launch_g<16>(ctx, stageA, stageF, val, rhs, accumulate, drop_val, status_flag, e_lo, e_hi, len_hi);
@@ -392,6 +395,7 @@ int launch_gather(afb_ctx* ctx, const double* stageA, const double* stageF, doub
     else e = launch_g<32>(ctx, stageA, stageF, val, rhs, accumulate, drop_val, status_flag, e_lo, e_hi);
     ctx->launches++;
     if (e != cudaSuccess) return cuda_fail(ctx, e, "k_gather launch");
+    ctx->k_gath = "k_gather";
     return 0;
 }
 
@@ -623,6 +627,7 @@ static int assemble_impl(afb_ctx* ctx, int nforms, const afb_form* forms, int nr
             Dc[k] += (size_t)dl * qk * e_lo;
         }
         // ---- K1: element blocks
+        ctx->k_elem = "k_element_generic";
         if (!sq.empty()) {
             int rc = launch_forms_sq(ctx, fm, oa, Dc, sq, e_lo, nel, sA, (long long)nrl * ncl);
             if (rc) return rc;
@@ -732,6 +737,13 @@ int afb_assemble_elemental(afb_ctx* ctx, int64_t e_lo, int64_t nel, const double
     AFB_CUDA(ctx, cudaStreamSynchronize(st));
     if (bad) set_error(ctx, "not a number in local matrix or rhs");
     return bad ? -1 : 0;
+}
+
+/* names of the element / gather kernels of the generic staged path that ran last (bench evidence), "elem|gather" */
+int afb_last_kernels(afb_ctx* ctx, char* buf, int capacity) {
+    if (!ctx || !buf || capacity <= 0) return -7;
+    snprintf(buf, (size_t)capacity, "%s|%s", ctx->k_elem, ctx->k_gath);
+    return 0;
 }
 
 int afb_last_times(afb_ctx* ctx, double* ms4) {

@@ -215,6 +215,8 @@ struct afb_ctx {
     afb::DevBuf stageA, stageF, tables, coef, io_val, io_rhs, flag, tmp1, tmp2, tmp3, xy;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     double times[4] = {0, 0, 0, 0};
+    const char* k_elem = "";     // kernels of the generic staged path that ran last (afb_last_kernels)
+    const char* k_gath = "";
 };
 
 // one scalar block form of the tensor representation (afb_tensor.cu): A_e(i,j) = sum_c T[c][i][j] g_e[c]

@@ -244,6 +244,7 @@ class Numbering:
         # ---- element -> global dof (local order: variable, component, 4 vertices, 6 edges)
         cols = []
         beg_ind_dev = self.beg_ind.to(dev)
+        node_gid = beg[0].to(dev)[self.owner[0]] + self.pos[0]   # GlobalID of every local node (BegElemID of its owner + position)
         for v, (fem, vec) in enumerate(self.vars):
             for c in range(vec):
                 for d in range(nd_types):
@@ -255,9 +256,12 @@ class Numbering:
                     ps = self.pos[d][ents]
                     for le in range(ents.shape[1]):
                         if d == 1 and nd == 2:
-                            # the two dofs of a P3 edge follow the orientation of the edge by global node ids (tetdofmap.inl:98-104)
+                            # the two dofs of a P3 edge follow the orientation of the edge by the GLOBAL IDS of its end points
+                            # (tetdofmap.inl:98-104).  Under a partition these are the rank-major ids INMOST assigns (owner's first
+                            # node id + position among its owned nodes), not the mesh node index: the two orders differ as soon
+                            # as the partition cuts the fastest mesh axis (found by the 8-rank parity leg, 2 x 2 x 2 blocks)
                             a, b = LOCAL_EDGES[le]
-                            flip = (gnode[tets[:, a]] > gnode[tets[:, b]]).long()
+                            flip = (node_gid[tets[:, a]] > node_gid[tets[:, b]]).long()
                             cols.append(index(v, c, d, ow[:, le], ps[:, le], flip))
                             cols.append(index(v, c, d, ow[:, le], ps[:, le], 1 - flip))
                             continue

@@ -159,6 +159,14 @@ def test_three_ranks_p3_p1(pkg, oracle):
     _run(3, (3, 3, 2), [(gc.P3, 1), (gc.P1, 1)])
 
 
+def test_eight_ranks_p3_blocks_cut_every_axis(pkg, oracle):
+    """2 x 2 x 2 blocks (the parity case of bench_multi.py at 8 GPUs): the partition cuts the fastest mesh axis, so the rank-major
+    GlobalIDs of the nodes are ordered differently from the mesh node indices -- the P3 edge pairs must follow the GlobalIDs
+    (tetdofmap.inl:98-104).  [An 8-GPU bench run hung on this case: half of the ranks failed the numbering check and left the
+    others alone in the exchange.]"""
+    _run(8, (5, 4, 3), [(gc.P3, 1)])
+
+
 @pytest.mark.parametrize("enum_type", ["ANITYPE", "MINIBLOCKS", "DIMUNION", "BYELEMTYPE", "ETDIMBLOCKS"])
 def test_two_ranks_other_enumerators(pkg, oracle, enum_type):
     """the other GlobEnumeration types across ranks (Taylor-Hood: vector + scalar variable, node and edge dofs): numbering against the
