@@ -13,6 +13,7 @@
 #include <array>
 #include <cstddef>
 #include <functional>
+#include <new>
 #include <stdexcept>
 #include <string>
 #include <type_traits>
@@ -20,6 +21,7 @@
 #include <vector>
 
 #include "../../../include/anifem_b200.h"
+#include "memory.hpp"
 
 namespace Ani {
 
@@ -46,14 +48,52 @@ struct Operator {
     using Dim = std::integral_constant<int, OPERATOR == IDEN ? vec : (OPERATOR == GRAD ? 3 * vec : 1)>;
 };
 
-template <int TensorTypeSparse = PerPoint, bool isConstant = false, long idim = -1, long jdim = -1>
-struct DfuncTraits {
-    using IsConstant = std::integral_constant<bool, isConstant>;
-    using TensorSparsity = std::integral_constant<int, TensorTypeSparse>;
+/// fem/diff_tensor.h:29-53: signature class of the tensor callback
+enum TensorTypeAggregate {
+    OnePointTensor = 0,   ///< TensorType f(const Coord<>& X, double* D, TensorDims Ddims, void* user_data, int iTet), once per point
+    FusiveTensor = 1      ///< TensorType f(ArrayView<> X, ArrayView<> D, TensorDims Ddims, void* user_data, const AniMemory<>& mem), once per call
 };
+template <int TensorTypeSparse = PerPoint, bool isConstant = false, long idim = -1, long jdim = -1, int aggregateType = OnePointTensor>
+struct DfuncTraitsCommon {
+    using AggregateType = std::integral_constant<int, aggregateType>;
+    using IsConstant = std::integral_constant<bool, isConstant>;
+    /// > 0: the TensorType is known at compile time; <= 0: one of TensorTypeSparsity (per point / per tet / one type per call)
+    using TensorSparsity = std::integral_constant<int, TensorTypeSparse>;
+    using iD = std::integral_constant<long, idim>;
+    using jD = std::integral_constant<long, jdim>;
+};
+template <int TensorTypeSparse = PerPoint, bool isConstant = false, long idim = -1, long jdim = -1>
+using DfuncTraits = DfuncTraitsCommon<TensorTypeSparse, isConstant, idim, jdim>;
+template <long idim = -1, long jdim = -1>
+using DfuncTraitsFusive = DfuncTraitsCommon<PerSelection, false, idim, jdim, FusiveTensor>;
 
 using TensorDims = std::pair<std::size_t, std::size_t>;
 template <typename Scalar = double> using Coord = std::array<Scalar, 3>;
+
+/// fem/fem_memory.h:15-52: pointer + size
+template <typename T = double>
+struct ArrayView {
+    T* data = nullptr;
+    std::size_t size = 0;
+    ArrayView() = default;
+    ArrayView(T* d, std::size_t n) : data(d), size(n) {}
+    T& operator[](std::size_t i) { return data[i]; }
+    const T& operator[](std::size_t i) const { return data[i]; }
+    T* begin() const { return data; }
+    T* end() const { return data + size; }
+};
+/// fem/fem_memory.h:195-213: what a FusiveTensor callback sees of the running call.  Filled here: q, f, XYG (physical quadrature
+/// points, 3 x q x f) and XYL / WG (the rule); the scratch arrays of the reference's host evaluation do not exist (the element
+/// kernels run on the device) and stay empty.
+template <typename ScalarType = double, typename IndexType = int>
+struct AniMemory {
+    using Scalar = ScalarType;
+    using ArrayR = ArrayView<Scalar>;
+    using ArrayI = ArrayView<IndexType>;
+    ArrayR XYP, PSI, XYG, DET, MES, NRM, U, V, DIFF, DU, XYL, WG, extraR;
+    ArrayI extraI;
+    std::size_t q = 0, f = 1;
+};
 
 // column-major dense matrix view (fem/fem_memory.h:55-130)
 template <typename ScalarType = double>
@@ -67,27 +107,6 @@ struct DenseMatrix {
     const ScalarType& operator()(std::size_t i, std::size_t j) const { return data[i + nRow * j]; }
     void SetZero() { for (std::size_t i = 0; i < nRow * nCol; ++i) data[i] = 0; }
 };
-
-/// fem/operations/dc_on_dof.h:13-52: essential conditions on a local matrix / rhs (host-side helpers of a local assembler)
-template <typename Scalar>
-inline void applyDirNonExists(DenseMatrix<Scalar>& A, int k) {
-    for (std::size_t i = 0; i < A.nRow; ++i) A.data[i + A.nRow * k] = 0;
-    for (std::size_t i = 0; i < A.nCol; ++i) A.data[k + A.nRow * i] = 0;
-}
-template <typename Scalar>
-inline void applyDirMatrix(DenseMatrix<Scalar>& A, int k) {
-    applyDirNonExists(A, k);
-    A.data[k + A.nRow * k] = 1.0;
-}
-/// F(i) -= A(i,k) * bc for all i;  F(k) = bc;  row and column k of A zeroed;  A(k,k) = 1   (dc_on_dof.h:27-45)
-template <typename Scalar>
-inline void applyDir(DenseMatrix<Scalar>& A, DenseMatrix<Scalar>& F, int k, Scalar bc) {
-    for (std::size_t i = 0; i < A.nRow; ++i) F.data[i] -= A.data[i + A.nRow * k] * bc;
-    F.data[k] = bc;
-    applyDirMatrix(A, k);
-}
-template <typename Scalar>
-inline void applyDirResidual(DenseMatrix<Scalar>& F, int k) { F.data[k] = 0.0; }
 
 // coordinates of `fusion` tetrahedra: XYk is 3 x fusion col-major (fem/geometry.h:96-200)
 template <typename ScalarType = const double>
@@ -124,27 +143,27 @@ inline void check(afb_ctx* c, int rc) {
 }  // namespace b200
 
 // ---- memory arguments of the reference overloads ----------------------------------------------------------------------
-// The reference carves its scratch (XYG, PSI, U, V, DU, ...) out of caller memory (fem/fem_memory.h:195-520; sizes from
-// fem3Dtet_memory_requirements, int_tet.h:154-160).  Here the scratch lives on the device, so the requirement is zero and
-// the overloads that take a memory argument accept and ignore it: reference call sites compile unchanged.
-template <typename ScalarType = double, typename IndexType = int>
-struct PlainMemory {
-    ScalarType* ddata = nullptr;
-    IndexType* idata = nullptr;
-    std::size_t dSize = 0, iSize = 0;
-    bool ge(const PlainMemory& o) const { return dSize >= o.dSize && iSize >= o.iSize; }
-    void allocateFromPlainMemory(ScalarType* d, IndexType* i) { ddata = d; idata = i; }
-};
-template <typename ScalarType = double, typename IndexType = int>
-struct PlainMemoryX : public PlainMemory<ScalarType, IndexType> {
-    void** pdata = nullptr;
-    std::size_t pSize = 0;
-};
-template <typename ScalarType = double, typename IndexType = int>
-struct DynMem {  // fem/fem_memory.h:262-520: pool of chunks; nothing is drawn from it here
-    void defragment() {}
-    void clear() {}
-};
+// PlainMemory / PlainMemoryX / DynMem (memory.hpp) are the reference's views and planners (fem/fem_memory.h:262-520).  The scratch
+// of the element kernels lives on the device, so fem3Dtet_memory_requirements reports zero sizes and the overloads that take a
+// memory argument do not draw from it: reference call sites that size, allocate and pass these objects compile and run unchanged.
+template <typename ScalarType, typename IndexType>
+void* PlainMemoryX<ScalarType, IndexType>::allocateFromRaw(void* mem_in, std::size_t mem_sz, std::size_t dsize, std::size_t isize, std::size_t msize) {
+    char *p = static_cast<char*>(mem_in), *end = p + mem_sz;
+    ScalarType* d = nullptr;
+    IndexType* i = nullptr;
+    DenseMatrix<ScalarType>* m = nullptr;
+    if (dsize && !(d = mem_detail::carve<ScalarType>(p, end, dsize))) return nullptr;
+    if (isize && !(i = mem_detail::carve<IndexType>(p, end, isize))) return nullptr;
+    if (msize && !(m = mem_detail::carve<DenseMatrix<ScalarType>>(p, end, msize))) return nullptr;
+    if (dsize) { ddata = d; dSize = dsize; }
+    if (isize) { idata = i; iSize = isize; }
+    if (msize) { mdata = m; mSize = msize; for (std::size_t k = 0; k < msize; ++k) new (m + k) DenseMatrix<ScalarType>(); }
+    return p;
+}
+template <typename ScalarType, typename IndexType>
+std::size_t PlainMemoryX<ScalarType, IndexType>::enoughRawSize() const {
+    return mem_detail::worst_bytes<ScalarType>(dSize) + mem_detail::worst_bytes<IndexType>(iSize) + mem_detail::worst_bytes<DenseMatrix<ScalarType>>(mSize);
+}
 
 // ---- runtime twins of the operators (fem/fem_space.h:170-306, ApplyOpBase / FemSpace::getOP) -------------------------
 struct ApplyOpBase {
@@ -170,9 +189,39 @@ struct FemSpace {
 namespace b200 {
 /// core shared by the compile-time and the runtime front ends
 /// face_num < 0: volume integral (fem3Dtet); 0..3: surface integral over that face of every tet (fem3Dface, int_face.inl:160-199)
+/// evaluation of the callback at the points of the call: D[dl*(n + q*r)], one TensorType per point
 template <typename Functor>
-void fem3Dtet_core(const ApplyOpBase& oa, const ApplyOpBase& ob, bool is_constant, const Tetras<const double>& XYZ, const Functor& Dfnc,
+void eval_tensor_points(std::integral_constant<int, OnePointTensor>, int sparsity, const Functor& Dfnc, std::vector<double>& XYG, int q, int f, std::size_t dl,
+                        TensorDims dims, void* user_data, const double*, const double*, std::vector<double>& D, std::vector<int>& types) {
+    for (int r = 0; r < f; ++r)
+        for (int n = 0; n < q; ++n) {
+            const std::size_t p = n + static_cast<std::size_t>(q) * r;
+            // PerSelection (diff_tensor.h:657-690): one type for the whole call, the callback is told tet 0
+            types.push_back(Dfnc(std::array<double, 3>{XYG[3 * p], XYG[3 * p + 1], XYG[3 * p + 2]}, D.data() + dl * p, dims, user_data, sparsity == PerSelection ? 0 : r));
+        }
+    if (sparsity == PerSelection) for (auto& t : types) t = types[0];
+    else if (sparsity == PerTetra)   // the type of a tet is the type of its first point (diff_tensor.h:559-566)
+        for (int r = 0; r < f; ++r) for (int n = 1; n < q; ++n) types[n + static_cast<std::size_t>(q) * r] = types[static_cast<std::size_t>(q) * r];
+}
+/// FusiveTensor (diff_tensor.h:101-135, 900-905): ONE call fills the tensors of all points; the callback writes the col-major
+/// (Ddims.first x Ddims.second) matrix of point (n, r) at D[first*second*(n + q*r)]
+template <typename Functor>
+void eval_tensor_points(std::integral_constant<int, FusiveTensor>, int, const Functor& Dfnc, std::vector<double>& XYG, int q, int f, std::size_t dl,
+                        TensorDims dims, void* user_data, const double* xyl, const double* wg, std::vector<double>& D, std::vector<int>& types) {
+    AniMemory<double, int> mem;
+    mem.q = static_cast<std::size_t>(q); mem.f = static_cast<std::size_t>(f);
+    mem.XYG = ArrayView<double>(XYG.data(), XYG.size());
+    mem.XYL = ArrayView<double>(const_cast<double*>(xyl), xyl ? static_cast<std::size_t>(4) * q : 0);
+    mem.WG = ArrayView<double>(const_cast<double*>(wg), wg ? static_cast<std::size_t>(q) : 0);
+    const int t = Dfnc(ArrayView<double>(XYG.data(), XYG.size()), ArrayView<double>(D.data(), D.size()), dims, user_data, mem);
+    (void)dl;
+    types.assign(static_cast<std::size_t>(q) * f, t);
+}
+
+template <typename FuncTraits, typename Functor>
+void fem3Dtet_core(const ApplyOpBase& oa, const ApplyOpBase& ob, const Tetras<const double>& XYZ, const Functor& Dfnc,
                    DenseMatrix<double>& A, int order, void* user_data, int face_num = -1) {
+    constexpr bool is_constant = FuncTraits::IsConstant::value && FuncTraits::AggregateType::value == OnePointTensor;
     const int f = XYZ.fusion;
     if (f <= 0) return;
     if (face_num > 3) throw std::runtime_error("Wrong face index");
@@ -195,7 +244,8 @@ void fem3Dtet_core(const ApplyOpBase& oa, const ApplyOpBase& ob, bool is_constan
     if (is_constant) {
         layout = AFB_COEF_CONST;
         D.assign(dl, 0.0);
-        types.push_back(Dfnc(std::array<double, 3>{0, 0, 0}, D.data(), dims, user_data, 0));
+        std::vector<double> X0(3, 0.0);   // a constant tensor is asked for once (a FusiveTensor callback never takes this branch)
+        eval_tensor_points(typename FuncTraits::AggregateType(), PerPoint, Dfnc, X0, 1, 1, dl, dims, user_data, nullptr, nullptr, D, types);
     } else {
         layout = AFB_COEF_PER_POINT;
         std::vector<double> XYG(static_cast<std::size_t>(3) * q * f);
@@ -217,11 +267,13 @@ void fem3Dtet_core(const ApplyOpBase& oa, const ApplyOpBase& ob, bool is_constan
         }
         D.assign(dl * q * f, 0.0);
         types.reserve(static_cast<std::size_t>(q) * f);
-        for (int r = 0; r < f; ++r)
-            for (int n = 0; n < q; ++n) {
-                const std::size_t p = n + static_cast<std::size_t>(q) * r;
-                types.push_back(Dfnc(std::array<double, 3>{XYG[3 * p], XYG[3 * p + 1], XYG[3 * p + 2]}, D.data() + dl * p, dims, user_data, r));
-            }
+        std::vector<double> xyl, wg;
+        if (FuncTraits::AggregateType::value == FusiveTensor && face_num < 0) {
+            xyl.resize(static_cast<std::size_t>(4) * q); wg.resize(q);
+            afb_tet_quadrature(order, xyl.data(), wg.data(), q);
+        }
+        eval_tensor_points(typename FuncTraits::AggregateType(), FuncTraits::TensorSparsity::value, Dfnc, XYG, q, f, dl, dims, user_data,
+                           xyl.empty() ? nullptr : xyl.data(), wg.empty() ? nullptr : wg.data(), D, types);
     }
     bool uniform = true;
     for (int t : types) uniform = uniform && t == types[0];
@@ -260,7 +312,7 @@ void fem3Dtet_core(const ApplyOpBase& oa, const ApplyOpBase& ob, bool is_constan
 /// Dmem a col-major (Ddims.first x Ddims.second) = (Dim(OpB) x Dim(OpA)) matrix (fem/operations/int_tet.h:31-47).
 template <typename OpA, typename OpB, typename FuncTraits = DfuncTraits<>, typename Functor>
 void fem3Dtet(const Tetras<const double>& XYZ, const Functor& Dfnc, DenseMatrix<double>& A, int order = 5, void* user_data = nullptr) {
-    b200::fem3Dtet_core(ApplyOpBase(OpA::op, OpA::fem, OpA::vec), ApplyOpBase(OpB::op, OpB::fem, OpB::vec), FuncTraits::IsConstant::value, XYZ, Dfnc, A,
+    b200::fem3Dtet_core<FuncTraits>(ApplyOpBase(OpA::op, OpA::fem, OpA::vec), ApplyOpBase(OpB::op, OpB::fem, OpB::vec), XYZ, Dfnc, A,
                         order, user_data);
 }
 
@@ -290,19 +342,19 @@ void fem3Dtet(const Tetras<const double>& XYZ, const Functor& Dfnc, DenseMatrix<
 template <typename FuncTraits = DfuncTraits<>, typename Functor>
 void fem3Dtet(const Tetras<const double>& XYZ, const ApplyOpBase& applyOpU, const ApplyOpBase& applyOpV, const Functor& Dfnc, DenseMatrix<double>& A,
               DynMem<>& /*wmem*/, int order = 5, void* user_data = nullptr) {
-    b200::fem3Dtet_core(applyOpU, applyOpV, FuncTraits::IsConstant::value, XYZ, Dfnc, A, order, user_data);
+    b200::fem3Dtet_core<FuncTraits>(applyOpU, applyOpV, XYZ, Dfnc, A, order, user_data);
 }
 template <typename FuncTraits = DfuncTraits<>, typename Functor>
 void fem3Dtet(const Tetras<const double>& XYZ, const ApplyOpBase& applyOpU, const ApplyOpBase& applyOpV, const Functor& Dfnc, DenseMatrix<double>& A,
               PlainMemoryX<> /*mem*/, int order = 5, void* user_data = nullptr) {
-    b200::fem3Dtet_core(applyOpU, applyOpV, FuncTraits::IsConstant::value, XYZ, Dfnc, A, order, user_data);
+    b200::fem3Dtet_core<FuncTraits>(applyOpU, applyOpV, XYZ, Dfnc, A, order, user_data);
 }
 /// Elemental matrix of the surface integral int_f (D OpA(u)) . OpB(v) over face face_num of every tet: face k = vertices
 /// {k, k+1, k+2 mod 4} (fem/operations/int_face.h:15-29,49-66); the callback sees the points of the triangle rule on the face.
 template <typename OpA, typename OpB, typename FuncTraits = DfuncTraits<>, typename Functor>
 void fem3Dface(const Tetras<const double>& XYZ, int face_num, const Functor& Dfnc, DenseMatrix<double>& A, int order = 5, void* user_data = nullptr) {
     if (face_num < 0) throw std::runtime_error("Wrong face index");
-    b200::fem3Dtet_core(ApplyOpBase(OpA::op, OpA::fem, OpA::vec), ApplyOpBase(OpB::op, OpB::fem, OpB::vec), FuncTraits::IsConstant::value, XYZ, Dfnc, A,
+    b200::fem3Dtet_core<FuncTraits>(ApplyOpBase(OpA::op, OpA::fem, OpA::vec), ApplyOpBase(OpB::op, OpB::fem, OpB::vec), XYZ, Dfnc, A,
                         order, user_data, face_num);
 }
 template <typename OpA, typename OpB, typename FuncTraits = DfuncTraits<>, typename Functor>
@@ -320,7 +372,7 @@ template <typename FuncTraits = DfuncTraits<>, typename Functor>
 void fem3Dface(const Tetras<const double>& XYZ, int face_num, const ApplyOpBase& applyOpU, const ApplyOpBase& applyOpV, const Functor& Dfnc,
                DenseMatrix<double>& A, PlainMemoryX<> /*mem*/, int order = 5, void* user_data = nullptr) {
     if (face_num < 0) throw std::runtime_error("Wrong face index");
-    b200::fem3Dtet_core(applyOpU, applyOpV, FuncTraits::IsConstant::value, XYZ, Dfnc, A, order, user_data, face_num);
+    b200::fem3Dtet_core<FuncTraits>(applyOpU, applyOpV, XYZ, Dfnc, A, order, user_data, face_num);
 }
 template <typename OpA, typename OpB, typename ScalarType = double, typename IndexType = int>
 PlainMemory<ScalarType, IndexType> fem3Dface_memory_requirements(int /*order*/, int /*fusion*/ = 1) { return PlainMemory<ScalarType, IndexType>(); }
@@ -332,3 +384,5 @@ template <typename FuncTraits = DfuncTraits<>>
 PlainMemoryX<> fem3Dtet_memory_requirements(const ApplyOpBase&, const ApplyOpBase&, int /*order*/, int /*fusion*/ = 1) { return PlainMemoryX<>(); }
 
 }  // namespace Ani
+
+#include "dc_on_dof.hpp"   // applyDir / applyVectorDir helpers of a local assembler (needs DenseMatrix, ArrayView)

@@ -236,6 +236,40 @@ int main() {
         try { fem3Dface<OP1, OP2>(F1, F2, F3, F4, 4, ddotn, A, 3); } catch (const std::runtime_error&) { thrown = true; }
         EXPECT(thrown);
     }
+    // --- DfuncTraitsFusive (one callback invocation fills the tensors of all points, diff_tensor.h:29-53,101-135) and PerSelection
+    //     (one tensor type per call) give the same matrices as the per-point callback
+    {
+        using OP = Operator<GRAD, FemFix<FEM_P2>>;
+        double XY[4][6] = {{0, 0, 0, 1, 1, 1}, {1, 0.1, 0, 2.2, 1, 1}, {0, 1.3, 0.2, 1, 2, 1.5}, {0.1, 0.2, 0.9, 1, 1.1, 2.5}};
+        const int f = 2, order = 3;
+        auto Kpt = [](const std::array<double, 3>& X, double* D, TensorDims dims, void*, int) {
+            for (std::size_t i = 0; i < dims.first * dims.second; ++i) D[i] = 0;
+            for (int k = 0; k < 3; ++k) D[k + 3 * k] = 1 + X[0] + 0.5 * k;
+            D[0 + 3 * 1] = D[1 + 3 * 0] = 0.25 * X[1];
+            return TENSOR_SYMMETRIC;
+        };
+        int calls = 0;
+        auto Kfus = [&](ArrayView<double> X, ArrayView<double> D, TensorDims dims, void*, const AniMemory<double, int>& mem) {
+            ++calls;
+            const std::size_t dl = dims.first * dims.second;
+            EXPECT(X.size == 3 * mem.q * mem.f && D.size == dl * mem.q * mem.f && mem.XYG.data == X.data && mem.WG.size == mem.q);
+            for (std::size_t p = 0; p < mem.q * mem.f; ++p) {
+                double* Dp = D.data + dl * p;
+                for (std::size_t i = 0; i < dl; ++i) Dp[i] = 0;
+                for (int k = 0; k < 3; ++k) Dp[k + 3 * k] = 1 + X[3 * p] + 0.5 * k;
+                Dp[0 + 3 * 1] = Dp[1 + 3 * 0] = 0.25 * X[3 * p + 1];
+            }
+            return TENSOR_SYMMETRIC;
+        };
+        std::vector<double> a1(100 * f), a2(100 * f), a3(100 * f);
+        DenseMatrix<> A1(a1.data(), 10, 10 * f), A2(a2.data(), 10, 10 * f), A3(a3.data(), 10, 10 * f);
+        auto T = make_tetras(XY[0], XY[1], XY[2], XY[3], f);
+        fem3Dtet<OP, OP, DfuncTraits<>>(T, Kpt, A1, order);
+        fem3Dtet<OP, OP, DfuncTraitsFusive<>>(T, Kfus, A2, order);
+        fem3Dtet<OP, OP, DfuncTraits<PerSelection>>(T, Kpt, A3, order);
+        EXPECT(calls == 1);
+        EXPECT(a1 == a2 && a1 == a3);
+    }
     // --- the MatFuncWrap plug-in point (func_wrap.h:310-347, assembler.h:326-328): the local assembler lambda of
     //     examples/tutorials/ex1.cpp:83-106 unchanged (P1, D(x) = 1 + x^2 per quadrature point, F = 1, Dirichlet u = 0 on the
     //     boundary through applyDir), installed with SetMatRHSFunc(GenerateElemMatRhs(...)) + a data gatherer; the result equals

@@ -26,6 +26,15 @@ def test_ring_plan_and_kernel_emulation_on_cpu(pkg):
     assert out.returncode == 0 and "all passed" in out.stdout
 
 
+def test_host_api_memory_views_and_planners(pkg):
+    """tests/cxx/test_host_api.cpp: PlainMemory / PlainMemoryX / DynMem (fem/fem_memory.h:262-520) behave like the reference's
+    (sizes, alignment of the carved arrays, parts returning their memory); no GPU involved"""
+    subprocess.check_call(["make", "-s", "-C", CXX_DIR, "test_host_api"])
+    out = subprocess.run([os.path.join(CXX_DIR, "test_host_api")], capture_output=True, text=True, timeout=120)
+    print(out.stdout, out.stderr)
+    assert out.returncode == 0 and "all passed" in out.stdout
+
+
 @pytest.mark.gpu
 def test_shim_runs_reference_style_tests(pkg):
     exe = os.path.join(CXX_DIR, "test_shim")
