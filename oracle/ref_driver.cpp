@@ -517,4 +517,29 @@ int ref_assemble_csr(int nforms, const RefForm* forms, long ntet, const double* 
     return st;
 }
 
+
+// ---- essential conditions on a local matrix (fem/operations/dc_on_dof.h): the reference's own helpers on caller data.
+// A: n x n column-major, F: n; dof_id[d], Vorth d x d column-major, bc[ndc], dc_orth[ndc] or NULL.
+// what: 0 applyVectorDir(A, F), 1 applyVectorDirMatrix(A), 2 applyVectorDirResidual(F), 3 applyDir(A, F, dof_id[0], bc[0]),
+//       4 applyVectorDirMatrixExtCol(A as a column of n entries), 5 applyVectorDirMatrixExtRow(A as a row of n entries)
+int ref_dirichlet_local(int what, int n, double* A, double* F, int d, const unsigned* dof_id, const double* Vorth, int ndc, const double* bc,
+                        const unsigned* dc_orth) {
+    using namespace Ani;
+    try {
+        DenseMatrix<double> Am(A, n, n), Fm(F, n, 1), V(const_cast<double*>(Vorth), d, d);
+        std::vector<double> work((size_t)d * n + 16);
+        ArrayView<double> mem(work.data(), work.size()), bcv(const_cast<double*>(bc), ndc);
+        switch (what) {
+            case 0: applyVectorDir<double>(Am, Fm, dof_id, V, bcv, mem, (uint)ndc, dc_orth); break;
+            case 1: applyVectorDirMatrix<double>(Am, dof_id, V, mem, (uint)ndc, dc_orth); break;
+            case 2: applyVectorDirResidual<double>(Fm, dof_id, V, mem, (uint)ndc, dc_orth); break;
+            case 3: applyDir<double>(Am, Fm, (int)dof_id[0], bc[0]); break;
+            case 4: { ArrayView<double> col(A, n); applyVectorDirMatrixExtCol<double>(col, dof_id, V, mem, (uint)ndc, dc_orth); break; }
+            case 5: { ArrayView<double> row(A, n); applyVectorDirMatrixExtRow<double>(row, dof_id, V, (uint)ndc, dc_orth); break; }
+            default: return -7;
+        }
+        return 0;
+    } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
+
 }  // extern "C"

@@ -71,3 +71,39 @@ def test_host_enumerators_against_the_restated_definitions(asm_oracle, tmp_path,
     # NATURAL is the numbering afb_dofmap_natural builds on the device (same oracle DofMap the GPU tests compare with)
     dm = M.DofMap(te, variables, nnode=co.shape[0])
     assert np.array_equal(M.enumerate_dofs(te, variables, "NATURAL", co.shape[0])[0], dm.elem2dof)
+
+
+def test_local_dirichlet_helpers_against_the_reference(pkg):
+    """anifem_b200/dc_on_dof.hpp (applyDir, applyVectorDir, applyVectorDirMatrix[ExtCol|ExtRow], applyVectorDirResidual) against the
+    reference's own helpers (fem/operations/dc_on_dof.h) on seeded element matrices: committed outputs of the reference build
+    (tests/golden/ref_dirichlet_local.npz, generator make_golden_dc.py) and, when oracle/_ref is present, the live reference.
+    Same arithmetic in the same order => agreement to rounding (1e-14 of the matrix scale); plus the defining property
+    V u = b of the constrained local system."""
+    import ctypes
+    import dc_cases as dc
+    subprocess.check_call(["make", "-s", "-C", CXX_DIR, "libhostapi.so"])
+    mine = ctypes.CDLL(os.path.join(CXX_DIR, "libhostapi.so"))
+    gold = dict(np.load(os.path.join(ROOT, "tests", "golden", "ref_dirichlet_local.npz")))
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libanifem_ref.so")
+    live = ctypes.CDLL(ref_so) if os.path.exists(ref_so) else None
+    for k, case in enumerate(dc.CASES):
+        A, F, args = dc.make_case(case)
+        A0, F0 = A.copy(order="F"), F.copy()
+        assert dc.call(mine.mine_dirichlet_local, case, A, F, args) == 0
+        scale = max(1.0, np.abs(A0).max())
+        assert np.abs(A - gold["A%d" % k]).max() <= 1e-14 * scale and np.abs(F - gold["F%d" % k]).max() <= 1e-13 * scale, case
+        if live is not None and hasattr(live, "ref_dirichlet_local"):
+            A2, F2 = A0.copy(order="F"), F0.copy()
+            assert dc.call(live.ref_dirichlet_local, case, A2, F2, args) == 0
+            assert np.abs(A - A2).max() <= 1e-14 * scale and np.abs(F - F2).max() <= 1e-13 * scale, case
+        what, n, d, ndc, _, _ = case
+        if what == 0:   # the constrained equations read v_k . u(dofs) = b_k
+            dof_id, Vorth, bc, dc_orth = args
+            ids = dc_orth if dc_orth is not None else np.arange(ndc)
+            for kk in range(ndc):
+                row = A[dof_id[ids[kk]], :]
+                expect = np.zeros(n)
+                expect[dof_id] = Vorth[ids[kk], :]
+                assert np.abs(row - expect).max() <= 1e-14
+                if ndc == 1:   # with several conditions the reference's rhs update of condition k' also touches the entry of k
+                    assert abs(F[dof_id[ids[kk]]] - bc[kk]) <= 1e-14   # (rows are cleared after all rhs updates): reproduced, not "fixed"
