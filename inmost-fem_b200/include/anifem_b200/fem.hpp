@@ -22,6 +22,7 @@
 
 #include "../../../include/anifem_b200.h"
 #include "memory.hpp"
+#include "dofmap.hpp"
 
 namespace Ani {
 
@@ -184,6 +185,18 @@ struct FemSpace {
     ApplyOpBase getOP(OperatorType op) const { return ApplyOpBase(op, fem, vec); }
     unsigned dofMapSize() const { return static_cast<unsigned>(vec * b200_detail::base_nf(fem)); }
     FemSpace operator^(int k) const { return FemSpace(fem, vec * k); }
+    /// local dof map of the space (BaseFemSpace::dofMap, fem_space.h): P0 = one cell dof, P1 = node dofs, P2 = + one dof per edge,
+    /// P3 = + an oriented pair per edge and one per face; a vector space is `vec` copies.  These are the orders the device
+    /// numbering kernels use (afb_ctx.cu) and the rows / columns of every element matrix of this library.
+    DofT::DofMap dofMap() const {
+        std::array<DofT::uint, DofT::NGEOM_TYPES> n{{0, 0, 0, 0, 0, 0}};
+        if (fem == FEM_P0) n[5] = 1;
+        if (fem == FEM_P1 || fem == FEM_P2 || fem == FEM_P3) n[0] = 1;
+        if (fem == FEM_P2) n[1] = 1;
+        if (fem == FEM_P3) { n[1] = 2; n[3] = 1; }
+        DofT::DofMap base(std::make_shared<DofT::UniteDofMap>(n));
+        return vec == 1 ? base : DofT::pow(base, static_cast<DofT::uint>(vec));
+    }
 };
 
 namespace b200 {

@@ -14,6 +14,7 @@
 #include "anifem++/fem/operators.h"
 #include "anifem++/fem/spaces/spaces.h"
 #include "anifem++/fem/quadrature_formulas.h"
+#include "anifem++/fem/tetdofmap.h"
 
 #include <atomic>
 #include <cmath>
@@ -538,6 +539,63 @@ int ref_dirichlet_local(int what, int n, double* A, double* F, int d, const unsi
             case 5: { ArrayView<double> row(A, n); applyVectorDirMatrixExtRow<double>(row, dof_id, V, (uint)ndc, dc_orth); break; }
             default: return -7;
         }
+        return 0;
+    } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
+
+
+// ---- local dof maps (fem/tetdofmap.h): the reference's own classes built from a flat description.
+// spec: 1 n0..n5 = UniteDofMap | 2 dim <map> = VectorDofMap | 3 k <map>*k = ComplexDofMap | 4 k <map>*k = product with simplifications
+// (operator*) | 5 k <map> = operator^.  out[3*gid + {0,1,2}] = {etype, nelem, leid}; sel (or NULL): bits of the chosen nodes / edges /
+// faces / cell -> by_sp[0] = count, by_sp[1..] = tet indices of the dofs on the selection (ascending).  Returns NumDofOnTet or < 0.
+static Ani::DofT::DofMap ref_build_dofmap(const int*& p) {
+    using namespace Ani::DofT;
+    const int kind = *p++;
+    if (kind == 1) { std::array<uint, NGEOM_TYPES> n; for (int t = 0; t < NGEOM_TYPES; ++t) n[t] = (uint)*p++; return DofMap(std::make_shared<UniteDofMap>(n)); }
+    if (kind == 2) { const int dim = *p++; DofMap b = ref_build_dofmap(p); return DofMap(std::make_shared<VectorDofMap>(dim, b.base())); }
+    if (kind == 3) { const int k = *p++; std::vector<DofMap> v; for (int i = 0; i < k; ++i) v.push_back(ref_build_dofmap(p)); return merge(v); }
+    if (kind == 4) { const int k = *p++; std::vector<DofMap> v; for (int i = 0; i < k; ++i) v.push_back(ref_build_dofmap(p)); return merge_with_simplifications(v); }
+    if (kind == 5) { const int k = *p++; DofMap b = ref_build_dofmap(p); return b ^ (uint)k; }
+    throw std::runtime_error("bad dof map description");
+}
+int ref_dofmap_table(const int* spec, int* out, int cap, const int* sel, int* by_sp) {
+    using namespace Ani::DofT;
+    try {
+        const int* p = spec;
+        DofMap m = ref_build_dofmap(p);
+        const int n = (int)m.NumDofOnTet();
+        if (n > cap) return -2;
+        for (int g = 0; g < n; ++g) {
+            LocalOrder lo = m.LocalOrderOnTet(TetOrder((uint)g));
+            out[3 * g] = lo.etype; out[3 * g + 1] = lo.nelem; out[3 * g + 2] = (int)lo.leid;
+        }
+        if (sel && by_sp) {
+            TetGeomSparsity sp;
+            for (int d = 0; d < 4; ++d) for (int i = 0; i < 6; ++i) if ((sel[d] >> i) & 1) sp.set((uchar)d, i, false);
+            std::vector<int> ids;
+            for (auto it = m.beginBySparsity(sp, false); it != m.endBySparsity(); ++it) ids.push_back((int)(*it).gid);
+            std::sort(ids.begin(), ids.end());
+            by_sp[0] = (int)ids.size();
+            for (size_t k = 0; k < ids.size(); ++k) by_sp[1 + k] = ids[k];
+        }
+        return n;
+    } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
+// structural equality of two descriptions (DofMap::operator==)
+int ref_dofmap_equal(const int* spec_a, const int* spec_b) {
+    try {
+        const int *pa = spec_a, *pb = spec_b;
+        return ref_build_dofmap(pa) == ref_build_dofmap(pb) ? 1 : 0;
+    } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
+// closure of a selection: in/out bits of nodes / edges / faces / cell after set(dim, i, with_closure) then unset(udim, ui, with_closure)
+int ref_sparsity_ops(int dim, int i, int closure, int udim, int ui, int uclosure, int* bits) {
+    using namespace Ani::DofT;
+    try {
+        TetGeomSparsity sp;
+        sp.set((uchar)dim, i, closure != 0);
+        if (udim >= 0) sp.unset((uchar)udim, ui, uclosure != 0);
+        for (int d = 0; d < 4; ++d) { auto ids = sp.getElemsIds((uchar)d); bits[d] = 0; for (int k = 0; k < ids.second; ++k) bits[d] |= 1 << ids.first[k]; }
         return 0;
     } catch (std::exception& e) { g_err = e.what(); return -1; }
 }

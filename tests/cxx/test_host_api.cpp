@@ -87,6 +87,23 @@ int main() {
         auto req = fem3Dtet_memory_requirements<Operator<GRAD, FemFix<FEM_P2>>, Operator<GRAD, FemFix<FEM_P2>>>(5, 4);
         EXPECT(req.enoughRawSize() == 0 && req.dSize == 0 && req.iSize == 0);
     }
+    {   // FemSpace::dofMap: the local orders of the supported spaces as dof maps (sizes agree with the element matrices)
+        using namespace Ani::DofT;
+        for (int fem : {FEM_P0, FEM_P1, FEM_P2, FEM_P3})
+            for (int vec : {1, 3}) {
+                FemSpace s(fem, vec);
+                DofMap m = s.dofMap();
+                EXPECT(m.NumDofOnTet() == s.dofMapSize());
+                for (uint g = 0; g < m.NumDofOnTet(); ++g) EXPECT(m.TetDofID(m[g].getGeomOrder()) == g);
+            }
+        DofMap th = FemSpace(FEM_P2, 3).dofMap() * FemSpace(FEM_P1).dofMap();   // Taylor-Hood: 30 velocity dofs, then 4 pressure dofs
+        EXPECT(th.NumDofOnTet() == 34 && th[30].etype == NODE && th[30].leid == 3 && th[10].nelem == 0 && th[10].leid == 1);
+        TetGeomSparsity face1;
+        face1.setFace(1, true);
+        int on_face = 0;
+        for (auto it = th.beginBySparsity(face1); it != th.endBySparsity(); ++it) ++on_face;
+        EXPECT(on_face == 3 * (3 + 3) + 3);   // P2^3: 3 nodes + 3 edges of the face per component; P1: 3 nodes
+    }
     if (fails) { std::printf("test_host_api: %d FAILED\n", fails); return 1; }
     std::printf("test_host_api: all passed\n");
     return 0;

@@ -107,3 +107,37 @@ def test_local_dirichlet_helpers_against_the_reference(pkg):
                 assert np.abs(row - expect).max() <= 1e-14
                 if ndc == 1:   # with several conditions the reference's rhs update of condition k' also touches the entry of k
                     assert abs(F[dof_id[ids[kk]]] - bc[kk]) <= 1e-14   # (rows are cleared after all rhs updates): reproduced, not "fixed"
+
+
+def test_local_dof_maps_against_the_reference(pkg):
+    """anifem_b200/dofmap.hpp (UniteDofMap / VectorDofMap / ComplexDofMap, operator* / ^ / merge, TetGeomSparsity, iteration over a
+    selection) against the reference's Ani::DofT (fem/tetdofmap.h) on the maps of the reference's own test
+    (tests/fem/tetdofmap_test.cpp: arr1 = {3,2,1,1,3,4}, arr2 = {1,2,0,1,0,3}, vector, complex, products) and on the Lagrange /
+    Taylor-Hood layouts: the dof -> (entity type, entity, dof on entity) tables, the dofs on five selections, structural
+    equalities of products and the closure arithmetic of selections are bit-exact against committed outputs of the reference
+    build (tests/golden/ref_dofmap.npz, generator make_golden_dofmap.py) and, when oracle/_ref is present, the live reference.
+    In this library TetDofID is the exact inverse of LocalOrderOnTet for vector / complex maps as well (checked inside
+    mine_dofmap_table); the reference's VectorDofMap::TetDofIDExt divides by the per-tet count (tetdofmap.cpp:449-451) and is
+    not compared."""
+    import ctypes
+    import dofmap_cases as dmc
+    subprocess.check_call(["make", "-s", "-C", CXX_DIR, "libhostapi.so"])
+    mine = dmc.collect(ctypes.CDLL(os.path.join(CXX_DIR, "libhostapi.so")), "mine")
+    gold = dict(np.load(os.path.join(ROOT, "tests", "golden", "ref_dofmap.npz")))
+    assert set(mine) == set(gold)
+    for k in sorted(gold):
+        assert np.array_equal(mine[k], gold[k]), k
+    assert np.array_equal(mine["equalities"], np.array([e for _, _, e in dmc.EQUALITIES]))
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libanifem_ref.so")
+    if os.path.exists(ref_so):
+        L = ctypes.CDLL(ref_so)
+        if hasattr(L, "ref_dofmap_table"):
+            live = dmc.collect(L, "ref")
+            for k in sorted(live):
+                assert np.array_equal(mine[k], live[k]), k
+    # the local orders the numbering kernels hard-wire (afb_ctx.cu) are these maps: P2 = 4 vertex dofs then 6 edge dofs, P3 = 4
+    # vertices, 6 x 2 edge dofs, 4 face dofs; Taylor-Hood = 3 x P2 then P1
+    p3 = mine["table_p3"]
+    assert [tuple(r) for r in p3[:4]] == [(1, i, 0) for i in range(4)] and tuple(p3[4]) == (2, 0, 0) and tuple(p3[5]) == (2, 0, 1) and tuple(p3[16]) == (8, 0, 0)
+    th = mine["table_taylor_hood"]
+    assert th.shape[0] == 34 and tuple(th[10]) == (1, 0, 1) and tuple(th[30]) == (1, 0, 3)
