@@ -140,7 +140,11 @@ def run(args, pkg, rank, world, local_rank):
     parity = None
     if not getattr(args, "no_parity", False):
         parity = parity_check(pkg, par, rank, world, local_rank)
-        if not parity["ok"]:
+        # the case that exercises the timed workload's own space decides whether a number may be printed at all; a failure of
+        # another case (e.g. P3 while C2 = P2 is timed) is reported in the line (parity.ok = false) and fails the run at the end
+        own_case = "p2" if getattr(args, "config", "c2") == "c2" else "taylor_hood"
+        own_ok = all(c["ok"] for c in parity["checked"] if c["case"] == own_case)
+        if not own_ok:
             if rank == 0:
                 print(json.dumps({"error": "multi-GPU parity check failed", "parity": parity}))
             dist.barrier()
@@ -285,4 +289,4 @@ def run(args, pkg, rank, world, local_rank):
         ctx.close()
     dist.barrier()
     dist.destroy_process_group()
-    return 0
+    return 0 if (parity is None or parity["ok"]) else 3
