@@ -35,6 +35,15 @@ def test_host_api_memory_views_and_planners(pkg):
     assert out.returncode == 0 and "all passed" in out.stdout
 
 
+def test_inmost_adapter_against_the_mock_inmost(pkg):
+    """anifem_b200/inmost_adapter.hpp (INMOST::Mesh -> SoA arrays for Assembler::SetMesh, CSR <-> INMOST::Sparse::Matrix / Vector)
+    compiled against oracle/mock_inmost/inmost.h, the bounded INMOST surface the reference itself compiles on here"""
+    subprocess.check_call(["make", "-s", "-C", CXX_DIR, "test_inmost_adapter"])
+    out = subprocess.run([os.path.join(CXX_DIR, "test_inmost_adapter")], capture_output=True, text=True, timeout=120)
+    print(out.stdout, out.stderr)
+    assert out.returncode == 0 and "all passed" in out.stdout
+
+
 @pytest.mark.gpu
 def test_shim_runs_reference_style_tests(pkg):
     exe = os.path.join(CXX_DIR, "test_shim")
