@@ -43,6 +43,7 @@ template <int D, int F> struct FemInfo<FemVec<D, F>> { static constexpr int fem 
 
 template <int OPERATOR, typename FEMTYPE>
 struct Operator {
+    static constexpr bool composite = false;   ///< FemVecT / FemCom spaces are specialised in composite.hpp
     static constexpr int op = OPERATOR, fem = b200_detail::FemInfo<FEMTYPE>::fem, vec = b200_detail::FemInfo<FEMTYPE>::vec;
     static_assert(OPERATOR == IDEN || OPERATOR == GRAD || (OPERATOR == DIV && vec == 3), "operator out of scope of the B200 path");
     using Nfa = std::integral_constant<int, vec * b200_detail::base_nf(fem)>;
@@ -324,7 +325,8 @@ void fem3Dtet_core(const ApplyOpBase& oa, const ApplyOpBase& ob, const Tetras<co
 /// Dfnc: TensorType(const std::array<double,3>& x, double* Dmem, TensorDims Ddims, void* user_data, int iTet) with
 /// Dmem a col-major (Ddims.first x Ddims.second) = (Dim(OpB) x Dim(OpA)) matrix (fem/operations/int_tet.h:31-47).
 template <typename OpA, typename OpB, typename FuncTraits = DfuncTraits<>, typename Functor>
-void fem3Dtet(const Tetras<const double>& XYZ, const Functor& Dfnc, DenseMatrix<double>& A, int order = 5, void* user_data = nullptr) {
+typename std::enable_if<!(OpA::composite || OpB::composite)>::type fem3Dtet(const Tetras<const double>& XYZ, const Functor& Dfnc, DenseMatrix<double>& A,
+                                                                             int order = 5, void* user_data = nullptr) {
     b200::fem3Dtet_core<FuncTraits>(ApplyOpBase(OpA::op, OpA::fem, OpA::vec), ApplyOpBase(OpB::op, OpB::fem, OpB::vec), XYZ, Dfnc, A,
                         order, user_data);
 }
@@ -396,6 +398,26 @@ PlainMemory<ScalarType, IndexType> fem3Dtet_memory_requirements(int /*order*/, i
 template <typename FuncTraits = DfuncTraits<>>
 PlainMemoryX<> fem3Dtet_memory_requirements(const ApplyOpBase&, const ApplyOpBase&, int /*order*/, int /*fusion*/ = 1) { return PlainMemoryX<>(); }
 
+}  // namespace Ani
+
+#include "composite.hpp"   // FemVecT / FemCom operators (needs Operator, Tetras, DenseMatrix, eval_tensor_points)
+
+namespace Ani {
+/// fem3Dtet with a composite space on either side (fem/operators.h:157-259): block by block on the scalar parts, every block one
+/// batched call of the element kernel with the general sub-tensor of the block
+template <typename OpA, typename OpB, typename FuncTraits = DfuncTraits<>, typename Functor>
+typename std::enable_if<(OpA::composite || OpB::composite)>::type fem3Dtet(const Tetras<const double>& XYZ, const Functor& Dfnc, DenseMatrix<double>& A,
+                                                                            int order = 5, void* user_data = nullptr) {
+    const b200::CompositeOp ca = b200::Describe<OpA>::get(), cb = b200::Describe<OpB>::get();
+    const bool is_constant = FuncTraits::IsConstant::value && FuncTraits::AggregateType::value == OnePointTensor;
+    const int f = XYZ.fusion;
+    afb_ctx* ctx = b200::default_context();
+    b200::fem3Dtet_composite<FuncTraits>(ca, cb, XYZ, Dfnc, A, order, user_data,
+        [&](int opA, int femA, int opB, int femB, const std::vector<double>& Dsub, std::vector<double>& Ablk) {
+            afb_form fm{opA, femA, 1, opB, femB, 1, order, TENSOR_GENERAL, is_constant ? AFB_COEF_CONST : AFB_COEF_PER_POINT, AFB_HOST, Dsub.data(), 1.0, 0, 0};
+            b200::check(ctx, afb_fem3dtet_batched(ctx, &fm, f, XYZ.XY0, XYZ.XY1, XYZ.XY2, XYZ.XY3, Ablk.data(), AFB_HOST));
+        });
+}
 }  // namespace Ani
 
 #include "dc_on_dof.hpp"   // applyDir / applyVectorDir helpers of a local assembler (needs DenseMatrix, ArrayView)

@@ -600,4 +600,34 @@ int ref_sparsity_ops(int dim, int i, int closure, int udim, int ui, int uclosure
     } catch (std::exception& e) { g_err = e.what(); return -1; }
 }
 
+
+// ---- composite spaces (fem/operators.h:71-74, 157-259): the reference's own FemVecT / FemCom operators on caller data.
+// which: 0  IDEN(FemCom<FemVec<3,P2>, FemFix<P1>>) x same            (34 x 34, tensor 4 x 4)
+//        1  GRAD(FemVecT<2, FemFix<P1>>) x GRAD(FemCom<FemFix<P1>, FemFix<P1>>)   (8 x 8, tensor 6 x 6)
+//        2  IDEN(FemCom<FemFix<P2>, FemFix<P0>>) -> GRAD(FemFix<P1>)   (4 x 11, tensor 3 x 2)
+//        3  IDEN(FemVecT<3, FemFix<P1>>) x same                       (12 x 12, tensor 3 x 3)
+//        4  GRAD(FemCom<FemVecT<2, FemFix<P2>>, FemFix<P1>>) x IDEN(FemCom<FemFix<P1>, FemFix<P1>, FemFix<P0>>)  (9 x 24, tensor 3 x 9)
+// D in the user-callback layout (col-major Dim(OpB) x Dim(OpA)); A: nfB x (nfA * f) col-major.  Returns 0, or -1 (message in ref_last_error).
+int ref_fem3dtet_composite(int which, int order, int ttype, int layout, const double* D, long f, const double* XY0, const double* XY1,
+                           const double* XY2, const double* XY3, double* A) {
+    try {
+        using Stokes = FemCom<FemVec<3, FEM_P2>, FemFix<FEM_P1>>;
+        using P1x2 = FemVecT<2, FemFix<FEM_P1>>;
+        using P1P1 = FemCom<FemFix<FEM_P1>, FemFix<FEM_P1>>;
+        using P2P0 = FemCom<FemFix<FEM_P2>, FemFix<FEM_P0>>;
+        using P1x3 = FemVecT<3, FemFix<FEM_P1>>;
+        using Mixed = FemCom<FemVecT<2, FemFix<FEM_P2>>, FemFix<FEM_P1>>;
+        using Tri = FemCom<FemFix<FEM_P1>, FemFix<FEM_P1>, FemFix<FEM_P0>>;
+        switch (which) {
+            case 0: return run_template<Operator<IDEN, Stokes>, Operator<IDEN, Stokes>, DfuncTraits<>>(order, ttype, layout, D, XY0, XY1, XY2, XY3, A, 0, f, (int)f);
+            case 1: return run_template<Operator<GRAD, P1x2>, Operator<GRAD, P1P1>, DfuncTraits<>>(order, ttype, layout, D, XY0, XY1, XY2, XY3, A, 0, f, (int)f);
+            case 2: return run_template<Operator<IDEN, P2P0>, Operator<GRAD, FemFix<FEM_P1>>, DfuncTraits<>>(order, ttype, layout, D, XY0, XY1, XY2, XY3, A, 0, f, (int)f);
+            case 3: return run_template<Operator<IDEN, P1x3>, Operator<IDEN, P1x3>, DfuncTraits<>>(order, ttype, layout, D, XY0, XY1, XY2, XY3, A, 0, f, (int)f);
+            case 4: return run_template<Operator<GRAD, Mixed>, Operator<IDEN, Tri>, DfuncTraits<>>(order, ttype, layout, D, XY0, XY1, XY2, XY3, A, 0, f, (int)f);
+        }
+        g_err = "unknown composite case";
+        return -7;
+    } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
+
 }  // extern "C"

@@ -1,0 +1,111 @@
+// Composite element spaces (anifem_b200/composite.hpp: FemVecT, FemCom) on the CPU: the composition code of the product --
+// flattening into scalar parts, sub-tensors per block, placement of the blocks -- runs with the REFERENCE build's scalar fem3Dtet
+// as block evaluator (oracle/_ref/libanifem_ref.so, test infrastructure) and is compared with the reference's own FemCom / FemVecT
+// operators on the same seeded tetrahedra and tensors.  In the product the block evaluator is afb_fem3dtet_batched.
+#include <cmath>
+#include <cstdio>
+#include <random>
+
+#include "anifem_b200/fem.hpp"
+
+extern "C" {
+int ref_fem3dtet(int opA, int femA, int vecA, int opB, int femB, int vecB, int order, int ttype, int layout, const double* D, long f, const double* XY0,
+                 const double* XY1, const double* XY2, const double* XY3, double* A, int mode, int fuse, int nthreads);
+int ref_fem3dtet_composite(int which, int order, int ttype, int layout, const double* D, long f, const double* XY0, const double* XY1, const double* XY2,
+                           const double* XY3, double* A);
+const char* ref_last_error();
+}
+
+using namespace Ani;
+static int fails = 0;
+#define EXPECT(c)                                                                  \
+    do {                                                                           \
+        if (!(c)) { std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #c); ++fails; } \
+    } while (0)
+
+struct Data {   // tensor data in the user-callback layout, read back by the callbacks of both sides
+    int ttype, layout, q;
+    const double* D;
+    std::size_t len;
+    mutable long calls = 0;
+};
+
+template <typename OpA, typename OpB>
+static void run_case(int which, int order, int ttype, int layout, unsigned seed) {
+    const int f = 3;
+    std::mt19937 rng(seed);
+    std::uniform_real_distribution<double> U(-1.0, 1.0);
+    std::vector<double> XY[4];
+    for (int k = 0; k < 4; ++k) XY[k].resize(3 * f);
+    for (int r = 0; r < f; ++r) {
+        const double base[4][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+        for (int k = 0; k < 4; ++k) for (int d = 0; d < 3; ++d) XY[k][d + 3 * r] = base[k][d] + 0.2 * U(rng) + r;
+    }
+    const int q = afb_tet_quadrature(order, nullptr, nullptr, 0);
+    const int dimA = OpA::Dim::value, dimB = OpB::Dim::value, nfa = OpA::Nfa::value, nfb = OpB::Nfa::value;
+    const std::size_t len = ttype == TENSOR_NULL ? 0 : (ttype == TENSOR_SCALAR ? 1 : static_cast<std::size_t>(dimA) * dimB);
+    const std::size_t nrec = layout == 0 ? 1 : (layout == 1 ? f : static_cast<std::size_t>(q) * f);
+    std::vector<double> D(std::max<std::size_t>(1, len * nrec));
+    for (auto& x : D) x = U(rng);
+    if (ttype == TENSOR_SYMMETRIC)   // the promise of the flag: symmetric records (the reference reads them without transposition)
+        for (std::size_t p = 0; p < nrec; ++p)
+            for (int k = 0; k < dimB; ++k)
+                for (int l = 0; l < k; ++l) D[len * p + l + static_cast<std::size_t>(dimB) * k] = D[len * p + k + static_cast<std::size_t>(dimB) * l];
+    std::vector<double> want(static_cast<std::size_t>(nfa) * nfb * f, 0.0), got(want.size(), -7.0);
+    if (ref_fem3dtet_composite(which, order, ttype, layout, D.data(), f, XY[0].data(), XY[1].data(), XY[2].data(), XY[3].data(), want.data()) != 0) {
+        std::printf("reference composite case %d failed: %s\n", which, ref_last_error());
+        ++fails;
+        return;
+    }
+    Data dat{ttype, layout, q, D.data(), len};
+    auto Dfnc = [&dat](const std::array<double, 3>&, double* Dm, TensorDims, void*, int iTet) {
+        const long n = dat.layout == 2 ? dat.calls % dat.q : 0;
+        dat.calls++;
+        const double* src = dat.D;
+        if (dat.layout == 1) src += dat.len * iTet;
+        if (dat.layout == 2) src += dat.len * (n + static_cast<std::size_t>(dat.q) * iTet);
+        for (std::size_t i = 0; i < dat.len; ++i) Dm[i] = src[i];
+        return static_cast<TensorType>(dat.ttype);
+    };
+    DenseMatrix<> A(got.data(), nfb, static_cast<std::size_t>(nfa) * f);
+    auto T = make_tetras(XY[0].data(), XY[1].data(), XY[2].data(), XY[3].data(), f);
+    const b200::CompositeOp ca = b200::Describe<OpA>::get(), cb = b200::Describe<OpB>::get();
+    EXPECT(ca.nfa == nfa && ca.dim == dimA && cb.nfa == nfb && cb.dim == dimB);
+    int blocks = 0;
+    b200::fem3Dtet_composite<DfuncTraits<>>(ca, cb, T, Dfnc, A, order, nullptr,
+        [&](int opA, int femA, int opB, int femB, const std::vector<double>& Dsub, std::vector<double>& Ablk) {
+            ++blocks;
+            // per-point general sub-tensor, evaluated by the reference's scalar fem3Dtet (runtime operators)
+            const int rc = ref_fem3dtet(opA, femA, 1, opB, femB, 1, order, TENSOR_GENERAL, 2, Dsub.data(), f, XY[0].data(), XY[1].data(), XY[2].data(),
+                                        XY[3].data(), Ablk.data(), 0, 1, 1);
+            if (rc) { std::printf("reference block failed: %s\n", ref_last_error()); ++fails; }
+        });
+    double scale = 0, err = 0;
+    for (std::size_t k = 0; k < want.size(); ++k) { scale = std::fmax(scale, std::fabs(want[k])); err = std::fmax(err, std::fabs(want[k] - got[k])); }
+    std::printf("case %d (order %d, tensor %d, layout %d): %d x %d, %d blocks evaluated of %zu, max |dA| / |A| = %.2e\n", which, order, ttype, layout, nfb, nfa,
+                blocks, ca.parts.size() * cb.parts.size(), err / scale);
+    EXPECT(scale > 0 && err <= 1e-13 * scale);
+}
+
+int main() {
+    using Stokes = FemCom<FemVec<3, FEM_P2>, FemFix<FEM_P1>>;
+    using P1x2 = FemVecT<2, FemFix<FEM_P1>>;
+    using P1P1 = FemCom<FemFix<FEM_P1>, FemFix<FEM_P1>>;
+    using P2P0 = FemCom<FemFix<FEM_P2>, FemFix<FEM_P0>>;
+    using P1x3 = FemVecT<3, FemFix<FEM_P1>>;
+    using Mixed = FemCom<FemVecT<2, FemFix<FEM_P2>>, FemFix<FEM_P1>>;
+    using Tri = FemCom<FemFix<FEM_P1>, FemFix<FEM_P1>, FemFix<FEM_P0>>;
+    static_assert(Operator<IDEN, Stokes>::Nfa::value == 34 && Operator<IDEN, Stokes>::Dim::value == 4, "Taylor-Hood sizes");
+    static_assert(Operator<GRAD, Mixed>::Nfa::value == 24 && Operator<GRAD, Mixed>::Dim::value == 9, "mixed sizes");
+    // per-point layout everywhere: the composition hands per-point sub-tensors to the block evaluator
+    run_case<Operator<IDEN, Stokes>, Operator<IDEN, Stokes>>(0, 4, TENSOR_GENERAL, 2, 1);
+    run_case<Operator<IDEN, Stokes>, Operator<IDEN, Stokes>>(0, 3, TENSOR_SCALAR, 2, 2);    // block-diagonal: 4 of 16 blocks
+    run_case<Operator<GRAD, P1x2>, Operator<GRAD, P1P1>>(1, 2, TENSOR_GENERAL, 2, 3);
+    run_case<Operator<IDEN, P2P0>, Operator<GRAD, FemFix<FEM_P1>>>(2, 3, TENSOR_GENERAL, 2, 4);
+    run_case<Operator<IDEN, P1x3>, Operator<IDEN, P1x3>>(3, 2, TENSOR_NULL, 2, 5);
+    run_case<Operator<IDEN, P1x3>, Operator<IDEN, P1x3>>(3, 2, TENSOR_SYMMETRIC, 2, 6);
+    run_case<Operator<GRAD, Mixed>, Operator<IDEN, Tri>>(4, 3, TENSOR_GENERAL, 2, 7);
+    if (fails) { std::printf("test_composite: %d FAILED\n", fails); return 1; }
+    std::printf("test_composite: all passed\n");
+    return 0;
+}

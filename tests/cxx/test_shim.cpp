@@ -18,6 +18,15 @@ static double norm(const DenseMatrix<>& A) { double s = 0; for (std::size_t i = 
 
 #define EXPECT(cond) do { if (!(cond)) { std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond); ++fails; } } while (0)
 
+// compile check of the composite-space front end (FemVecT / FemCom, composite.hpp); the composition itself is verified on the CPU
+// by tests/cxx/test_composite.cpp -- this function is not called
+void compile_check_composite(const Tetras<const double>& T, DenseMatrix<double>& A) {
+    using Stokes = FemCom<FemVec<3, FEM_P2>, FemFix<FEM_P1>>;
+    auto D = [](const std::array<double, 3>&, double* Dm, TensorDims d, void*, int) { for (std::size_t i = 0; i < d.first * d.second; ++i) Dm[i] = 0; return TENSOR_GENERAL; };
+    fem3Dtet<Operator<IDEN, Stokes>, Operator<IDEN, Stokes>>(T, D, A, 3);
+    fem3Dtet<Operator<GRAD, FemVecT<2, FemFix<FEM_P1>>>, Operator<GRAD, FemFix<FEM_P1>>, DfuncTraits<TENSOR_GENERAL, true>>(T, D, A, 2);
+}
+
 int main() {
     int fails = 0;
     double XY1p[] = {0, 0, 0}, XY2p[] = {2, 1, 1}, XY3p[] = {1, 2, 1}, XY4p[] = {2, 1, 2};

@@ -56,3 +56,21 @@ def test_no_cpu_fallback(pkg):
     with pytest.raises(pkg.AfbError) as e:
         pkg.Context(0)
     assert e.value.code == -4 and "no CPU fallback" in str(e.value)
+
+
+def test_new_entries_reject_a_missing_context(pkg):
+    """the entries added in round 2 (MatFuncWrap scatter, communicator, halo plan / exchange, distributed assembly, kernel names)
+    return -7 without touching a device when no context is given -- no CPU path behind them"""
+    import ctypes
+    L = pkg.lib()
+    assert L.afb_assemble_elemental(None, 0, 1, None, None, 0, None, None, 1e-100, 0) == -7
+    assert L.afb_comm_init(None, None, 0, 1) == -7
+    assert L.afb_comm_set(None, None, 0, 1) == -7
+    assert L.afb_halo_plan_set(None, 1, 0, 0, None, None, None, None, None, None, 0) == -7
+    assert L.afb_halo_exchange_start(None, None, None) == -7
+    assert L.afb_halo_exchange_finish(None, None, None) == -7
+    assert L.afb_halo_exchange(None, None, None) == -7
+    assert L.afb_assemble_distributed(None, 0, None, 0, None, None, None, 1e-100) == -7
+    buf = ctypes.create_string_buffer(16)
+    assert L.afb_last_kernels(None, buf, 16) == -7
+    assert L.afb_comm_unique_id(None) == -7

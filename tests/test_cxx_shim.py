@@ -44,6 +44,21 @@ def test_inmost_adapter_against_the_mock_inmost(pkg):
     assert out.returncode == 0 and "all passed" in out.stdout
 
 
+def test_composite_spaces_composition_against_the_reference(pkg):
+    """anifem_b200/composite.hpp (FemVecT / FemCom under IDEN / GRAD, fem/operators.h:157-259): the product's composition code
+    (flattening into scalar parts, sub-tensor per block, placement) with the reference build's scalar fem3Dtet as block evaluator
+    reproduces the reference's own composite operators on seeded tets -- Taylor-Hood IDEN x IDEN (general and scalar tensors),
+    GRAD(FemVecT<2,P1>) x GRAD(FemCom<P1,P1>), IDEN(FemCom<P2,P0>) -> GRAD(P1), vector mass with identity / symmetric tensors,
+    GRAD(FemCom<FemVecT<2,P2>,P1>) x IDEN(FemCom<P1,P1,P0>).  In the product the block evaluator is afb_fem3dtet_batched (the GPU
+    front end of fem3Dtet<composite> is compiled into test_shim but has not run on hardware)."""
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libanifem_ref.so")):
+        pytest.skip("oracle/_ref (the reference build) is not present")
+    subprocess.check_call(["make", "-s", "-C", CXX_DIR, "test_composite"])
+    out = subprocess.run([os.path.join(CXX_DIR, "test_composite")], capture_output=True, text=True, timeout=300)
+    print(out.stdout, out.stderr)
+    assert out.returncode == 0 and "all passed" in out.stdout
+
+
 @pytest.mark.gpu
 def test_shim_runs_reference_style_tests(pkg):
     exe = os.path.join(CXX_DIR, "test_shim")
