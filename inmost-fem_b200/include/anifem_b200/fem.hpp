@@ -420,4 +420,44 @@ typename std::enable_if<(OpA::composite || OpB::composite)>::type fem3Dtet(const
 }
 }  // namespace Ani
 
+#include "face_normal.hpp"   // fem3DfaceN: contraction of the tensor with the face normal (needs Tetras, eval_tensor_points)
+
+namespace Ani {
+/// int_f ((D OpA(u)) . N) . OpB(v) over face face_num of every tet (fem/operations/int_face.h:32-47, 97-133); A is nfB x (nfA*fusion).
+/// The callback fills a col-major (3 Dim(OpB) x Dim(OpA)) tensor, normal component fastest.
+template <typename FuncTraits = DfuncTraits<>, typename Functor>
+void fem3DfaceN(const Tetras<const double>& XYZ, int face_num, const ApplyOpBase& applyOpU, const ApplyOpBase& applyOpV, const Functor& Dfnc,
+                DenseMatrix<double>& A, int order = 5, void* user_data = nullptr) {
+    const int f = XYZ.fusion, nfa = static_cast<int>(applyOpU.Nfa()), nfb = static_cast<int>(applyOpV.Nfa());
+    if (A.size < static_cast<std::size_t>(nfa) * nfb * f)
+        throw std::runtime_error("Expected dimensions of A is " + std::to_string(nfb) + "x" + std::to_string(nfa * f) + ", but A has size = " + std::to_string(A.size));
+    A.nRow = nfb; A.nCol = static_cast<std::size_t>(nfa) * f;
+    afb_ctx* ctx = b200::default_context();
+    b200::fem3DfaceN_contract<FuncTraits>(static_cast<int>(applyOpU.Dim()), static_cast<int>(applyOpV.Dim()), XYZ, face_num, Dfnc, order, user_data,
+        [&](const std::vector<double>& DN, std::size_t per_tet) {
+            // one record per tet (constant tensor: the normal still differs from tet to tet) or one per point of the triangle rule
+            afb_form fm{applyOpU.op, applyOpU.fem, applyOpU.vec, applyOpV.op, applyOpV.fem, applyOpV.vec, order, TENSOR_GENERAL,
+                        per_tet == 1 ? AFB_COEF_PER_TET : AFB_COEF_PER_POINT, AFB_HOST, DN.data(), 1.0, 0, 0};
+            std::vector<int32_t> faces(f, face_num);
+            b200::check(ctx, afb_fem3dface_batched(ctx, &fm, f, faces.data(), XYZ.XY0, XYZ.XY1, XYZ.XY2, XYZ.XY3, A.data, AFB_HOST));
+        });
+}
+template <typename OpA, typename OpB, typename FuncTraits = DfuncTraits<>, typename Functor>
+void fem3DfaceN(const Tetras<const double>& XYZ, int face_num, const Functor& Dfnc, DenseMatrix<double>& A, int order = 5, void* user_data = nullptr) {
+    fem3DfaceN<FuncTraits>(XYZ, face_num, ApplyOpBase(OpA::op, OpA::fem, OpA::vec), ApplyOpBase(OpB::op, OpB::fem, OpB::vec), Dfnc, A, order, user_data);
+}
+template <typename OpA, typename OpB, typename FuncTraits = DfuncTraits<>, typename Functor>
+void fem3DfaceN(const DenseMatrix<double>& XY0, const DenseMatrix<double>& XY1, const DenseMatrix<double>& XY2, const DenseMatrix<double>& XY3,
+                int face_num, const Functor& Dfnc, DenseMatrix<double>& A, int order = 5, void* user_data = nullptr) {
+    fem3DfaceN<OpA, OpB, FuncTraits>(make_tetras(XY0.data, XY1.data, XY2.data, XY3.data, static_cast<int>(XY0.nCol)), face_num, Dfnc, A, order, user_data);
+}
+template <typename OpA, typename OpB, typename FuncTraits = DfuncTraits<>, typename Functor, typename ScalarType, typename IndexType>
+void fem3DfaceN(const Tetras<const double>& XYZ, int face_num, const Functor& Dfnc, DenseMatrix<double>& A, PlainMemory<ScalarType, IndexType>,
+                int order = 5, void* user_data = nullptr) {
+    fem3DfaceN<OpA, OpB, FuncTraits>(XYZ, face_num, Dfnc, A, order, user_data);
+}
+template <typename OpA, typename OpB, typename ScalarType = double, typename IndexType = int>
+PlainMemory<ScalarType, IndexType> fem3DfaceN_memory_requirements(int /*order*/, int /*fusion*/ = 1) { return PlainMemory<ScalarType, IndexType>(); }
+}  // namespace Ani
+
 #include "dc_on_dof.hpp"   // applyDir / applyVectorDir helpers of a local assembler (needs DenseMatrix, ArrayView)

@@ -630,4 +630,29 @@ int ref_fem3dtet_composite(int which, int order, int ttype, int layout, const do
     } catch (std::exception& e) { g_err = e.what(); return -1; }
 }
 
+
+// ---- fem3DfaceN (fem/operations/int_face.h:32-47, 97-133, dyn_ops.inl:44-50): int_f ((D OpA(u)) . N) . OpB(v), the callback
+// fills a col-major (3 Dim(OpB) x Dim(OpA)) tensor, normal component fastest.  Runtime operators, one tet per call, layouts as
+// ref_fem3dface.
+int ref_fem3dfaceN(int opA, int femA, int vecA, int opB, int femB, int vecB, int order, int ttype, int layout, const double* D,
+                   long f, const int* face, const double* XY0, const double* XY1, const double* XY2, const double* XY3, double* A) {
+    try {
+        auto oa = make_op(opA, femA, vecA), ob = make_op(opB, femB, vecB);
+        if (!oa || !ob) { g_err = "unsupported operator/space"; return -3; }
+        const long nfa = oa->Nfa(), nfb = ob->Nfa();
+        auto formula = triangle_quadrature_formulas(order);
+        TensorData td{ttype, layout, D, formula.GetNumPoints(), 0, 0};
+        TensorFunctor fn{&td};
+        for (long t = 0; t < f; ++t) {
+            td.base_tet = t; td.calls = 0;
+            auto XYZ = make_tetras(XY0 + 3 * t, XY1 + 3 * t, XY2 + 3 * t, XY3 + 3 * t, 1);
+            DenseMatrix<> Am(A + nfa * nfb * t, nfb, nfa, nfa * nfb);
+            DynMem<> wmem;
+            if (layout == 0) fem3DfaceN<DfuncTraits<PerPoint, true>>(XYZ, face[t], *oa, *ob, fn, Am, wmem, order, nullptr);
+            else fem3DfaceN<DfuncTraits<PerPoint, false>>(XYZ, face[t], *oa, *ob, fn, Am, wmem, order, nullptr);
+        }
+        return 0;
+    } catch (std::exception& e) { g_err = e.what(); return -4; }
+}
+
 }  // extern "C"

@@ -13,6 +13,10 @@ int ref_fem3dtet(int opA, int femA, int vecA, int opB, int femB, int vecB, int o
                  const double* XY1, const double* XY2, const double* XY3, double* A, int mode, int fuse, int nthreads);
 int ref_fem3dtet_composite(int which, int order, int ttype, int layout, const double* D, long f, const double* XY0, const double* XY1, const double* XY2,
                            const double* XY3, double* A);
+int ref_fem3dface(int opA, int femA, int vecA, int opB, int femB, int vecB, int order, int ttype, int layout, const double* D, long f, const int* face,
+                  const double* XY0, const double* XY1, const double* XY2, const double* XY3, double* A);
+int ref_fem3dfaceN(int opA, int femA, int vecA, int opB, int femB, int vecB, int order, int ttype, int layout, const double* D, long f, const int* face,
+                   const double* XY0, const double* XY1, const double* XY2, const double* XY3, double* A);
 const char* ref_last_error();
 }
 
@@ -87,7 +91,62 @@ static void run_case(int which, int order, int ttype, int layout, unsigned seed)
     EXPECT(scale > 0 && err <= 1e-13 * scale);
 }
 
+// fem3DfaceN: the product's contraction of the tensor with the face normal (face_normal.hpp) + the reference's fem3Dface as
+// evaluator, against the reference's own fem3DfaceN
+static void run_faceN(int opA, int femA, int opB, int femB, int vecB, int order, int ttype, bool constant, unsigned seed) {
+    const int f = 3;
+    std::mt19937 rng(seed);
+    std::uniform_real_distribution<double> U(-1.0, 1.0);
+    std::vector<double> XY[4];
+    for (int k = 0; k < 4; ++k) XY[k].resize(3 * f);
+    for (int r = 0; r < f; ++r) {
+        const double base[4][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+        for (int k = 0; k < 4; ++k) for (int d = 0; d < 3; ++d) XY[k][d + 3 * r] = base[k][d] + 0.25 * U(rng) - r;
+    }
+    if (seed & 1) for (int d = 0; d < 3; ++d) std::swap(XY[2][d], XY[3][d]);   // a negatively oriented tet among them
+    const ApplyOpBase oa(opA, femA, 1), ob(opB, femB, vecB);
+    const int dimA = static_cast<int>(oa.Dim()), dimB = static_cast<int>(ob.Dim()), nfa = static_cast<int>(oa.Nfa()), nfb = static_cast<int>(ob.Nfa());
+    const int q = afb_tri_quadrature(order, nullptr, nullptr, 0);
+    const std::size_t len = ttype == TENSOR_SCALAR ? 1 : static_cast<std::size_t>(3) * dimB * dimA;
+    const int layout = constant ? 0 : 2;
+    std::vector<double> D(len * (constant ? 1 : static_cast<std::size_t>(q) * f));
+    for (auto& x : D) x = U(rng);
+    for (int face = 0; face < 4; ++face) {
+        std::vector<int> faces(f, face);
+        std::vector<double> want(static_cast<std::size_t>(nfa) * nfb * f, 0.0), got(want.size(), -7.0);
+        if (ref_fem3dfaceN(opA, femA, 1, opB, femB, vecB, order, ttype, layout, D.data(), f, faces.data(), XY[0].data(), XY[1].data(), XY[2].data(), XY[3].data(),
+                           want.data()) != 0) { std::printf("reference fem3DfaceN failed: %s\n", ref_last_error()); ++fails; return; }
+        Data dat{ttype, layout, q, D.data(), len};
+        auto Dfnc = [&dat](const std::array<double, 3>&, double* Dm, TensorDims, void*, int iTet) {
+            const long n = dat.layout == 2 ? dat.calls % dat.q : 0;
+            dat.calls++;
+            const double* src = dat.D + (dat.layout == 2 ? dat.len * (n + static_cast<std::size_t>(dat.q) * iTet) : 0);
+            for (std::size_t i = 0; i < dat.len; ++i) Dm[i] = src[i];
+            return static_cast<TensorType>(dat.ttype);
+        };
+        auto T = make_tetras(XY[0].data(), XY[1].data(), XY[2].data(), XY[3].data(), f);
+        auto eval = [&](const std::vector<double>& DN, std::size_t per_tet) {
+            const int rc = ref_fem3dface(opA, femA, 1, opB, femB, vecB, order, TENSOR_GENERAL, per_tet == 1 ? 1 : 2, DN.data(), f, faces.data(), XY[0].data(),
+                                         XY[1].data(), XY[2].data(), XY[3].data(), got.data());
+            if (rc) { std::printf("reference fem3Dface failed: %s\n", ref_last_error()); ++fails; }
+        };
+        if (constant) b200::fem3DfaceN_contract<DfuncTraits<PerPoint, true>>(dimA, dimB, T, face, Dfnc, order, nullptr, eval);
+        else b200::fem3DfaceN_contract<DfuncTraits<>>(dimA, dimB, T, face, Dfnc, order, nullptr, eval);
+        double scale = 0, err = 0;
+        for (std::size_t k = 0; k < want.size(); ++k) { scale = std::fmax(scale, std::fabs(want[k])); err = std::fmax(err, std::fabs(want[k] - got[k])); }
+        if (!(scale > 0 && err <= 1e-13 * scale))
+            std::printf("fem3DfaceN op %d fem %d -> op %d fem %d vec %d, face %d: max |dA| / |A| = %.2e\n", opA, femA, opB, femB, vecB, face, err / scale);
+        EXPECT(scale > 0 && err <= 1e-13 * scale);
+    }
+}
+
 int main() {
+    run_faceN(GRAD, FEM_P2, IDEN, FEM_P2, 1, 4, TENSOR_GENERAL, false, 11);    // (K grad u) . N v, K per point
+    run_faceN(GRAD, FEM_P1, IDEN, FEM_P1, 1, 2, TENSOR_SCALAR, false, 12);     // s du/dn v
+    run_faceN(IDEN, FEM_P1, IDEN, FEM_P2, 1, 3, TENSOR_GENERAL, true, 13);     // (b u) . N v, constant b (3 x 1): per-tet records after the contraction
+    run_faceN(GRAD, FEM_P1, IDEN, FEM_P1, 3, 3, TENSOR_GENERAL, false, 14);    // vector test space: 9 x 3 tensor
+    run_faceN(GRAD, FEM_P3, IDEN, FEM_P0, 1, 5, TENSOR_GENERAL, false, 15);
+    std::printf("fem3DfaceN: 5 operator pairs x 4 faces done\n");
     using Stokes = FemCom<FemVec<3, FEM_P2>, FemFix<FEM_P1>>;
     using P1x2 = FemVecT<2, FemFix<FEM_P1>>;
     using P1P1 = FemCom<FemFix<FEM_P1>, FemFix<FEM_P1>>;
