@@ -197,6 +197,48 @@ struct Operator<OPERATOR, FemCom<Types...>> {
     static b200::CompositeOp describe() { return b200::make_composite_op<OPERATOR, Space>(); }
 };
 
+/// Runtime twins (fem/fem_space.h: ComplexFemSpace, VectorFemSpace, FemSpace::operator* / operator^, getOP): a space assembled at
+/// run time from scalar / vector parts, e.g. (FemSpace(FEM_P2) ^ 3) * FemSpace(FEM_P1) for Taylor-Hood.
+struct ApplyOpComposite {
+    b200::CompositeOp c;
+    unsigned Nfa() const { return static_cast<unsigned>(c.nfa); }
+    unsigned Dim() const { return static_cast<unsigned>(c.dim); }
+};
+struct ComplexFemSpace {
+    std::vector<FemSpace> parts;   ///< first-level factors in order
+    ComplexFemSpace() = default;
+    ComplexFemSpace(const FemSpace& s) : parts{s} {}
+    ComplexFemSpace(std::vector<FemSpace> p) : parts(std::move(p)) {}
+    unsigned dofMapSize() const { unsigned n = 0; for (auto& s : parts) n += s.dofMapSize(); return n; }
+    /// operator of the whole space: block diagonal over the scalar parts (IDEN, GRAD)
+    ApplyOpComposite getOP(OperatorType op) const {
+        if (op != IDEN && op != GRAD) throw std::runtime_error("composite spaces support IDEN and GRAD");
+        ApplyOpComposite a;
+        a.c.op = op; a.c.part_dim = op == GRAD ? 3 : 1;
+        int nfa = 0, comp = 0;
+        for (auto& s : parts)
+            for (int k = 0; k < s.vec; ++k) { a.c.parts.push_back(b200::OpPart{s.fem, nfa, comp}); nfa += b200_detail::base_nf(s.fem); ++comp; }
+        a.c.nfa = nfa; a.c.dim = comp * a.c.part_dim;
+        return a;
+    }
+    /// local dof map: the product of the factors' maps with the reference's simplifications
+    DofT::DofMap dofMap() const {
+        std::vector<DofT::DofMap> m;
+        for (auto& s : parts) m.push_back(s.dofMap());
+        return DofT::merge_with_simplifications(m);
+    }
+    ComplexFemSpace operator*(const ComplexFemSpace& o) const {
+        ComplexFemSpace r = *this;
+        for (auto& s : o.parts) {
+            if (!r.parts.empty() && r.parts.back().fem == s.fem) r.parts.back().vec += s.vec;   // equal neighbours fuse into a vector space
+            else r.parts.push_back(s);
+        }
+        return r;
+    }
+};
+inline ComplexFemSpace operator*(const FemSpace& a, const FemSpace& b) { return ComplexFemSpace(a) * ComplexFemSpace(b); }
+inline ComplexFemSpace operator*(const FemSpace& a, const ComplexFemSpace& b) { return ComplexFemSpace(a) * b; }
+
 namespace b200 {
 /// description of any operator as a composite (simple spaces: FemFix -> one part, FemVec<3,F> -> three parts)
 template <typename Op, bool = Op::composite> struct Describe;

@@ -420,6 +420,22 @@ typename std::enable_if<(OpA::composite || OpB::composite)>::type fem3Dtet(const
 }
 }  // namespace Ani
 
+namespace Ani {
+/// runtime-operator form on composite spaces (dyn_ops.h:26-32 with ComplexFemSpace::getOP)
+template <typename FuncTraits = DfuncTraits<>, typename Functor>
+void fem3Dtet(const Tetras<const double>& XYZ, const ApplyOpComposite& applyOpU, const ApplyOpComposite& applyOpV, const Functor& Dfnc, DenseMatrix<double>& A,
+              int order = 5, void* user_data = nullptr) {
+    const bool is_constant = FuncTraits::IsConstant::value && FuncTraits::AggregateType::value == OnePointTensor;
+    const int f = XYZ.fusion;
+    afb_ctx* ctx = b200::default_context();
+    b200::fem3Dtet_composite<FuncTraits>(applyOpU.c, applyOpV.c, XYZ, Dfnc, A, order, user_data,
+        [&](int opA, int femA, int opB, int femB, const std::vector<double>& Dsub, std::vector<double>& Ablk) {
+            afb_form fm{opA, femA, 1, opB, femB, 1, order, TENSOR_GENERAL, is_constant ? AFB_COEF_CONST : AFB_COEF_PER_POINT, AFB_HOST, Dsub.data(), 1.0, 0, 0};
+            b200::check(ctx, afb_fem3dtet_batched(ctx, &fm, f, XYZ.XY0, XYZ.XY1, XYZ.XY2, XYZ.XY3, Ablk.data(), AFB_HOST));
+        });
+}
+}  // namespace Ani
+
 #include "face_normal.hpp"   // fem3DfaceN: contraction of the tensor with the face normal (needs Tetras, eval_tensor_points)
 
 namespace Ani {

@@ -164,6 +164,19 @@ int main() {
     run_case<Operator<IDEN, P1x3>, Operator<IDEN, P1x3>>(3, 2, TENSOR_NULL, 2, 5);
     run_case<Operator<IDEN, P1x3>, Operator<IDEN, P1x3>>(3, 2, TENSOR_SYMMETRIC, 2, 6);
     run_case<Operator<GRAD, Mixed>, Operator<IDEN, Tri>>(4, 3, TENSOR_GENERAL, 2, 7);
+    {   // runtime twins: (P2 ^ 3) * P1 describes the same operator as the template FemCom<FemVec<3,P2>, FemFix<P1>>
+        const ComplexFemSpace UP = (FemSpace(FEM_P2) ^ 3) * FemSpace(FEM_P1);
+        const b200::CompositeOp a = UP.getOP(GRAD).c, b = b200::Describe<Operator<GRAD, Stokes>>::get();
+        EXPECT(UP.dofMapSize() == 34 && a.nfa == b.nfa && a.dim == b.dim && a.parts.size() == b.parts.size());
+        for (std::size_t k = 0; k < a.parts.size() && k < b.parts.size(); ++k)
+            EXPECT(a.parts[k].fem == b.parts[k].fem && a.parts[k].nfa_off == b.parts[k].nfa_off && a.parts[k].comp == b.parts[k].comp);
+        EXPECT(UP.dofMap().NumDofOnTet() == 34 && UP.dofMap() == FemSpace(FEM_P2, 3).dofMap() * FemSpace(FEM_P1).dofMap());
+        const ComplexFemSpace fused = FemSpace(FEM_P1) * FemSpace(FEM_P1) * FemSpace(FEM_P0);   // P1 * P1 fuses into P1 ^ 2
+        EXPECT(fused.parts.size() == 2 && fused.parts[0].vec == 2 && fused.getOP(IDEN).Nfa() == 9 && fused.getOP(IDEN).Dim() == 3);
+        bool thrown = false;
+        try { UP.getOP(DIV); } catch (std::runtime_error&) { thrown = true; }
+        EXPECT(thrown);
+    }
     if (fails) { std::printf("test_composite: %d FAILED\n", fails); return 1; }
     std::printf("test_composite: all passed\n");
     return 0;

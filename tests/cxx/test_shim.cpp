@@ -25,6 +25,9 @@ void compile_check_composite(const Tetras<const double>& T, DenseMatrix<double>&
     auto D = [](const std::array<double, 3>&, double* Dm, TensorDims d, void*, int) { for (std::size_t i = 0; i < d.first * d.second; ++i) Dm[i] = 0; return TENSOR_GENERAL; };
     fem3Dtet<Operator<IDEN, Stokes>, Operator<IDEN, Stokes>>(T, D, A, 3);
     fem3Dtet<Operator<GRAD, FemVecT<2, FemFix<FEM_P1>>>, Operator<GRAD, FemFix<FEM_P1>>, DfuncTraits<TENSOR_GENERAL, true>>(T, D, A, 2);
+    const ComplexFemSpace UP = (FemSpace(FEM_P2) ^ 3) * FemSpace(FEM_P1);
+    fem3Dtet(T, UP.getOP(IDEN), UP.getOP(IDEN), D, A, 3);
+    fem3DfaceN<Operator<GRAD, FemFix<FEM_P2>>, Operator<IDEN, FemFix<FEM_P2>>>(T, 1, D, A, 4);
 }
 
 int main() {
