@@ -49,8 +49,8 @@ def test_composite_spaces_composition_against_the_reference(pkg):
     (flattening into scalar parts, sub-tensor per block, placement) with the reference build's scalar fem3Dtet as block evaluator
     reproduces the reference's own composite operators on seeded tets -- Taylor-Hood IDEN x IDEN (general and scalar tensors),
     GRAD(FemVecT<2,P1>) x GRAD(FemCom<P1,P1>), IDEN(FemCom<P2,P0>) -> GRAD(P1), vector mass with identity / symmetric tensors,
-    GRAD(FemCom<FemVecT<2,P2>,P1>) x IDEN(FemCom<P1,P1,P0>).  In the product the block evaluator is afb_fem3dtet_batched (the GPU
-    front end of fem3Dtet<composite> is compiled into test_shim but has not run on hardware).
+    GRAD(FemCom<FemVecT<2,P2>,P1>) x IDEN(FemCom<P1,P1,P0>).  In the product the block evaluator is afb_fem3dtet_batched (GPU leg:
+    tests/test_zz_composite_gpu.py).
     Same binary: fem3DfaceN (face_normal.hpp) -- the contraction of the callback's tensor with the face normal + the reference's
     fem3Dface as evaluator against the reference's own fem3DfaceN, five operator pairs x four faces."""
     if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libanifem_ref.so")):
