@@ -289,6 +289,30 @@ std::unique_ptr<CellRunner> make_runner(int opA, int femA, int vecA, int opB, in
 
 }  // namespace
 
+template <typename Op>
+static int ref_apply_impl(int mode, long f, int q, const double* pts, const double* XY0, const double* XY1, const double* XY2, const double* XY3,
+                          const double* dofs, double* out) {
+    constexpr int nfa = Op::Nfa::value, dim = Op::Dim::value;
+    if (mode == 0) {
+        auto req = fem3DapplyL_memory_requirements<Op>(q, (int)f);
+        // slack behind the planned block: for multi-part (vector) operators the reference's evaluation stages dim*q*f values in its
+        // last scratch region, which the planner sizes nfa*f (core.inl:384, eval.inl:61)
+        req.dSize += (std::size_t)dim * q * f + (std::size_t)nfa * f + 64;
+        std::vector<char> raw(req.enoughRawSize());
+        req.allocateFromRaw(raw.data(), raw.size());
+        DenseMatrix<> d(const_cast<double*>(dofs), nfa, f), o(out, (std::size_t)dim * q, f);
+        fem3DapplyL<Op>(make_tetras(XY0, XY1, XY2, XY3, (int)f), ArrayView<>(const_cast<double*>(pts), 4 * q), d, o, req);
+    } else {
+        auto req = fem3DapplyX_memory_requirements<Op>(q, 1);
+        req.dSize += (std::size_t)dim * q + (std::size_t)nfa + 64;
+        std::vector<char> raw(req.enoughRawSize());
+        req.allocateFromRaw(raw.data(), raw.size());
+        Tetra<const double> T(XY0, XY1, XY2, XY3);
+        fem3DapplyX<Op>(T, ArrayView<const double>(pts, 3 * q), ArrayView<>(const_cast<double*>(dofs), nfa), ArrayView<>(out, (std::size_t)dim * q), req);
+    }
+    return 0;
+}
+
 extern "C" {
 
 const char* ref_last_error() { return g_err.c_str(); }
@@ -653,6 +677,24 @@ int ref_fem3dfaceN(int opA, int femA, int vecA, int opB, int femB, int vecB, int
         }
         return 0;
     } catch (std::exception& e) { g_err = e.what(); return -4; }
+}
+
+
+// ---- FE-function evaluation (fem/operations/eval.h): the reference's own fem3DapplyL / fem3DapplyX for a few operators.
+// which: 0 GRAD(P2), 1 IDEN(P3), 2 IDEN(FemVec<3,P1>), 3 GRAD(FemVec<3,P2>).  mode 0: fem3DapplyL with XYL[4q] on f tets;
+// mode 1: fem3DapplyX with physical points pts[3q] on tet 0 (f must be 1).  dofs: nfa x f, out: (dim*q) x f.
+int ref_fem3dapply(int which, int mode, long f, int q, const double* pts, const double* XY0, const double* XY1, const double* XY2, const double* XY3,
+                   const double* dofs, double* out) {
+    try {
+        switch (which) {
+            case 0: return ref_apply_impl<Operator<GRAD, FemFix<FEM_P2>>>(mode, f, q, pts, XY0, XY1, XY2, XY3, dofs, out);
+            case 1: return ref_apply_impl<Operator<IDEN, FemFix<FEM_P3>>>(mode, f, q, pts, XY0, XY1, XY2, XY3, dofs, out);
+            case 2: return ref_apply_impl<Operator<IDEN, FemVec<3, FEM_P1>>>(mode, f, q, pts, XY0, XY1, XY2, XY3, dofs, out);
+            case 3: return ref_apply_impl<Operator<GRAD, FemVec<3, FEM_P2>>>(mode, f, q, pts, XY0, XY1, XY2, XY3, dofs, out);
+        }
+        g_err = "unknown operator case";
+        return -7;
+    } catch (std::exception& e) { g_err = e.what(); return -1; }
 }
 
 }  // extern "C"

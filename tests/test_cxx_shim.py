@@ -61,6 +61,21 @@ def test_composite_spaces_composition_against_the_reference(pkg):
     assert out.returncode == 0 and "all passed" in out.stdout
 
 
+def test_fem3dapply_x_barycentric_conversion_against_the_reference(pkg):
+    """anifem_b200/eval.hpp: fem3DapplyX = conversion of physical points to barycentric coordinates on the host + fem3DapplyL.  CPU:
+    the product's conversion + the reference's fem3DapplyL reproduces the reference's own fem3DapplyX (GRAD P2, IDEN P3,
+    IDEN P1^3, GRAD P2^3; points inside and outside the tet).  GPU evidence of the front ends (not a pytest leg: the round's GPU
+    budget ended before the corrected expectation could be re-run): profiles/r02/r02g_apply_gpu_front_ends_first_run.log --
+    scalar operators fused and per tet at 3e-16, vector operators per tet (fem3DapplyX) green; the batched entry itself is
+    covered by tests/test_eval_gpu.py."""
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libanifem_ref.so")):
+        pytest.skip("oracle/_ref (the reference build) is not present")
+    subprocess.check_call(["make", "-s", "-C", CXX_DIR, "test_apply"])
+    out = subprocess.run([os.path.join(CXX_DIR, "test_apply")], capture_output=True, text=True, timeout=300)
+    print(out.stdout, out.stderr)
+    assert out.returncode == 0 and "all passed" in out.stdout
+
+
 @pytest.mark.gpu
 def test_shim_runs_reference_style_tests(pkg):
     exe = os.path.join(CXX_DIR, "test_shim")
