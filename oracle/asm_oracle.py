@@ -2,12 +2,17 @@
 (anifem++/inmost_interface + the cube generator of anifem++/utils).  Imported only by tests/,
 __graft_entry__.smoke() and bench.py's CPU-baseline legs -- never by the product.
 
-PARITY STATUS: **parity unpinned** at this level.  The reference's Assembler needs INMOST
-(un-vendored external pinned at INMOST-DEV/INMOST@f3392cef4cbb4d05b91c5cc94922040637bea4ee,
-cmake/Downloadinmost.cmake:4) which is absent here, and the reference holds no test for
-assembler.inl / global_enumerator.cpp / ordering.inl.  What INMOST decides (GlobalID of nodes /
-edges / faces, cell->node order, entity ownership) is replaced by the documented conventions
-below; everything AniFem++ itself decides is restated from its sources:
+PARITY STATUS: **pinned** on one rank since round 2, against the reference's OWN assembler: the unmodified
+inmost_interface/{global_enumerator.cpp, elemental_assembler.cpp, assembler.inl, ordering.inl} compile on top of
+oracle/mock_inmost/inmost.h (the bounded INMOST surface they use; INMOST itself is an un-vendored external pinned at
+INMOST-DEV/INMOST@f3392cef4cbb4d05b91c5cc94922040637bea4ee, cmake/Downloadinmost.cmake:4) into
+oracle/_ref/libanifem_refasm.so (oracle/Makefile target refasm, driver oracle/ref_asm_driver.cpp).  Its outputs on cubes and a
+scrambled mesh -- numbering of all six enumerators, AssembleTemplate pattern, Assemble values / drop rule / status -- are
+committed as tests/golden/ref_assembler.npz (generator tests/golden/make_golden_asm.py) and tests/test_oracle_golden.py checks
+this module against them (indices bit-exact, values 1e-13) and against the live build when present.
+Still ours and NOT pinned (INMOST's parallel mesh cannot be built here): what INMOST decides on SEVERAL ranks -- entity
+ownership and the rank-major GlobalIDs -- follows the documented conventions below; everything AniFem++ itself decides is
+restated from its sources:
 
   mesh          utils/mesh_utils.cpp:20-48 (6 tets per hex), :110-145 (node/hex loops)
   orientation   inmost_interface/ordering.inl:8-26      (swap nodes 2,3 if det<0)
